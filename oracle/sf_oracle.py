@@ -1,0 +1,307 @@
+# -*- coding: UTF-8 -*-
+"""
+CPU ORACLE for the SF/GPI hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import this
+module, and only as the checker / the CPU arm -- never as the thing shipped.  The product
+(`deep_successor_features_for_transfer_b200`) never imports it.
+
+It restates, function by function, the reference algorithm of okgarces/deep-successor-features-for-transfer
+with plain fp32 torch CPU tensors (no nn.Module, no torch.optim): every function cites the reference file:line it
+follows.  The arithmetic the reference delegates to a third-party dependency -- PyTorch (`aten::addmm`, `mse_loss`,
+autograd, `torch.optim.Adam`; NOT vendored under the reference, no version pin anywhere in it; the installed
+torch 2.11.0 is the de-facto pin) -- is restated here explicitly (Adam: torch/optim/adam.py::_single_tensor_adam).
+
+Pinning: the reference ships no tests / golden vectors, so this oracle is pinned against
+outputs of the reference itself, executed in the build container by `tests/golden/make_golden.py` (imports
+/root/reference/source unmodified) and committed under `tests/golden/*.npz`; `tests/test_oracle_golden.py`
+checks oracle == reference on those fixtures.
+"""
+import copy
+import math
+
+import torch
+
+ADAM_BETA1, ADAM_BETA2, ADAM_EPS = 0.9, 0.999, 1e-8   # torch.optim.Adam defaults, used at sfdqn.py:286 / tsfdqn.py:270
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# A1: psi network (main_tsfdqn_sequential_torch.py:44-75): Linear(S,H0) [no act] -> [Linear(H,H), act]*L -> Linear(H,A*D)
+# ----------------------------------------------------------------------------------------------------------------
+def act_fn(name):
+    if name == 'relu':
+        return torch.relu
+    if name == 'tanh':
+        return torch.tanh
+    if name in (None, 'none'):
+        return lambda t: t
+    raise Exception('Activation name not supported')      # utils/torch.py:24-27
+
+
+def mlp_forward(layers, acts, x):
+    """layers: list of (W[out,in], b[out]); acts: activation name after each layer ('none' | 'relu' | 'tanh')."""
+    h = x
+    for (W, b), a in zip(layers, acts):
+        h = act_fn(a)(torch.addmm(b, h, W.t()))
+    return h
+
+
+def make_acts(n_hidden_layers, activations):
+    """Activation pattern produced by sf_model_lambda: none after layer_input, act_k after layer_k, none after output."""
+    return ['none'] + list(activations)[:n_hidden_layers] + ['none']
+
+
+def init_linear(out_f, in_f, gen):
+    """nn.Linear default init (kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(in)) for W and b)."""
+    bound = 1.0 / math.sqrt(in_f)
+    W = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=gen) * 2 - 1) * bound
+    return W, b
+
+
+class OracleSF:
+    """
+    State of the SF library: N online/target psi nets, N reward maps w, per-policy Adam state (sfdqn.py:94-371),
+    plus the TSF g_i / shared h (tsfdqn.py:537-560, 711-739).  Pure tensors.
+    """
+
+    def __init__(self, S, A, D, hidden=(256, 256), activations=('relu', 'relu'), lr=None, wd=None, tsf_dim=None, beta=1,
+                 target_update_ev=1000):
+        self.S, self.A, self.D = S, A, D
+        self.hidden, self.activations = tuple(hidden), tuple(activations)
+        self.acts = make_acts(len(hidden), activations)
+        self.dims = [S, hidden[0]] + list(hidden) + [A * D]      # layer l maps dims[l] -> dims[l+1]
+        self.lr = dict(sf=1e-3, w=1e-3, g=1e-3, h=1e-3) if lr is None else dict(lr)
+        self.wd = dict(sf=0.0, w=0.0, g=0.0, h=0.0) if wd is None else dict(wd)
+        self.tsf_dim, self.beta = tsf_dim, beta
+        self.target_update_ev = target_update_ev
+        self.psi, self.tgt, self.w, self.g = [], [], [], []
+        self.h = None
+        self.adam = []                  # per policy: {'step': int, 'm': {key: tensor-list}, 'v': {...}}
+        self.updates_since_target_updated = []
+
+    @property
+    def n_tasks(self):
+        return len(self.psi)
+
+    # sfdqn.py:180-213 add_training_task + :242-288 build_successor (tsfdqn.py:137-170, 227-281, 711-739)
+    def add_policy(self, layers, w, g=None, h=None):
+        layers = [(W.clone().float(), b.clone().float()) for W, b in layers]
+        self.psi.append(layers)
+        self.tgt.append([(W.clone(), b.clone()) for W, b in layers])       # update_models_weights(model, target_model)
+        self.w.append(w.clone().float().reshape(1, self.D))
+        if self.tsf_dim is not None:
+            self.g.append((g[0].clone().float(), g[1].clone().float()))
+            if self.h is None:
+                self.h = (h[0].clone().float(), h[1].clone().float())
+        self.adam.append({'step': 0, 'm': None, 'v': None})
+        self.updates_since_target_updated.append(0)
+
+    def add_random_policy(self, gen):
+        layers = [init_linear(self.dims[l + 1], self.dims[l], gen) for l in range(len(self.dims) - 1)]
+        w = (torch.rand(1, self.D, generator=gen) * 0.02 - 0.01)           # U(-0.01, 0.01), sfdqn.py:197
+        g = h = None
+        if self.tsf_dim is not None:
+            g = init_linear(self.tsf_dim, self.S, gen)                    # tsfdqn.py:537-539
+            if self.h is None:
+                h = init_linear(self.D, self.tsf_dim, gen)                # tsfdqn.py:548-560
+        self.add_policy(layers, w, g, h)
+
+    # ---------------- A2 / A3: forwards ----------------
+    def get_successor(self, x, i):                                        # sfdqn.py:290-293
+        return mlp_forward(self.psi[i], self.acts, x).reshape(-1, self.A, self.D)
+
+    def get_successors(self, x):                                          # sfdqn.py:295-301
+        return torch.stack([self.get_successor(x, i) for i in range(self.n_tasks)], dim=1)
+
+    def get_next_successor(self, x, i):                                   # tsfdqn.py:296-299 (target nets)
+        return mlp_forward(self.tgt[i], self.acts, x).reshape(-1, self.A, self.D)
+
+    def get_next_successors(self, x):                                     # tsfdqn.py:301-307
+        return torch.stack([self.get_next_successor(x, i) for i in range(self.n_tasks)], dim=1)
+
+    # ---------------- A4 / A5: GPI ----------------
+    def GPI_w(self, x, w):                                                # sfdqn.py:215-240
+        psi = self.get_successors(x)                                      # [B,N,A,D]
+        q = torch.nn.functional.linear(psi, w.reshape(1, self.D))[:, :, :, 0]
+        task = torch.squeeze(torch.argmax(torch.max(q, dim=2).values, dim=1))
+        return q, task
+
+    def GPI(self, x, task_index):                                         # sfdqn.py:153-178
+        return self.GPI_w(x, self.w[task_index])
+
+    def next_actions(self, next_states, i, use_gpi):                      # sfdqn.py:314-322 / tsfdqn.py:604-612
+        if use_gpi:
+            q1, _ = self.GPI(next_states, i)
+            return torch.argmax(torch.max(q1, dim=1).values, dim=-1)
+        sf = self.get_successor(next_states, i)
+        q1 = torch.nn.functional.linear(sf, self.w[i])                    # [B,A,1]
+        return torch.squeeze(torch.argmax(q1, dim=1), dim=1)
+
+    # ---------------- A7: Adam (torch/optim/adam.py::_single_tensor_adam) ----------------
+    @staticmethod
+    def _adam_tensor(p, g, m, v, step, lr, wd):
+        if wd != 0:
+            g = g.add(p, alpha=wd)
+        m.lerp_(g, 1 - ADAM_BETA1)
+        v.mul_(ADAM_BETA2).addcmul_(g, g, value=1 - ADAM_BETA2)
+        bc1 = 1 - ADAM_BETA1 ** step
+        bc2 = 1 - ADAM_BETA2 ** step
+        step_size = lr / bc1
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(ADAM_EPS)
+        p.addcdiv_(m, denom, value=-step_size)
+
+    def _adam_step(self, i, groups):
+        """groups: list of (key, [params], [grads], lr, wd). Moments are per policy-optimizer, also for the shared h."""
+        st = self.adam[i]
+        if st['m'] is None:
+            st['m'], st['v'] = {}, {}
+        st['step'] += 1
+        for key, params, grads, lr, wd in groups:
+            if key not in st['m']:
+                st['m'][key] = [torch.zeros_like(p) for p in params]
+                st['v'][key] = [torch.zeros_like(p) for p in params]
+            for p, g, m, v in zip(params, grads, st['m'][key], st['v'][key]):
+                self._adam_tensor(p, g, m, v, st['step'], lr, wd)
+
+    def _target_sync(self, i):                                            # sfdqn.py:365-369, utils/torch.py:31-33
+        self.updates_since_target_updated[i] += 1
+        if self.updates_since_target_updated[i] >= self.target_update_ev:
+            for (Wt, bt), (W, b) in zip(self.tgt[i], self.psi[i]):
+                Wt.copy_(W)
+                bt.copy_(b)
+            self.updates_since_target_updated[i] = 0
+
+    # ---------------- A6: G2 train step, sfdqn.py:303-371 ----------------
+    def update_successor(self, transitions, i, use_gpi=True, with_reward_loss=True):
+        """with_reward_loss=False gives the G1 step of features/deep.py:93-131 (5-tuple transitions, l1 only)."""
+        if transitions is None:
+            return None
+        if with_reward_loss:
+            states, actions, rs, phis, next_states, gammas = transitions
+        else:
+            states, actions, phis, next_states, gammas = transitions
+            rs = None
+        B = len(gammas)
+        idx = torch.arange(B)
+        gammas = gammas.reshape(-1, 1)
+        with torch.no_grad():
+            next_actions = self.next_actions(next_states, i, use_gpi)
+            targets = phis + gammas * self.get_next_successor(next_states, i)[idx, next_actions, :]
+        flat = [t for Wb in self.psi[i] for t in Wb]
+        leaves = [t.detach().requires_grad_(True) for t in flat]
+        layers = [(leaves[2 * l], leaves[2 * l + 1]) for l in range(len(self.psi[i]))]
+        w_leaf = self.w[i].detach().requires_grad_(True)
+        cur = mlp_forward(layers, self.acts, states).reshape(B, self.A, self.D)
+        merge = cur.clone()
+        merge[idx, actions, :] = targets
+        l1 = torch.nn.functional.mse_loss(cur, merge)
+        if with_reward_loss:
+            l2 = torch.nn.functional.mse_loss(torch.nn.functional.linear(phis, w_leaf), rs)
+            loss = l1 + l2
+            grads = torch.autograd.grad(loss, leaves + [w_leaf])
+            groups = [('sf', flat, list(grads[:-1]), self.lr['sf'], self.wd['sf']),
+                      ('w', [self.w[i]], [grads[-1]], self.lr['w'], self.wd['w'])]
+        else:
+            l2 = torch.zeros(())
+            loss = l1
+            grads = torch.autograd.grad(loss, leaves)
+            groups = [('sf', flat, list(grads), self.lr['sf'], self.wd['sf'])]
+        self.last_grads = {k: [g.clone() for g in gr] for k, _, gr, _, _ in groups}
+        with torch.no_grad():
+            self._adam_step(i, groups)
+            self._target_sync(i)
+        return loss.detach(), l1.detach(), l2.detach()
+
+    # ---------------- A6': G3 TSF train step, tsfdqn.py:588-709 ----------------
+    def tsf_update_successor(self, transitions, i, use_gpi=True):
+        if transitions is None:
+            return None
+        if self.h is None:
+            raise Exception('Affine Function (h) is not initialized')       # tsfdqn.py:592-593
+        states, actions, rs, phis, next_states, gammas = transitions
+        B = len(gammas)
+        idx = torch.arange(B)
+        gammas = gammas.reshape(-1, 1)
+        with torch.no_grad():
+            next_actions = self.next_actions(next_states, i, use_gpi)
+            next_psis = self.get_next_successor(next_states, i)[idx, next_actions, :]
+        flat = [t for Wb in self.psi[i] for t in Wb]
+        leaves = [t.detach().requires_grad_(True) for t in flat]
+        layers = [(leaves[2 * l], leaves[2 * l + 1]) for l in range(len(self.psi[i]))]
+        w_leaf = self.w[i].detach().requires_grad_(True)
+        g_leaf = [t.detach().requires_grad_(True) for t in self.g[i]]
+        h_leaf = [t.detach().requires_grad_(True) for t in self.h]
+        lin = torch.nn.functional.linear
+        cur = mlp_forward(layers, self.acts, states).reshape(B, self.A, self.D)
+        ts, ts1 = lin(states, *g_leaf), lin(next_states, *g_leaf)           # :621-622
+        aff = lin(ts, *h_leaf) + lin(ts1, *h_leaf)                          # :623
+        tphis = aff * phis                                                  # :624
+        targets = tphis + gammas * next_psis                                # :629 (carries grad to g_i, h)
+        merge = cur.clone()
+        merge[idx, actions, :] = targets                                    # :632-633 (clone is NOT detached)
+        l1 = torch.nn.functional.mse_loss(cur, merge)
+        l2 = torch.nn.functional.mse_loss(lin(tphis, w_leaf), rs)
+        loss = l1 + torch.tensor(self.beta) * l2                            # :639-644
+        grads = torch.autograd.grad(loss, leaves + [w_leaf] + g_leaf + h_leaf)
+        n = len(leaves)
+        groups = [('sf', flat, list(grads[:n]), self.lr['sf'], self.wd['sf']),
+                  ('w', [self.w[i]], [grads[n]], self.lr['w'], self.wd['w']),
+                  ('g', list(self.g[i]), list(grads[n + 1:n + 3]), self.lr['g'], self.wd['g']),
+                  ('h', list(self.h), list(grads[n + 3:n + 5]), self.lr['h'], self.wd['h'])]
+        self.last_grads = {k: [g.clone() for g in gr] for k, _, gr, _, _ in groups}
+        with torch.no_grad():
+            self._adam_step(i, groups)
+            self._target_sync(i)
+        return loss.detach(), l1.detach(), l2.detach()
+
+    # ---------------- A6'': G1 ensemble step, agents/sfdqn.py:57-60 ----------------
+    def ensemble_update_sequential(self, transitions5):
+        """Literal reference loop (Gauss-Seidel: task k's GPI sees psi_0..psi_{k-1} already stepped)."""
+        return [self.update_successor(transitions5, i, True, with_reward_loss=False) for i in range(self.n_tasks)]
+
+    def ensemble_update_frozen(self, transitions, tsf=False, use_gpi=True, with_reward_loss=True):
+        """
+        Frozen-snapshot (Jacobi) ensemble step, SURVEY.md section 8c: every policy i is updated by the reference step
+        computed from the SAME pre-step library.  Implemented with reference-shaped steps only: deepcopy the library
+        once per task, step copy i, and collect policy i from copy i.
+        For TSF the shared h is stepped once per policy-optimizer, applied in policy order (h <- h + sum_i delta_i,
+        every delta_i computed from the pre-step h and optimizer i's own moments).
+        """
+        snaps, outs = [], []
+        for i in range(self.n_tasks):
+            c = copy.deepcopy(self)
+            if tsf:
+                outs.append(c.tsf_update_successor(transitions, i, use_gpi))
+            else:
+                outs.append(c.update_successor(transitions, i, use_gpi, with_reward_loss))
+            snaps.append(c)
+        h0 = None if self.h is None else [t.clone() for t in self.h]
+        for i, c in enumerate(snaps):
+            self.psi[i], self.tgt[i], self.w[i], self.adam[i] = c.psi[i], c.tgt[i], c.w[i], c.adam[i]
+            self.updates_since_target_updated[i] = c.updates_since_target_updated[i]
+            if tsf:
+                self.g[i] = c.g[i]
+                for t, t0, tc in zip(self.h, h0, c.h):
+                    t.add_(tc - t0)
+        return outs
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Synthetic replay batches (SURVEY.md section 8d "Synthetic inputs")
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_transitions(B, S, A, D, gen, hopper=False, five_tuple=False):
+    states = torch.randn(B, S, generator=gen)
+    next_states = torch.randn(B, S, generator=gen)
+    if hopper:                                                            # tasks/hopper_phi.py:59
+        states, next_states = torch.sigmoid(states), torch.sigmoid(next_states)
+    actions = torch.randint(0, A, (B,), generator=gen, dtype=torch.int64)
+    phis = torch.rand(B, D, generator=gen) * 2.5 - 1.5                   # U(-1.5, 1), tsfdqn.py:541
+    w_true = torch.zeros(D, 1)
+    w_true[0, 0] = 1.0                                                    # one-hot, tasks/reacher.py:85-88
+    rs = phis @ w_true
+    gammas = torch.full((B,), 0.9)
+    gammas[torch.rand(B, generator=gen) < 0.01] = 0.0                    # 1 % terminals
+    if five_tuple:
+        return states, actions, phis, next_states, gammas
+    return states, actions, rs, phis, next_states, gammas
