@@ -1,0 +1,125 @@
+# -*- coding: UTF-8 -*-
+"""
+ctypes binding of libsfgpi.so (C ABI declared in include/sfgpi.h).  There is NO fallback: if the shared library is missing
+and cannot be built, or a call returns non-zero, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_PATH = os.path.join(HERE, 'libsfgpi.so')
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu']
+MAX_LAYERS = 8
+MAX_SEGMENTS = 8
+ACT = {'none': 0, 'relu': 1, 'tanh': 2}
+
+
+def build(force=False, verbose=False):
+    """nvcc -> libsfgpi.so, sm_100a only (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'sfgpi.h')]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
+           '-shared', '-o', LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, '-Xptxas=-v')
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed building libsfgpi.so:\n' + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+class NetDesc(C.Structure):
+    _fields_ = [('n_layers', C.c_int32), ('dims', C.c_int32 * (MAX_LAYERS + 1)), ('acts', C.c_int32 * MAX_LAYERS),
+                ('w_off', C.c_int32 * MAX_LAYERS), ('b_off', C.c_int32 * MAX_LAYERS), ('row_stride', C.c_int32),
+                ('n_actions', C.c_int32), ('n_features', C.c_int32)]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [('net', NetDesc), ('params', C.c_void_p), ('policy_lo', C.c_int32), ('n_pol', C.c_int32),
+                ('x', C.c_void_p), ('B', C.c_int32), ('psi_out', C.c_void_p), ('acts_out', C.c_void_p * MAX_LAYERS),
+                ('sel_actions', C.c_void_p), ('sel_keys', C.c_void_p), ('sel_key_stride', C.c_int32),
+                ('sel_out', C.c_void_p), ('w', C.c_void_p), ('n_w', C.c_int32), ('w_diag', C.c_int32),
+                ('key_action', C.c_void_p), ('key_task', C.c_void_p), ('task_base', C.c_int32), ('q_out', C.c_void_p),
+                ('mode', C.c_int32)]
+
+
+class TdArgs(C.Structure):
+    _fields_ = [('variant', C.c_int32), ('n_pol', C.c_int32), ('B', C.c_int32), ('S', C.c_int32), ('A', C.c_int32),
+                ('D', C.c_int32), ('G', C.c_int32), ('beta', C.c_float), ('cur_sel', C.c_void_p), ('next_sel', C.c_void_p),
+                ('phis', C.c_void_p), ('rs', C.c_void_p), ('gammas', C.c_void_p), ('states', C.c_void_p),
+                ('next_states', C.c_void_p), ('w', C.c_void_p), ('g', C.c_void_p), ('h', C.c_void_p),
+                ('w_stride', C.c_int32), ('g_stride', C.c_int32), ('d_out', C.c_void_p), ('loss_part', C.c_void_p),
+                ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32)]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [('net', NetDesc), ('params', C.c_void_p), ('policy_lo', C.c_int32), ('n_pol', C.c_int32),
+                ('x', C.c_void_p), ('B', C.c_int32), ('acts', C.c_void_p * MAX_LAYERS), ('actions', C.c_void_p),
+                ('d_out', C.c_void_p), ('dz', C.c_void_p * MAX_LAYERS), ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
+
+
+class AdamSegment(C.Structure):
+    _fields_ = [('param', C.c_void_p), ('param_stride', C.c_int64), ('m', C.c_void_p), ('m_stride', C.c_int64),
+                ('v', C.c_void_p), ('v_stride', C.c_int64), ('grad_part', C.c_void_p), ('grad_pol_stride', C.c_int64),
+                ('grad_part_stride', C.c_int64), ('n_part', C.c_int32), ('len', C.c_int32), ('lr', C.c_float),
+                ('weight_decay', C.c_float)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [('n_seg', C.c_int32), ('n_pol', C.c_int32), ('seg', AdamSegment * MAX_SEGMENTS), ('step', C.c_void_p),
+                ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
+                ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
+                ('losses', C.c_void_p), ('sequential_shared', C.c_int32)]
+
+
+# every symbol include/sfgpi.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'sfgpi_mlp_forward': (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
+    'sfgpi_keys_fill': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    'sfgpi_keys_decode': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_gpi_from_psi': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_td_step': (C.c_int, [C.POINTER(TdArgs), C.c_void_p]),
+    'sfgpi_mlp_backward': (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
+    'sfgpi_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
+    'sfgpi_last_error': (C.c_char_p, []),
+    'sfgpi_version': (C.c_int, []),
+}
+
+_lib = None
+launch_count = 0          # kernels launched through the C ABI (bench.py reports it as gpu_launches)
+LAUNCHES_PER_CALL = {'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
+                     'sfgpi_td_step': 1, 'sfgpi_mlp_backward': 2, 'sfgpi_adam_step': 2}
+
+
+def lib():
+    """Loads (building first if needed) libsfgpi.so.  Raises if that is impossible -- there is no other code path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)           # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed (rc={rc}): {lib().sfgpi_last_error().decode()}')
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())

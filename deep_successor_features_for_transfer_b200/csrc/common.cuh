@@ -1,0 +1,171 @@
+// Shared device helpers for the fp32 (CUDA-core, 1e-5 parity) path of the SF/GPI hot path.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/sfgpi.h"
+
+namespace sfgpi {
+
+constexpr int kThreads = 256;      // 8 warps per CTA: warp = 8-row band, lane = column (mod 32)
+constexpr int kBM = 64;            // rows (states) per CTA tile
+constexpr int kKC = 32;            // reduction chunk staged in shared memory
+constexpr int kNC = 256;           // output-column chunk: 8 columns per lane, interleaved by 32
+constexpr int kWsNT = kKC + 4;     // row stride of a [n][k] weight chunk: 36 == 4 (mod 32) -> conflict-free LDS.128
+constexpr int kWsNN = kNC + 4;     // row stride of a [k_red][n] chunk (lanes read consecutive words)
+constexpr int kWsFloats = kNC * kWsNT;   // one weight stage (9216 floats) -- also holds a [32][260] NN chunk (8320)
+constexpr int kMaxSmem = 227 * 1024;
+
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SFGPI_ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == SFGPI_ACT_TANH) return tanhf(v);
+    return v;
+}
+// derivative of the activation expressed through its OUTPUT a (torch: threshold_backward / tanh_backward)
+__device__ __forceinline__ float act_grad(float a, int act) {
+    if (act == SFGPI_ACT_RELU) return a > 0.0f ? 1.0f : 0.0f;
+    if (act == SFGPI_ACT_TANH) return 1.0f - a * a;
+    return 1.0f;
+}
+
+// ---- packed (value, index) keys: signed int64 max == (max value, then smallest index) -------------------------
+__device__ __forceinline__ long long pack_key(float v, uint32_t idx) {
+    v += 0.0f;                                   // -0 -> +0 so that equal values order equally
+    int32_t b = __float_as_int(v);
+    b = b >= 0 ? b : (b ^ 0x7FFFFFFF);           // monotone map float -> int32
+    return (long long)(((unsigned long long)(uint32_t)b << 32) | (unsigned long long)(0xFFFFFFFFu - idx));
+}
+__device__ __forceinline__ uint32_t key_index(long long k) { return 0xFFFFFFFFu - (uint32_t)((unsigned long long)k & 0xFFFFFFFFull); }
+__device__ __forceinline__ float key_value(long long k) {
+    int32_t b = (int32_t)((unsigned long long)k >> 32);
+    b = b >= 0 ? b : (b ^ 0x7FFFFFFF);
+    return __int_as_float(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-level GEMM building blocks.  Thread (ty = warp, tx = lane) owns rows ty*8+r (r<8) and columns c*32+tx (c<8) of a
+// 64 x 256 output chunk; nc8 = ceil(valid_cols/32) bounds the (warp-uniform) column loop.
+// ---------------------------------------------------------------------------------------------------------------
+
+// Stage W[n0+n][k0 .. k0+klen) (global, [n][K] row-major) into Ws[n][0..klen4) for n < ncols; zero-fill the rest of the
+// touched rectangle (rows up to nc8*32, columns up to klen4).
+__device__ __forceinline__ void stage_w_nt(float *Ws, const float *__restrict__ W, int K, int k0, int klen, int klen4,
+                                           int ncols, int nc8, bool aligned) {
+    const int tid = threadIdx.x;
+    const int nrows = nc8 * 32;
+    if (aligned) {                                // K % 4 == 0 and 16B-aligned base: 8 lanes cover one 128 B row segment
+        const int q = tid & 7, nq = klen4 >> 2;
+        for (int n = tid >> 3; n < nrows; n += kThreads / 8) {
+            if (q < nq) {
+                float *dst = Ws + n * kWsNT + q * 4;
+                if (n < ncols) cp_async16(dst, W + (size_t)n * K + k0 + q * 4);
+                else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    } else {
+        for (int e = tid; e < nrows * klen4; e += kThreads) {
+            int n = e / klen4, k = e - n * klen4;
+            Ws[n * kWsNT + k] = (n < ncols && k < klen) ? W[(size_t)n * K + k0 + k] : 0.0f;
+        }
+    }
+}
+
+// acc[r][c] += sum_k As[(ty*8+r)*lda + k] * W[n0 + c*32+tx][k]    (NT: both operands contiguous along k)
+__device__ __forceinline__ void cta_gemm_nt(float (&acc)[8][8], const float *As, int lda, const float *__restrict__ W,
+                                            int K, int ncols, float *Ws /* 2 stages */) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nc8 = (ncols + 31) >> 5;
+    const bool aligned = ((K & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    const int nchunks = (K + kKC - 1) / kKC;
+    {
+        int klen = min(kKC, K);
+        stage_w_nt(Ws, W, K, 0, klen, (klen + 3) & ~3, ncols, nc8, aligned);
+        cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int k0 = ch * kKC;
+        const int klen4 = (min(kKC, K - k0) + 3) & ~3;
+        if (ch + 1 < nchunks) {
+            int k1 = k0 + kKC, klen1 = min(kKC, K - k1);
+            stage_w_nt(Ws + ((ch + 1) & 1) * kWsFloats, W, K, k1, klen1, (klen1 + 3) & ~3, ncols, nc8, aligned);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float *Wb = Ws + (ch & 1) * kWsFloats + tx * kWsNT;
+        const float *Ab = As + (ty * 8) * lda + k0;
+        for (int kk = 0; kk < klen4; kk += 4) {
+            float4 a[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float4 *>(Ab + r * lda + kk);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < nc8) {
+                    const float4 b = *reinterpret_cast<const float4 *>(Wb + c * 32 * kWsNT + kk);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        acc[r][c] = fmaf(a[r].x, b.x, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].y, b.y, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].z, b.z, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].w, b.w, acc[r][c]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Stage M[r0 + r][c0 .. c0+ncols) (global, row-major with leading dim ld) into Ms[r][0..nc8*32) for r < nrows_valid,
+// zero-filling rows up to nrows_pad and columns up to nc8*32.  Used for the NN / TN operands (reduction index = row).
+__device__ __forceinline__ void stage_rows(float *Ms, int lds, const float *__restrict__ M, int ld, int nrows_valid,
+                                           int nrows_pad, int ncols, int ncols_pad, bool aligned) {
+    const int tid = threadIdx.x;
+    if (aligned) {
+        const int nq = ncols_pad >> 2;
+        for (int e = tid; e < nrows_pad * nq; e += kThreads) {
+            int r = e / nq, q = e - r * nq;
+            float *dst = Ms + r * lds + q * 4;
+            if (r < nrows_valid && q * 4 + 3 < ncols) cp_async16(dst, M + (size_t)r * ld + q * 4);
+            else {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nrows_valid) {
+                    const float *src = M + (size_t)r * ld + q * 4;
+                    if (q * 4 + 0 < ncols) v.x = src[0];
+                    if (q * 4 + 1 < ncols) v.y = src[1];
+                    if (q * 4 + 2 < ncols) v.z = src[2];
+                    if (q * 4 + 3 < ncols) v.w = src[3];
+                }
+                *reinterpret_cast<float4 *>(dst) = v;
+            }
+        }
+    } else {
+        for (int e = tid; e < nrows_pad * ncols_pad; e += kThreads) {
+            int r = e / ncols_pad, c = e - r * ncols_pad;
+            Ms[r * lds + c] = (r < nrows_valid && c < ncols) ? M[(size_t)r * ld + c] : 0.0f;
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace sfgpi

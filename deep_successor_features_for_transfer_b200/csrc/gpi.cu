@@ -1,0 +1,123 @@
+// GPI helpers: packed-key fill / decode, the unfused GPI epilogue on a materialised psi, error plumbing.
+#include <stdarg.h>
+#include <limits.h>
+#include "common.cuh"
+
+namespace sfgpi {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA error: %s", what, cudaGetErrorString(e));
+        return SFGPI_E_CUDA;
+    }
+    return SFGPI_OK;
+}
+
+__global__ void keys_fill_kernel(long long *keys, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) keys[i] = LLONG_MIN;
+}
+
+__global__ void keys_decode_kernel(const long long *__restrict__ keys, long long n, long long *__restrict__ index_out,
+                                   float *__restrict__ value_out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const long long k = keys[i];
+        if (index_out) index_out[i] = (long long)key_index(k);
+        if (value_out) value_out[i] = key_value(k);
+    }
+}
+
+// One warp per state: lanes stride over the N*A (policy, action) cells, each cell a D-long dot product with w.
+// psi [B][N][A][D] is read exactly once (HBM-bound: 4*N*A*D bytes per state), q [B][N][A] optionally written.
+__global__ void __launch_bounds__(256) gpi_from_psi_kernel(const float *__restrict__ psi, const float *__restrict__ w, int B,
+                                                           int N, int A, int D, int task_base, float *__restrict__ q_out,
+                                                           long long *__restrict__ key_action,
+                                                           long long *__restrict__ key_task) {
+    extern __shared__ float w_s[];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) w_s[d] = w[d];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
+        const float *pb = psi + (size_t)b * N * A * D;
+        long long kA = LLONG_MIN, kT = LLONG_MIN;
+        for (int cell = lane; cell < N * A; cell += 32) {
+            const float *pv = pb + (size_t)cell * D;
+            float q = 0.0f;
+            if ((D & 3) == 0) {
+                for (int d = 0; d < D; d += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(pv + d);
+                    q = fmaf(v.x, w_s[d], q);
+                    q = fmaf(v.y, w_s[d + 1], q);
+                    q = fmaf(v.z, w_s[d + 2], q);
+                    q = fmaf(v.w, w_s[d + 3], q);
+                }
+            } else {
+                for (int d = 0; d < D; ++d) q = fmaf(pv[d], w_s[d], q);
+            }
+            if (q_out) q_out[(size_t)b * N * A + cell] = q;
+            const int j = cell / A, act = cell - j * A;
+            const long long ka = pack_key(q, (uint32_t)act), kt = pack_key(q, (uint32_t)(task_base + j));
+            kA = ka > kA ? ka : kA;
+            kT = kt > kT ? kt : kT;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long oa = __shfl_xor_sync(0xffffffffu, kA, o), ot = __shfl_xor_sync(0xffffffffu, kT, o);
+            kA = oa > kA ? oa : kA;
+            kT = ot > kT ? ot : kT;
+        }
+        if (lane == 0) {
+            if (key_action) key_action[b] = kA;
+            if (key_task) key_task[b] = kT;
+        }
+    }
+}
+
+}  // namespace sfgpi
+
+using namespace sfgpi;
+
+extern "C" const char *sfgpi_last_error(void) { return g_err; }
+extern "C" int sfgpi_version(void) { return 100; }
+
+extern "C" int sfgpi_keys_fill(int64_t *keys, int64_t n, void *stream) {
+    if (n <= 0) return SFGPI_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    keys_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(keys), (long long)n);
+    return check_launch("sfgpi_keys_fill");
+}
+
+extern "C" int sfgpi_keys_decode(const int64_t *keys, int64_t n, int64_t *index_out, float *value_out, void *stream) {
+    if (n <= 0) return SFGPI_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    keys_decode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long *>(keys), (long long)n,
+                                                                  reinterpret_cast<long long *>(index_out), value_out);
+    return check_launch("sfgpi_keys_decode");
+}
+
+extern "C" int sfgpi_gpi_from_psi(const float *psi, const float *w, int32_t B, int32_t N, int32_t A, int32_t D,
+                                  int32_t task_base, float *q_out, int64_t *key_action, int64_t *key_task, void *stream) {
+    if (B < 0 || N < 1 || A < 1 || D < 1 || D > 8192) { set_error("sfgpi_gpi_from_psi: invalid sizes"); return SFGPI_E_INVALID; }
+    if (B == 0) return SFGPI_OK;
+    int blocks = (B + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gpi_from_psi_kernel<<<blocks, 256, D * sizeof(float), (cudaStream_t)stream>>>(
+        psi, w, B, N, A, D, task_base, q_out, reinterpret_cast<long long *>(key_action), reinterpret_cast<long long *>(key_task));
+    return check_launch("sfgpi_gpi_from_psi");
+}

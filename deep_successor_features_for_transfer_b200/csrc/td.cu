@@ -1,0 +1,192 @@
+// TD target, the two MSE losses and every gradient that does not flow through the psi MLP, fused in one kernel
+// (sfdqn.py:330-345; tsfdqn.py:621-645; features/deep.py:112-121).  Elementwise / tiny-GEMM work: HBM-bound on the
+// [B][D] operands, deterministic two-stage reductions (per-CTA partials, summed by the Adam kernel).
+#include "common.cuh"
+
+namespace sfgpi {
+
+constexpr int kTdRows = 32;       // transitions per CTA
+constexpr int kTdThreads = 128;
+
+// smem layout (floats): see carve-up below
+__global__ void __launch_bounds__(kTdThreads) td_kernel(const __grid_constant__ sfgpi_td_args a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int B = a.B, S = a.S, D = a.D, G = a.G;
+    const int pl = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+    const int row0 = blk * kTdRows;
+    const int rows = min(kTdRows, B - row0);
+    const bool tsf = a.variant == 2, reward = a.variant >= 1;
+
+    // carve-up
+    float *w_s = sm;                              // [D]
+    float *phi_s = w_s + D;                       // [32][D]  phi (raw)
+    float *tphi_s = phi_s + kTdRows * D;          // [32][D]  phi~ (transformed)
+    float *diff_s = tphi_s + kTdRows * D;         // [32][D]  then reused as daff
+    float *e_s = diff_s + kTdRows * D;            // [32]
+    float *red_s = e_s + kTdRows;                 // [8] block-reduction scratch
+    float *Wg_s = red_s + 8;                      // [G][S]   (tsf only from here)
+    float *bg_s = Wg_s + G * S;                   // [G]
+    float *Wh_s = bg_s + G;                       // [D][G]
+    float *bh_s = Wh_s + D * G;                   // [D]
+    float *ss_s = bh_s + D;                       // [32][S]  s + s'
+    float *u_s = ss_s + kTdRows * S;              // [32][G]  g(s) + g(s')
+    float *du_s = u_s + kTdRows * G;              // [32][G]
+
+    const float *cur = a.cur_sel + (size_t)pl * B * D;
+    const float *nxt = a.next_sel + (size_t)pl * B * D;
+    float *dout = a.d_out + (size_t)pl * B * D;
+
+    if (reward) for (int d = tid; d < D; d += kTdThreads) w_s[d] = a.w[(size_t)pl * a.w_stride + d];
+    for (int e = tid; e < kTdRows * D; e += kTdThreads) {
+        int r = e / D;
+        phi_s[e] = r < rows ? a.phis[(size_t)row0 * D + e] : 0.0f;
+    }
+    if (tsf) {
+        const float *gp = a.g + (size_t)pl * a.g_stride;
+        for (int e = tid; e < G * S; e += kTdThreads) Wg_s[e] = gp[e];
+        for (int e = tid; e < G; e += kTdThreads) bg_s[e] = gp[G * S + e];
+        for (int e = tid; e < D * G; e += kTdThreads) Wh_s[e] = a.h[e];
+        for (int e = tid; e < D; e += kTdThreads) bh_s[e] = a.h[D * G + e];
+        for (int e = tid; e < kTdRows * S; e += kTdThreads) {
+            int r = e / S;
+            ss_s[e] = r < rows ? a.states[(size_t)row0 * S + e] + a.next_states[(size_t)row0 * S + e] : 0.0f;
+        }
+    }
+    __syncthreads();
+
+    // u = g(s) + g(s') = Wg (s + s') + 2 bg                                   (tsfdqn.py:621-622)
+    if (tsf) {
+        for (int e = tid; e < kTdRows * G; e += kTdThreads) {
+            int r = e / G, g = e - r * G;
+            float acc = 2.0f * bg_s[g];
+            for (int s = 0; s < S; ++s) acc = fmaf(Wg_s[g * S + s], ss_s[r * S + s], acc);
+            u_s[e] = acc;
+        }
+        __syncthreads();
+    }
+
+    // phi~, target, diff, d_out, l1 partial                                    (tsfdqn.py:623-633 / sfdqn.py:330-335)
+    const float c1 = 2.0f / ((float)B * (float)a.A * (float)D);
+    float l1_acc = 0.0f;
+    for (int e = tid; e < kTdRows * D; e += kTdThreads) {
+        int r = e / D, d = e - r * D;
+        float tphi = phi_s[e], df = 0.0f;
+        if (tsf) {
+            float aff = 2.0f * bh_s[d];
+            for (int g = 0; g < G; ++g) aff = fmaf(Wh_s[d * G + g], u_s[r * G + g], aff);
+            tphi *= aff;
+        }
+        if (r < rows) {
+            const size_t gi = (size_t)row0 * D + e;
+            const float target = fmaf(a.gammas[row0 + r], nxt[gi], tphi);
+            df = cur[gi] - target;
+            dout[gi] = c1 * df;
+            l1_acc = fmaf(df, df, l1_acc);
+        }
+        tphi_s[e] = tphi;
+        diff_s[e] = df;
+    }
+    __syncthreads();
+
+    // reward head: e = w . phi~ - r, l2 partial                                (sfdqn.py:339-341 / tsfdqn.py:638-642)
+    float l2_acc = 0.0f;
+    if (reward) {
+        if (tid < kTdRows) {
+            float ev = 0.0f;
+            if (tid < rows) {
+                for (int d = 0; d < D; ++d) ev = fmaf(w_s[d], tphi_s[tid * D + d], ev);
+                ev -= a.rs[row0 + tid];
+                l2_acc = ev * ev;
+            }
+            e_s[tid] = ev;
+        }
+        __syncthreads();
+    }
+
+    // loss partials (deterministic tree inside the CTA, one slot per CTA)
+    {
+        float s1 = warp_sum(l1_acc), s2 = warp_sum(l2_acc);
+        if ((tid & 31) == 0) { red_s[tid >> 5] = s1; red_s[4 + (tid >> 5)] = s2; }
+        __syncthreads();
+        if (tid == 0) {
+            float *lp = a.loss_part + ((size_t)pl * nblk + blk) * 2;
+            lp[0] = (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
+            lp[1] = (red_s[4] + red_s[5]) + (red_s[6] + red_s[7]);
+        }
+    }
+    if (!reward) return;
+
+    float *gpart = a.aux_grad_part + ((size_t)pl * nblk + blk) * a.aux_len;
+    const float c2 = 2.0f * a.beta / (float)B;           // variant 1: beta == 1
+
+    // dL/dw[d] = c2 * sum_b e_b * phi~[b][d]
+    for (int d = tid; d < D; d += kTdThreads) {
+        float acc = 0.0f;
+        for (int r = 0; r < kTdRows; ++r) acc = fmaf(e_s[r], tphi_s[r * D + d], acc);
+        gpart[d] = c2 * acc;
+    }
+    if (!tsf) return;
+
+    // daff = (dL/dphi~) * phi,  dL/dphi~ = -c1*diff + c2*e*w                   (targets carry grad, tsfdqn.py:629)
+    __syncthreads();
+    for (int e = tid; e < kTdRows * D; e += kTdThreads) {
+        int r = e / D, d = e - r * D;
+        diff_s[e] = (c2 * e_s[r] * w_s[d] - c1 * diff_s[e]) * phi_s[e];
+    }
+    __syncthreads();
+    float *daff_s = diff_s;
+    // du = daff . Wh
+    for (int e = tid; e < kTdRows * G; e += kTdThreads) {
+        int r = e / G, g = e - r * G;
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = fmaf(daff_s[r * D + d], Wh_s[d * G + g], acc);
+        du_s[e] = acc;
+    }
+    __syncthreads();
+    // parameter gradients: g.W [G][S], g.b [G], h.W [D][G], h.b [D]
+    float *gW = gpart + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
+    for (int e = tid; e < G * S; e += kTdThreads) {
+        int g = e / S, s = e - g * S;
+        float acc = 0.0f;
+        for (int r = 0; r < kTdRows; ++r) acc = fmaf(du_s[r * G + g], ss_s[r * S + s], acc);
+        gW[e] = acc;
+    }
+    for (int g = tid; g < G; g += kTdThreads) {
+        float acc = 0.0f;
+        for (int r = 0; r < kTdRows; ++r) acc += du_s[r * G + g];
+        gb[g] = 2.0f * acc;
+    }
+    for (int e = tid; e < D * G; e += kTdThreads) {
+        int d = e / G, g = e - d * G;
+        float acc = 0.0f;
+        for (int r = 0; r < kTdRows; ++r) acc = fmaf(daff_s[r * D + d], u_s[r * G + g], acc);
+        hW[e] = acc;
+    }
+    for (int d = tid; d < D; d += kTdThreads) {
+        float acc = 0.0f;
+        for (int r = 0; r < kTdRows; ++r) acc += daff_s[r * D + d];
+        hb[d] = 2.0f * acc;
+    }
+}
+
+}  // namespace sfgpi
+
+using namespace sfgpi;
+
+extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
+    const sfgpi_td_args &a = *args;
+    if (a.variant < 0 || a.variant > 2 || a.B < 0 || a.n_pol < 0 || a.D < 1) { set_error("sfgpi_td_step: invalid arguments"); return SFGPI_E_INVALID; }
+    if (a.B == 0 || a.n_pol == 0) return SFGPI_OK;
+    const bool tsf = a.variant == 2;
+    const int want_aux = a.variant == 0 ? 0 : (tsf ? a.D + a.G * a.S + a.G + a.D * a.G + a.D : a.D);
+    if (a.aux_len < want_aux) { set_error("sfgpi_td_step: aux_len %d < %d", a.aux_len, want_aux); return SFGPI_E_INVALID; }
+    size_t fl = a.D + 3 * (size_t)kTdRows * a.D + kTdRows + 8;
+    if (tsf) fl += (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D + (size_t)kTdRows * a.S + 2 * (size_t)kTdRows * a.G;
+    const size_t bytes = fl * sizeof(float);
+    if (bytes > (size_t)kMaxSmem) { set_error("sfgpi_td_step: D/G too large for shared memory (%zu B)", bytes); return SFGPI_E_SMEM; }
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    dim3 grid((a.B + kTdRows - 1) / kTdRows, a.n_pol);
+    td_kernel<<<grid, kTdThreads, bytes, (cudaStream_t)stream>>>(a);
+    return check_launch("sfgpi_td_step");
+}

@@ -1,0 +1,428 @@
+# -*- coding: UTF-8 -*-
+"""
+PackedSFLibrary: HBM-resident storage + kernel orchestration for an ensemble of N successor-feature networks.
+
+Replaces the reference's per-task Python objects -- N `nn.Sequential` psi nets + N target copies + N `nn.Linear` reward
+maps + N `torch.optim.Adam` (sfdqn.py:180-288, tsfdqn.py:137-281) -- by a handful of packed fp32 buffers
+
+    online / target / exp_avg / exp_avg_sq : [cap][row_stride]      one row per policy (layout: include/sfgpi.h)
+    w, w_m, w_v                            : [cap][D]
+    g, g_m, g_v                            : [cap][G*S + G]          (TSF g_i: Linear(S,G), tsfdqn.py:537)
+    h : [D*G + D] shared;  h_m, h_v        : [cap][D*G + D]          (one Adam state per policy-optimizer, tsfdqn.py:255-270)
+    step                                   : [cap] int32 (device)    Adam step counters
+
+and runs every reference hot-path function through the C ABI (libsfgpi.so).  The per-task `nn.Module` objects handed back to
+the agents hold VIEWS of row i, so `.parameters()`, `state_dict()`, `update_models_weights` and `fit_w[i].weight` keep
+working.  No torch op is on the compute path; torch only owns the memory and the stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, MAX_LAYERS, ptr
+
+INT64_MIN = -(1 << 63)
+
+
+class NetSpec:
+    """Shape of one psi network, adopted from the `nn.Sequential` that `pytorch_model_handle` returns."""
+
+    def __init__(self, dims, acts, n_actions, n_features):
+        assert len(acts) == len(dims) - 1
+        if len(acts) > MAX_LAYERS:
+            raise ValueError(f'at most {MAX_LAYERS} Linear layers are supported')
+        if dims[-1] != n_actions * n_features:
+            raise ValueError('psi output width must be n_actions * n_features')
+        if acts[-1] != 'none':
+            raise ValueError('the psi output layer must be linear (no activation)')
+        self.dims, self.acts = list(dims), list(acts)
+        self.n_actions, self.n_features = n_actions, n_features
+        off, self.w_off, self.b_off = 0, [], []
+        for l in range(len(acts)):
+            self.w_off.append(off)
+            off += (dims[l + 1] * dims[l] + 3) & ~3
+            self.b_off.append(off)
+            off += (dims[l + 1] + 3) & ~3
+        self.n_params = sum(dims[l + 1] * dims[l] + dims[l + 1] for l in range(len(acts)))
+        self.row_stride = (off + 31) & ~31
+
+    @staticmethod
+    def from_module(model, n_actions, n_features):
+        """Introspects Linear / ReLU / Tanh / Unflatten (utils/torch.py:19-22); anything else is rejected (no fallback)."""
+        dims, acts, linears = [], [], []
+        for m in model.children() if isinstance(model, torch.nn.Sequential) else [model]:
+            if isinstance(m, torch.nn.Linear):
+                if m.bias is None:
+                    raise ValueError('psi Linear layers must have a bias')
+                if not dims:
+                    dims.append(m.in_features)
+                elif m.in_features != dims[-1]:
+                    raise ValueError('inconsistent layer widths in psi model')
+                dims.append(m.out_features)
+                acts.append('none')
+                linears.append(m)
+            elif isinstance(m, torch.nn.ReLU):
+                acts[-1] = 'relu'
+            elif isinstance(m, torch.nn.Tanh):
+                acts[-1] = 'tanh'
+            elif isinstance(m, (torch.nn.Unflatten, torch.nn.Identity)):
+                pass
+            else:
+                raise TypeError(f'unsupported layer in psi model: {type(m).__name__} (Linear/ReLU/Tanh/Unflatten only)')
+        return NetSpec(dims, acts, n_actions, n_features), linears
+
+    def same_shape(self, other):
+        return self.dims == other.dims and self.acts == other.acts
+
+    def desc(self):
+        d = _lib.NetDesc()
+        d.n_layers = len(self.acts)
+        for i, v in enumerate(self.dims):
+            d.dims[i] = v
+        for l in range(len(self.acts)):
+            d.acts[l] = ACT[self.acts[l]]
+            d.w_off[l] = self.w_off[l]
+            d.b_off[l] = self.b_off[l]
+        d.row_stride, d.n_actions, d.n_features = self.row_stride, self.n_actions, self.n_features
+        return d
+
+    def views(self, row):
+        """[(W_l view, b_l view)] into one policy row."""
+        out = []
+        for l in range(len(self.acts)):
+            o, i = self.dims[l + 1], self.dims[l]
+            out.append((row[self.w_off[l]:self.w_off[l] + o * i].view(o, i), row[self.b_off[l]:self.b_off[l] + o]))
+        return out
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class PackedSFLibrary:
+    def __init__(self, device=None, lr=None, wd=None, tsf_dim=None, capacity=4):
+        if not torch.cuda.is_available():
+            raise RuntimeError('deep_successor_features_for_transfer_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        _lib.lib()                                   # fail loudly right here if the native library is missing
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lr = dict(sf=1e-3, w=1e-3, g=1e-3, h=1e-3) if lr is None else dict(lr)
+        self.wd = dict(sf=0.0, w=0.0, g=0.0, h=0.0) if wd is None else dict(wd)
+        self.G = tsf_dim
+        self.spec = None
+        self.n = 0
+        self.cap = 0
+        self._cap0 = capacity
+        self._views = []            # per policy: dict of modules whose .data must be re-pointed after a re-pack
+        self._ws = {}
+        self.h = None
+
+    # ------------------------------------------------------------------ storage
+    def _alloc(self, cap):
+        sp, dev = self.spec, self.device
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        new = dict(online=z(cap, sp.row_stride), target=z(cap, sp.row_stride), m=z(cap, sp.row_stride),
+                   v=z(cap, sp.row_stride), w=z(cap, sp.n_features), w_m=z(cap, sp.n_features), w_v=z(cap, sp.n_features),
+                   step=torch.zeros(cap, dtype=torch.int32, device=dev))
+        if self.G is not None:
+            gl = self.G * sp.dims[0] + self.G
+            hl = sp.n_features * self.G + sp.n_features
+            new.update(g=z(cap, gl), g_m=z(cap, gl), g_v=z(cap, gl), h_m=z(cap, hl), h_v=z(cap, hl))
+        for k, t in new.items():
+            old = getattr(self, k, None)
+            if old is not None and self.n > 0:
+                t[:self.n].copy_(old[:self.n])
+            setattr(self, k, t)
+        self.cap = cap
+        self._ws = {}
+        for i, mods in enumerate(self._views):
+            self._point_views(i, mods)
+
+    def _point_views(self, i, mods):
+        for (W, b), lin in zip(self.spec.views(self.online[i]), mods['online']):
+            lin.weight.data, lin.bias.data = W, b
+        for (W, b), lin in zip(self.spec.views(self.target[i]), mods['target']):
+            lin.weight.data, lin.bias.data = W, b
+        mods['w'].weight.data = self.w[i].view(1, -1)
+        if mods.get('g') is not None:
+            S = self.spec.dims[0]
+            mods['g'].weight.data = self.g[i, :self.G * S].view(self.G, S)
+            mods['g'].bias.data = self.g[i, self.G * S:]
+
+    def add_policy(self, model, target_model, w_linear, g_linear=None, h_linear=None, n_actions=None, n_features=None):
+        """Adopts freshly built reference-style modules into packed storage (sfdqn.py:180-288)."""
+        spec, lin_on = NetSpec.from_module(model, n_actions, n_features)
+        spec_t, lin_tg = NetSpec.from_module(target_model, n_actions, n_features)
+        if self.spec is None:
+            self.spec = spec
+        if not (self.spec.same_shape(spec) and self.spec.same_shape(spec_t)):
+            raise ValueError('all psi networks of a library must share one architecture')
+        if (g_linear is None) != (self.G is None):
+            raise ValueError('g/h functions must be given iff the library was built with tsf_dim')
+        if self.n == self.cap:
+            self._alloc(max(self._cap0, 2 * self.cap))
+        i = self.n
+        with torch.no_grad():
+            for (W, b), lin in zip(self.spec.views(self.online[i]), lin_on):
+                W.copy_(lin.weight.data)
+                b.copy_(lin.bias.data)
+            for (W, b), lin in zip(self.spec.views(self.target[i]), lin_tg):
+                W.copy_(lin.weight.data)
+                b.copy_(lin.bias.data)
+            self.w[i].copy_(w_linear.weight.data.reshape(-1))
+            mods = dict(online=lin_on, target=lin_tg, w=w_linear, g=g_linear)
+            if g_linear is not None:
+                S = self.spec.dims[0]
+                if g_linear.out_features != self.G or g_linear.in_features != S:
+                    raise ValueError('g function shape mismatch')
+                self.g[i, :self.G * S].copy_(g_linear.weight.data.reshape(-1))
+                self.g[i, self.G * S:].copy_(g_linear.bias.data)
+                if self.h is None:
+                    D = self.spec.n_features
+                    self.h = torch.cat([h_linear.weight.data.reshape(-1), h_linear.bias.data.reshape(-1)]).float().to(self.device).contiguous()
+                    h_linear.weight.data = self.h[:D * self.G].view(D, self.G)
+                    h_linear.bias.data = self.h[D * self.G:]
+                    self.h_module = h_linear
+        self._views.append(mods)
+        self._point_views(i, mods)
+        self.n += 1
+        return i
+
+    def reset(self):
+        self.spec, self.n, self.cap, self._views, self._ws, self.h = None, 0, 0, [], {}, None
+        for k in ('online', 'target', 'm', 'v', 'w', 'w_m', 'w_v', 'step', 'g', 'g_m', 'g_v', 'h_m', 'h_v'):
+            if hasattr(self, k):
+                delattr(self, k)
+
+    # ------------------------------------------------------------------ workspaces
+    def _f(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def _workspace(self, B, n_pol, n_keys):
+        key = (B, n_pol, n_keys)
+        ws = self._ws.get(key)
+        if ws is None:
+            sp = self.spec
+            L, D = len(sp.acts), sp.n_features
+            ws = dict(acts=[self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)],
+                      dz=[self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)],
+                      cur_sel=self._f(n_pol, B, D), next_sel=self._f(n_pol, B, D), d_out=self._f(n_pol, B, D),
+                      keys=torch.empty(n_keys, B, dtype=torch.int64, device=self.device))
+            nblk = (B + 31) // 32
+            ws['nblk'] = nblk
+            ws['loss_part'] = self._f(n_pol, nblk, 2)
+            tiles = sum(((sp.dims[l + 1] + 63) // 64) * ((sp.dims[l] + 255) // 256) for l in range(L))
+            n_split = max(1, min((B + 127) // 128, -(-296 // (tiles * n_pol))))
+            ws['n_split'] = n_split
+            ws['grad_part'] = torch.zeros(n_pol, n_split, sp.row_stride, dtype=torch.float32, device=self.device)
+            if self.G is not None:
+                S = sp.dims[0]
+                ws['aux_len'] = D + self.G * S + self.G + D * self.G + D
+            else:
+                ws['aux_len'] = D
+            ws['aux_part'] = self._f(n_pol, nblk, ws['aux_len'])
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward-only entry points
+    def _check_x(self, x):
+        x = torch.as_tensor(x)
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        if x.dim() != 2 or x.shape[1] != self.spec.dims[0]:
+            raise ValueError(f'expected states of shape [B, {self.spec.dims[0]}], got {tuple(x.shape)}')
+        return x
+
+    def _fwd_args(self, params, lo, n_pol, x, B=None):
+        a = _lib.ForwardArgs()
+        a.net = self.spec.desc()
+        a.params, a.policy_lo, a.n_pol = ptr(params), lo, n_pol
+        a.x, a.B = ptr(x), (x.shape[0] if B is None else B)
+        a.mode = 0
+        return a
+
+    def forward_psi(self, x, lo=0, n_pol=None, target=False):
+        """psi_j(x) for j in [lo, lo+n_pol): [B][n_pol][A][D] (get_successors / get_next_successors)."""
+        x = self._check_x(x)
+        n_pol = self.n - lo if n_pol is None else n_pol
+        sp = self.spec
+        out = self._f(x.shape[0], n_pol, sp.n_actions, sp.n_features)
+        a = self._fwd_args(self.target if target else self.online, lo, n_pol, x)
+        a.psi_out = ptr(out)
+        _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+        return out
+
+    def gpi(self, x, w_vec, lo=0, n_pol=None, want_q=True, task_base=0, keys_out=None):
+        """
+        Fused GPI_w (sfdqn.py:215-240): returns (q [B][n_pol][A] or None, key_action [B], key_task [B]) -- packed int64
+        keys, decode with decode_keys().  psi[B,N,A,D] is never materialised.
+        """
+        x = self._check_x(x)
+        n_pol = self.n - lo if n_pol is None else n_pol
+        B, sp = x.shape[0], self.spec
+        w_vec = w_vec.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        if w_vec.numel() != sp.n_features:
+            raise ValueError('reward vector must have n_features elements')
+        keys = torch.empty(2, B, dtype=torch.int64, device=self.device) if keys_out is None else keys_out
+        _lib.call('sfgpi_keys_fill', ptr(keys), 2 * B, _stream())
+        q = self._f(B, n_pol, sp.n_actions) if want_q else None
+        a = self._fwd_args(self.online, lo, n_pol, x)
+        a.w, a.n_w, a.w_diag = ptr(w_vec), 1, 0
+        a.key_action, a.key_task = C.c_void_p(keys[0].data_ptr()), C.c_void_p(keys[1].data_ptr())
+        a.task_base = task_base
+        a.q_out = ptr(q)
+        _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+        return q, keys[0], keys[1]
+
+    def decode_keys(self, keys, want_value=False):
+        idx = torch.empty(keys.shape, dtype=torch.int64, device=self.device)
+        val = self._f(*keys.shape) if want_value else None
+        _lib.call('sfgpi_keys_decode', ptr(keys), keys.numel(), ptr(idx), ptr(val), _stream())
+        return (idx, val) if want_value else idx
+
+    def gpi_from_psi(self, psi, w_vec, task_base=0, want_q=True):
+        """Unfused GPI epilogue on a materialised psi [B][N][A][D]."""
+        psi = psi.to(device=self.device, dtype=torch.float32).contiguous()
+        B, N, A, D = psi.shape
+        w_vec = w_vec.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        keys = torch.empty(2, B, dtype=torch.int64, device=self.device)
+        q = self._f(B, N, A) if want_q else None
+        _lib.call('sfgpi_gpi_from_psi', ptr(psi), ptr(w_vec), B, N, A, D, task_base, ptr(q),
+                  C.c_void_p(keys[0].data_ptr()), C.c_void_p(keys[1].data_ptr()), _stream())
+        return q, keys[0], keys[1]
+
+    # ------------------------------------------------------------------ the train step
+    def _build_plan(self, B, policy, use_gpi, variant, beta):
+        """Pre-builds every C-ABI argument block of one train step; only the six input pointers change per call."""
+        sp = self.spec
+        D, A, S, L = sp.n_features, sp.n_actions, sp.dims[0], len(sp.acts)
+        ensemble = policy == 'all'
+        lo, n_pol = (0, self.n) if ensemble else (int(policy), 1)
+        if not (0 <= lo < self.n):
+            raise IndexError('policy index out of range')
+        ws = self._workspace(B, n_pol, n_pol)
+        keys = ws['keys']
+        P = lambda tns, i=lo: C.c_void_p(tns[i].data_ptr())
+
+        # (1) online forward on s: saves hidden outputs, gathers psi(s)[a_b]            sfdqn.py:328
+        a1 = self._fwd_args(self.online, lo, n_pol, None, B)
+        for l in range(L - 1):
+            a1.acts_out[l] = ws['acts'][l].data_ptr()
+        a1.sel_out = ptr(ws['cur_sel'])
+        # (2) next actions: GPI over the whole library (or own psi) with w_i            sfdqn.py:314-322
+        if use_gpi:
+            a2 = self._fwd_args(self.online, 0, self.n, None, B)
+            a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 0
+        else:
+            a2 = self._fwd_args(self.online, lo, n_pol, None, B)
+            a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 1
+        a2.key_action = ptr(keys)
+        # (3) target forward on s', gather psi^-(s')[a*]                                sfdqn.py:330-331
+        a3 = self._fwd_args(self.target, lo, n_pol, None, B)
+        a3.sel_keys, a3.sel_key_stride, a3.sel_out = ptr(keys), B, ptr(ws['next_sel'])
+        # (4) TD target, losses, d_out and the reward-head / g / h gradients            sfdqn.py:330-345, tsfdqn.py:621-645
+        t = _lib.TdArgs()
+        t.variant, t.n_pol, t.B, t.S, t.A, t.D, t.G = variant, n_pol, B, S, A, D, (self.G or 0)
+        t.beta = float(beta) if variant == 2 else 1.0
+        t.cur_sel, t.next_sel = ptr(ws['cur_sel']), ptr(ws['next_sel'])
+        t.w, t.w_stride = P(self.w), D
+        if variant == 2:
+            t.g, t.g_stride, t.h = P(self.g), self.g.shape[1], ptr(self.h)
+        t.d_out, t.loss_part, t.aux_grad_part, t.aux_len = ptr(ws['d_out']), ptr(ws['loss_part']), ptr(ws['aux_part']), ws['aux_len']
+        # (5) backward through psi: dgrad chain + split-K wgrad
+        b = _lib.BackwardArgs()
+        b.net, b.params, b.policy_lo, b.n_pol = sp.desc(), ptr(self.online), lo, n_pol
+        b.B, b.d_out = B, ptr(ws['d_out'])
+        for l in range(L - 1):
+            b.acts[l] = ws['acts'][l].data_ptr()
+            b.dz[l] = ws['dz'][l].data_ptr()
+        b.grad_part, b.n_split = ptr(ws['grad_part']), ws['n_split']
+        # (6) Adam over (psi | w | g | h) for all stepped optimizers, + loss reduction    sfdqn.py:362, tsfdqn.py:700
+        ad = _lib.AdamArgs()
+        ad.n_pol, ad.step = n_pol, C.c_void_p(self.step[lo:].data_ptr())
+        ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
+        rs_, nblk, al = sp.row_stride, ws['nblk'], ws['aux_len']
+
+        def seg(k, param, pstride, m, v, mstride, grad, gpol, gpart, npart, length, lr, wd):
+            s = ad.seg[k]
+            s.param, s.param_stride, s.m, s.m_stride, s.v, s.v_stride = param, pstride, m, mstride, v, mstride
+            s.grad_part, s.grad_pol_stride, s.grad_part_stride, s.n_part = grad, gpol, gpart, npart
+            s.len, s.lr, s.weight_decay = length, lr, wd
+
+        seg(0, P(self.online), rs_, P(self.m), P(self.v), rs_, ptr(ws['grad_part']), ws['n_split'] * rs_, rs_, ws['n_split'],
+            rs_, self.lr['sf'], self.wd['sf'])
+        nseg = 1
+        aux = ws['aux_part']
+        if variant >= 1:
+            seg(1, P(self.w), D, P(self.w_m), P(self.w_v), D, ptr(aux), nblk * al, al, nblk, D, self.lr['w'], self.wd['w'])
+            nseg = 2
+        if variant == 2:
+            gl, hl = self.g.shape[1], self.h.numel()
+            seg(2, P(self.g), gl, P(self.g_m), P(self.g_v), gl, C.c_void_p(aux.data_ptr() + 4 * D), nblk * al, al, nblk, gl,
+                self.lr['g'], self.wd['g'])
+            seg(3, ptr(self.h), 0, P(self.h_m), P(self.h_v), hl, C.c_void_p(aux.data_ptr() + 4 * (D + gl)), nblk * al, al, nblk,
+                hl, self.lr['h'], self.wd['h'])
+            nseg = 4
+        ad.n_seg = nseg
+        ad.loss_part, ad.n_loss_part = ptr(ws['loss_part']), nblk
+        ad.l1_scale, ad.l2_scale = 1.0 / (B * A * D), 1.0 / B
+        ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
+        ad.sequential_shared = 1
+        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, ring=0,
+                    losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
+
+    def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
+        """
+        One fused SF TD update.  policy = int -> sequential semantics (sfdqn.py:303-371 / tsfdqn.py:588-709): only that
+        policy's (psi, w, g, h) are stepped, next actions by GPI over all policies (use_gpi) or its own psi.
+        policy = 'all' -> frozen-snapshot ensemble semantics (agents/sfdqn.py:57-60 batched): every policy is stepped from
+        the same pre-step library; with use_gpi every policy i gets a* = argmax_a max_j psi_j(s',a).w_i.
+        variant: 0 = G1 (l1 only, 5-tuple), 1 = G2, 2 = G3 (TSF).  Returns losses [n_pol][3] = (loss, l1, l2) on device
+        (no host sync; the buffer is one slot of a 64-deep ring, valid for the next 63 steps).
+        """
+        if variant == 0:
+            states, actions, phis, next_states, gammas = transitions
+            rs = None
+        else:
+            states, actions, rs, phis, next_states, gammas = transitions
+        sp, dev = self.spec, self.device
+        f32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        states, next_states, phis, gammas = self._check_x(states), self._check_x(next_states), f32(phis), f32(gammas).reshape(-1)
+        actions = torch.as_tensor(actions).to(device=dev, dtype=torch.int64, non_blocking=True).reshape(-1).contiguous()
+        B, D = states.shape[0], sp.n_features
+        if rs is not None:
+            rs = f32(rs).reshape(-1)
+            if rs.numel() != B:
+                raise ValueError('rs must hold one reward per transition')
+        if not (phis.shape == (B, D) and gammas.numel() == B and actions.numel() == B and next_states.shape[0] == B):
+            raise ValueError('inconsistent transition batch shapes')
+        if variant == 2 and self.G is None:
+            raise Exception('Affine Function (h) is not initialized')          # tsfdqn.py:592-593
+        key = ('plan', B, policy, bool(use_gpi), variant, float(beta))
+        plan = self._ws.get(key)
+        if plan is None:
+            plan = self._ws[key] = self._build_plan(B, policy, use_gpi, variant, beta)
+        ws, a1, a2, a3, t, b, ad = (plan[k] for k in ('ws', 'a1', 'a2', 'a3', 't', 'b', 'ad'))
+        a1.x, a1.sel_actions = states.data_ptr(), actions.data_ptr()
+        a2.x = a3.x = next_states.data_ptr()
+        t.phis, t.gammas, t.states, t.next_states = phis.data_ptr(), gammas.data_ptr(), states.data_ptr(), next_states.data_ptr()
+        t.rs = None if rs is None else rs.data_ptr()
+        b.x, b.actions = states.data_ptr(), actions.data_ptr()
+        plan['ring'] = (plan['ring'] + 1) % 64
+        losses = plan['losses'][plan['ring']]
+        ad.losses = losses.data_ptr()
+        st = _stream()
+        _lib.call('sfgpi_mlp_forward', C.byref(a1), st)
+        _lib.call('sfgpi_keys_fill', ptr(ws['keys']), ws['keys'].numel(), st)
+        _lib.call('sfgpi_mlp_forward', C.byref(a2), st)
+        _lib.call('sfgpi_mlp_forward', C.byref(a3), st)
+        _lib.call('sfgpi_td_step', C.byref(t), st)
+        _lib.call('sfgpi_mlp_backward', C.byref(b), st)
+        _lib.call('sfgpi_adam_step', C.byref(ad), st)
+        return losses
+
+    def target_sync(self, i):
+        """update_models_weights(psi_model, target_psi_model) (utils/torch.py:31-33): one contiguous D2D row copy."""
+        self.target[i].copy_(self.online[i])

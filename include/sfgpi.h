@@ -1,0 +1,191 @@
+/*
+ * sfgpi.h -- C ABI of the B200-native SF/GPI hot path (libsfgpi.so, sm_100a only).
+ *
+ * Drop-in boundary for the data-parallel hot path of okgarces/deep-successor-features-for-transfer.  The reference
+ * is pure Python/PyTorch; each entry point below replaces the eager-op sequence of the reference function it cites.
+ * A reference-side binding is a ctypes stub.  Conventions:
+ *   - every pointer is a DEVICE pointer unless named host_*; tensors are dense, row-major, fp32 unless noted;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
+ *   - buffers are borrowed for the call, never owned; outputs are caller-allocated;
+ *   - return value: 0 = ok, negative = SFGPI_E_* (sfgpi_last_error() gives the text).  No CPU fallback exists.
+ *
+ * Packed parameter storage ("library"): one row of `row_stride` floats per policy,
+ *   row = [ W_0 | b_0 | W_1 | b_1 | ... | W_{L-1} | b_{L-1} | (pad) ],  W_l is [dims[l+1]][dims[l]] (nn.Linear layout),
+ * every tensor offset a multiple of 4 floats.  Online nets, target nets, Adam exp_avg and exp_avg_sq are four
+ * buffers [N][row_stride] of identical layout.
+ */
+#ifndef SFGPI_H
+#define SFGPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFGPI_MAX_LAYERS 8
+#define SFGPI_MAX_SEGMENTS 8
+
+#define SFGPI_ACT_NONE 0
+#define SFGPI_ACT_RELU 1
+#define SFGPI_ACT_TANH 2
+
+#define SFGPI_OK 0
+#define SFGPI_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define SFGPI_E_SMEM (-2)      /* shape needs more shared memory than an SM has */
+#define SFGPI_E_CUDA (-3)      /* CUDA runtime error at launch */
+
+/* psi network shape = product of the mains' sf_model_lambda (main_tsfdqn_sequential_torch.py:44-75). */
+typedef struct {
+    int32_t n_layers;                      /* number of Linear layers L (>= 1) */
+    int32_t dims[SFGPI_MAX_LAYERS + 1];    /* dims[0] = S ... dims[L] = A*D */
+    int32_t acts[SFGPI_MAX_LAYERS];        /* SFGPI_ACT_* applied after layer l */
+    int32_t w_off[SFGPI_MAX_LAYERS];       /* float offset of W_l inside a policy row */
+    int32_t b_off[SFGPI_MAX_LAYERS];       /* float offset of b_l inside a policy row */
+    int32_t row_stride;                    /* floats per policy row */
+    int32_t n_actions;                     /* A */
+    int32_t n_features;                    /* D;  dims[L] == A*D */
+} sfgpi_net_desc;
+
+/*
+ * Fused ensemble psi forward (A1/A2/A3 + the epilogues of A4/A6).  For every policy j in [policy_lo, policy_lo+n_pol)
+ * and every state b: psi_j(x_b) through the whole MLP in one kernel (activations never leave the SM), then any of:
+ *   psi_out   [B][n_pol][A*D]        get_successor(s) / get_next_successors      (sfdqn.py:290-301, tsfdqn.py:283-307)
+ *   acts_out  [l][n_pol][B][dims[l+1]] post-activation outputs of layers 0..L-2, saved for the backward pass
+ *   sel_out   [n_pol][B][D]          psi_j(x_b)[a_b,:] with a_b = sel_actions[b] (int64, shared by all policies)
+ *                                    or decoded from packed GPI keys sel_keys[(j_local)*sel_key_stride + b]
+ *                                    (sfdqn.py:331 `target_psi_model(next_states)[indices, next_actions,:]`)
+ *   GPI       q = psi . w  for n_w reward vectors w [n_w][D]; q_out [B][n_pol][A] (first vector only);
+ *             key_action[wi][b] = max over (j,a) of pack(q, a), key_task[wi][b] = max of pack(q, task_base+j)
+ *             (atomicMax on int64; keys must be pre-filled with INT64_MIN; see sfgpi_pack semantics below)
+ *             = GPI_w of sfdqn.py:215-240 without materialising psi[B,N,A,D].
+ * Any output pointer may be NULL.  `params` is the [N][row_stride] buffer to read (online or target).
+ * mode: 0 = fp32 CUDA-core path (1e-5 parity mode).
+ */
+typedef struct {
+    sfgpi_net_desc net;
+    const float *params;
+    int32_t policy_lo, n_pol;
+    const float *x;                 /* [B][S] */
+    int32_t B;
+    float *psi_out;
+    float *acts_out[SFGPI_MAX_LAYERS];
+    const int64_t *sel_actions;
+    const int64_t *sel_keys;
+    int32_t sel_key_stride;
+    float *sel_out;
+    const float *w;
+    int32_t n_w;
+    int32_t w_diag;                 /* 1: policy slot p is scored with w[p] only (keys [n_pol][B]); 0: all n_w vectors */
+    int64_t *key_action;
+    int64_t *key_task;
+    int32_t task_base;
+    float *q_out;
+    int32_t mode;
+} sfgpi_forward_args;
+
+int sfgpi_mlp_forward(const sfgpi_forward_args *args, void *stream);
+
+/*
+ * Packed (value,index) keys: key = (orderable_i32(q) << 32) | (0xFFFFFFFF - index); signed int64 max == max q, ties
+ * -> smallest index (torch.argmax first-index rule, sfdqn.py:239,316).  Signed so that the cross-GPU reduction is a
+ * plain NCCL/gloo MAX all-reduce on int64.  Decode: action/task as int64 (torch index dtype), value as fp32.
+ */
+int sfgpi_keys_fill(int64_t *keys, int64_t n, void *stream);
+int sfgpi_keys_decode(const int64_t *keys, int64_t n, int64_t *index_out, float *value_out, void *stream);
+
+/*
+ * Unfused GPI epilogue on a materialised psi [B][N][A][D] (GPI_w, sfdqn.py:236-239): q_out [B][N][A] (nullable),
+ * key_action/key_task [B] written directly (no pre-fill needed).
+ */
+int sfgpi_gpi_from_psi(const float *psi, const float *w, int32_t B, int32_t N, int32_t A, int32_t D, int32_t task_base,
+                       float *q_out, int64_t *key_action, int64_t *key_task, void *stream);
+
+/*
+ * TD target, losses and their gradients (sfdqn.py:330-345; tsfdqn.py:621-645; features/deep.py:112-121), batched over
+ * n_pol policies that all see the same replay batch.
+ *   variant 0 (G1): loss = l1                        (no reward head)
+ *   variant 1 (G2): loss = l1 + l2,  l2 = MSE(w.phi, r)
+ *   variant 2 (G3): phi~ = phi * (h(g(s)) + h(g(s'))), targets carry grad into g,h; loss = l1 + beta*l2
+ * Inputs per policy p: cur_sel/next_sel [n_pol][B][D].  Outputs: d_out [n_pol][B][D] = dLoss/dpsi(s)[a_b,:];
+ * loss_part [n_pol][n_blocks][2] partial sums of (diff^2, e^2); aux_grad_part [n_pol][n_blocks][aux_len] partial
+ * gradients of [w (D) | g.W (G*S) | g.b (G) | h.W (D*G) | h.b (D)] (variant 1: only w).  n_blocks = ceil(B/32).
+ */
+typedef struct {
+    int32_t variant, n_pol, B, S, A, D, G;
+    float beta;
+    const float *cur_sel, *next_sel;
+    const float *phis;              /* [B][D] */
+    const float *rs;                /* [B] */
+    const float *gammas;            /* [B] */
+    const float *states, *next_states;   /* [B][S] (variant 2) */
+    const float *w;                 /* [n_pol][w_stride] */
+    const float *g;                 /* [n_pol][g_stride]: W[G][S] | b[G] */
+    const float *h;                 /* W[D][G] | b[D], shared */
+    int32_t w_stride, g_stride;
+    float *d_out;
+    float *loss_part;
+    float *aux_grad_part;
+    int32_t aux_len;
+} sfgpi_td_args;
+
+int sfgpi_td_step(const sfgpi_td_args *args, void *stream);
+
+/*
+ * Backward of the psi MLP for n_pol policies: fused dgrad chain (dZ_l for every layer, activations' derivative from the
+ * saved outputs) followed by split-K wgrad + bias grad.  The last layer's dZ is the sparse d_out (only the taken
+ * action's D columns are non-zero, sfdqn.py:334-335).
+ *   dz [l][n_pol][B][dims[l+1]] for l = 0..L-2 (scratch, caller-allocated);
+ *   grad_part [n_pol][n_split][row_stride]: split-K partial gradients in library row layout.
+ */
+typedef struct {
+    sfgpi_net_desc net;
+    const float *params;
+    int32_t policy_lo, n_pol;
+    const float *x;                 /* [B][S] */
+    int32_t B;
+    const float *acts[SFGPI_MAX_LAYERS];
+    const int64_t *actions;         /* [B] */
+    const float *d_out;             /* [n_pol][B][D] */
+    float *dz[SFGPI_MAX_LAYERS];
+    float *grad_part;
+    int32_t n_split;
+} sfgpi_backward_args;
+
+int sfgpi_mlp_backward(const sfgpi_backward_args *args, void *stream);
+
+/*
+ * Fused multi-tensor Adam (torch/optim/adam.py::_single_tensor_adam order; sfdqn.py:282-286, tsfdqn.py:255-270) for
+ * n_pol optimizers in one launch.  A segment is a contiguous parameter range with its own lr / weight decay and its
+ * own gradient source (sum of n_part partials).  Per-policy strides select optimizer p's slice; stride 0 = shared
+ * tensor (TSF's h, whose moments are nevertheless per optimizer).  `step` [n_pol] int32 is incremented on device.
+ * Also reduces loss_part -> losses [n_pol][3] = (loss, l1, l2) when loss_part != NULL.
+ */
+typedef struct {
+    float *param;  int64_t param_stride;
+    float *m;      int64_t m_stride;
+    float *v;      int64_t v_stride;
+    const float *grad_part; int64_t grad_pol_stride; int64_t grad_part_stride; int32_t n_part;
+    int32_t len;
+    float lr, weight_decay;
+} sfgpi_adam_segment;
+
+typedef struct {
+    int32_t n_seg, n_pol;
+    sfgpi_adam_segment seg[SFGPI_MAX_SEGMENTS];
+    int32_t *step;                  /* [n_pol] */
+    double beta1, beta2, eps;       /* doubles: torch derives 1-beta and beta**t in double before the fp32 cast */
+    const float *loss_part; int32_t n_loss_part; float l1_scale, l2_scale, beta_loss;
+    float *losses;
+    int32_t sequential_shared;      /* 1: segments with param_stride 0 are stepped by optimizer 0..n_pol-1 in order */
+} sfgpi_adam_args;
+
+int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
+
+const char *sfgpi_last_error(void);
+int sfgpi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFGPI_H */

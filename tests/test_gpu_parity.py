@@ -1,0 +1,280 @@
+"""
+-m gpu: the parity tests proper.  Every call goes Python API -> ctypes -> C ABI (libsfgpi.so) -> sm_100a kernels and is
+compared with (a) the committed outputs of the unmodified reference (tests/golden) and (b) the CPU oracle on the same
+seeded inputs.  Tolerances (fp32 mode, BASELINE north_star: 1e-5 relative):
+  FWD_TOL  1e-5  scale-normalised max error on psi / q / losses
+  STEP_TOL 1e-4  on post-step weights after <= 4 Adam steps (Adam's m/(sqrt(v)+eps) turns a 1e-7 relative gradient
+                 difference on near-zero gradients into a visible fraction of lr; the mean error stays < 1e-6)
+  GPI argmax: bit-exact except where the reference's top-1/top-2 gap is below FWD_TOL * max|q| (ties inside tolerance).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.sf_oracle import OracleSF, synthetic_transitions
+from tests.golden_util import load, oracle_from_golden, transitions, n_layers, rel_err, t
+from tests import gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, STEP_TOL = 1e-5, 1e-4
+G2 = ['g2_reacher_gpi', 'g2_reacher_nogpi', 'g2_reacher_sync', 'g2_reacher_h256', 'g2_cartpole_tanh', 'g2_hopper_gpi']
+
+
+def mean_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().mean() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('name', G2)
+def test_g2_forward_gpi_vs_golden(name):
+    meta, z = load(name)
+    sf = gu.build_g2(meta, z)
+    x = t(z['tr0.states']).cuda()
+    psi = sf.get_successors(x)
+    assert psi.shape == tuple(z['out.psi_all'].shape)
+    assert rel_err(psi.cpu(), z['out.psi_all']) < FWD_TOL
+    assert rel_err(sf.get_successor(x, 1).cpu(), z['out.psi_all'][:, 1]) < FWD_TOL
+    q, task = sf.GPI(x, meta['policy'])
+    assert rel_err(q.cpu(), z['out.q']) < FWD_TOL
+    ok, nbad = gu.argmax_mismatch_ok(t(z['out.q']), t(z['out.task']), task.cpu(), 'task', FWD_TOL)
+    assert ok and nbad <= 1
+    q1, task1 = sf.GPI(x[:1], meta['policy'])
+    assert q1.shape == tuple(z['out.q_b1'].shape) and task1.dim() == 0 and task1.dtype == torch.int64
+    assert int(task1) == int(z['out.task_b1'])
+    # unfused epilogue on the materialised psi gives the same answer as the fused one
+    q2, _, kt = sf._library.gpi_from_psi(psi, sf.fit_w[meta['policy']].weight)
+    assert rel_err(q2.cpu(), z['out.q']) < FWD_TOL
+    assert torch.equal(sf._library.decode_keys(kt).cpu(), task.cpu().reshape(-1))
+
+
+@pytest.mark.parametrize('name', G2)
+def test_g2_update_successor_vs_golden(name):
+    meta, z = load(name)
+    sf = gu.build_g2(meta, z)
+    i = meta['policy']
+    for k in range(meta['K']):
+        out = sf.update_successor(gu.cuda_tr(transitions(z, k)), i, meta['use_gpi'])
+        assert isinstance(out, tuple) and len(out) == 3 and out[0].dim() == 0
+        assert np.allclose([float(v) for v in out], z['out.losses'][k], rtol=2e-5, atol=1e-8)
+    post, tgt = gu.psi_params(sf, i), gu.psi_params(sf, i, target=True)
+    st = sf.psi[i][0][2].state
+    lins = gu.linears(sf.psi[i][0][0].net)
+    for l in range(n_layers(meta)):
+        assert rel_err(post[l][0], z[f'post.psi.W{l}']) < STEP_TOL and mean_err(post[l][0], z[f'post.psi.W{l}']) < 2e-6
+        assert rel_err(post[l][1], z[f'post.psi.b{l}']) < STEP_TOL
+        assert rel_err(tgt[l][0], z[f'post.tgt.W{l}']) < STEP_TOL
+        assert rel_err(st[lins[l].weight]['exp_avg'].cpu(), z[f'post.adam.W{l}.m']) < 2e-5
+        assert rel_err(st[lins[l].weight]['exp_avg_sq'].cpu(), z[f'post.adam.W{l}.v']) < 4e-5
+        assert rel_err(st[lins[l].bias]['exp_avg'].cpu(), z[f'post.adam.b{l}.m']) < 2e-5
+    assert rel_err(sf.fit_w[i].weight.data.cpu(), z['post.w']) < STEP_TOL
+    assert int(sf._library.step[i]) == int(z['post.adam.w.step'])
+    assert sf.updates_since_target_updated == list(z['post.updates_since_target_updated'])
+    for j in range(meta['N']):                                   # untouched policies stay bit-identical
+        if j != i:
+            for l, (W, b) in enumerate(gu.psi_params(sf, j)):
+                assert torch.equal(W, t(z[f'init.psi{j}.W{l}']))
+    assert sf.update_successor(None, i) is None                 # empty replay -> None (sfdqn.py:304-305)
+
+
+@pytest.mark.parametrize('name', ['g3_reacher_gpi', 'g3_reacher_beta30'])
+def test_g3_tsf_vs_golden(name):
+    meta, z = load(name)
+    dsf, ag = gu.build_g3(meta, z)
+    assert rel_err(dsf.get_next_successors(t(z['tr0.states']).cuda()).cpu(), z['out.next_psi_all']) < FWD_TOL
+    for k in range(meta['K']):
+        out = ag.update_successor(gu.cuda_tr(transitions(z, k)), meta['policies'][k], meta['use_gpi'])
+        assert np.allclose([float(v) for v in out], z['out.losses'][k], rtol=2e-5, atol=1e-8)
+    for i in sorted(set(meta['policies'])):
+        for l, (W, b) in enumerate(gu.psi_params(dsf, i)):
+            assert rel_err(W, z[f'post.psi{i}.W{l}']) < STEP_TOL
+            assert rel_err(b, z[f'post.psi{i}.b{l}']) < STEP_TOL
+        assert rel_err(dsf.fit_w[i].weight.data.cpu(), z[f'post.w{i}']) < STEP_TOL
+        assert rel_err(ag.g_functions[i].weight.data.cpu(), z[f'post.g{i}.W']) < STEP_TOL
+        assert rel_err(ag.g_functions[i].bias.data.cpu(), z[f'post.g{i}.b']) < STEP_TOL
+        st = dsf.psi[i][0][2].state
+        assert rel_err(st[ag.h_function.weight]['exp_avg'].cpu(), z[f'post.adam{i}.hW.m']) < 2e-5
+        assert rel_err(st[ag.g_functions[i].weight]['exp_avg_sq'].cpu(), z[f'post.adam{i}.gW.v']) < 4e-5
+    assert rel_err(ag.h_function.weight.data.cpu(), z['post.h.W']) < STEP_TOL
+    assert rel_err(ag.h_function.bias.data.cpu(), z['post.h.b']) < STEP_TOL
+    with pytest.raises(Exception):
+        dsf.update_successor(None, 0)                            # 'This function should not be called'
+
+
+def test_g1_ensemble_vs_golden():
+    from deep_successor_features_for_transfer_b200.ensemble import DeepSF as DeepSFEnsemble
+    meta, z = load('g1_reacher_ensemble')
+    tr = gu.cuda_tr(transitions(z, 0, five=True))
+
+    def build():
+        sf = DeepSFEnsemble(pytorch_model_handle=gu.model_lambda(meta['hidden'], meta['acts']),
+                            hyperparameters={'learning_rate_w': 0.5, 'learning_rate_sf': meta['lr']})
+        sf.reset()
+        for i in range(meta['N']):
+            sf.add_training_task(gu.FakeTask(meta['S'], meta['A'], meta['D'], i))
+        for i in range(meta['N']):
+            layers = [(t(z[f'init.psi{i}.W{l}']), t(z[f'init.psi{i}.b{l}'])) for l in range(n_layers(meta))]
+            gu.load_policy(sf, i, layers, t(z[f'init.w{i}']))
+        return sf
+
+    sf = build()                                                 # fused all-policy step == frozen-snapshot reference
+    losses = sf.update_successors(tr)
+    assert losses.shape == (meta['N'],)
+    for i in range(meta['N']):
+        for l, (W, b) in enumerate(gu.psi_params(sf, i)):
+            assert rel_err(W, z[f'post_frozen.psi{i}.W{l}']) < STEP_TOL
+            assert rel_err(b, z[f'post_frozen.psi{i}.b{l}']) < STEP_TOL
+    sf = build()                                                 # literal reference loop (Gauss-Seidel), one call per task
+    for i in range(meta['N']):
+        sf.update_successor(tr, i)
+    for i in range(meta['N']):
+        for l, (W, b) in enumerate(gu.psi_params(sf, i)):
+            assert rel_err(W, z[f'post_seq.psi{i}.W{l}']) < STEP_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# oracle comparisons on fresh seeded inputs, at sizes the oracle finishes in seconds
+# ------------------------------------------------------------------------------------------------------------------
+def make_oracle(S, A, D, hidden, acts, N, seed, tsf_dim=None, beta=1):
+    gen = torch.Generator().manual_seed(seed)
+    o = OracleSF(S, A, D, hidden, acts, tsf_dim=tsf_dim, beta=beta)
+    for _ in range(N):
+        o.add_random_policy(gen)
+    return o, gen
+
+
+@pytest.mark.parametrize('S,A,D,hidden,N,B,hopper', [
+    (4, 9, 12, (256, 256), 4, 4096, False),       # BASELINE config 1/2 shapes
+    (11, 27, 50, (256, 256), 3, 777, True),       # Hopper shapes, ragged batch (not a multiple of the 64-row tile)
+    (4, 2, 20, (256, 256), 3, 32, False),         # CartPole, config 5
+    (7, 5, 9, (48, 48), 5, 130, False),           # odd everything: S, D, widths not multiples of 4/32
+])
+def test_forward_gpi_vs_oracle(S, A, D, hidden, N, B, hopper):
+    meta = dict(S=S, A=A, D=D, hidden=list(hidden), acts=['relu'] * len(hidden), N=N)
+    o, gen = make_oracle(S, A, D, hidden, meta['acts'], N, seed=77)
+    sf = gu.build_g2(meta, oracle=o)
+    x = synthetic_transitions(B, S, A, D, gen, hopper=hopper)[0]
+    psi_ref = o.get_successors(x)
+    assert rel_err(sf.get_successors(x.cuda()).cpu(), psi_ref) < FWD_TOL
+    q_ref, task_ref = o.GPI(x, 1)
+    q, task = sf.GPI(x.cuda(), 1)
+    assert rel_err(q.cpu(), q_ref) < FWD_TOL
+    ok, nbad = gu.argmax_mismatch_ok(q_ref, task_ref, task.cpu(), 'task', FWD_TOL)
+    assert ok and nbad <= max(1, B // 1000)
+    # action key: argmax_a max_j q (sfdqn.py:316)
+    _, key_a, _ = sf._library.gpi(x.cuda(), sf.fit_w[1].weight, want_q=False)
+    act, val = sf._library.decode_keys(key_a, want_value=True)
+    act_ref = torch.argmax(torch.max(q_ref, dim=1).values, dim=-1)
+    ok, nbad = gu.argmax_mismatch_ok(q_ref, act_ref, act.cpu(), 'action', FWD_TOL)
+    assert ok and nbad <= max(1, B // 1000)
+    assert rel_err(val.cpu(), q_ref.reshape(B, -1).max(dim=1).values) < FWD_TOL
+
+
+@pytest.mark.parametrize('use_gpi', [True, False])
+def test_g2_steps_vs_oracle_reacher_b4096(use_gpi):
+    S, A, D, hidden, N, B = 4, 9, 12, (256, 256), 4, 4096
+    meta = dict(S=S, A=A, D=D, hidden=list(hidden), acts=['relu', 'relu'], N=N)
+    o, gen = make_oracle(S, A, D, hidden, meta['acts'], N, seed=5)
+    sf = gu.build_g2(meta, oracle=o)
+    for k in range(3):
+        tr = synthetic_transitions(B, S, A, D, gen)
+        ref = o.update_successor(tr, 2, use_gpi)
+        out = sf.update_successor(gu.cuda_tr(tr), 2, use_gpi)
+        assert np.allclose([float(v) for v in out], [float(v) for v in ref], rtol=2e-5, atol=1e-8)
+    for l, (W, b) in enumerate(gu.psi_params(sf, 2)):
+        assert rel_err(W, o.psi[2][l][0]) < STEP_TOL and mean_err(W, o.psi[2][l][0]) < 2e-6
+        assert rel_err(b, o.psi[2][l][1]) < STEP_TOL
+    assert rel_err(sf.fit_w[2].weight.data.cpu(), o.w[2]) < STEP_TOL
+
+
+def test_g3_steps_vs_oracle_reacher_b4096():
+    S, A, D, hidden, N, B = 4, 9, 12, (256, 256), 4, 4096
+    meta = dict(S=S, A=A, D=D, hidden=list(hidden), acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True)
+    o, gen = make_oracle(S, A, D, hidden, meta['acts'], N, seed=6, tsf_dim=100, beta=1)
+    dsf, ag = gu.build_g3(meta, oracle=o)
+    for k, pol in enumerate([0, 3, 0]):
+        tr = synthetic_transitions(B, S, A, D, gen)
+        ref = o.tsf_update_successor(tr, pol, True)
+        out = ag.update_successor(gu.cuda_tr(tr), pol, True)
+        assert np.allclose([float(v) for v in out], [float(v) for v in ref], rtol=2e-5, atol=1e-8)
+    for pol in (0, 3):
+        for l, (W, b) in enumerate(gu.psi_params(dsf, pol)):
+            assert rel_err(W, o.psi[pol][l][0]) < STEP_TOL
+        assert rel_err(ag.g_functions[pol].weight.data.cpu(), o.g[pol][0]) < STEP_TOL
+    assert rel_err(ag.h_function.weight.data.cpu(), o.h[0]) < STEP_TOL
+    assert rel_err(ag.h_function.bias.data.cpu(), o.h[1]) < STEP_TOL
+
+
+@pytest.mark.parametrize('variant', ['g2', 'g3'])
+def test_ensemble_all_policies_vs_frozen_oracle(variant):
+    S, A, D, hidden, N, B = 4, 9, 12, (64, 64), 5, 200
+    tsf = variant == 'g3'
+    meta = dict(S=S, A=A, D=D, hidden=list(hidden), acts=['relu', 'relu'], N=N, gdim=16, beta=30, use_gpi=True)
+    o, gen = make_oracle(S, A, D, hidden, meta['acts'], N, seed=9, tsf_dim=16 if tsf else None, beta=30)
+    if tsf:
+        sf, ag = gu.build_g3(meta, oracle=o)
+    else:
+        sf = ag = gu.build_g2(meta, oracle=o)
+    for k in range(2):
+        tr = synthetic_transitions(B, S, A, D, gen)
+        ref = o.ensemble_update_frozen(tr, tsf=tsf, use_gpi=True)
+        losses = ag.update_successor_all(gu.cuda_tr(tr), use_gpi=True).cpu()
+        for i in range(N):
+            assert np.allclose(losses[i].numpy(), [float(v) for v in ref[i]], rtol=3e-5, atol=1e-8)
+    for i in range(N):
+        for l, (W, b) in enumerate(gu.psi_params(sf, i)):
+            assert rel_err(W, o.psi[i][l][0]) < STEP_TOL
+        assert rel_err(sf.fit_w[i].weight.data.cpu(), o.w[i]) < STEP_TOL
+    if tsf:
+        assert rel_err(ag.h_function.weight.data.cpu(), o.h[0]) < STEP_TOL
+
+
+def test_edge_cases_and_errors():
+    meta = dict(S=4, A=9, D=12, hidden=[64, 64], acts=['relu', 'relu'], N=2)
+    o, gen = make_oracle(4, 9, 12, (64, 64), meta['acts'], 2, seed=3)
+    sf = gu.build_g2(meta, oracle=o)
+    with pytest.raises(ValueError):
+        sf.get_successors(torch.zeros(3, 5).cuda())              # wrong state width
+    with pytest.raises(Exception):
+        sf._library.train_step(gu.cuda_tr(synthetic_transitions(8, 4, 9, 12, gen)), 7)     # policy out of range
+    assert sf.get_successors(torch.zeros(0, 4).cuda()).shape == (0, 2, 9, 12)             # empty batch
+    # growing the library re-packs storage: earlier modules must still be live views
+    for i in range(2, 7):
+        sf.add_training_task(gu.FakeTask(4, 9, 12, i))
+    x = torch.randn(5, 4, generator=gen)
+    assert rel_err(sf.get_successor(x.cuda(), 1).cpu(), o.get_successor(x, 1)) < FWD_TOL
+    W0 = gu.linears(sf.psi[0][0][0].net)[0].weight
+    assert W0.data.data_ptr() == sf._library.online[0].data_ptr()
+    # unsupported layer types are rejected, there is no fallback
+    from deep_successor_features_for_transfer_b200.sfdqn import DeepSF
+    bad = DeepSF(lambda *a: (torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Sigmoid(), torch.nn.Linear(8, 108)),
+                             torch.nn.MSELoss(), None), hyperparameters=dict(gu.HYPER))
+    bad.reset()
+    with pytest.raises(TypeError):
+        bad.add_training_task(gu.FakeTask(4, 9, 12, 0))
+
+
+def test_full_size_properties_hopper_gpi():
+    """BASELINE config 3 shapes at full batch (65 536 states), 8 policies = one GPU's shard: size-independent properties."""
+    S, A, D, N, B = 11, 27, 50, 8, 65536
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make_oracle(S, A, D, (256, 256), meta['acts'], N, seed=11)
+    sf = gu.build_g2(meta, oracle=o)
+    x = torch.sigmoid(torch.randn(B, S, generator=gen)).cuda()
+    q, key_a, key_t = sf._library.gpi(x, sf.fit_w[0].weight)
+    act, val = sf._library.decode_keys(key_a, want_value=True)
+    task = sf._library.decode_keys(key_t)
+    qmax = q.reshape(B, -1).max(dim=1).values
+    assert torch.equal(val, qmax)                                                   # key value == max of the returned q
+    assert torch.equal(act, torch.argmax(q.max(dim=1).values, dim=-1))              # first-index tie rule, actions
+    assert torch.equal(task, torch.argmax(q.max(dim=2).values, dim=1))              # first-index tie rule, tasks
+    # sharding invariance: max over two policy shards' keys == keys over all policies (what the NCCL MAX all-reduce does)
+    _, ka0, kt0 = sf._library.gpi(x, sf.fit_w[0].weight, lo=0, n_pol=3, want_q=False, task_base=0)
+    _, ka1, kt1 = sf._library.gpi(x, sf.fit_w[0].weight, lo=3, n_pol=5, want_q=False, task_base=3)
+    assert torch.equal(torch.maximum(ka0, ka1), key_a) and torch.equal(torch.maximum(kt0, kt1), key_t)
+    # linearity in w: q(2w) == 2 q(w) exactly (power-of-two scaling)
+    q2, _, _ = sf._library.gpi(x, 2.0 * sf.fit_w[0].weight)
+    assert torch.equal(q2, 2.0 * q)
+    # spot-check 512 states against the oracle
+    idx = torch.randperm(B, generator=gen)[:512]
+    q_ref, _ = o.GPI(x.cpu()[idx], 0)
+    assert rel_err(q.cpu()[idx], q_ref) < FWD_TOL
