@@ -1,0 +1,305 @@
+# -*- coding: UTF-8 -*-
+"""
+bench.py -- headline benchmark of the SF/GPI hot path (contract: one JSON line on stdout, rank 0).
+
+Workload (BASELINE.json configs[1]): TSFDQN on Reacher shapes (S=4, A=9, D=12, MLP 256-256
+relu, g: 4->100, h: 100->12, beta=1), synthetic replay batch B=4096, 4 source policies PER GPU, GPI next actions.
+One "step" = one replay batch on which EVERY policy of the library is updated (fused all-task TD update, frozen-snapshot
+semantics) => transitions x tasks = B * N_total SF TD updates per step.  Multi-GPU: policies sharded 4 per GPU (weak
+scaling), the batch replicated, GPI's max over policies exchanged as packed int64 keys (NCCL MAX all-reduce).
+
+  value : updates/s with the batches already resident in HBM (CUDA events per step, L2 flushed between steps)
+  e2e   : same metric through the public API (TSFDQN.update_successor_all) from pinned HOST batches, H2D copies and the
+          D2H read of the losses inside the timed region (wall clock, synchronised both sides)
+  --impl reference : the reference algorithm on the host cores (CPU oracle port, torch CPU fp32, all threads): the same
+          all-task update done the way the reference does it, one update_successor call per task on the same batch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    'tsfdqn_reacher_b4096': dict(S=4, A=9, D=12, hidden=[256, 256], acts=['relu', 'relu'], gdim=100, beta=1, B=4096,
+                                 n_local=4, hopper=False),
+}
+SEED = 1024
+
+
+def flops_per_net_pass(S, hidden, AD):
+    dims = [S, hidden[0]] + list(hidden) + [AD]
+    return 2 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p['bf16_tflops_sustained'], src='measured')
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_oracle(cfg, n, seed):
+    from oracle.sf_oracle import OracleSF
+    gen = torch.Generator().manual_seed(seed)
+    o = OracleSF(cfg['S'], cfg['A'], cfg['D'], cfg['hidden'], cfg['acts'], tsf_dim=cfg['gdim'], beta=cfg['beta'])
+    for _ in range(n):
+        o.add_random_policy(gen)
+    return o, gen
+
+
+def cpu_all_task_update(o, tr):
+    """The all-task update the way the reference does it: one update_successor per task on the same batch."""
+    for i in range(o.n_tasks):
+        o.tsf_update_successor(tr, i, True)
+
+
+def time_cpu(cfg, n_policies, steps, warmup, threads):
+    from oracle.sf_oracle import synthetic_transitions
+    torch.set_num_threads(threads)
+    o, gen = make_oracle(cfg, n_policies, SEED)
+    batches = [synthetic_transitions(cfg['B'], cfg['S'], cfg['A'], cfg['D'], gen) for _ in range(2)]
+    for k in range(warmup):
+        cpu_all_task_update(o, batches[k % 2])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        cpu_all_task_update(o, batches[k % 2])
+    dt = time.perf_counter() - t0
+    return cfg['B'] * n_policies * steps / dt, dt / steps
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_total = cfg['n_local'] * world
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    val, per = time_cpu(cfg, n_total, steps, warm, cores)
+    sample = f'{steps} all-task steps ({n_total} update_successor calls each) of the same workload, B={cfg["B"]}'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'SF TD updates (transitions x tasks)/s', 'value': val, 'unit': 'updates/s',
+        'n_gpus': world, 'steps': steps, 'warmup': warm, 'ms_per_step': per * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, cfg, n_total, world),
+        'cpu_baseline': {'value': val, 'unit': 'updates/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(name, cfg, n_total, world):
+    return {'workload': f'{name}: TSFDQN Reacher S4/A9/D12 MLP 256-256 relu, g 4->100, h 100->12, beta=1, B={cfg["B"]}, '
+                        f'{cfg["n_local"]} policies/GPU ({n_total} total), all-task fused TD update with GPI next actions',
+            'batch': cfg['B'], 'policies_total': n_total, 'policies_per_gpu': cfg['n_local'],
+            'parallelism': f'policy-sharded x{world}' if world > 1 else 'single GPU',
+            'l2': 'flushed between timed steps (256 MiB write), flush excluded from the per-step CUDA-event time',
+            'precision_mode': 'fp32 (1e-5 parity mode)'}
+
+
+def build_agent(cfg, n_local):
+    from tests.gpu_util import FakeTask, model_lambda, HYPER
+    from deep_successor_features_for_transfer_b200.tsfdqn import DeepTSF, TSFDQN, ReplayBuffer
+    hyper = dict(HYPER, g_h_function_dims=cfg['gdim'], beta_loss_coefficient=cfg['beta'])
+    dsf = DeepTSF(pytorch_model_handle=model_lambda(cfg['hidden'], cfg['acts']), use_true_reward=False,
+                  target_update_ev=1000, hyperparameters=hyper)
+    ag = TSFDQN(deep_sf=dsf, buffer_handle=lambda: ReplayBuffer(), gamma=0.9, T=500, encoding=None, use_gpi=True,
+                hyperparameters=hyper)
+    ag.reset()
+    for i in range(n_local):
+        ag.add_training_task(FakeTask(cfg['S'], cfg['A'], cfg['D'], i))
+    return dsf, ag
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='tsfdqn_reacher_b4096')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, cfg, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch.distributed as dist
+    from oracle.sf_oracle import synthetic_transitions
+    from deep_successor_features_for_transfer_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(SEED + rank)
+    B, S, A, D, n_local = cfg['B'], cfg['S'], cfg['A'], cfg['D'], cfg['n_local']
+    n_total = n_local * world
+    dsf, ag = build_agent(cfg, n_local)
+    lib = dsf._library
+    if world > 1:
+        lib.enable_sharding()
+    gen = torch.Generator().manual_seed(SEED)                       # identical batches on every rank (replicated replay)
+    host = [synthetic_transitions(B, S, A, D, gen) for _ in range(8)]
+    pinned = [tuple(t.pin_memory() for t in tr) for tr in host]
+    resident = [tuple(t.to(dev) for t in tr) for tr in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: HBM-resident inputs, CUDA events per step ----------------
+    for k in range(args.warmup):
+        ag.update_successor_all(resident[k % 8], use_gpi=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = _lib.launch_count
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        ag.update_successor_all(resident[k % 8], use_gpi=True)
+        ev[k][1].record()
+    barrier()
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax)
+    updates_per_step = B * n_total
+    value = updates_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---------------- e2e: public API from pinned host batches, losses read back every step ----------------
+    e2e_steps = args.steps
+    for k in range(3):
+        ag.update_successor_all(pinned[k % 8], use_gpi=True).cpu()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        losses = ag.update_successor_all(pinned[k % 8], use_gpi=True)
+        losses_host = losses.cpu()                                  # D2H read of the step's result (syncs)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = updates_per_step * e2e_steps / float(e2e_t)
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+    d2h = losses_host.numel() * 4
+
+    # ---------------- roofline of the dominant kernel: the fused GPI forward (mlp_forward_kernel) ----------------
+    F = flops_per_net_pass(S, cfg['hidden'], A * D)
+    peaks = load_peaks()
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200.library import _stream
+    x = resident[0][4]
+    kkeys = torch.empty(B, dtype=torch.int64, device=dev)
+    ka = lib._fwd_args(lib.online, 0, lib.n, x)
+    ka.w, ka.n_w, ka.w_diag, ka.key_action = lib.w[0].data_ptr(), 1, 0, kkeys.data_ptr()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(23)]
+    for a, b in kev:
+        flush.fill_(1)
+        _lib.call('sfgpi_keys_fill', kkeys.data_ptr(), B, _stream())
+        a.record()
+        _lib.call('sfgpi_mlp_forward', C.byref(ka), _stream())
+        b.record()
+    torch.cuda.synchronize()
+    k_ms = sorted(a.elapsed_time(b) for a, b in kev[3:])[10]       # median of 20 after 3 warm-up launches
+    k_flops = n_local * B * (F + 2 * A * D)
+    achieved = k_flops / (k_ms * 1e-3) / 1e12
+    roofline = {'kernel': 'mlp_forward_kernel (fused ensemble MLP + GPI epilogue, fp32 CUDA-core mode)', 'bound': 'tensor',
+                'achieved': achieved, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_burst'],
+                'traffic': None, 'peak_source': f'{peaks["src"]} bf16 cuBLAS burst', 'kernel_ms': k_ms,
+                'flops_per_launch': k_flops}
+    step_flops = 5 * F * B * n_local                               # N GPI + N online + N target + 2N backward = 5N passes
+    step_tflops = step_flops * args.steps / (total_ms * 1e-3) / 1e12
+
+    out = None
+    if rank == 0:
+        out = {
+            'metric': 'SF TD updates (transitions x tasks)/s', 'value': value, 'unit': 'updates/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, cfg, n_total, world),
+            'clocks': clocks,
+            'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': float(e2e_t) / e2e_steps * 1e3},
+            'gpu_launches': launches,
+            'roofline': roofline,
+            'step_tflops_per_gpu': step_tflops,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cval, cper = time_cpu(cfg, n_total, 10, 2, cores)
+            out['cpu_baseline'] = {'value': cval, 'unit': 'updates/s', 'cores': cores, 'kind': 'port',
+                                   'sample': f'10 all-task steps ({n_total} update_successor calls each), B={B}, '
+                                             f'{cper * 1e3:.1f} ms/step, oracle port on torch CPU fp32'}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

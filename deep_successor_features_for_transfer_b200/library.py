@@ -117,6 +117,18 @@ class PackedSFLibrary:
         self._views = []            # per policy: dict of modules whose .data must be re-pointed after a re-pack
         self._ws = {}
         self.h = None
+        self.shard = None           # dist.ShardContext once enable_sharding() was called
+
+    def enable_sharding(self, group=None):
+        """Declare this library one policy shard of a multi-GPU ensemble (call on every rank after the tasks were added)."""
+        from .dist import ShardContext
+        self.shard = ShardContext(self.n, group)
+        self._ws = {k: v for k, v in self._ws.items() if not (isinstance(k, tuple) and k and k[0] == 'plan')}
+        return self.shard
+
+    @property
+    def _sharded(self):
+        return self.shard is not None and self.shard.world > 1
 
     # ------------------------------------------------------------------ storage
     def _alloc(self, cap):
@@ -254,7 +266,7 @@ class PackedSFLibrary:
         _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
         return out
 
-    def gpi(self, x, w_vec, lo=0, n_pol=None, want_q=True, task_base=0, keys_out=None):
+    def gpi(self, x, w_vec, lo=0, n_pol=None, want_q=True, task_base=None, keys_out=None, reduce=True):
         """
         Fused GPI_w (sfdqn.py:215-240): returns (q [B][n_pol][A] or None, key_action [B], key_task [B]) -- packed int64
         keys, decode with decode_keys().  psi[B,N,A,D] is never materialised.
@@ -271,9 +283,12 @@ class PackedSFLibrary:
         a = self._fwd_args(self.online, lo, n_pol, x)
         a.w, a.n_w, a.w_diag = ptr(w_vec), 1, 0
         a.key_action, a.key_task = C.c_void_p(keys[0].data_ptr()), C.c_void_p(keys[1].data_ptr())
-        a.task_base = task_base
+        a.task_base = (self.shard.lo + lo if self.shard is not None else lo) if task_base is None else task_base
         a.q_out = ptr(q)
         _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+        if self._sharded and reduce:
+            from .dist import allreduce_max_keys
+            allreduce_max_keys(keys, self.shard.group)          # packed (value,index) MAX over NVLink: global GPI
         return q, keys[0], keys[1]
 
     def decode_keys(self, keys, want_value=False):
@@ -312,16 +327,31 @@ class PackedSFLibrary:
             a1.acts_out[l] = ws['acts'][l].data_ptr()
         a1.sel_out = ptr(ws['cur_sel'])
         # (2) next actions: GPI over the whole library (or own psi) with w_i            sfdqn.py:314-322
+        #     sharded: this rank scores its local policies for ALL n_total reward vectors (gathered into w_all); the
+        #     per-rank keys [n_total][B] are MAX-all-reduced, then rows [shard.lo, shard.lo + n) are this rank's own.
+        sharded = self._sharded and use_gpi
+        if sharded and not ensemble:
+            raise NotImplementedError('sharded libraries step all local policies at once (policy="all"); the single-policy '
+                                      'step with cross-GPU GPI is train_step_owner()/gpi_assist()')
+        key_row0 = 0
+        w_all = None
         if use_gpi:
             a2 = self._fwd_args(self.online, 0, self.n, None, B)
-            a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 0
+            if sharded and ensemble:
+                nt = self.shard.n_total
+                keys = ws['keys_all'] = ws.get('keys_all', torch.empty(nt, B, dtype=torch.int64, device=self.device))
+                w_all = ws['w_all'] = ws.get('w_all', self._f(nt, D))
+                a2.w, a2.n_w, a2.w_diag, key_row0 = ptr(w_all), nt, 0, self.shard.lo
+            else:
+                a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 0
+            a2.task_base = self.shard.lo if self.shard is not None else 0
         else:
             a2 = self._fwd_args(self.online, lo, n_pol, None, B)
             a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 1
         a2.key_action = ptr(keys)
         # (3) target forward on s', gather psi^-(s')[a*]                                sfdqn.py:330-331
         a3 = self._fwd_args(self.target, lo, n_pol, None, B)
-        a3.sel_keys, a3.sel_key_stride, a3.sel_out = ptr(keys), B, ptr(ws['next_sel'])
+        a3.sel_keys, a3.sel_key_stride, a3.sel_out = C.c_void_p(keys[key_row0:].data_ptr()), B, ptr(ws['next_sel'])
         # (4) TD target, losses, d_out and the reward-head / g / h gradients            sfdqn.py:330-345, tsfdqn.py:621-645
         t = _lib.TdArgs()
         t.variant, t.n_pol, t.B, t.S, t.A, t.D, t.G = variant, n_pol, B, S, A, D, (self.G or 0)
@@ -370,7 +400,7 @@ class PackedSFLibrary:
         ad.l1_scale, ad.l2_scale = 1.0 / (B * A * D), 1.0 / B
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
-        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, ring=0,
+        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, ring=0, keys=keys, w_all=w_all, sharded=sharded,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
     def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
@@ -414,14 +444,34 @@ class PackedSFLibrary:
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
         st = _stream()
+        keys, sharded = plan['keys'], plan['sharded']
         _lib.call('sfgpi_mlp_forward', C.byref(a1), st)
-        _lib.call('sfgpi_keys_fill', ptr(ws['keys']), ws['keys'].numel(), st)
+        _lib.call('sfgpi_keys_fill', ptr(keys), keys.numel(), st)
+        if sharded and plan['w_all'] is not None:
+            self._gather_w(plan['w_all'])
         _lib.call('sfgpi_mlp_forward', C.byref(a2), st)
+        if sharded:
+            from .dist import allreduce_max_keys
+            allreduce_max_keys(keys, self.shard.group)
         _lib.call('sfgpi_mlp_forward', C.byref(a3), st)
         _lib.call('sfgpi_td_step', C.byref(t), st)
         _lib.call('sfgpi_mlp_backward', C.byref(b), st)
+        h0 = self.h.clone() if (self._sharded and variant == 2) else None
         _lib.call('sfgpi_adam_step', C.byref(ad), st)
+        if h0 is not None:                        # every rank applied only its own optimizers' deltas to the shared h
+            import torch.distributed as dist
+            delta = self.h - h0
+            dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.shard.group)
+            self.h.copy_(h0 + delta)
         return losses
+
+    def _gather_w(self, w_all):
+        import torch.distributed as dist
+        if self.shard.uniform:
+            dist.all_gather_into_tensor(w_all, self.w[:self.n].contiguous(), group=self.shard.group)
+        else:
+            parts = [w_all[sum(self.shard.counts[:r]):sum(self.shard.counts[:r + 1])] for r in range(self.shard.world)]
+            dist.all_gather(parts, self.w[:self.n].contiguous(), group=self.shard.group)
 
     def target_sync(self, i):
         """update_models_weights(psi_model, target_psi_model) (utils/torch.py:31-33): one contiguous D2D row copy."""
