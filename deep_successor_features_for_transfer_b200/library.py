@@ -102,7 +102,7 @@ def _stream():
 
 
 class PackedSFLibrary:
-    def __init__(self, device=None, lr=None, wd=None, tsf_dim=None, capacity=4):
+    def __init__(self, device=None, lr=None, wd=None, tsf_dim=None, capacity=4, precision='fp32'):
         if not torch.cuda.is_available():
             raise RuntimeError('deep_successor_features_for_transfer_b200 needs a CUDA device (sm_100a); there is no CPU path')
         _lib.lib()                                   # fail loudly right here if the native library is missing
@@ -118,6 +118,43 @@ class PackedSFLibrary:
         self._ws = {}
         self.h = None
         self.shard = None           # dist.ShardContext once enable_sharding() was called
+        self.set_precision(precision)
+
+    def set_precision(self, precision):
+        """
+        'fp32': CUDA-core kernels, 1e-5 parity with the reference.  'bf16': the ensemble MLP forwards (GPI, online, target)
+        run on the tcgen05 tensor cores with bf16 operands / fp32 accumulation (stated tolerance 2e-2 on psi / q); the
+        backward pass, TD and Adam stay fp32 on fp32 master weights.
+        """
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self._ws = {}
+        self._shadow = {}
+
+    def _shadow_for(self, which):
+        """bf16 shadow [cap][rows_per_policy][256] of the online / target rows, (re)allocated with the storage."""
+        buf = self._shadow.get(which)
+        if buf is None or buf[1] != self.cap:
+            desc = self.spec.desc()
+            rpp = _lib.lib().sfgpi_bf16_rows_per_policy(C.byref(desc))
+            buf = (torch.zeros(self.cap * rpp * 256, dtype=torch.bfloat16, device=self.device), self.cap)
+            self._shadow[which] = buf
+        return buf[0]
+
+    def _pack(self, which, lo, n_pol):
+        desc = self.spec.desc()
+        _lib.call('sfgpi_pack_bf16', C.byref(desc), ptr(self.target if which == 'target' else self.online), lo, n_pol,
+                  ptr(self._shadow_for(which)), _stream())
+
+    def _forward(self, a, which, fresh=False):
+        """Dispatch one fused forward: fp32 CUDA-core kernel or the tcgen05 kernel on the bf16 shadow (packed on demand)."""
+        if self.precision == 'fp32':
+            _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+        else:
+            if not fresh:
+                self._pack(which, a.policy_lo, a.n_pol)
+            _lib.call('sfgpi_mlp_forward_tc', C.byref(a), ptr(self._shadow_for(which)), self.cap, _stream())
 
     def enable_sharding(self, group=None):
         """Declare this library one policy shard of a multi-GPU ensemble (call on every rank after the tasks were added)."""
@@ -263,7 +300,7 @@ class PackedSFLibrary:
         out = self._f(x.shape[0], n_pol, sp.n_actions, sp.n_features)
         a = self._fwd_args(self.target if target else self.online, lo, n_pol, x)
         a.psi_out = ptr(out)
-        _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+        self._forward(a, 'target' if target else 'online')
         return out
 
     def gpi(self, x, w_vec, lo=0, n_pol=None, want_q=True, task_base=None, keys_out=None, reduce=True):
@@ -285,7 +322,7 @@ class PackedSFLibrary:
         a.key_action, a.key_task = C.c_void_p(keys[0].data_ptr()), C.c_void_p(keys[1].data_ptr())
         a.task_base = (self.shard.lo + lo if self.shard is not None else lo) if task_base is None else task_base
         a.q_out = ptr(q)
-        _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+        self._forward(a, 'online')
         if self._sharded and reduce:
             from .dist import allreduce_max_keys
             allreduce_max_keys(keys, self.shard.group)          # packed (value,index) MAX over NVLink: global GPI
@@ -445,15 +482,18 @@ class PackedSFLibrary:
         ad.losses = losses.data_ptr()
         st = _stream()
         keys, sharded = plan['keys'], plan['sharded']
-        _lib.call('sfgpi_mlp_forward', C.byref(a1), st)
+        if self.precision != 'fp32':
+            self._pack('online', 0, self.n)                     # one refresh of the bf16 shadows per step
+            self._pack('target', a3.policy_lo, a3.n_pol)
+        self._forward(a1, 'online', fresh=True)
         _lib.call('sfgpi_keys_fill', ptr(keys), keys.numel(), st)
         if sharded and plan['w_all'] is not None:
             self._gather_w(plan['w_all'])
-        _lib.call('sfgpi_mlp_forward', C.byref(a2), st)
+        self._forward(a2, 'online', fresh=True)
         if sharded:
             from .dist import allreduce_max_keys
             allreduce_max_keys(keys, self.shard.group)
-        _lib.call('sfgpi_mlp_forward', C.byref(a3), st)
+        self._forward(a3, 'target', fresh=True)
         _lib.call('sfgpi_td_step', C.byref(t), st)
         _lib.call('sfgpi_mlp_backward', C.byref(b), st)
         h0 = self.h.clone() if (self._sharded and variant == 2) else None

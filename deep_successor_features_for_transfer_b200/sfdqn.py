@@ -115,6 +115,7 @@ class DeepSF:
         self.device = _device()
         self._tsf_dim = None
         self._library = None
+        self.precision = kwargs.get('precision', self.hyperparameters.get('precision', 'fp32'))
 
     # ---- library construction -------------------------------------------------------------------------------------
     def _hyper(self, kind, default):
@@ -122,7 +123,7 @@ class DeepSF:
 
     def _new_library(self):
         lr, wd = self._hyper('learning_rate', 1e-3), self._hyper('weight_decay', 0.0)
-        return PackedSFLibrary(self.device, lr=lr, wd=wd, tsf_dim=self._tsf_dim)
+        return PackedSFLibrary(self.device, lr=lr, wd=wd, tsf_dim=self._tsf_dim, precision=self.precision)
 
     def reset(self):
         self.n_tasks = 0
