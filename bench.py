@@ -140,19 +140,20 @@ def run_reference(args, cfg, rank, world):
     }))
 
 
-def workload_config(name, cfg, n_total, world):
+def workload_config(name, cfg, n_total, world, precision='fp32'):
     return {'workload': f'{name}: TSFDQN Reacher S4/A9/D12 MLP 256-256 relu, g 4->100, h 100->12, beta=1, B={cfg["B"]}, '
                         f'{cfg["n_local"]} policies/GPU ({n_total} total), all-task fused TD update with GPI next actions',
             'batch': cfg['B'], 'policies_total': n_total, 'policies_per_gpu': cfg['n_local'],
             'parallelism': f'policy-sharded x{world}' if world > 1 else 'single GPU',
             'l2': 'flushed between timed steps (256 MiB write), flush excluded from the per-step CUDA-event time',
-            'precision_mode': 'fp32 (1e-5 parity mode)'}
+            'precision_mode': ('bf16 operands on tcgen05, fp32 accumulate, fp32 master weights / backward / Adam (tolerance 2e-2)'
+                               if precision == 'bf16' else 'fp32 (1e-5 parity mode)')}
 
 
-def build_agent(cfg, n_local):
+def build_agent(cfg, n_local, precision='fp32'):
     from tests.gpu_util import FakeTask, model_lambda, HYPER
     from deep_successor_features_for_transfer_b200.tsfdqn import DeepTSF, TSFDQN, ReplayBuffer
-    hyper = dict(HYPER, g_h_function_dims=cfg['gdim'], beta_loss_coefficient=cfg['beta'])
+    hyper = dict(HYPER, g_h_function_dims=cfg['gdim'], beta_loss_coefficient=cfg['beta'], precision=precision)
     dsf = DeepTSF(pytorch_model_handle=model_lambda(cfg['hidden'], cfg['acts']), use_true_reward=False,
                   target_update_ev=1000, hyperparameters=hyper)
     ag = TSFDQN(deep_sf=dsf, buffer_handle=lambda: ReplayBuffer(), gamma=0.9, T=500, encoding=None, use_gpi=True,
@@ -171,6 +172,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='tsfdqn_reacher_b4096')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help='bf16: tcgen05 tensor-core forwards (stated tolerance 2e-2); fp32: CUDA-core 1e-5 parity mode')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))
@@ -191,7 +194,7 @@ def main():
     torch.manual_seed(SEED + rank)
     B, S, A, D, n_local = cfg['B'], cfg['S'], cfg['A'], cfg['D'], cfg['n_local']
     n_total = n_local * world
-    dsf, ag = build_agent(cfg, n_local)
+    dsf, ag = build_agent(cfg, n_local, args.precision)
     lib = dsf._library
     if world > 1:
         lib.enable_sharding()
@@ -263,13 +266,15 @@ def main():
         flush.fill_(1)
         _lib.call('sfgpi_keys_fill', kkeys.data_ptr(), B, _stream())
         a.record()
-        _lib.call('sfgpi_mlp_forward', C.byref(ka), _stream())
+        lib._forward(ka, 'online', fresh=True)
         b.record()
     torch.cuda.synchronize()
     k_ms = sorted(a.elapsed_time(b) for a, b in kev[3:])[10]       # median of 20 after 3 warm-up launches
     k_flops = n_local * B * (F + 2 * A * D)
     achieved = k_flops / (k_ms * 1e-3) / 1e12
-    roofline = {'kernel': 'mlp_forward_kernel (fused ensemble MLP + GPI epilogue, fp32 CUDA-core mode)', 'bound': 'tensor',
+    kname = ('mlp_forward_tc_kernel (fused ensemble MLP + GPI epilogue; tcgen05 bf16 MMA, TMEM accumulators, TMA weights)'
+             if args.precision == 'bf16' else 'mlp_forward_kernel (fused ensemble MLP + GPI epilogue, fp32 CUDA-core mode)')
+    roofline = {'kernel': kname, 'bound': 'tensor',
                 'achieved': achieved, 'peak': peaks['tf_burst'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_burst'],
                 'traffic': None, 'peak_source': f'{peaks["src"]} bf16 cuBLAS burst', 'kernel_ms': k_ms,
                 'flops_per_launch': k_flops}
@@ -281,8 +286,8 @@ def main():
         out = {
             'metric': 'SF TD updates (transitions x tasks)/s', 'value': value, 'unit': 'updates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.workload, cfg, n_total, world),
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, cfg, n_total, world, args.precision),
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_t) / e2e_steps * 1e3},

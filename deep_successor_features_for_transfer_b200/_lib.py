@@ -91,14 +91,17 @@ SYMBOLS = {
     'sfgpi_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
     'sfgpi_bf16_rows_per_policy': (C.c_int, [C.POINTER(NetDesc)]),
     'sfgpi_pack_bf16': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    'sfgpi_mlp_forward_tc': (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p, C.c_int32, C.c_void_p]),
+    'sfgpi_gpi_fold_rows': (C.c_int, [C.POINTER(NetDesc), C.c_int32]),
+    'sfgpi_fold_gpi': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_mlp_forward_tc': (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
 }
 
 _lib = None
 launch_count = 0          # kernels launched through the C ABI (bench.py reports it as gpu_launches)
-LAUNCHES_PER_CALL = {'sfgpi_pack_bf16': 1, 'sfgpi_mlp_forward_tc': 1, 'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
+LAUNCHES_PER_CALL = {'sfgpi_pack_bf16': 1, 'sfgpi_fold_gpi': 1, 'sfgpi_mlp_forward_tc': 1, 'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
                      'sfgpi_td_step': 1, 'sfgpi_mlp_backward': 2, 'sfgpi_adam_step': 2}
 
 

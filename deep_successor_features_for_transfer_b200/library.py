@@ -154,7 +154,20 @@ class PackedSFLibrary:
         else:
             if not fresh:
                 self._pack(which, a.policy_lo, a.n_pol)
-            _lib.call('sfgpi_mlp_forward_tc', C.byref(a), ptr(self._shadow_for(which)), self.cap, _stream())
+            wq = bq = None
+            if a.w:                                             # GPI form: fold the reward vectors into the output layer
+                desc = self.spec.desc()
+                nw = 1 if a.w_diag else a.n_w
+                nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(desc), nw)
+                key = ('fold', a.n_pol, nq)
+                buf = self._ws.get(key)
+                if buf is None:
+                    buf = self._ws[key] = (torch.empty(a.n_pol * nq * 256, dtype=torch.bfloat16, device=self.device),
+                                           self._f(a.n_pol * nq))
+                wq, bq = buf
+                _lib.call('sfgpi_fold_gpi', C.byref(desc), ptr(self.target if which == 'target' else self.online), a.policy_lo,
+                          a.n_pol, a.w, a.n_w, a.w_diag, ptr(wq), ptr(bq), _stream())
+            _lib.call('sfgpi_mlp_forward_tc', C.byref(a), ptr(self._shadow_for(which)), self.cap, ptr(wq), ptr(bq), _stream())
 
     def enable_sharding(self, group=None):
         """Declare this library one policy shard of a multi-GPU ensemble (call on every rank after the tasks were added)."""

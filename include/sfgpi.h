@@ -186,12 +186,22 @@ int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
  * Tensor-core mode (mode 1): bf16 operands on tcgen05 with fp32 accumulation in TMEM, weights streamed by TMA.  Same
  * arguments and epilogues as sfgpi_mlp_forward; needs the bf16 shadow of the library produced by sfgpi_pack_bf16
  * ([n_policies_total][sfgpi_bf16_rows_per_policy()][256] bf16: the hidden 256x256 matrices, then the output matrix padded to
- * a multiple of 16 rows).  Shapes: every hidden width == 256, S <= 16.  Stated tolerance vs fp32: 2e-2 scale-relative on
+ * a multiple of 16 rows, preceded by the input matrix zero-padded to 256 columns).  Shapes: hidden widths == 256, S <= 64.  Stated tolerance vs fp32: 2e-2 scale-relative on
  * psi / q (bf16 inputs, fp32 accumulate), GPI argmax equal wherever the fp32 top-1/top-2 gap exceeds it.
  */
 int sfgpi_bf16_rows_per_policy(const sfgpi_net_desc *net);
 int sfgpi_pack_bf16(const sfgpi_net_desc *net, const float *params, int32_t policy_lo, int32_t n_pol, void *out_bf16, void *stream);
-int sfgpi_mlp_forward_tc(const sfgpi_forward_args *args, const void *params_bf16, int32_t n_policies_total, void *stream);
+/*
+ * GPI form of the tensor-core forward: q = psi . w is folded into the output layer,
+ *   Wq[p][wi*A + a][:] = sum_d w[wi][d] * W_out[p][a*D + d][:],  bq likewise from b_out   (fp32 accumulate, bf16 Wq),
+ * so the last GEMM has n_w*A columns instead of A*D and psi[B,N,A,D] is never formed (GPI_w, sfdqn.py:215-240).
+ * wq_out: bf16 [n_pol][sfgpi_gpi_fold_rows()][256]; bq_out: fp32 [n_pol][sfgpi_gpi_fold_rows()].
+ */
+int sfgpi_gpi_fold_rows(const sfgpi_net_desc *net, int32_t n_w);
+int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, int32_t policy_lo, int32_t n_pol, const float *w, int32_t n_w,
+                   int32_t w_diag, void *wq_out, float *bq_out, void *stream);
+int sfgpi_mlp_forward_tc(const sfgpi_forward_args *args, const void *params_bf16, int32_t n_policies_total, const void *wq,
+                         const float *bq, void *stream);
 
 const char *sfgpi_last_error(void);
 int sfgpi_version(void);
