@@ -1,10 +1,10 @@
 // Fused ensemble psi-MLP forward on the 5th-gen tensor cores (mode 1: bf16 operands, fp32 accumulation in TMEM).
 //
 // Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0      TMA producer: streams the policy's bf16 weights (K-major, 128B-swizzled boxes of 128 rows x 64 k = 16 KB)
-//               through a 4-stage mbarrier ring;
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N<=128, K=16) into TMEM, commits free the ring stages;
-//   warps 2-5   epilogue group of tile slot X, warps 6-9 of tile slot Y: thread = TMEM lane = one state (row).  They stage
+//   warps 0-3   TMA producers: stream the policy's bf16 weights (K-major, 128B-swizzled boxes of 128 rows x 64 k = 16 KB)
+//               through a 4-stage mbarrier ring, one stage per producer warp;
+//   warp 4      MMA issuer: one thread issues tcgen05.mma (M=128, N<=128, K=16) into TMEM, commits free the ring stages;
+//   warps 5-8   epilogue group of tile slot X, warps 9-12 of tile slot Y: thread = TMEM lane = one state (row).  They stage
 //               the bf16 state tile, and after every MMA layer read the accumulator with tcgen05.ld, apply bias +
 //               activation, round to bf16 and write the next layer's A operand straight into shared memory in the UMMA
 //               K-major SWIZZLE_128B layout (activations never touch HBM).
@@ -29,7 +29,8 @@ constexpr int kNB = 128;                 // weight rows (output columns) per sta
 constexpr int kStageBytes = kNB * kKB * 2;          // 16 KB
 constexpr int kNStage = 4;
 constexpr int kABytes = kTM * kH * 2;               // 64 KB per tile slot
-constexpr int kThreadsTc = 320;
+constexpr int kThreadsTc = 416;                      // 4 producer warps + 1 MMA warp + 2 x 4 epilogue warps
+constexpr int kMmaWarp = 4, kEpiWarp0 = 5;
 constexpr int kBiasFloatsMax = 6144;                // all layers' biases of one policy, fp32 (24 KB)
 
 struct TcParams {
@@ -150,7 +151,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
         tma_prefetch_desc(&tmap);
         if (p.gpi) tma_prefetch_desc(&tmap_q);
     }
-    if (warp == 1) tmem_alloc(holder_addr, 512);
+    if (warp == kMmaWarp) tmem_alloc(holder_addr, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -160,8 +161,11 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
     const int B = a.B, L = net.n_layers, A_ = net.n_actions, D = net.n_features, AD = A_ * D;
     const int S = net.dims[0];
 
-    if (warp == 0) {
-        // =========================== TMA producer ===========================
+    if (warp < kNStage) {
+        // =========================== TMA producers ===========================
+        // One issuing thread sustains only ~27 B/cycle of 128-row boxes (its bulk-tensor copies do not overlap: scripts/
+        // tma_bench.cu), well below the 64 B/cycle the MMA consumes; issuers in different warps scale linearly.  So ring stage
+        // s is owned by producer warp s.
         if (lane == 0) {
             uint32_t n = 0;
             for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
@@ -178,6 +182,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                         for (int kb = 0; kb < ii.n_kb; ++kb)
                             for (int nb = 0; nb < nblocks; ++nb, ++n) {
                                 const int s = n % kNStage;
+                                if (s != warp) continue;
                                 mbar_wait(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
                                 mbar_arrive_expect_tx(W_FULL(s), kStageBytes);
                                 tma_load_2d(W_addr + s * kStageBytes, tm, W_FULL(s), kb * kKB, rbase + nb * kNB);
@@ -185,7 +190,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             // The issuing thread is latency-bound (one thread, dependent uniform-datapath ops): a naive loop costs ~170 cycles per
@@ -235,10 +240,10 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
         }
     } else {
         // =========================== epilogue groups ===========================
-        const int slot = (warp - 2) >> 2;                   // warps 2-5 -> X, 6-9 -> Y
+        const int slot = (warp - kEpiWarp0) >> 2;           // warps 5-8 -> X, 9-12 -> Y
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int r = quad * 32 + lane;                     // row inside the tile == TMEM lane
-        const int et = threadIdx.x - 64;                    // 0..255 among epilogue threads
+        const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..255 among epilogue threads
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * 256u;
         const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
         const int n_bias = (1 + p.Lh) * kH + p.n_final;     // [b_0 | b_1..b_Lh | b_final]
@@ -366,7 +371,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
