@@ -1,0 +1,138 @@
+"""
+CPU-only tests (no compute calls): the C-ABI library loads and exports every symbol include/sfgpi.h declares, the ctypes
+structs mirror the header field for field, and the multi-GPU host logic (shard ranges, packed (value,index) keys, MAX
+all-reduce) behaves on a world_size-2 gloo group exactly like the single-process computation.
+"""
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from deep_successor_features_for_transfer_b200 import _lib, dist as sdist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'sfgpi.h')
+
+
+def header_text():
+    with open(HEADER) as f:
+        return re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set(re.findall(r'\b(sfgpi_[a-z0-9_]+)\s*\(', header_text()))
+    assert declared, 'no prototypes found in include/sfgpi.h'
+    handle = _lib.lib()                              # builds with nvcc if the .so is missing; raises if it cannot
+    for name in sorted(declared):
+        assert hasattr(handle, name), f'libsfgpi.so does not export {name}'
+    assert declared == set(_lib.SYMBOLS), f'binding/header mismatch: {declared ^ set(_lib.SYMBOLS)}'
+    assert handle.sfgpi_version() >= 100
+    assert isinstance(handle.sfgpi_last_error(), bytes)
+
+
+def c_struct_fields(name):
+    text = header_text()
+    end = re.search(r'\}\s*' + name + r'\s*;', text)
+    assert end, name
+    body = text[text.rfind('typedef struct {', 0, end.start()) + len('typedef struct {'):end.start()]
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r'^(const\s+)?[A-Za-z_0-9]+(\s+const)?\s*', '', decl, count=1)      # drop the base type
+        for part in decl.split(','):
+            fields.append(re.sub(r'[\*\s]|\[.*?\]', '', part))
+    return fields
+
+
+@pytest.mark.parametrize('cname,pyname', [('sfgpi_net_desc', 'NetDesc'), ('sfgpi_forward_args', 'ForwardArgs'),
+                                          ('sfgpi_td_args', 'TdArgs'), ('sfgpi_backward_args', 'BackwardArgs'),
+                                          ('sfgpi_adam_segment', 'AdamSegment'), ('sfgpi_adam_args', 'AdamArgs')])
+def test_ctypes_structs_mirror_header(cname, pyname):
+    assert c_struct_fields(cname) == [f[0] for f in getattr(_lib, pyname)._fields_]
+
+
+def test_negative_sizes_are_rejected_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable here: rc < 0 and an error text."""
+    a = _lib.ForwardArgs()
+    a.net.n_layers = 0
+    rc = _lib.lib().sfgpi_mlp_forward(a, None)
+    assert rc < 0 and len(_lib.lib().sfgpi_last_error()) > 0
+
+
+def test_shard_range_partitions_exactly():
+    for n_total in (1, 4, 7, 64, 256):
+        for world in (1, 2, 3, 8):
+            rng = [sdist.shard_range(n_total, world, r) for r in range(world)]
+            assert rng[0][0] == 0 and rng[-1][1] == n_total
+            assert all(rng[r][1] == rng[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in rng]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_key_packing_orders_like_argmax_first_index():
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(257, 5, 9, generator=g)
+    q[::7] = q[::7].round()                                         # force exact ties (and +-0)
+    q[3, :, :] = 0.0
+    q[4, 0, 0], q[4, 1, 0] = 0.0, -0.0
+    ka, kt = sdist.gpi_keys_from_q(q)
+    va, ia = sdist.unpack_keys(ka)
+    vt, it = sdist.unpack_keys(kt)
+    assert torch.equal(ia, torch.argmax(q.max(dim=1).values, dim=-1))          # sfdqn.py:316
+    assert torch.equal(it, torch.argmax(q.max(dim=2).values, dim=-1))          # sfdqn.py:239
+    assert torch.equal(va, q.reshape(257, -1).max(dim=1).values + 0.0) and torch.equal(va, vt)
+    v, i = sdist.unpack_keys(sdist.pack_keys(torch.tensor([-1.5, 0.0, 2.0 ** 127, -2.0 ** 127]), torch.tensor([0, 7, 2 ** 31, 5])))
+    assert v.tolist() == [-1.5, 0.0, 2.0 ** 127, -2.0 ** 127] and i.tolist() == [0, 7, 2 ** 31, 5]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, q_all, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        n_total = q_all.shape[1]
+        lo, hi = sdist.shard_range(n_total, world, rank)
+        ctx = sdist.ShardContext(hi - lo)
+        assert (ctx.lo, ctx.n_total, ctx.world, ctx.rank) == (lo, n_total, world, rank)
+        ka, kt = sdist.gpi_keys_from_q(q_all[:, lo:hi], task_base=lo)           # this rank's policies only
+        keys = torch.stack([ka, kt])
+        sdist.allreduce_max_keys(keys)                                          # the one data-path collective
+        if rank == 0:
+            out.put(keys)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_total', [4, 5])
+def test_sharded_gpi_equals_unsharded_gloo_world2(n_total):
+    """Policies sharded over 2 ranks (even and uneven), keys MAX-all-reduced over gloo == single-process GPI."""
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(300, n_total, 9, generator=g)
+    q[::5] = q[::5].round()                                       # ties across ranks must resolve to the smallest index
+    ctx = mp.get_context('spawn')
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    keys = out.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    ka, kt = sdist.gpi_keys_from_q(q)
+    assert torch.equal(keys[0], ka) and torch.equal(keys[1], kt)
+    _, task = sdist.unpack_keys(keys[1])
+    assert torch.equal(task, torch.argmax(q.max(dim=2).values, dim=-1))
