@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libsfgpi.so')
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -47,7 +47,7 @@ class ForwardArgs(C.Structure):
                 ('sel_actions', C.c_void_p), ('sel_keys', C.c_void_p), ('sel_key_stride', C.c_int32),
                 ('sel_out', C.c_void_p), ('w', C.c_void_p), ('n_w', C.c_int32), ('w_diag', C.c_int32),
                 ('key_action', C.c_void_p), ('key_task', C.c_void_p), ('task_base', C.c_int32), ('q_out', C.c_void_p),
-                ('mode', C.c_int32)]
+                ('mode', C.c_int32), ('acts_bf16_out', C.c_void_p)]
 
 
 class TdArgs(C.Structure):
@@ -63,6 +63,13 @@ class BackwardArgs(C.Structure):
     _fields_ = [('net', NetDesc), ('params', C.c_void_p), ('policy_lo', C.c_int32), ('n_pol', C.c_int32),
                 ('x', C.c_void_p), ('B', C.c_int32), ('acts', C.c_void_p * MAX_LAYERS), ('actions', C.c_void_p),
                 ('d_out', C.c_void_p), ('dz', C.c_void_p * MAX_LAYERS), ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
+
+
+class BackwardTcArgs(C.Structure):
+    _fields_ = [('net', NetDesc), ('params_bf16', C.c_void_p), ('n_policies_total', C.c_int32), ('policy_lo', C.c_int32),
+                ('n_pol', C.c_int32), ('x', C.c_void_p), ('B', C.c_int32), ('acts_bf16', C.c_void_p), ('actions', C.c_void_p),
+                ('d_out', C.c_void_p), ('dz_bf16', C.c_void_p), ('dzo_bf16', C.c_void_p), ('xo_bf16', C.c_void_p),
+                ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
 
 
 class AdamSegment(C.Structure):
@@ -95,6 +102,9 @@ SYMBOLS = {
     'sfgpi_fold_gpi': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_mlp_forward_tc': (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_bwd_tc_out_pad': (C.c_int, [C.POINTER(NetDesc)]),
+    'sfgpi_bwd_tc_splits': (C.c_int, [C.c_int32, C.c_int32]),
+    'sfgpi_mlp_backward_tc': (C.c_int, [C.POINTER(BackwardTcArgs), C.c_void_p]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
 }
@@ -102,7 +112,7 @@ SYMBOLS = {
 _lib = None
 launch_count = 0          # kernels launched through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES_PER_CALL = {'sfgpi_pack_bf16': 1, 'sfgpi_fold_gpi': 1, 'sfgpi_mlp_forward_tc': 1, 'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
-                     'sfgpi_td_step': 1, 'sfgpi_mlp_backward': 2, 'sfgpi_adam_step': 2}
+                     'sfgpi_td_step': 1, 'sfgpi_mlp_backward': 2, 'sfgpi_mlp_backward_tc': 3, 'sfgpi_adam_step': 2}
 
 
 def lib():

@@ -1,0 +1,552 @@
+// Backward of the psi MLP on the 5th-gen tensor cores (bf16 operands, fp32 accumulation in TMEM).  Two kernels:
+//
+// (1) mlp_dgrad_tc_kernel -- the dZ chain dZ_{L-1} -> dZ_{L-2} -> ... -> dZ_0 for one 128-row tile per slot, same persistent
+//     warp-specialised structure as the forward kernel (4 TMA producer warps, 1 MMA-issuer warp, 2 x 4 epilogue warps, two
+//     tiles ping-ponging on 2 x 256 TMEM columns).  dA_{l-1}[b][k] = sum_n dZ_l[b][n] W_l[n][k]: A = dZ_l is K-major in
+//     shared memory exactly like a forward activation; B = W_l is read from the SAME bf16 shadow as the forward, as an
+//     MN-major operand (its rows are the reduction index), so no transposed copy of the weights exists.  The last layer's
+//     dZ is D-sparse (sfdqn.py:334-335: only psi(s)[b, a_b, :] is in the loss); the epilogue threads expand d_out[b][D] into
+//     the dense row on the fly.  Each epilogue multiplies by the activation derivative (from the bf16 activations the forward
+//     saved), writes the next A operand in place and the row-major bf16 dZ_l to HBM for the wgrad kernel.
+//
+// (2) mlp_wgrad_tc_kernel -- dW_l[n][k] = sum_b dZ_l[b][n] in_l[b][k] and db_l[n] = sum_b dZ_l[b][n], split-K over the batch.
+//     Both operands are MN-major (the reduction index b is the row of the row-major [B][width] tensors), TMA-loaded as
+//     {64 x 64} 128B-swizzled boxes straight from the tensors the forward / dgrad kernels wrote.  One CTA = (policy, layer,
+//     128-row tile of dW_l, batch split): acc[128][256] in TMEM, plus 64 auxiliary columns against xo = [x | 1 | 0..] that
+//     yield the bias gradient (the ones column) and, for layer 0, dW_0 itself.  fp32 partials go to grad_part, which the
+//     Adam kernel sums in a fixed order (deterministic).
+#include "tc_common.cuh"
+
+namespace sfgpi {
+namespace tc {
+
+constexpr int kNB = 128;                            // N columns per dgrad weight stage
+constexpr int kStageBytes = kNB * kKB * 2;          // 16 KB = two {64 x 64} boxes
+constexpr int kBoxBytes = 64 * 64 * 2;              // 8 KB
+constexpr int kNStage = 4;
+constexpr int kABytes = kTM * kH * 2;               // 64 KB per tile slot
+constexpr int kThreadsDg = 416;                     // 4 producer warps + 1 MMA warp + 2 x 4 epilogue warps
+constexpr int kMmaWarp = 4, kEpiWarp0 = 5;
+constexpr int kXoCols = 64;                         // width of the auxiliary operand xo = [x | 1 | 0 ...]
+
+struct DgParams {
+    sfgpi_net_desc net;
+    int policy_lo, n_pol, B;
+    const long long *actions;        // [B]
+    const float *d_out;              // [n_pol][B][D]
+    const __nv_bfloat16 *acts;       // [L-1][n_pol][B][256]
+    __nv_bfloat16 *dz;               // [L-1][n_pol][B][256]
+    __nv_bfloat16 *dzo;              // [n_pol][B][ADp]
+    int rows_per_policy, L, AD, AD16, ADp, n_chunks, n_items;
+    int tiles_per_policy, pairs_per_policy, total_pairs, paired;
+};
+
+struct DgItem { int row_base, K; };                 // shadow row of the first reduction index, reduction length (mult. of 16)
+
+__device__ __forceinline__ DgItem dg_item(const DgParams &p, int it) {
+    DgItem r;
+    if (it < p.n_chunks) { r.row_base = (p.L - 1) * kH + it * 256; r.K = min(256, p.AD16 - it * 256); }
+    else { const int l = p.L - 2 - (it - p.n_chunks); r.row_base = l * kH; r.K = kH; }
+    return r;
+}
+
+// Expanded dense chunk c of this row's dZ_{L-1}: columns [256c, 256c+256) of a row that is zero except d_out[0..D) at
+// [sel, sel+D).  Written to the A slot (K-major SW128) and, as the wgrad operand, to dzo (row-major bf16).
+__device__ __forceinline__ void build_dzo_chunk(const DgParams &p, int c, uint32_t Arow, int r, bool row_ok, int sel,
+                                                const float *drow, __nv_bfloat16 *dzo_row) {
+    const int D = p.net.n_features;
+    const int cend = min(256, p.ADp - c * 256);
+#pragma unroll 1
+    for (int j = 0; j * 8 < cend; ++j) {
+        const int col0 = c * 256 + j * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const unsigned off = (unsigned)(col0 + i - sel);
+            v[i] = (row_ok && off < (unsigned)D) ? drow[off] : 0.0f;
+        }
+        const uint32_t q0 = pack_bf16x2(v[0], v[1]), q1 = pack_bf16x2(v[2], v[3]), q2 = pack_bf16x2(v[4], v[5]),
+                       q3 = pack_bf16x2(v[6], v[7]);
+        sts128(Arow + a_chunk_off(r, j * 8), q0, q1, q2, q3);
+        if (row_ok) *reinterpret_cast<uint4 *>(dzo_row + col0) = make_uint4(q0, q1, q2, q3);
+    }
+}
+
+// dZ_lo = acc * act'(act_lo): 256 accumulator columns of one row -> bf16 -> next A operand (in place) + HBM row.
+template <int ACT>
+__device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, int r, bool row_ok, const uint4 *act_row,
+                                               uint4 *dz_row, bool write_a) {
+    uint32_t v[2][32];
+    uint4 am[2][4] = {};
+    if (ACT != SFGPI_ACT_NONE && row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) am[0][g] = __ldg(act_row + g);
+    }
+    tmem_ld32(t_lane, v[0]);
+#pragma unroll
+    for (int cb = 0; cb < kH / 32; ++cb) {
+        const int c0 = cb * 32;
+        tmem_wait_ld();
+        if (cb + 1 < kH / 32) {
+            tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
+            if (ACT != SFGPI_ACT_NONE && row_ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) am[(cb + 1) & 1][g] = __ldg(act_row + (cb + 1) * 4 + g);
+            }
+        }
+        const uint32_t(&u)[32] = v[cb & 1];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint4 aq = am[cb & 1][g];
+            const uint32_t aw[4] = {aq.x, aq.y, aq.z, aq.w};
+            float h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float gv = row_ok ? __uint_as_float(u[8 * g + i]) : 0.0f;
+                if (ACT != SFGPI_ACT_NONE) {
+                    const uint32_t ab = (i & 1) ? (aw[i >> 1] >> 16) : (aw[i >> 1] & 0xFFFFu);      // bf16 bits of act[col]
+                    if (ACT == SFGPI_ACT_RELU) gv = ((short)ab > 0) ? gv : 0.0f;                    // threshold_backward
+                    else { const float av = __uint_as_float(ab << 16); gv *= (1.0f - av * av); }      // tanh_backward
+                }
+                h[i] = gv;
+            }
+            const uint32_t q0 = pack_bf16x2(h[0], h[1]), q1 = pack_bf16x2(h[2], h[3]), q2 = pack_bf16x2(h[4], h[5]),
+                           q3 = pack_bf16x2(h[6], h[7]);
+            if (write_a) sts128(Arow + a_chunk_off(r, c0 + 8 * g), q0, q1, q2, q3);
+            if (row_ok) dz_row[(c0 >> 3) + g] = make_uint4(q0, q1, q2, q3);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsDg, 1)
+mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ CUtensorMap tmap_w) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const sfgpi_net_desc &net = p.net;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- carve-up: [A slot X 64K][A slot Y 64K][weight ring 4 x 16K][barriers] ----
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t W_addr = sbase + 2 * kABytes;
+    const uint32_t bar0 = W_addr + kNStage * kStageBytes;
+    auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (kNStage + s); };
+    auto SLOT_READY = [&](int s) { return bar0 + 8u * (2 * kNStage + s); };
+    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * kNStage + 2 + s); };
+    const uint32_t holder_addr = bar0 + 8u * (2 * kNStage + 4);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kNStage; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 128); mbar_init(ACC_FULL(s), 1); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == kMmaWarp) tmem_alloc(holder_addr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
+
+    const int B = p.B, D = net.n_features;
+
+    if (warp < kNStage) {
+        // =========================== TMA producers (ring stage s is owned by producer warp s) ===========================
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+                const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
+                const int row0 = (p.policy_lo + pl) * p.rows_per_policy;
+                const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
+                for (int it = 0; it < p.n_items; ++it) {
+                    const DgItem ii = dg_item(p, it);
+                    const int n_kb = (ii.K + kKB - 1) / kKB;
+                    for (int slot = 0; slot < (has_y ? 2 : 1); ++slot)
+                        for (int kb = 0; kb < n_kb; ++kb)
+                            for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
+                                const int s = n % kNStage;
+                                if (s != warp) continue;
+                                mbar_wait(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
+                                mbar_arrive_expect_tx(W_FULL(s), kStageBytes);
+                                const int wrow = row0 + ii.row_base + kb * kKB;       // 64 reduction rows of W
+                                tma_load_2d(W_addr + s * kStageBytes, &tmap_w, W_FULL(s), nb * kNB, wrow);
+                                tma_load_2d(W_addr + s * kStageBytes + kBoxBytes, &tmap_w, W_FULL(s), nb * kNB + 64, wrow);
+                            }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            uint32_t n = 0, ready_cnt[2] = {0, 0};
+            const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
+            const uint64_t bdesc0 = umma_desc_mn_sw128(W_addr, kBoxBytes);
+            const uint32_t idesc = umma_idesc_bf16_major(kTM, kNB, 0u, 1u);
+            for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+                const int pip = pair % p.pairs_per_policy;
+                const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
+                for (int it = 0; it < p.n_items; ++it) {
+                    const DgItem ii = dg_item(p, it);
+                    const int n_kb = (ii.K + kKB - 1) / kKB;
+                    const bool fresh = (it == 0) || (it >= p.n_chunks);          // output-layer chunks 1.. accumulate
+                    for (int slot = 0; slot < (has_y ? 2 : 1); ++slot) {
+                        mbar_wait(SLOT_READY(slot), ready_cnt[slot] & 1);
+                        ++ready_cnt[slot];
+                        tc_fence_after();
+                        const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
+                        for (int kb = 0; kb < n_kb; ++kb) {
+                            const uint64_t ad = (slot ? adesc_y : adesc_x) + (uint64_t)(kb * ((kTM * 128) >> 4));
+                            const int n_k16 = min(4, (ii.K - kb * kKB) >> 4);
+                            for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
+                                const int s = n % kNStage;
+                                mbar_wait(W_FULL(s), (n / kNStage) & 1);
+                                tc_fence_after();
+                                const uint64_t bd = bdesc0 + (uint64_t)(s * (kStageBytes >> 4));
+                                const uint32_t d = d_base + nb * kNB;
+                                for (int k16 = 0; k16 < n_k16; ++k16)
+                                    umma_bf16(d, ad + 2 * k16, bd + 128 * k16, idesc, (!fresh || kb || k16) ? 1u : 0u);
+                                umma_commit(W_EMPTY(s));
+                            }
+                        }
+                        umma_commit(ACC_FULL(slot));
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue groups ===========================
+        const int slot = (warp - kEpiWarp0) >> 2;
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * 256u;
+        const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
+        uint32_t full_cnt = 0;
+
+        for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+            const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
+            const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
+            if (slot == 1 && !has_y) continue;
+            const int tile = p.paired ? 2 * pip + slot : pip;
+            const int b = tile * kTM + r;
+            const bool row_ok = b < B;
+            const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
+            const int sel = row_ok ? (int)p.actions[b] * D : 0;
+            const float *drow = p.d_out + prow * D;
+            __nv_bfloat16 *dzo_row = p.dzo + prow * p.ADp;
+
+            build_dzo_chunk(p, 0, Arow, r, row_ok, sel, drow, dzo_row);
+            fence_proxy_async();
+            mbar_arrive(SLOT_READY(slot));
+
+            for (int it = 0; it < p.n_items; ++it) {
+                mbar_wait(ACC_FULL(slot), full_cnt & 1);
+                ++full_cnt;
+                tc_fence_after();
+                if (it + 1 < p.n_chunks) {                       // more output-layer chunks: refill the A slot
+                    build_dzo_chunk(p, it + 1, Arow, r, row_ok, sel, drow, dzo_row);
+                    fence_proxy_async();
+                    mbar_arrive(SLOT_READY(slot));
+                    continue;
+                }
+                const int lo = (it < p.n_chunks) ? p.L - 2 : p.L - 3 - (it - p.n_chunks);    // produces dZ_lo
+                const int act = net.acts[lo];
+                const size_t off = (((size_t)lo * p.n_pol + pl) * B + (row_ok ? b : 0)) * kH;
+                const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + off);
+                uint4 *dz_row = reinterpret_cast<uint4 *>(p.dz + off);
+                const bool write_a = lo > 0;
+                if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a);
+                else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a);
+                else dgrad_epilogue<SFGPI_ACT_TANH>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a);
+                tc_fence_before();
+                if (write_a) {
+                    fence_proxy_async();
+                    mbar_arrive(SLOT_READY(slot));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 256;                     // 3 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int kWgStages = 3;
+constexpr int kWgABytes = 2 * kBoxBytes;            // dZ tile: 64 b x 128 n
+constexpr int kWgBBytes = 4 * kBoxBytes;            // in tile: 64 b x 256 k
+constexpr int kWgXBytes = kBoxBytes;                // xo tile: 64 b x 64
+constexpr int kWgStageBytes = kWgABytes + kWgBBytes + kWgXBytes;      // 56 KB
+
+struct WgParams {
+    sfgpi_net_desc net;
+    int n_pol, B, L, AD, S;
+    int n_split, bs;                 // batch rows per split (multiple of 64)
+    int mt_out, items_per_policy;    // 128-row tiles of the output layer's dW; mt_out + 2 * (L - 1) items per policy
+    float *grad_part;                // [n_pol][n_split][row_stride]
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ CUtensorMap tmap_dz,
+                    const __grid_constant__ CUtensorMap tmap_dzo, const __grid_constant__ CUtensorMap tmap_acts,
+                    const __grid_constant__ CUtensorMap tmap_xo) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const sfgpi_net_desc &net = p.net;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t bar0 = sbase + kWgStages * kWgStageBytes;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (kWgStages + s); };
+    const uint32_t ACC_FULL = bar0 + 8u * (2 * kWgStages);
+    const uint32_t holder_addr = ACC_FULL + 8u;
+
+    // ---- decode the work item: (policy, layer l, 128-row tile mt of dW_l, batch split) ----
+    const int pl = blockIdx.y;
+    const int split = blockIdx.x / p.items_per_policy;
+    int t = blockIdx.x - split * p.items_per_policy;
+    int l, mt;
+    if (t < p.mt_out) { l = p.L - 1; mt = t; }
+    else { t -= p.mt_out; l = p.L - 2 - (t >> 1); mt = t & 1; }       // hidden layers L-2 .. 1, then layer 0
+    const bool main_mma = l >= 1;                                       // layer 0's input is x itself: only the aux MMA
+    const int b_lo = split * p.bs, b_hi = min(p.B, b_lo + p.bs);
+    const int n_kb = (b_hi - b_lo + 63) / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(ACC_FULL, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_dz); tma_prefetch_desc(&tmap_dzo); tma_prefetch_desc(&tmap_acts); tma_prefetch_desc(&tmap_xo);
+    }
+    if (warp == 3) tmem_alloc(holder_addr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
+
+    if (warp < kWgStages) {
+        if (lane == 0) {
+            const uint32_t bytes = kWgABytes + kWgXBytes + (main_mma ? kWgBBytes : 0);
+            for (int kb = warp; kb < n_kb; kb += kWgStages) {
+                const int s = warp;                                      // stage s is owned by producer warp s
+                mbar_wait(EMPTY(s), ((kb / kWgStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(FULL(s), bytes);
+                const uint32_t st = sbase + s * kWgStageBytes;
+                const int b0 = b_lo + kb * 64;
+                for (int h = 0; h < 2; ++h) {
+                    if (l == p.L - 1) tma_load_3d(st + h * kBoxBytes, &tmap_dzo, FULL(s), mt * 128 + h * 64, b0, pl);
+                    else tma_load_3d(st + h * kBoxBytes, &tmap_dz, FULL(s), mt * 128 + h * 64, b0, l * p.n_pol + pl);
+                }
+                if (main_mma)
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_3d(st + kWgABytes + j * kBoxBytes, &tmap_acts, FULL(s), j * 64, b0, (l - 1) * p.n_pol + pl);
+                tma_load_2d(st + kWgABytes + kWgBBytes, &tmap_xo, FULL(s), 0, b0);
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0) {
+            const uint32_t idesc_main = umma_idesc_bf16_major(kTM, 256, 1u, 1u);
+            const uint32_t idesc_aux = umma_idesc_bf16_major(kTM, kXoCols, 1u, 1u);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int s = kb % kWgStages;
+                mbar_wait(FULL(s), (kb / kWgStages) & 1);
+                tc_fence_after();
+                const uint32_t st = sbase + s * kWgStageBytes;
+                const uint64_t ad = umma_desc_mn_sw128(st, kBoxBytes);
+                const uint64_t bd = umma_desc_mn_sw128(st + kWgABytes, kBoxBytes);
+                const uint64_t xd = umma_desc_mn_sw128(st + kWgABytes + kWgBBytes, kBoxBytes);
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                    const uint32_t accum = (kb | k16) ? 1u : 0u;
+                    if (main_mma) umma_bf16(tmem_base, ad + 128 * k16, bd + 128 * k16, idesc_main, accum);
+                    umma_bf16(tmem_base + 256u, ad + 128 * k16, xd + 128 * k16, idesc_aux, accum);
+                }
+                umma_commit(EMPTY(s));
+            }
+            umma_commit(ACC_FULL);
+        }
+    } else {
+        // ---- epilogue: thread = TMEM lane = one row n of dW_l ----
+        const int quad = warp & 3;
+        const int n_loc = quad * 32 + lane;
+        const int n = mt * 128 + n_loc;
+        const int N_l = net.dims[l + 1], K_l = net.dims[l];
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float *gp = p.grad_part + ((size_t)pl * p.n_split + split) * net.row_stride;
+        mbar_wait(ACC_FULL, 0);
+        tc_fence_after();
+        const bool ok = n < N_l;
+        if (main_mma) {
+            float *wrow = gp + net.w_off[l] + (size_t)n * K_l;              // K_l == 256
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + c0, v);
+                tmem_wait_ld();
+                if (ok) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        *reinterpret_cast<float4 *>(wrow + c0 + 4 * g) =
+                            make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                        __uint_as_float(v[4 * g + 3]));
+                }
+            }
+        }
+        // aux columns: [0,S) = sum_b dZ[b][n] x[b][s] (dW_0 when l == 0), column S = sum_b dZ[b][n] (bias gradient)
+#pragma unroll 1
+        for (int c0 = 0; c0 <= p.S; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + 256u + c0, v);
+            tmem_wait_ld();
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int c = c0 + i;
+                    if (c == p.S) gp[net.b_off[l] + n] = __uint_as_float(v[i]);
+                    else if (c < p.S && l == 0) gp[net.w_off[0] + (size_t)n * p.S + c] = __uint_as_float(v[i]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// xo[b][c] = x[b][c] for c < S, 1 for c == S, 0 otherwise  (bf16 [B][64])
+__global__ void build_xo_kernel(const float *__restrict__ x, int B, int S, __nv_bfloat16 *__restrict__ xo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * kXoCols) return;
+    const int b = i / kXoCols, c = i - b * kXoCols;
+    xo[i] = __float2bfloat16_rn(c < S ? x[(size_t)b * S + c] : (c == S ? 1.0f : 0.0f));
+}
+
+static int make_tmap_bf16(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims, const uint32_t *box) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return SFGPI_E_CUDA; }
+    cuuint64_t gdim[3], gstride[2];
+    cuuint32_t bx[3], estride[3] = {1, 1, 1};
+    uint64_t pitch = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        pitch *= dims[i];
+        if (i + 1 < rank) gstride[i] = pitch;
+    }
+    CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstride, bx, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return SFGPI_E_CUDA; }
+    return SFGPI_OK;
+}
+
+}  // namespace tc
+}  // namespace sfgpi
+
+using namespace sfgpi;
+using namespace sfgpi::tc;
+
+extern "C" int sfgpi_bwd_tc_out_pad(const sfgpi_net_desc *net) { return (net->n_actions * net->n_features + 63) & ~63; }
+
+extern "C" int sfgpi_bwd_tc_splits(int32_t B, int32_t want) {
+    if (B <= 0) return 1;
+    if (want < 1) want = 1;
+    const int bs = (((B + want - 1) / want) + 63) & ~63;
+    return (B + bs - 1) / bs;
+}
+
+extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream) {
+    const sfgpi_backward_tc_args &a = *args;
+    const sfgpi_net_desc &net = a.net;
+    const int L = net.n_layers;
+    if (L < 3 || L > SFGPI_MAX_LAYERS || net.dims[0] > kXoCols - 1 || net.acts[L - 1] != SFGPI_ACT_NONE ||
+        net.dims[L] != net.n_actions * net.n_features) {
+        set_error("sfgpi_mlp_backward_tc: needs >= 3 Linear layers, S <= 63, a linear output layer");
+        return SFGPI_E_INVALID;
+    }
+    for (int l = 1; l < L; ++l)
+        if (net.dims[l] != kH) { set_error("sfgpi_mlp_backward_tc: every hidden width must be 256"); return SFGPI_E_INVALID; }
+    if (a.B < 0 || a.n_pol < 0 || a.n_split < 1) { set_error("sfgpi_mlp_backward_tc: invalid sizes"); return SFGPI_E_INVALID; }
+    if (a.B == 0 || a.n_pol == 0) return SFGPI_OK;
+    if (sfgpi_bwd_tc_splits(a.B, a.n_split) != a.n_split) {
+        set_error("sfgpi_mlp_backward_tc: n_split %d leaves empty batch splits for B=%d (use sfgpi_bwd_tc_splits)", a.n_split, a.B);
+        return SFGPI_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int AD = net.n_actions * net.n_features, ADp = sfgpi_bwd_tc_out_pad(&net), S = net.dims[0];
+
+    build_xo_kernel<<<(a.B * kXoCols + 255) / 256, 256, 0, st>>>(a.x, a.B, S, reinterpret_cast<__nv_bfloat16 *>(a.xo_bf16));
+    int rc = check_launch("sfgpi_mlp_backward_tc(xo)");
+    if (rc) return rc;
+
+    // ---------------- dgrad chain ----------------
+    DgParams dp;
+    dp.net = net;
+    dp.policy_lo = a.policy_lo; dp.n_pol = a.n_pol; dp.B = a.B;
+    dp.actions = reinterpret_cast<const long long *>(a.actions);
+    dp.d_out = a.d_out;
+    dp.acts = reinterpret_cast<const __nv_bfloat16 *>(a.acts_bf16);
+    dp.dz = reinterpret_cast<__nv_bfloat16 *>(a.dz_bf16);
+    dp.dzo = reinterpret_cast<__nv_bfloat16 *>(a.dzo_bf16);
+    dp.rows_per_policy = sfgpi_bf16_rows_per_policy(&net);
+    dp.L = L; dp.AD = AD; dp.AD16 = (AD + 15) & ~15; dp.ADp = ADp;
+    dp.n_chunks = (dp.AD16 + 255) / 256;
+    dp.n_items = dp.n_chunks + (L - 2);
+    dp.tiles_per_policy = (a.B + kTM - 1) / kTM;
+    const int total_tiles = dp.tiles_per_policy * a.n_pol;
+    dp.paired = total_tiles > 148 ? 1 : 0;
+    dp.pairs_per_policy = dp.paired ? (dp.tiles_per_policy + 1) / 2 : dp.tiles_per_policy;
+    dp.total_pairs = dp.pairs_per_policy * a.n_pol;
+    CUtensorMap tmap_w;
+    {
+        const uint64_t dims[2] = {(uint64_t)kH, (uint64_t)a.n_policies_total * dp.rows_per_policy};
+        const uint32_t box[2] = {64, 64};
+        rc = make_tmap_bf16(&tmap_w, a.params_bf16, 2, dims, box);
+        if (rc) return rc;
+    }
+    const int dg_smem = 2 * kABytes + kNStage * kStageBytes + 256;
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem); cfg = true; }
+    mlp_dgrad_tc_kernel<<<dp.total_pairs < 148 ? dp.total_pairs : 148, kThreadsDg, dg_smem, st>>>(dp, tmap_w);
+    rc = check_launch("sfgpi_mlp_backward_tc(dgrad)");
+    if (rc) return rc;
+
+    // ---------------- wgrad ----------------
+    WgParams wp;
+    wp.net = net;
+    wp.n_pol = a.n_pol; wp.B = a.B; wp.L = L; wp.AD = AD; wp.S = S;
+    wp.n_split = a.n_split;
+    wp.bs = (((a.B + a.n_split - 1) / a.n_split) + 63) & ~63;
+    wp.mt_out = (AD + 127) / 128;
+    wp.items_per_policy = wp.mt_out + 2 * (L - 1);
+    wp.grad_part = a.grad_part;
+    CUtensorMap tm_dz, tm_dzo, tm_acts, tm_xo;
+    {
+        const uint64_t d3[3] = {(uint64_t)kH, (uint64_t)a.B, (uint64_t)(L - 1) * a.n_pol};
+        const uint64_t do3[3] = {(uint64_t)ADp, (uint64_t)a.B, (uint64_t)a.n_pol};
+        const uint64_t dx[2] = {(uint64_t)kXoCols, (uint64_t)a.B};
+        const uint32_t box3[3] = {64, 64, 1}, box2[2] = {64, 64};
+        if ((rc = make_tmap_bf16(&tm_dz, a.dz_bf16, 3, d3, box3))) return rc;
+        if ((rc = make_tmap_bf16(&tm_dzo, a.dzo_bf16, 3, do3, box3))) return rc;
+        if ((rc = make_tmap_bf16(&tm_acts, a.acts_bf16, 3, d3, box3))) return rc;
+        if ((rc = make_tmap_bf16(&tm_xo, a.xo_bf16, 2, dx, box2))) return rc;
+    }
+    const int wg_smem = kWgStages * kWgStageBytes + 256;
+    static bool cfg2 = false;
+    if (!cfg2) { cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem); cfg2 = true; }
+    dim3 grid(wp.items_per_policy * a.n_split, a.n_pol);
+    mlp_wgrad_tc_kernel<<<grid, kWgThreads, wg_smem, st>>>(wp, tm_dz, tm_dzo, tm_acts, tm_xo);
+    return check_launch("sfgpi_mlp_backward_tc(wgrad)");
+}

@@ -22,9 +22,6 @@
 namespace sfgpi {
 namespace tc {
 
-constexpr int kTM = 128;                 // rows per tile (UMMA M)
-constexpr int kH = 256;                  // hidden width == K of every hidden MMA layer (the shipped configs' MLP width)
-constexpr int kKB = 64;                  // k elements per stage (one 128B swizzle span of bf16)
 constexpr int kNB = 128;                 // weight rows (output columns) per stage
 constexpr int kStageBytes = kNB * kKB * 2;          // 16 KB
 constexpr int kNStage = 4;
@@ -62,28 +59,6 @@ __device__ __forceinline__ ItemInfo item_info(const TcParams &p, int it) {
     return r;
 }
 
-// explicit shared-space accesses (32-bit shared addresses; keeps everything on LDS/STS instead of generic LD/ST)
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-
-// byte offset of the 16-byte chunk holding columns [c, c+8) of row r inside a [128][256] bf16 K-major SW128 operand
-__device__ __forceinline__ uint32_t a_chunk_off(int r, int c) {
-    const int kb = c >> 6, j = (c & 63) >> 3;
-    return (uint32_t)(kb * (kTM * 128) + r * 128 + ((j ^ (r & 7)) << 4));
-}
-
 __device__ __forceinline__ float act_apply_fast(float v, int act) {
     return act == SFGPI_ACT_RELU ? fmaxf(v, 0.0f) : (act == SFGPI_ACT_TANH ? tanhf(v) : v);
 }
@@ -91,7 +66,8 @@ __device__ __forceinline__ float act_apply_fast(float v, int act) {
 // One hidden-type epilogue for one row: 256 accumulator columns -> bias + activation -> bf16 -> next layer's A operand.
 // The TMEM load of the next 32 columns is in flight while the current 32 are processed.
 template <int ACT>
-__device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save,
+                                                uint4 *save_bf16) {
     uint32_t v[2][32];
     tmem_ld32(t_lane, v[0]);
 #pragma unroll
@@ -114,6 +90,10 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
 #pragma unroll
         for (int g = 0; g < 4; ++g)
             sts128(Arow + a_chunk_off(r, c0 + 8 * g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        if (save_bf16) {                               // row-major bf16 copy for the tensor-core backward pass
+#pragma unroll
+            for (int g = 0; g < 4; ++g) save_bf16[(c0 >> 3) + g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
         if (save) {                                    // the bf16-rounded values the next layer really consumed
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -309,9 +289,13 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                     const uint32_t bias = bias_addr + 4u * (it * kH);
                     const int act = net.acts[it];
                     float *save = (a.acts_out[it] && row_ok) ? a.acts_out[it] + ((size_t)pl * B + b) * kH : nullptr;
-                    if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU>(t_lane, bias, Arow, r, save);
-                    else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE>(t_lane, bias, Arow, r, save);
-                    else hidden_epilogue<SFGPI_ACT_TANH>(t_lane, bias, Arow, r, save);
+                    uint4 *save16 = (a.acts_bf16_out && row_ok)
+                        ? reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.acts_bf16_out) +
+                                                    (((size_t)it * a.n_pol + pl) * B + b) * kH)
+                        : nullptr;
+                    if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU>(t_lane, bias, Arow, r, save, save16);
+                    else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE>(t_lane, bias, Arow, r, save, save16);
+                    else hidden_epilogue<SFGPI_ACT_TANH>(t_lane, bias, Arow, r, save, save16);
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(SLOT_READY(slot));
@@ -426,22 +410,6 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
     }
     wq[((size_t)pl * nqpad + row) * kH + k] = __float2bfloat16_rn(acc);
     if (k == 0) bq[(size_t)pl * nqpad + row] = bacc;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
 }
 
 static int make_tmap(CUtensorMap *tm, const void *base, uint64_t rows) {

@@ -54,6 +54,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void *tmap,
         : "memory");
 }
 
+// 3-D tiled load (crd2 = outermost): used for the [slab][row][col] activation / dZ tensors so that a row tile is clipped
+// (zero-filled) at the end of ITS slab instead of running into the next one.
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void *tmap, uint32_t bar, int crd0, int crd1, int crd2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(crd0), "r"(crd1), "r"(crd2)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM / tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {      // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols) : "memory");
@@ -101,9 +110,23 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
+// MN-major operand tile (the reduction index k is the ROW of the source matrix, the M/N index is contiguous) in the canonical
+// 128B-swizzled layout  ((8,n),(8,k)) : ((1,LBO),(8,SBO))  in 16-byte units (cute/atom/mma_traits_sm100.hpp): one atom =
+// 64 M/N-elements (one 128 B row) x 8 k-rows; 8-row k groups SBO = 1024 B apart; 64-wide M/N blocks LBO bytes apart.
+// This is exactly what a TMA box {64 elements, R rows} with SWIZZLE_128B of a row-major [k][mn] matrix produces
+// (LBO = R * 128 when consecutive boxes hold consecutive 64-wide column blocks).  A K=16 step advances the address by 2048 B.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // kind::f16 instruction descriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major A and B, N>>3 @17, M>>4 @24.
 __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// same with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__device__ __forceinline__ uint32_t umma_idesc_bf16_major(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return umma_idesc_bf16(M, N) | (a_mn << 15) | (b_mn << 16);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -111,6 +134,48 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+constexpr int kTM = 128;                 // rows per tile (UMMA M)
+constexpr int kH = 256;                  // hidden width == K of every hidden MMA layer (the shipped configs' MLP width)
+constexpr int kKB = 64;                  // k elements per stage (one 128B swizzle span of bf16)
+
+// explicit shared-space accesses (32-bit shared addresses; keeps everything on LDS/STS instead of generic LD/ST)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+// byte offset of the 16-byte chunk holding columns [c, c+8) of row r inside a [128][256] bf16 K-major SW128 operand
+__device__ __forceinline__ uint32_t a_chunk_off(int r, int c) {
+    const int kb = c >> 6, j = (c & 63) >> 3;
+    return (uint32_t)(kb * (kTM * 128) + r * 128 + ((j ^ (r & 7)) << 4));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
 
 }  // namespace tc
 }  // namespace sfgpi

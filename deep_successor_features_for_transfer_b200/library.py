@@ -267,15 +267,25 @@ class PackedSFLibrary:
         if ws is None:
             sp = self.spec
             L, D = len(sp.acts), sp.n_features
-            ws = dict(acts=[self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)],
-                      dz=[self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)],
-                      cur_sel=self._f(n_pol, B, D), next_sel=self._f(n_pol, B, D), d_out=self._f(n_pol, B, D),
+            ws = dict(cur_sel=self._f(n_pol, B, D), next_sel=self._f(n_pol, B, D), d_out=self._f(n_pol, B, D),
                       keys=torch.empty(n_keys, B, dtype=torch.int64, device=self.device))
             nblk = (B + 31) // 32
             ws['nblk'] = nblk
             ws['loss_part'] = self._f(n_pol, nblk, 2)
-            tiles = sum(((sp.dims[l + 1] + 63) // 64) * ((sp.dims[l] + 255) // 256) for l in range(L))
-            n_split = max(1, min((B + 127) // 128, -(-296 // (tiles * n_pol))))
+            if self.precision == 'fp32':
+                ws['acts'] = [self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)]
+                ws['dz'] = [self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)]
+                tiles = sum(((sp.dims[l + 1] + 63) // 64) * ((sp.dims[l] + 255) // 256) for l in range(L))
+                n_split = max(1, min((B + 127) // 128, -(-296 // (tiles * n_pol))))
+            else:
+                # tensor-core backward: bf16 row-major activations / dZ (MN-major UMMA operands), split-K over the batch
+                desc = sp.desc()
+                bf = lambda *shape: torch.zeros(*shape, dtype=torch.bfloat16, device=self.device)
+                adp = _lib.lib().sfgpi_bwd_tc_out_pad(C.byref(desc))
+                ws['acts16'], ws['dz16'] = bf(L - 1, n_pol, B, 256), bf(L - 1, n_pol, B, 256)
+                ws['dzo16'], ws['xo16'] = bf(n_pol, B, adp), bf(B, 64)
+                items = (sp.dims[-1] + 127) // 128 + 2 * (L - 1)
+                n_split = _lib.lib().sfgpi_bwd_tc_splits(B, max(1, -(-222 // (items * n_pol))))
             ws['n_split'] = n_split
             ws['grad_part'] = torch.zeros(n_pol, n_split, sp.row_stride, dtype=torch.float32, device=self.device)
             if self.G is not None:
@@ -373,8 +383,12 @@ class PackedSFLibrary:
 
         # (1) online forward on s: saves hidden outputs, gathers psi(s)[a_b]            sfdqn.py:328
         a1 = self._fwd_args(self.online, lo, n_pol, None, B)
-        for l in range(L - 1):
-            a1.acts_out[l] = ws['acts'][l].data_ptr()
+        tc = self.precision != 'fp32'
+        if tc:
+            a1.acts_bf16_out = ws['acts16'].data_ptr()
+        else:
+            for l in range(L - 1):
+                a1.acts_out[l] = ws['acts'][l].data_ptr()
         a1.sel_out = ptr(ws['cur_sel'])
         # (2) next actions: GPI over the whole library (or own psi) with w_i            sfdqn.py:314-322
         #     sharded: this rank scores its local policies for ALL n_total reward vectors (gathered into w_all); the
@@ -412,12 +426,18 @@ class PackedSFLibrary:
             t.g, t.g_stride, t.h = P(self.g), self.g.shape[1], ptr(self.h)
         t.d_out, t.loss_part, t.aux_grad_part, t.aux_len = ptr(ws['d_out']), ptr(ws['loss_part']), ptr(ws['aux_part']), ws['aux_len']
         # (5) backward through psi: dgrad chain + split-K wgrad
-        b = _lib.BackwardArgs()
-        b.net, b.params, b.policy_lo, b.n_pol = sp.desc(), ptr(self.online), lo, n_pol
-        b.B, b.d_out = B, ptr(ws['d_out'])
-        for l in range(L - 1):
-            b.acts[l] = ws['acts'][l].data_ptr()
-            b.dz[l] = ws['dz'][l].data_ptr()
+        if tc:
+            b = _lib.BackwardTcArgs()
+            b.net, b.params_bf16, b.n_policies_total = sp.desc(), ptr(self._shadow_for('online')), self.cap
+            b.policy_lo, b.n_pol, b.B, b.d_out = lo, n_pol, B, ptr(ws['d_out'])
+            b.acts_bf16, b.dz_bf16, b.dzo_bf16, b.xo_bf16 = (ptr(ws[k]) for k in ('acts16', 'dz16', 'dzo16', 'xo16'))
+        else:
+            b = _lib.BackwardArgs()
+            b.net, b.params, b.policy_lo, b.n_pol = sp.desc(), ptr(self.online), lo, n_pol
+            b.B, b.d_out = B, ptr(ws['d_out'])
+            for l in range(L - 1):
+                b.acts[l] = ws['acts'][l].data_ptr()
+                b.dz[l] = ws['dz'][l].data_ptr()
         b.grad_part, b.n_split = ptr(ws['grad_part']), ws['n_split']
         # (6) Adam over (psi | w | g | h) for all stepped optimizers, + loss reduction    sfdqn.py:362, tsfdqn.py:700
         ad = _lib.AdamArgs()
@@ -450,7 +470,7 @@ class PackedSFLibrary:
         ad.l1_scale, ad.l2_scale = 1.0 / (B * A * D), 1.0 / B
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
-        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, ring=0, keys=keys, w_all=w_all, sharded=sharded,
+        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, tc=tc, ring=0, keys=keys, w_all=w_all, sharded=sharded,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
     def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
@@ -508,7 +528,7 @@ class PackedSFLibrary:
             allreduce_max_keys(keys, self.shard.group)
         self._forward(a3, 'target', fresh=True)
         _lib.call('sfgpi_td_step', C.byref(t), st)
-        _lib.call('sfgpi_mlp_backward', C.byref(b), st)
+        _lib.call('sfgpi_mlp_backward_tc' if plan['tc'] else 'sfgpi_mlp_backward', C.byref(b), st)
         h0 = self.h.clone() if (self._sharded and variant == 2) else None
         _lib.call('sfgpi_adam_step', C.byref(ad), st)
         if h0 is not None:                        # every rank applied only its own optimizers' deltas to the shared h
@@ -517,6 +537,48 @@ class PackedSFLibrary:
             dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.shard.group)
             self.h.copy_(h0 + delta)
         return losses
+
+    def psi_gradients(self, states, actions, d_out, lo=0, n_pol=None):
+        """
+        Gradient of sum_{p,b,d} psi_p(s_b)[a_b, d] * d_out[p, b, d] w.r.t. every psi parameter: the backward pass of the train
+        step on its own (what autograd computes at sfdqn.py:345 for a given dLoss/dpsi).  Returns [n_pol][row_stride] fp32 in
+        library row layout.  Runs the online forward (saving activations) and the backward kernels of the current precision mode.
+        """
+        x = self._check_x(states)
+        n_pol = self.n - lo if n_pol is None else n_pol
+        B, sp = x.shape[0], self.spec
+        L, D = len(sp.acts), sp.n_features
+        actions = torch.as_tensor(actions).to(device=self.device, dtype=torch.int64).reshape(-1).contiguous()
+        d_out = torch.as_tensor(d_out).to(device=self.device, dtype=torch.float32).contiguous()
+        if d_out.shape != (n_pol, B, D) or actions.numel() != B:
+            raise ValueError('d_out must be [n_pol, B, D] and actions [B]')
+        ws = self._workspace(B, n_pol, n_pol)
+        st = _stream()
+        a1 = self._fwd_args(self.online, lo, n_pol, x)
+        a1.sel_actions, a1.sel_out = actions.data_ptr(), ptr(ws['cur_sel'])
+        if self.precision != 'fp32':
+            self._pack('online', lo, n_pol)
+            a1.acts_bf16_out = ws['acts16'].data_ptr()
+            self._forward(a1, 'online', fresh=True)
+            b = _lib.BackwardTcArgs()
+            b.net, b.params_bf16, b.n_policies_total = sp.desc(), ptr(self._shadow_for('online')), self.cap
+            b.acts_bf16, b.dz_bf16, b.dzo_bf16, b.xo_bf16 = (ptr(ws[k]) for k in ('acts16', 'dz16', 'dzo16', 'xo16'))
+            name = 'sfgpi_mlp_backward_tc'
+        else:
+            for l in range(L - 1):
+                a1.acts_out[l] = ws['acts'][l].data_ptr()
+            self._forward(a1, 'online')
+            b = _lib.BackwardArgs()
+            b.net, b.params = sp.desc(), ptr(self.online)
+            for l in range(L - 1):
+                b.acts[l] = ws['acts'][l].data_ptr()
+                b.dz[l] = ws['dz'][l].data_ptr()
+            name = 'sfgpi_mlp_backward'
+        b.policy_lo, b.n_pol, b.B = lo, n_pol, B
+        b.x, b.actions, b.d_out = x.data_ptr(), actions.data_ptr(), d_out.data_ptr()
+        b.grad_part, b.n_split = ptr(ws['grad_part']), ws['n_split']
+        _lib.call(name, C.byref(b), st)
+        return ws['grad_part'].sum(dim=1)
 
     def _gather_w(self, w_all):
         import torch.distributed as dist

@@ -82,6 +82,8 @@ typedef struct {
     int32_t task_base;
     float *q_out;
     int32_t mode;
+    void *acts_bf16_out;            /* tensor-core mode only: [L-1][n_pol][B][256] bf16 post-activation outputs (row-major),
+                                       the operands of sfgpi_mlp_backward_tc */
 } sfgpi_forward_args;
 
 int sfgpi_mlp_forward(const sfgpi_forward_args *args, void *stream);
@@ -202,6 +204,35 @@ int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, int32_t polic
                    int32_t w_diag, void *wq_out, float *bq_out, void *stream);
 int sfgpi_mlp_forward_tc(const sfgpi_forward_args *args, const void *params_bf16, int32_t n_policies_total, const void *wq,
                          const float *bq, void *stream);
+
+/*
+ * Tensor-core backward (bf16 operands, fp32 accumulate), the mode-1 twin of sfgpi_mlp_backward: dgrad chain + split-K wgrad of
+ * autograd's backward through psi (sfdqn.py:345, tsfdqn.py:645).  Reads the online rows' bf16 shadow (sfgpi_pack_bf16), the
+ * bf16 activations saved by sfgpi_mlp_forward_tc (acts_bf16_out) and the sparse d_out of sfgpi_td_step; writes fp32 split
+ * partials in library row layout for sfgpi_adam_step.  Scratch (caller-allocated, bf16): dz_bf16 [L-1][n_pol][B][256],
+ * dzo_bf16 [n_pol][B][sfgpi_bwd_tc_out_pad()], xo_bf16 [B][64].  n_split must equal sfgpi_bwd_tc_splits(B, wanted).
+ * Same shape limits and stated tolerance as sfgpi_mlp_forward_tc, and S <= 63.
+ */
+typedef struct {
+    sfgpi_net_desc net;
+    const void *params_bf16;
+    int32_t n_policies_total;
+    int32_t policy_lo, n_pol;
+    const float *x;                 /* [B][S] */
+    int32_t B;
+    const void *acts_bf16;          /* [L-1][n_pol][B][256] */
+    const int64_t *actions;         /* [B] */
+    const float *d_out;             /* [n_pol][B][D] */
+    void *dz_bf16;
+    void *dzo_bf16;
+    void *xo_bf16;
+    float *grad_part;               /* [n_pol][n_split][row_stride] */
+    int32_t n_split;
+} sfgpi_backward_tc_args;
+
+int sfgpi_bwd_tc_out_pad(const sfgpi_net_desc *net);
+int sfgpi_bwd_tc_splits(int32_t B, int32_t want);
+int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 
 const char *sfgpi_last_error(void);
 int sfgpi_version(void);

@@ -89,3 +89,58 @@ def test_bf16_train_step_vs_oracle(variant, N):
     losses = ag.update_successor_all(gu.cuda_tr(tr), use_gpi=True).cpu()
     for i in range(N):
         assert np.allclose(losses[i].numpy(), [float(v) for v in ref[i]], rtol=3e-2, atol=1e-6)
+
+
+def _rb(t):
+    """Straight-through bf16 rounding: the value the tensor core consumes, the fp32 gradient path."""
+    return t + (t.bfloat16().float() - t).detach()
+
+
+def torch_psi_grads(o, lo, n_pol, x, actions, d_out, emulate_bf16=False):
+    """
+    Autograd reference of PackedSFLibrary.psi_gradients: list over policies of [(dW_l, db_l)].  emulate_bf16 rounds the
+    operands of every GEMM (inputs, weights, stored activations) to bf16 exactly where the tensor-core forward does, so the
+    ReLU masks are the ones the kernels see: a mask that flips because a pre-activation sits within bf16 noise of zero is
+    a full-size element error (relative Frobenius error = sqrt(fraction flipped), ~5 % at 0.3 % flips) and says nothing
+    about the backward kernels.
+    """
+    from oracle.sf_oracle import act_fn
+    out = []
+    B = x.shape[0]
+    rb = _rb if emulate_bf16 else (lambda t: t)
+    for p in range(n_pol):
+        layers = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in o.psi[lo + p]]
+        h = rb(x)
+        for (W, b), a in zip(layers, o.acts):
+            h = act_fn(a)(torch.addmm(b, h, rb(W).t()))
+            if W is not layers[-1][0]:
+                h = rb(h)
+        psi = h.view(B, o.A, o.D)
+        (psi[torch.arange(B), actions] * d_out[p]).sum().backward()
+        out.append([(W.grad, b.grad) for W, b in layers])
+    return out
+
+
+@pytest.mark.parametrize('precision,tol', [('bf16', 1.5e-2), ('fp32', 2e-5)])
+@pytest.mark.parametrize('S,A,D,N,B,hopper', [
+    (4, 9, 12, 3, 1000, False),          # Reacher: one output-layer chunk (K = 112), ragged last tile, 2 batch splits
+    (4, 9, 12, 5, 33 * 128 - 5, False),  # paired tiles in the dgrad kernel
+    (11, 27, 50, 2, 300, True),          # Hopper: 6 output-layer chunks in dgrad, 11 output tiles in wgrad, S = 11
+    (4, 2, 20, 2, 32, False),            # CartPole shape, half a tile
+])
+def test_psi_backward_vs_autograd(precision, tol, S, A, D, N, B, hopper):
+    """The backward kernels alone (tensor-core and fp32) against torch autograd on the oracle's weights."""
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=77)
+    sf = gu.build_g2(meta, oracle=o, hyper=dict(gu.HYPER, precision=precision))
+    lib = sf._library
+    tr = synthetic_transitions(B, S, A, D, gen, hopper=hopper)
+    x, actions = tr[0], tr[1]
+    lo, n_pol = (1, N - 1)
+    d_out = torch.randn(n_pol, B, D, generator=gen) * 1e-4
+    ref = torch_psi_grads(o, lo, n_pol, x, actions, d_out, emulate_bf16=precision == 'bf16')
+    got = lib.psi_gradients(x.cuda(), actions.cuda(), d_out.cuda(), lo, n_pol).cpu()
+    for p in range(n_pol):
+        for l, ((W, b), (gW, gb)) in enumerate(zip(lib.spec.views(got[p]), ref[p])):
+            assert fro_err(W, gW) < tol, f'policy {p} layer {l}: dW error {fro_err(W, gW)}'
+            assert fro_err(b, gb) < tol, f'policy {p} layer {l}: db error {fro_err(b, gb)}'
