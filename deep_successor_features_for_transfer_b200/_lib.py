@@ -56,7 +56,13 @@ class TdArgs(C.Structure):
                 ('phis', C.c_void_p), ('rs', C.c_void_p), ('gammas', C.c_void_p), ('states', C.c_void_p),
                 ('next_states', C.c_void_p), ('w', C.c_void_p), ('g', C.c_void_p), ('h', C.c_void_p),
                 ('w_stride', C.c_int32), ('g_stride', C.c_int32), ('d_out', C.c_void_p), ('loss_part', C.c_void_p),
-                ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32)]
+                ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32), ('next_psi', C.c_void_p), ('next_keys', C.c_void_p),
+                ('next_key_stride', C.c_int32)]
+
+
+class ForwardTcJob(C.Structure):
+    _fields_ = [('args', ForwardArgs), ('params_bf16', C.c_void_p), ('n_policies_total', C.c_int32), ('wq', C.c_void_p),
+                ('bq', C.c_void_p)]
 
 
 class BackwardArgs(C.Structure):
@@ -83,7 +89,7 @@ class AdamArgs(C.Structure):
     _fields_ = [('n_seg', C.c_int32), ('n_pol', C.c_int32), ('seg', AdamSegment * MAX_SEGMENTS), ('step', C.c_void_p),
                 ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
                 ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
-                ('losses', C.c_void_p), ('sequential_shared', C.c_int32)]
+                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p)]
 
 
 # every symbol include/sfgpi.h declares: name -> (restype, argtypes)
@@ -93,6 +99,7 @@ SYMBOLS = {
     'sfgpi_keys_decode': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_gpi_from_psi': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_td_partials': (C.c_int, [C.c_int32]),
     'sfgpi_td_step': (C.c_int, [C.POINTER(TdArgs), C.c_void_p]),
     'sfgpi_mlp_backward': (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     'sfgpi_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
@@ -105,6 +112,7 @@ SYMBOLS = {
     'sfgpi_bwd_tc_out_pad': (C.c_int, [C.POINTER(NetDesc)]),
     'sfgpi_bwd_tc_splits': (C.c_int, [C.c_int32, C.c_int32]),
     'sfgpi_mlp_backward_tc': (C.c_int, [C.POINTER(BackwardTcArgs), C.c_void_p]),
+    'sfgpi_mlp_forward_tc_jobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
 }

@@ -20,6 +20,33 @@ __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g,
     p = p - __fdiv_rn(step_size * m, denom);               // addcdiv_(value = -step_size): self + value*t1/t2
 }
 
+// bias corrections of optimizer q for its NEXT step: {1 - beta1^t, sqrt(1 - beta2^t)} in double, as torch computes them on
+// the host.  Read from a.consts when the caller maintains it (adam_finish_kernel refreshes it after every step, so no
+// double-precision pow sits on the critical path of the step), else computed here.
+__device__ __forceinline__ void bias_corrections(const sfgpi_adam_args &a, int q, double &bc1, float &sqrt_bc2) {
+    if (a.consts != nullptr) {
+        bc1 = a.consts[2 * q];
+        sqrt_bc2 = (float)a.consts[2 * q + 1];
+    } else {
+        const double t = (double)(a.step[q] + 1);
+        bc1 = 1.0 - pow(a.beta1, t);
+        sqrt_bc2 = (float)sqrt(1.0 - pow(a.beta2, t));
+    }
+}
+
+// fixed-order sum of n_part gradient partials, `stride` floats apart; four independent chains keep the loads in flight
+__device__ __forceinline__ float sum_partials(const float *__restrict__ gp, int n_part, size_t stride) {
+    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+    int k = 0;
+    for (; k + 4 <= n_part; k += 4) {
+        const float t0 = __ldg(gp + (size_t)k * stride), t1 = __ldg(gp + (size_t)(k + 1) * stride),
+                    t2 = __ldg(gp + (size_t)(k + 2) * stride), t3 = __ldg(gp + (size_t)(k + 3) * stride);
+        g0 += t0; g1 += t1; g2 += t2; g3 += t3;
+    }
+    for (; k < n_part; ++k) g0 += __ldg(gp + (size_t)k * stride);
+    return (g0 + g1) + (g2 + g3);
+}
+
 __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constant__ sfgpi_adam_args a, int blocks_per_pol) {
     __shared__ float sqrt_bc2_s, step_size_s[SFGPI_MAX_SEGMENTS];
     const int p = blockIdx.y;                               // optimizer (policy slot)
@@ -36,11 +63,11 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             a.losses[p * 3 + 2] = l2;
         }
     }
-    // ---- bias corrections in double, as torch computes them on the host (1 - beta ** step) ----
     if (threadIdx.x == 0) {
-        const double t = (double)(a.step[p] + 1);
-        const double bc1 = 1.0 - pow(a.beta1, t);
-        sqrt_bc2_s = (float)sqrt(1.0 - pow(a.beta2, t));
+        double bc1;
+        float sb2;
+        bias_corrections(a, p, bc1, sb2);
+        sqrt_bc2_s = sb2;
         for (int s = 0; s < a.n_seg; ++s) step_size_s[s] = (float)((double)a.seg[s].lr / bc1);
     }
     __syncthreads();
@@ -52,29 +79,52 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
         const bool shared = (sg.param_stride == 0 && a.n_pol > 1);
         if (shared && p != 0) continue;
         const float step_size = step_size_s[s];
-        for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.len; i += blocks_per_pol * kAdamThreads) {
-            if (!shared) {
-                const float *gp = sg.grad_part + (size_t)p * sg.grad_pol_stride + i;
-                float g = 0.0f;
-                for (int k = 0; k < sg.n_part; ++k) g += gp[(size_t)k * sg.grad_part_stride];
-                float *pp = sg.param + (size_t)p * sg.param_stride + i;
-                float *pm = sg.m + (size_t)p * sg.m_stride + i;
-                float *pv = sg.v + (size_t)p * sg.v_stride + i;
-                float pw = *pp, m = *pm, v = *pv;
-                adam_elem(pw, m, v, g, step_size, sqrt_bc2, sg.weight_decay, kc);
-                *pp = pw; *pm = m; *pv = v;
+        if (!shared) {
+            const float *gp0 = sg.grad_part + (size_t)p * sg.grad_pol_stride;
+            float *pp0 = sg.param + (size_t)p * sg.param_stride;
+            float *pm0 = sg.m + (size_t)p * sg.m_stride;
+            float *pv0 = sg.v + (size_t)p * sg.v_stride;
+            const bool vec = ((sg.len | sg.grad_part_stride) & 3) == 0 &&
+                             ((reinterpret_cast<uintptr_t>(gp0) | reinterpret_cast<uintptr_t>(pp0) |
+                               reinterpret_cast<uintptr_t>(pm0) | reinterpret_cast<uintptr_t>(pv0)) & 15) == 0;
+            if (vec) {                                        // 128-bit path: 4 parameters per thread per trip
+                const int n4 = sg.len >> 2;
+                for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < n4; i += blocks_per_pol * kAdamThreads) {
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < sg.n_part; ++k) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(gp0 + (size_t)k * sg.grad_part_stride) + i);
+                        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+                    }
+                    float4 pw = reinterpret_cast<float4 *>(pp0)[i], m = reinterpret_cast<float4 *>(pm0)[i],
+                           v = reinterpret_cast<float4 *>(pv0)[i];
+                    adam_elem(pw.x, m.x, v.x, g.x, step_size, sqrt_bc2, sg.weight_decay, kc);
+                    adam_elem(pw.y, m.y, v.y, g.y, step_size, sqrt_bc2, sg.weight_decay, kc);
+                    adam_elem(pw.z, m.z, v.z, g.z, step_size, sqrt_bc2, sg.weight_decay, kc);
+                    adam_elem(pw.w, m.w, v.w, g.w, step_size, sqrt_bc2, sg.weight_decay, kc);
+                    reinterpret_cast<float4 *>(pp0)[i] = pw;
+                    reinterpret_cast<float4 *>(pm0)[i] = m;
+                    reinterpret_cast<float4 *>(pv0)[i] = v;
+                }
             } else {
-                // shared tensor (TSF's h) stepped by every optimizer from the SAME pre-step value; deltas added in
-                // optimizer order (frozen-snapshot ensemble semantics).  Each optimizer has its own step.
+                for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.len; i += blocks_per_pol * kAdamThreads) {
+                    const float g = sum_partials(gp0 + i, sg.n_part, (size_t)sg.grad_part_stride);
+                    float pw = pp0[i], m = pm0[i], v = pv0[i];
+                    adam_elem(pw, m, v, g, step_size, sqrt_bc2, sg.weight_decay, kc);
+                    pp0[i] = pw; pm0[i] = m; pv0[i] = v;
+                }
+            }
+        } else {
+            // shared tensor (TSF's h) stepped by every optimizer from the SAME pre-step value; deltas added in
+            // optimizer order (frozen-snapshot ensemble semantics).  Each optimizer has its own step.
+            for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.len; i += blocks_per_pol * kAdamThreads) {
                 const float p0 = sg.param[i];
                 float pacc = p0;
                 for (int q = 0; q < a.n_pol; ++q) {
-                    const double t = (double)(a.step[q] + 1);
-                    const double qbc1 = 1.0 - pow(a.beta1, t);
-                    const float qsb2 = (float)sqrt(1.0 - pow(a.beta2, t));
-                    const float *gp = sg.grad_part + (size_t)q * sg.grad_pol_stride + i;
-                    float g = 0.0f;
-                    for (int k = 0; k < sg.n_part; ++k) g += gp[(size_t)k * sg.grad_part_stride];
+                    double qbc1;
+                    float qsb2;
+                    bias_corrections(a, q, qbc1, qsb2);
+                    const float g = sum_partials(sg.grad_part + (size_t)q * sg.grad_pol_stride + i, sg.n_part,
+                                                 (size_t)sg.grad_part_stride);
                     float *pm = sg.m + (size_t)q * sg.m_stride + i;
                     float *pv = sg.v + (size_t)q * sg.v_stride + i;
                     float pw = p0, m = *pm, v = *pv;
@@ -88,9 +138,18 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
     }
 }
 
-__global__ void adam_bump_step_kernel(int32_t *step, int n) {
+// step += 1 and, when the caller keeps them, the bias corrections of the step after that
+__global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double beta1, double beta2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) step[i] += 1;
+    if (i < n) {
+        const int s = step[i] + 1;
+        step[i] = s;
+        if (consts != nullptr) {
+            const double t = (double)(s + 1);
+            consts[2 * i] = 1.0 - pow(beta1, t);
+            consts[2 * i + 1] = sqrt(1.0 - pow(beta2, t));
+        }
+    }
 }
 
 }  // namespace sfgpi
@@ -117,6 +176,6 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     adam_kernel<<<grid, kAdamThreads, 0, st>>>(a, blocks);
     int rc = check_launch("sfgpi_adam_step");
     if (rc) return rc;
-    adam_bump_step_kernel<<<(a.n_pol + 127) / 128, 128, 0, st>>>(a.step, a.n_pol);
-    return check_launch("sfgpi_adam_step(bump)");
+    adam_finish_kernel<<<(a.n_pol + 127) / 128, 128, 0, st>>>(a.step, a.consts, a.n_pol, a.beta1, a.beta2);
+    return check_launch("sfgpi_adam_step(finish)");
 }

@@ -151,7 +151,8 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
 
     if (warp < kNStage) {
         // =========================== TMA producers (ring stage s is owned by producer warp s) ===========================
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();             // whole-warp loop, elected issue (tc_common.cuh)
             uint32_t n = 0;
             for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
                 const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
@@ -165,18 +166,19 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                             for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
                                 const int s = n % kNStage;
                                 if (s != warp) continue;
-                                mbar_wait(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
-                                mbar_arrive_expect_tx(W_FULL(s), kStageBytes);
+                                mbar_wait_warp(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
+                                mbar_arrive_expect_tx_e(W_FULL(s), kStageBytes, leader);
                                 const int wrow = row0 + ii.row_base + kb * kKB;       // 64 reduction rows of W
-                                tma_load_2d(W_addr + s * kStageBytes, &tmap_w, W_FULL(s), nb * kNB, wrow);
-                                tma_load_2d(W_addr + s * kStageBytes + kBoxBytes, &tmap_w, W_FULL(s), nb * kNB + 64, wrow);
+                                tma_load_2d_e(W_addr + s * kStageBytes, &tmap_w, W_FULL(s), nb * kNB, wrow, leader);
+                                tma_load_2d_e(W_addr + s * kStageBytes + kBoxBytes, &tmap_w, W_FULL(s), nb * kNB + 64, wrow, leader);
                             }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             uint32_t n = 0, ready_cnt[2] = {0, 0};
             const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
             const uint64_t bdesc0 = umma_desc_mn_sw128(W_addr, kBoxBytes);
@@ -189,7 +191,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     const int n_kb = (ii.K + kKB - 1) / kKB;
                     const bool fresh = (it == 0) || (it >= p.n_chunks);          // output-layer chunks 1.. accumulate
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot) {
-                        mbar_wait(SLOT_READY(slot), ready_cnt[slot] & 1);
+                        mbar_wait_warp(SLOT_READY(slot), ready_cnt[slot] & 1);
                         ++ready_cnt[slot];
                         tc_fence_after();
                         const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
@@ -198,16 +200,24 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                             const int n_k16 = min(4, (ii.K - kb * kKB) >> 4);
                             for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
                                 const int s = n % kNStage;
-                                mbar_wait(W_FULL(s), (n / kNStage) & 1);
+                                mbar_wait_warp(W_FULL(s), (n / kNStage) & 1);
                                 tc_fence_after();
                                 const uint64_t bd = bdesc0 + (uint64_t)(s * (kStageBytes >> 4));
                                 const uint32_t d = d_base + nb * kNB;
-                                for (int k16 = 0; k16 < n_k16; ++k16)
-                                    umma_bf16(d, ad + 2 * k16, bd + 128 * k16, idesc, (!fresh || kb || k16) ? 1u : 0u);
-                                umma_commit(W_EMPTY(s));
+                                const uint32_t acc0 = (!fresh || kb) ? 1u : 0u;
+                                if (n_k16 == 4) {
+                                    umma_bf16_e(d, ad, bd, idesc, acc0, leader);
+                                    umma_bf16_e(d, ad + 2, bd + 128, idesc, 1u, leader);
+                                    umma_bf16_e(d, ad + 4, bd + 256, idesc, 1u, leader);
+                                    umma_bf16_e(d, ad + 6, bd + 384, idesc, 1u, leader);
+                                } else {
+                                    for (int k16 = 0; k16 < n_k16; ++k16)
+                                        umma_bf16_e(d, ad + 2 * k16, bd + 128 * k16, idesc, (acc0 || k16) ? 1u : 0u, leader);
+                                }
+                                umma_commit_e(W_EMPTY(s), leader);
                             }
                         }
-                        umma_commit(ACC_FULL(slot));
+                        umma_commit_e(ACC_FULL(slot), leader);
                     }
                 }
             }
@@ -331,31 +341,36 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
 
     if (warp < kWgStages) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             const uint32_t bytes = kWgABytes + kWgXBytes + (main_mma ? kWgBBytes : 0);
             for (int kb = warp; kb < n_kb; kb += kWgStages) {
                 const int s = warp;                                      // stage s is owned by producer warp s
-                mbar_wait(EMPTY(s), ((kb / kWgStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(FULL(s), bytes);
+                mbar_wait_warp(EMPTY(s), ((kb / kWgStages) & 1) ^ 1);
+                mbar_arrive_expect_tx_e(FULL(s), bytes, leader);
                 const uint32_t st = sbase + s * kWgStageBytes;
                 const int b0 = b_lo + kb * 64;
+#pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (l == p.L - 1) tma_load_3d(st + h * kBoxBytes, &tmap_dzo, FULL(s), mt * 128 + h * 64, b0, pl);
-                    else tma_load_3d(st + h * kBoxBytes, &tmap_dz, FULL(s), mt * 128 + h * 64, b0, l * p.n_pol + pl);
+                    if (l == p.L - 1) tma_load_3d_e(st + h * kBoxBytes, &tmap_dzo, FULL(s), mt * 128 + h * 64, b0, pl, leader);
+                    else tma_load_3d_e(st + h * kBoxBytes, &tmap_dz, FULL(s), mt * 128 + h * 64, b0, l * p.n_pol + pl, leader);
                 }
-                if (main_mma)
+                if (main_mma) {
+#pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        tma_load_3d(st + kWgABytes + j * kBoxBytes, &tmap_acts, FULL(s), j * 64, b0, (l - 1) * p.n_pol + pl);
-                tma_load_2d(st + kWgABytes + kWgBBytes, &tmap_xo, FULL(s), 0, b0);
+                        tma_load_3d_e(st + kWgABytes + j * kBoxBytes, &tmap_acts, FULL(s), j * 64, b0, (l - 1) * p.n_pol + pl, leader);
+                }
+                tma_load_2d_e(st + kWgABytes + kWgBBytes, &tmap_xo, FULL(s), 0, b0, leader);
             }
         }
     } else if (warp == 3) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             const uint32_t idesc_main = umma_idesc_bf16_major(kTM, 256, 1u, 1u);
             const uint32_t idesc_aux = umma_idesc_bf16_major(kTM, kXoCols, 1u, 1u);
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int s = kb % kWgStages;
-                mbar_wait(FULL(s), (kb / kWgStages) & 1);
+                mbar_wait_warp(FULL(s), (kb / kWgStages) & 1);
                 tc_fence_after();
                 const uint32_t st = sbase + s * kWgStageBytes;
                 const uint64_t ad = umma_desc_mn_sw128(st, kBoxBytes);
@@ -364,12 +379,12 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16) {
                     const uint32_t accum = (kb | k16) ? 1u : 0u;
-                    if (main_mma) umma_bf16(tmem_base, ad + 128 * k16, bd + 128 * k16, idesc_main, accum);
-                    umma_bf16(tmem_base + 256u, ad + 128 * k16, xd + 128 * k16, idesc_aux, accum);
+                    if (main_mma) umma_bf16_e(tmem_base, ad + 128 * k16, bd + 128 * k16, idesc_main, accum, leader);
+                    umma_bf16_e(tmem_base + 256u, ad + 128 * k16, xd + 128 * k16, idesc_aux, accum, leader);
                 }
-                umma_commit(EMPTY(s));
+                umma_commit_e(EMPTY(s), leader);
             }
-            umma_commit(ACC_FULL);
+            umma_commit_e(ACC_FULL, leader);
         }
     } else {
         // ---- epilogue: thread = TMEM lane = one row n of dW_l ----

@@ -18,6 +18,7 @@
 //               so the layer has only n_w * A columns and the epilogue is a running (max, argmax) per reward vector --
 //               psi[B,N,A,D] is never formed, not even on chip.  (GPI_w, sfdqn.py:215-240.)
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace sfgpi {
 namespace tc {
@@ -104,13 +105,32 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
     }
 }
 
+// Up to kMaxJobs independent forwards (e.g. online psi(s), GPI on s', target psi(s') of one train step) share ONE launch: the
+// persistent tile loop runs over the concatenated pair lists, so the small per-step forwards fill the machine together
+// instead of queueing as three single-wave kernels.
+constexpr int kMaxJobs = 3;
+struct TcMulti {
+    long long *timeline;             // developer aid (env SFGPI_TIMELINE=1): clock64() stamps of CTA 0's roles, else NULL
+    int n_jobs, total_pairs;
+    int pair_start[kMaxJobs + 1];
+    TcParams job[kMaxJobs];
+};
+struct TmapSet { CUtensorMap w[kMaxJobs]; CUtensorMap q[kMaxJobs]; };
+
+// role 0 = epilogue X (thread 0), 1 = MMA issuer, 2 = producer warp 0, 3 = epilogue Y (thread 0); 64 slots each
+#define TL_STAMP(role, cnt) do { if (m.timeline != nullptr && blockIdx.x == 0 && (cnt) < 64) m.timeline[(role) * 64 + (cnt)++] = clock64(); } while (0)
+
+__device__ __forceinline__ int job_of_pair(const TcMulti &m, int pair) {
+    int j = 0;
+    while (j + 1 < m.n_jobs && pair >= m.pair_start[j + 1]) ++j;
+    return j;
+}
+
 __global__ void __launch_bounds__(kThreadsTc, 1)
-mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmap,
-                      const __grid_constant__ CUtensorMap tmap_q) {
+mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ TmapSet maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const sfgpi_forward_args &a = p.a;
-    const sfgpi_net_desc &net = a.net;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (m.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) m.timeline[255] = clock64();      // kernel entry
 
     // ---- carve-up: [A slot X 64K][A slot Y 64K][weight ring 4 x 16K][biases 24K][barriers] ----
     const uint32_t sbase = smem_u32(smem_raw);
@@ -128,8 +148,10 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
         for (int s = 0; s < kNStage; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 128); mbar_init(ACC_FULL(s), 1); }
         fence_mbar_init();
-        tma_prefetch_desc(&tmap);
-        if (p.gpi) tma_prefetch_desc(&tmap_q);
+        for (int j = 0; j < m.n_jobs; ++j) {
+            tma_prefetch_desc(&maps.w[j]);
+            if (m.job[j].gpi) tma_prefetch_desc(&maps.q[j]);
+        }
     }
     if (warp == kMmaWarp) tmem_alloc(holder_addr, 512);
     tc_fence_before();
@@ -138,17 +160,21 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
 
-    const int B = a.B, L = net.n_layers, A_ = net.n_actions, D = net.n_features, AD = A_ * D;
-    const int S = net.dims[0];
 
     if (warp < kNStage) {
         // =========================== TMA producers ===========================
         // One issuing thread sustains only ~27 B/cycle of 128-row boxes (its bulk-tensor copies do not overlap: scripts/
         // tma_bench.cu), well below the 64 B/cycle the MMA consumes; issuers in different warps scale linearly.  So ring stage
         // s is owned by producer warp s.
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one();
             uint32_t n = 0;
-            for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+            int tlc = 0;
+            for (int gpair = blockIdx.x; gpair < m.total_pairs; gpair += gridDim.x) {
+                const int jb = job_of_pair(m, gpair);
+                const TcParams &p = m.job[jb];
+                const sfgpi_forward_args &a = p.a;
+                const int pair = gpair - m.pair_start[jb];
                 const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
                 const int row0 = (a.policy_lo + pl) * p.rows_per_policy;
                 const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
@@ -156,31 +182,35 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                     const ItemInfo ii = item_info(p, it);
                     const int nblocks = (ii.n_cols + kNB - 1) / kNB;
                     const bool folded = ii.kind == 2 && p.gpi;
-                    const void *tm = folded ? (const void *)&tmap_q : (const void *)&tmap;
+                    const void *tm = folded ? (const void *)&maps.q[jb] : (const void *)&maps.w[jb];
                     const int rbase = folded ? pl * p.n_final + ii.row_base : row0 + ii.row_base;
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot)
                         for (int kb = 0; kb < ii.n_kb; ++kb)
                             for (int nb = 0; nb < nblocks; ++nb, ++n) {
                                 const int s = n % kNStage;
                                 if (s != warp) continue;
-                                mbar_wait(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
-                                mbar_arrive_expect_tx(W_FULL(s), kStageBytes);
-                                tma_load_2d(W_addr + s * kStageBytes, tm, W_FULL(s), kb * kKB, rbase + nb * kNB);
+                                mbar_wait_warp(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
+                                if (warp == 0 && leader) TL_STAMP(2, tlc);
+                                mbar_arrive_expect_tx_e(W_FULL(s), kStageBytes, leader);
+                                tma_load_2d_e(W_addr + s * kStageBytes, tm, W_FULL(s), kb * kKB, rbase + nb * kNB, leader);
                             }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            // The issuing thread is latency-bound (one thread, dependent uniform-datapath ops): a naive loop costs ~170 cycles per
-            // MMA, 2.6x the 64-cycle execution of an M=128,N=128,K=16 MMA (scripts/umma_bench.cu).  So: base descriptors are
-            // built once, the loop only adds immediates to them, the K=16 steps are unrolled.
+        // Whole warp runs the loop (operands stay in uniform registers), the elected lane issues: see tc_common.cuh.
+        {
+            const uint32_t leader = elect_one();
             uint32_t n = 0, ready_cnt[2] = {0, 0};
+            int tlc = 0;
             const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
             const uint64_t bdesc0 = umma_desc_k_sw128(W_addr);
-            for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
-                const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
+            for (int gpair = blockIdx.x; gpair < m.total_pairs; gpair += gridDim.x) {
+                const int jb = job_of_pair(m, gpair);
+                const TcParams &p = m.job[jb];
+                const int pair = gpair - m.pair_start[jb];
+                const int pip = pair % p.pairs_per_policy;
                 const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
                 for (int it = 0; it < p.n_items; ++it) {
                     const ItemInfo ii = item_info(p, it);
@@ -188,32 +218,35 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                     const uint32_t idesc_full = umma_idesc_bf16(kTM, kNB);
                     const uint32_t idesc_last = umma_idesc_bf16(kTM, (uint32_t)(ii.n_cols - (nblocks - 1) * kNB));
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot) {
-                        mbar_wait(SLOT_READY(slot), ready_cnt[slot] & 1);
+                        mbar_wait_warp(SLOT_READY(slot), ready_cnt[slot] & 1);
                         ++ready_cnt[slot];
                         tc_fence_after();
+                        if (leader) TL_STAMP(1, tlc);                         // slot ready
                         const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
                         for (int kb = 0; kb < ii.n_kb; ++kb) {
                             const uint64_t ad = (slot ? adesc_y : adesc_x) + (uint64_t)(kb * ((kTM * 128) >> 4));
                             for (int nb = 0; nb < nblocks; ++nb, ++n) {
                                 const int s = n % kNStage;
-                                mbar_wait(W_FULL(s), (n / kNStage) & 1);
+                                mbar_wait_warp(W_FULL(s), (n / kNStage) & 1);
                                 tc_fence_after();
+                                if (leader && kb == 0 && nb == 0) TL_STAMP(1, tlc);   // first weight stage landed
                                 const uint32_t idesc = (nb == nblocks - 1) ? idesc_last : idesc_full;
                                 const uint64_t bd = bdesc0 + (uint64_t)(s * (kStageBytes >> 4));
                                 const uint32_t d = d_base + nb * kNB;
                                 if (ii.n_k16 == 4) {
-                                    umma_bf16(d, ad, bd, idesc, kb ? 1u : 0u);
-                                    umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                                    umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                                    umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                                    umma_bf16_e(d, ad, bd, idesc, kb ? 1u : 0u, leader);
+                                    umma_bf16_e(d, ad + 2, bd + 2, idesc, 1u, leader);
+                                    umma_bf16_e(d, ad + 4, bd + 4, idesc, 1u, leader);
+                                    umma_bf16_e(d, ad + 6, bd + 6, idesc, 1u, leader);
                                 } else {
                                     for (int k16 = 0; k16 < ii.n_k16; ++k16)
-                                        umma_bf16(d, ad + 2 * k16, bd + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+                                        umma_bf16_e(d, ad + 2 * k16, bd + 2 * k16, idesc, (kb | k16) ? 1u : 0u, leader);
                                 }
-                                umma_commit(W_EMPTY(s));             // stage free once these MMAs have read it
+                                umma_commit_e(W_EMPTY(s), leader);           // stage free once these MMAs have read it
                             }
                         }
-                        umma_commit(ACC_FULL(slot));                  // accumulator of this item complete
+                        umma_commit_e(ACC_FULL(slot), leader);                // accumulator of this item complete
+                        if (leader) TL_STAMP(1, tlc);                         // all MMAs of the item issued
                     }
                 }
             }
@@ -226,17 +259,28 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
         const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..255 among epilogue threads
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * 256u;
         const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
-        const int n_bias = (1 + p.Lh) * kH + p.n_final;     // [b_0 | b_1..b_Lh | b_final]
         uint32_t full_cnt = 0;
         int cur_policy = -1;
+        int tlc = 0;
+        const int tl_role = (et == 0) ? 0 : ((et == 128) ? 3 : -1);
+#define TL_EPI() do { if (tl_role >= 0) TL_STAMP(tl_role, tlc); } while (0)
+        TL_EPI();                                            // set-up done
 
-        for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+        for (int gpair = blockIdx.x; gpair < m.total_pairs; gpair += gridDim.x) {
+            const int jb = job_of_pair(m, gpair);
+            const TcParams &p = m.job[jb];
+            const sfgpi_forward_args &a = p.a;
+            const sfgpi_net_desc &net = a.net;
+            const int B = a.B, L = net.n_layers, A_ = net.n_actions, D = net.n_features, AD = A_ * D;
+            const int S = net.dims[0];
+            const int n_bias = (1 + p.Lh) * kH + p.n_final;     // [b_0 | b_1..b_Lh | b_final]
+            const int pair = gpair - m.pair_start[jb];
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
             const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
             const int tile = p.paired ? 2 * pip + slot : pip;
             const float *P = a.params + (size_t)(a.policy_lo + pl) * net.row_stride;
 
-            if (pl != cur_policy) {                          // per-policy biases -> smem (all 256 epilogue threads)
+            if (jb * 65536 + pl != cur_policy) {             // per-(job, policy) biases -> smem (all 256 epilogue threads)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int e = et; e < n_bias; e += 256) {
                     float v;
@@ -248,7 +292,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                     sts32(bias_addr + 4u * e, v);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                cur_policy = pl;
+                cur_policy = jb * 65536 + pl;
             }
             if (slot == 1 && !has_y) continue;               // (uniform per group) nothing to do for Y in this pair
 
@@ -267,6 +311,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                 }
                 fence_proxy_async();                          // generic-proxy smem writes -> visible to the UMMA (async proxy)
                 mbar_arrive(SLOT_READY(slot));
+                TL_EPI();                                     // state tile staged
             }
 
             int sel_base = -(1 << 30);
@@ -284,6 +329,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                 mbar_wait(ACC_FULL(slot), full_cnt & 1);
                 ++full_cnt;
                 tc_fence_after();
+                TL_EPI();                                     // accumulator of item `it` complete
                 if (ii.kind != 2) {
                     // -------- input / hidden layer: bias + act, bf16, write next A operand (in place), optional save --------
                     const uint32_t bias = bias_addr + 4u * (it * kH);
@@ -348,6 +394,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant_
                     tc_fence_before();
                     if (it + 1 < p.n_items) mbar_arrive(SLOT_READY(slot));     // next chunk may overwrite the accumulator
                 }
+                TL_EPI();                                     // epilogue of item `it` done
             }
         }
     }
@@ -479,57 +526,103 @@ extern "C" int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, in
     return check_launch("sfgpi_fold_gpi");
 }
 
-// mode-1 forward.  `params_bf16` = shadow produced by sfgpi_pack_bf16 for the same `params` (n_policies_total rows sets);
-// GPI form (args->w != NULL) additionally needs wq / bq from sfgpi_fold_gpi for the same (policy_lo, n_pol, w).
-extern "C" int sfgpi_mlp_forward_tc(const sfgpi_forward_args *args, const void *params_bf16, int32_t n_policies_total,
-                                    const void *wq, const float *bq, void *stream) {
-    const sfgpi_forward_args &a = *args;
-    const sfgpi_net_desc &net = a.net;
-    const char *why = "";
-    if (!tc_shape_ok(net, &why)) { set_error("sfgpi_mlp_forward_tc: tensor-core path %s", why); return SFGPI_E_INVALID; }
-    if (a.B < 0 || a.n_pol < 0 || net.dims[net.n_layers] != net.n_actions * net.n_features) {
-        set_error("sfgpi_mlp_forward_tc: invalid sizes");
-        return SFGPI_E_INVALID;
-    }
-    if (a.B == 0 || a.n_pol == 0) return SFGPI_OK;
-    TcParams p;
-    p.a = a;
-    p.gpi = a.w != nullptr ? 1 : 0;
-    if (p.gpi && (a.psi_out || a.sel_out)) {
-        set_error("sfgpi_mlp_forward_tc: the GPI form cannot also emit psi / gathered rows (launch the psi form separately)");
-        return SFGPI_E_INVALID;
-    }
-    if (p.gpi && (!wq || !bq)) { set_error("sfgpi_mlp_forward_tc: GPI form needs the folded weights"); return SFGPI_E_INVALID; }
-    p.nw = p.gpi ? (a.w_diag ? 1 : a.n_w) : 0;
-    p.Lh = net.n_layers - 2;
-    p.rows_per_policy = sfgpi_bf16_rows_per_policy(&net);
-    p.n_final = p.gpi ? sfgpi_gpi_fold_rows(&net, p.nw) : ((net.n_actions * net.n_features + 15) & ~15);
-    p.n_items = 1 + p.Lh + (p.n_final + 255) / 256;
-    p.ks0 = (net.dims[0] + 15) / 16;
-    p.bq = bq;
-    if ((1 + p.Lh) * kH + p.n_final > kBiasFloatsMax) {
-        set_error("sfgpi_mlp_forward_tc: %d bias floats exceed the shared-memory budget", (1 + p.Lh) * kH + p.n_final);
-        return SFGPI_E_SMEM;
-    }
-    p.tiles_per_policy = (a.B + kTM - 1) / kTM;
-    const int total_tiles = p.tiles_per_policy * a.n_pol;
-    p.paired = total_tiles > 148 ? 1 : 0;                    // small problems: one tile per CTA, no ping-pong partner
-    p.pairs_per_policy = p.paired ? (p.tiles_per_policy + 1) / 2 : p.tiles_per_policy;
-    p.total_pairs = p.pairs_per_policy * a.n_pol;
-
-    CUtensorMap tmap, tmap_q;
-    int rc = make_tmap(&tmap, params_bf16, (uint64_t)n_policies_total * p.rows_per_policy);
-    if (rc) return rc;
-    if (p.gpi) {
-        rc = make_tmap(&tmap_q, wq, (uint64_t)a.n_pol * p.n_final);
+// mode-1 forward, up to 3 independent jobs in one launch.  Per job: `params_bf16` = shadow produced by sfgpi_pack_bf16 for
+// the same `params` (n_policies_total row sets); GPI form (args.w != NULL) additionally needs wq / bq from sfgpi_fold_gpi for
+// the same (policy_lo, n_pol, w).
+extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32_t n_jobs, void *stream) {
+    if (n_jobs < 1 || n_jobs > kMaxJobs) { set_error("sfgpi_mlp_forward_tc_jobs: 1..%d jobs per launch", kMaxJobs); return SFGPI_E_INVALID; }
+    TcMulti m;
+    TmapSet maps;
+    m.n_jobs = 0;
+    int total_tiles = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const sfgpi_forward_args &a = jobs[j].args;
+        const sfgpi_net_desc &net = a.net;
+        const char *why = "";
+        if (!tc_shape_ok(net, &why)) { set_error("sfgpi_mlp_forward_tc: tensor-core path %s", why); return SFGPI_E_INVALID; }
+        if (a.B < 0 || a.n_pol < 0 || net.dims[net.n_layers] != net.n_actions * net.n_features) {
+            set_error("sfgpi_mlp_forward_tc: invalid sizes");
+            return SFGPI_E_INVALID;
+        }
+        if (a.B == 0 || a.n_pol == 0) continue;
+        TcParams &p = m.job[m.n_jobs];
+        p.a = a;
+        p.gpi = a.w != nullptr ? 1 : 0;
+        if (p.gpi && (a.psi_out || a.sel_out)) {
+            set_error("sfgpi_mlp_forward_tc: the GPI form cannot also emit psi / gathered rows (use a separate job)");
+            return SFGPI_E_INVALID;
+        }
+        if (p.gpi && (!jobs[j].wq || !jobs[j].bq)) { set_error("sfgpi_mlp_forward_tc: GPI form needs the folded weights"); return SFGPI_E_INVALID; }
+        p.nw = p.gpi ? (a.w_diag ? 1 : a.n_w) : 0;
+        p.Lh = net.n_layers - 2;
+        p.rows_per_policy = sfgpi_bf16_rows_per_policy(&net);
+        p.n_final = p.gpi ? sfgpi_gpi_fold_rows(&net, p.nw) : ((net.n_actions * net.n_features + 15) & ~15);
+        p.n_items = 1 + p.Lh + (p.n_final + 255) / 256;
+        p.ks0 = (net.dims[0] + 15) / 16;
+        p.bq = jobs[j].bq;
+        if ((1 + p.Lh) * kH + p.n_final > kBiasFloatsMax) {
+            set_error("sfgpi_mlp_forward_tc: %d bias floats exceed the shared-memory budget", (1 + p.Lh) * kH + p.n_final);
+            return SFGPI_E_SMEM;
+        }
+        p.tiles_per_policy = (a.B + kTM - 1) / kTM;
+        total_tiles += p.tiles_per_policy * a.n_pol;
+        int rc = make_tmap(&maps.w[m.n_jobs], jobs[j].params_bf16, (uint64_t)jobs[j].n_policies_total * p.rows_per_policy);
         if (rc) return rc;
-    } else {
-        tmap_q = tmap;
+        if (p.gpi) {
+            rc = make_tmap(&maps.q[m.n_jobs], jobs[j].wq, (uint64_t)a.n_pol * p.n_final);
+            if (rc) return rc;
+        } else {
+            maps.q[m.n_jobs] = maps.w[m.n_jobs];
+        }
+        ++m.n_jobs;
     }
+    if (m.n_jobs == 0) return SFGPI_OK;
+    static long long *tl_buf = nullptr;
+    static const bool tl_on = getenv("SFGPI_TIMELINE") != nullptr;
+    if (tl_on && !tl_buf) cudaMalloc(&tl_buf, 256 * sizeof(long long));
+    if (tl_on) cudaMemsetAsync(tl_buf, 0, 256 * sizeof(long long), (cudaStream_t)stream);
+    m.timeline = tl_on ? tl_buf : nullptr;
+    const int paired = total_tiles > 148 ? 1 : 0;                // small launches: one tile per CTA, no ping-pong partner
+    m.total_pairs = 0;
+    for (int j = 0; j < m.n_jobs; ++j) {
+        TcParams &p = m.job[j];
+        p.paired = paired;
+        p.pairs_per_policy = paired ? (p.tiles_per_policy + 1) / 2 : p.tiles_per_policy;
+        p.total_pairs = p.pairs_per_policy * p.a.n_pol;
+        m.pair_start[j] = m.total_pairs;
+        m.total_pairs += p.total_pairs;
+    }
+    for (int j = m.n_jobs; j <= kMaxJobs; ++j) m.pair_start[j] = m.total_pairs;
+    for (int j = m.n_jobs; j < kMaxJobs; ++j) { m.job[j] = m.job[0]; maps.w[j] = maps.w[0]; maps.q[j] = maps.q[0]; }
     const int smem_bytes = 2 * kABytes + kNStage * kStageBytes + kBiasFloatsMax * 4 + 256;
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); cfg = true; }
-    const int grid = p.total_pairs < 148 ? p.total_pairs : 148;
-    mlp_forward_tc_kernel<<<grid, kThreadsTc, smem_bytes, (cudaStream_t)stream>>>(p, tmap, tmap_q);
+    const int grid = m.total_pairs < 148 ? m.total_pairs : 148;
+    mlp_forward_tc_kernel<<<grid, kThreadsTc, smem_bytes, (cudaStream_t)stream>>>(m, maps);
+    if (tl_on) {                                                 // developer aid: dump CTA 0's role timelines (cycles since t0)
+        long long h[256];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(h, tl_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        long long t0 = 0;
+        for (int i = 0; i < 256; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+        static const char *role[4] = {"epiX", "mma", "tma0", "epiY"};
+        fprintf(stderr, "[sfgpi timeline] jobs=%d pairs=%d grid=%d\n", m.n_jobs, m.total_pairs, grid);
+        for (int r = 0; r < 4; ++r) {
+            fprintf(stderr, "  %-4s:", role[r]);
+            for (int i = 0; i < 64 && h[r * 64 + i]; ++i) fprintf(stderr, " %lld", h[r * 64 + i] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
     return check_launch("sfgpi_mlp_forward_tc");
+}
+
+extern "C" int sfgpi_mlp_forward_tc(const sfgpi_forward_args *args, const void *params_bf16, int32_t n_policies_total,
+                                    const void *wq, const float *bq, void *stream) {
+    sfgpi_forward_tc_job job;
+    job.args = *args;
+    job.params_bf16 = params_bf16;
+    job.n_policies_total = n_policies_total;
+    job.wq = wq;
+    job.bq = bq;
+    return sfgpi_mlp_forward_tc_jobs(&job, 1, stream);
 }

@@ -84,6 +84,73 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- warp-uniform issue: the WHOLE warp runs the issue loop (so every operand is provably warp-uniform and lives in uniform
+// registers) and only the instruction itself is predicated on the elected lane.  Issuing from inside `if (lane == 0)` makes
+// ptxas treat the descriptors as per-thread values: every UTCHMMA / UTMALDG is then wrapped in an ELECT + 7x R2UR "waterfall"
+// loop that costs ~170 cycles per MMA (measured: in-kernel clock64 timeline), 2.6x the 64-cycle MMA it feeds.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar), "r"(leader)
+        : "memory");
+}
+// whole-warp wait without the clock-based watchdog (keeps the loop's control flow value-uniform); bounded by a spin count
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint32_t bar, uint32_t bytes, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(bar), "r"(bytes), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(uint32_t smem_dst, const void *tmap, uint32_t bar, int crd0, int crd1, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(crd0), "r"(crd1), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_e(uint32_t smem_dst, const void *tmap, uint32_t bar, int crd0, int crd1, int crd2,
+                                              uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(crd0), "r"(crd1), "r"(crd2), "r"(leader)
+        : "memory");
+}
+
 // mbarrier arrives once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

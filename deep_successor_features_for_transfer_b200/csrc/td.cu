@@ -1,22 +1,34 @@
 // TD target, the two MSE losses and every gradient that does not flow through the psi MLP, fused in one kernel
 // (sfdqn.py:330-345; tsfdqn.py:621-645; features/deep.py:112-121).  Elementwise / tiny-GEMM work: HBM-bound on the
 // [B][D] operands, deterministic two-stage reductions (per-CTA partials, summed by the Adam kernel).
+//
+// Thread-block clusters: 8 CTAs (8 x 32 transitions) form a cluster and sum their gradient / loss partials through
+// distributed shared memory in a fixed rank order before anything is written, so the Adam kernel reads ceil(B/256) partials
+// per parameter instead of ceil(B/32) (that read loop was the longest latency chain of the whole train step).
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sfgpi {
 
 constexpr int kTdRows = 32;       // transitions per CTA
 constexpr int kTdThreads = 128;
+constexpr int kTdCluster = 8;     // CTAs per cluster (portable maximum)
 
 // smem layout (floats): see carve-up below
-__global__ void __launch_bounds__(kTdThreads) td_kernel(const __grid_constant__ sfgpi_td_args a) {
+__global__ void __cluster_dims__(kTdCluster, 1, 1) __launch_bounds__(kTdThreads)
+td_kernel(const __grid_constant__ sfgpi_td_args a) {
     extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const int B = a.B, S = a.S, D = a.D, G = a.G;
-    const int pl = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+    const int pl = blockIdx.y, blk = blockIdx.x;
+    const int clu = blk / kTdCluster, nclu = gridDim.x / kTdCluster;
     const int row0 = blk * kTdRows;
-    const int rows = min(kTdRows, B - row0);
+    const int rows = max(0, min(kTdRows, B - row0));         // the grid is padded to whole clusters: trailing CTAs add zeros
     const bool tsf = a.variant == 2, reward = a.variant >= 1;
+    const int n_acc = a.aux_len + 2;                         // [aux gradient partials | sum diff^2 | sum e^2]
 
     // carve-up
     float *w_s = sm;                              // [D]
@@ -32,6 +44,8 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(const __grid_constant__ 
     float *ss_s = bh_s + D;                       // [32][S]  s + s'
     float *u_s = ss_s + kTdRows * S;              // [32][G]  g(s) + g(s')
     float *du_s = u_s + kTdRows * G;              // [32][G]
+    float *gacc_s = tsf ? du_s + kTdRows * G : Wg_s;      // [aux_len + 2] this CTA's partials, summed across the cluster
+    for (int e = tid; e < n_acc; e += kTdThreads) gacc_s[e] = 0.0f;
 
     const float *cur = a.cur_sel + (size_t)pl * B * D;
     const float *nxt = a.next_sel + (size_t)pl * B * D;
@@ -79,7 +93,14 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(const __grid_constant__ 
         }
         if (r < rows) {
             const size_t gi = (size_t)row0 * D + e;
-            const float target = fmaf(a.gammas[row0 + r], nxt[gi], tphi);
+            float nv;
+            if (a.next_psi != nullptr) {                 // gather psi^-(s')[a*] from the full target output by the GPI key
+                const int astar = (int)key_index(a.next_keys[(size_t)pl * a.next_key_stride + row0 + r]);
+                nv = a.next_psi[((size_t)(row0 + r) * a.n_pol + pl) * ((size_t)a.A * D) + (size_t)astar * D + d];
+            } else {
+                nv = nxt[gi];
+            }
+            const float target = fmaf(a.gammas[row0 + r], nv, tphi);
             df = cur[gi] - target;
             dout[gi] = c1 * df;
             l1_acc = fmaf(df, df, l1_acc);
@@ -110,23 +131,22 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(const __grid_constant__ 
         if ((tid & 31) == 0) { red_s[tid >> 5] = s1; red_s[4 + (tid >> 5)] = s2; }
         __syncthreads();
         if (tid == 0) {
-            float *lp = a.loss_part + ((size_t)pl * nblk + blk) * 2;
-            lp[0] = (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
-            lp[1] = (red_s[4] + red_s[5]) + (red_s[6] + red_s[7]);
+            gacc_s[a.aux_len] = (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
+            gacc_s[a.aux_len + 1] = (red_s[4] + red_s[5]) + (red_s[6] + red_s[7]);
         }
     }
-    if (!reward) return;
-
-    float *gpart = a.aux_grad_part + ((size_t)pl * nblk + blk) * a.aux_len;
+    float *gpart = gacc_s;
     const float c2 = 2.0f * a.beta / (float)B;           // variant 1: beta == 1
 
-    // dL/dw[d] = c2 * sum_b e_b * phi~[b][d]
-    for (int d = tid; d < D; d += kTdThreads) {
-        float acc = 0.0f;
-        for (int r = 0; r < kTdRows; ++r) acc = fmaf(e_s[r], tphi_s[r * D + d], acc);
-        gpart[d] = c2 * acc;
+    if (reward) {
+        // dL/dw[d] = c2 * sum_b e_b * phi~[b][d]
+        for (int d = tid; d < D; d += kTdThreads) {
+            float acc = 0.0f;
+            for (int r = 0; r < kTdRows; ++r) acc = fmaf(e_s[r], tphi_s[r * D + d], acc);
+            gpart[d] = c2 * acc;
+        }
     }
-    if (!tsf) return;
+    if (tsf) {
 
     // daff = (dL/dphi~) * phi,  dL/dphi~ = -c1*diff + c2*e*w                   (targets carry grad, tsfdqn.py:629)
     __syncthreads();
@@ -168,11 +188,34 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(const __grid_constant__ 
         for (int r = 0; r < kTdRows; ++r) acc += daff_s[r * D + d];
         hb[d] = 2.0f * acc;
     }
+    }   // tsf
+
+    // ---- cluster reduction through distributed shared memory: rank r sums slice r of the 8 CTAs' partials, rank order ----
+    cluster.sync();
+    {
+        const unsigned rk = cluster.block_rank();
+        const int per = (n_acc + kTdCluster - 1) / kTdCluster;
+        const int e_lo = rk * per, e_hi = min(n_acc, e_lo + per);
+        const float *remote[kTdCluster];
+#pragma unroll
+        for (int q = 0; q < kTdCluster; ++q) remote[q] = cluster.map_shared_rank(gacc_s, q);
+        for (int e = e_lo + tid; e < e_hi; e += kTdThreads) {
+            float v[kTdCluster];
+#pragma unroll
+            for (int q = 0; q < kTdCluster; ++q) v[q] = remote[q][e];
+            const float sum = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            if (e < a.aux_len) a.aux_grad_part[((size_t)pl * nclu + clu) * a.aux_len + e] = sum;
+            else a.loss_part[((size_t)pl * nclu + clu) * 2 + (e - a.aux_len)] = sum;
+        }
+    }
+    cluster.sync();                                          // nobody leaves while its shared memory is still being read
 }
 
 }  // namespace sfgpi
 
 using namespace sfgpi;
+
+extern "C" int sfgpi_td_partials(int32_t B) { return B <= 0 ? 1 : (B + kTdRows * kTdCluster - 1) / (kTdRows * kTdCluster); }
 
 extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     const sfgpi_td_args &a = *args;
@@ -181,12 +224,12 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     const bool tsf = a.variant == 2;
     const int want_aux = a.variant == 0 ? 0 : (tsf ? a.D + a.G * a.S + a.G + a.D * a.G + a.D : a.D);
     if (a.aux_len < want_aux) { set_error("sfgpi_td_step: aux_len %d < %d", a.aux_len, want_aux); return SFGPI_E_INVALID; }
-    size_t fl = a.D + 3 * (size_t)kTdRows * a.D + kTdRows + 8;
+    size_t fl = a.D + 3 * (size_t)kTdRows * a.D + kTdRows + 8 + (size_t)a.aux_len + 2;
     if (tsf) fl += (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D + (size_t)kTdRows * a.S + 2 * (size_t)kTdRows * a.G;
     const size_t bytes = fl * sizeof(float);
     if (bytes > (size_t)kMaxSmem) { set_error("sfgpi_td_step: D/G too large for shared memory (%zu B)", bytes); return SFGPI_E_SMEM; }
     if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    dim3 grid((a.B + kTdRows - 1) / kTdRows, a.n_pol);
+    dim3 grid(sfgpi_td_partials(a.B) * kTdCluster, a.n_pol);
     td_kernel<<<grid, kTdThreads, bytes, (cudaStream_t)stream>>>(a);
     return check_launch("sfgpi_td_step");
 }

@@ -16,6 +16,7 @@ the agents hold VIEWS of row i, so `.parameters()`, `state_dict()`, `update_mode
 working.  No torch op is on the compute path; torch only owns the memory and the stream.
 """
 import ctypes as C
+import math
 
 import numpy as np
 import torch
@@ -147,6 +148,21 @@ class PackedSFLibrary:
         _lib.call('sfgpi_pack_bf16', C.byref(desc), ptr(self.target if which == 'target' else self.online), lo, n_pol,
                   ptr(self._shadow_for(which)), _stream())
 
+    def _fold(self, a, which):
+        """GPI form of the tensor-core forward: fold the reward vectors of `a` into the output layer -> (wq, bq)."""
+        desc = self.spec.desc()
+        nw = 1 if a.w_diag else a.n_w
+        nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(desc), nw)
+        key = ('fold', a.n_pol, nq)
+        buf = self._ws.get(key)
+        if buf is None:
+            buf = self._ws[key] = (torch.empty(a.n_pol * nq * 256, dtype=torch.bfloat16, device=self.device),
+                                   self._f(a.n_pol * nq))
+        wq, bq = buf
+        _lib.call('sfgpi_fold_gpi', C.byref(desc), ptr(self.target if which == 'target' else self.online), a.policy_lo,
+                  a.n_pol, a.w, a.n_w, a.w_diag, ptr(wq), ptr(bq), _stream())
+        return wq, bq
+
     def _forward(self, a, which, fresh=False):
         """Dispatch one fused forward: fp32 CUDA-core kernel or the tcgen05 kernel on the bf16 shadow (packed on demand)."""
         if self.precision == 'fp32':
@@ -154,20 +170,12 @@ class PackedSFLibrary:
         else:
             if not fresh:
                 self._pack(which, a.policy_lo, a.n_pol)
-            wq = bq = None
-            if a.w:                                             # GPI form: fold the reward vectors into the output layer
-                desc = self.spec.desc()
-                nw = 1 if a.w_diag else a.n_w
-                nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(desc), nw)
-                key = ('fold', a.n_pol, nq)
-                buf = self._ws.get(key)
-                if buf is None:
-                    buf = self._ws[key] = (torch.empty(a.n_pol * nq * 256, dtype=torch.bfloat16, device=self.device),
-                                           self._f(a.n_pol * nq))
-                wq, bq = buf
-                _lib.call('sfgpi_fold_gpi', C.byref(desc), ptr(self.target if which == 'target' else self.online), a.policy_lo,
-                          a.n_pol, a.w, a.n_w, a.w_diag, ptr(wq), ptr(bq), _stream())
+            wq, bq = self._fold(a, which) if a.w else (None, None)     # GPI form
             _lib.call('sfgpi_mlp_forward_tc', C.byref(a), ptr(self._shadow_for(which)), self.cap, ptr(wq), ptr(bq), _stream())
+
+    def _forward_jobs(self, jobs, n):
+        """Tensor-core mode: several forwards in ONE launch (jobs: ctypes array of ForwardTcJob, already filled in)."""
+        _lib.call('sfgpi_mlp_forward_tc_jobs', C.byref(jobs), n, _stream())
 
     def enable_sharding(self, group=None):
         """Declare this library one policy shard of a multi-GPU ensemble (call on every rank after the tasks were added)."""
@@ -186,7 +194,10 @@ class PackedSFLibrary:
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
         new = dict(online=z(cap, sp.row_stride), target=z(cap, sp.row_stride), m=z(cap, sp.row_stride),
                    v=z(cap, sp.row_stride), w=z(cap, sp.n_features), w_m=z(cap, sp.n_features), w_v=z(cap, sp.n_features),
-                   step=torch.zeros(cap, dtype=torch.int32, device=dev))
+                   step=torch.zeros(cap, dtype=torch.int32, device=dev),
+                   # Adam bias corrections of every optimizer's NEXT step (t = step + 1), double like torch's host math
+                   adam_consts=torch.tensor([[1.0 - 0.9 ** 1, math.sqrt(1.0 - 0.999 ** 1)]], dtype=torch.float64,
+                                            device=dev).repeat(cap, 1).contiguous())
         if self.G is not None:
             gl = self.G * sp.dims[0] + self.G
             hl = sp.n_features * self.G + sp.n_features
@@ -253,7 +264,7 @@ class PackedSFLibrary:
 
     def reset(self):
         self.spec, self.n, self.cap, self._views, self._ws, self.h = None, 0, 0, [], {}, None
-        for k in ('online', 'target', 'm', 'v', 'w', 'w_m', 'w_v', 'step', 'g', 'g_m', 'g_v', 'h_m', 'h_v'):
+        for k in ('online', 'target', 'm', 'v', 'w', 'w_m', 'w_v', 'step', 'adam_consts', 'g', 'g_m', 'g_v', 'h_m', 'h_v'):
             if hasattr(self, k):
                 delattr(self, k)
 
@@ -269,7 +280,7 @@ class PackedSFLibrary:
             L, D = len(sp.acts), sp.n_features
             ws = dict(cur_sel=self._f(n_pol, B, D), next_sel=self._f(n_pol, B, D), d_out=self._f(n_pol, B, D),
                       keys=torch.empty(n_keys, B, dtype=torch.int64, device=self.device))
-            nblk = (B + 31) // 32
+            nblk = _lib.lib().sfgpi_td_partials(B)        # one TD partial per 8-CTA cluster (256 transitions)
             ws['nblk'] = nblk
             ws['loss_part'] = self._f(n_pol, nblk, 2)
             if self.precision == 'fp32':
@@ -415,12 +426,22 @@ class PackedSFLibrary:
         a2.key_action = ptr(keys)
         # (3) target forward on s', gather psi^-(s')[a*]                                sfdqn.py:330-331
         a3 = self._fwd_args(self.target, lo, n_pol, None, B)
-        a3.sel_keys, a3.sel_key_stride, a3.sel_out = C.c_void_p(keys[key_row0:].data_ptr()), B, ptr(ws['next_sel'])
+        if tc:
+            # tensor-core mode: the three forwards share one launch, so the target nets cannot wait for a*; they emit the full
+            # psi^-(s') [B][n_pol][A*D] and the TD kernel gathers row a* by the (all-reduced) GPI key.
+            ws['next_psi'] = ws.get('next_psi', None)
+            if ws['next_psi'] is None:
+                ws['next_psi'] = self._f(B, n_pol, A * D)
+            a3.psi_out = ptr(ws['next_psi'])
+        else:
+            a3.sel_keys, a3.sel_key_stride, a3.sel_out = C.c_void_p(keys[key_row0:].data_ptr()), B, ptr(ws['next_sel'])
         # (4) TD target, losses, d_out and the reward-head / g / h gradients            sfdqn.py:330-345, tsfdqn.py:621-645
         t = _lib.TdArgs()
         t.variant, t.n_pol, t.B, t.S, t.A, t.D, t.G = variant, n_pol, B, S, A, D, (self.G or 0)
         t.beta = float(beta) if variant == 2 else 1.0
         t.cur_sel, t.next_sel = ptr(ws['cur_sel']), ptr(ws['next_sel'])
+        if tc:
+            t.next_psi, t.next_keys, t.next_key_stride = ptr(ws['next_psi']), C.c_void_p(keys[key_row0:].data_ptr()), B
         t.w, t.w_stride = P(self.w), D
         if variant == 2:
             t.g, t.g_stride, t.h = P(self.g), self.g.shape[1], ptr(self.h)
@@ -442,6 +463,7 @@ class PackedSFLibrary:
         # (6) Adam over (psi | w | g | h) for all stepped optimizers, + loss reduction    sfdqn.py:362, tsfdqn.py:700
         ad = _lib.AdamArgs()
         ad.n_pol, ad.step = n_pol, C.c_void_p(self.step[lo:].data_ptr())
+        ad.consts = C.c_void_p(self.adam_consts[lo:].data_ptr())
         ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
         rs_, nblk, al = sp.row_stride, ws['nblk'], ws['aux_len']
 
@@ -518,15 +540,28 @@ class PackedSFLibrary:
         if self.precision != 'fp32':
             self._pack('online', 0, self.n)                     # one refresh of the bf16 shadows per step
             self._pack('target', a3.policy_lo, a3.n_pol)
-        self._forward(a1, 'online', fresh=True)
         _lib.call('sfgpi_keys_fill', ptr(keys), keys.numel(), st)
         if sharded and plan['w_all'] is not None:
             self._gather_w(plan['w_all'])
-        self._forward(a2, 'online', fresh=True)
-        if sharded:
-            from .dist import allreduce_max_keys
-            allreduce_max_keys(keys, self.shard.group)
-        self._forward(a3, 'target', fresh=True)
+        if plan['tc']:
+            wq, bq = self._fold(a2, 'online')
+            jobs = plan.get('jobs')
+            if jobs is None:
+                jobs = plan['jobs'] = (_lib.ForwardTcJob * 3)()
+            for j, (aj, which) in enumerate(((a1, 'online'), (a2, 'online'), (a3, 'target'))):
+                jobs[j].args, jobs[j].params_bf16, jobs[j].n_policies_total = aj, self._shadow_for(which).data_ptr(), self.cap
+            jobs[1].wq, jobs[1].bq = wq.data_ptr(), bq.data_ptr()
+            self._forward_jobs(jobs, 3)
+            if sharded:
+                from .dist import allreduce_max_keys
+                allreduce_max_keys(keys, self.shard.group)
+        else:
+            self._forward(a1, 'online', fresh=True)
+            self._forward(a2, 'online', fresh=True)
+            if sharded:
+                from .dist import allreduce_max_keys
+                allreduce_max_keys(keys, self.shard.group)
+            self._forward(a3, 'target', fresh=True)
         _lib.call('sfgpi_td_step', C.byref(t), st)
         _lib.call('sfgpi_mlp_backward_tc' if plan['tc'] else 'sfgpi_mlp_backward', C.byref(b), st)
         h0 = self.h.clone() if (self._sharded and variant == 2) else None

@@ -111,7 +111,8 @@ int sfgpi_gpi_from_psi(const float *psi, const float *w, int32_t B, int32_t N, i
  *   variant 2 (G3): phi~ = phi * (h(g(s)) + h(g(s'))), targets carry grad into g,h; loss = l1 + beta*l2
  * Inputs per policy p: cur_sel/next_sel [n_pol][B][D].  Outputs: d_out [n_pol][B][D] = dLoss/dpsi(s)[a_b,:];
  * loss_part [n_pol][n_blocks][2] partial sums of (diff^2, e^2); aux_grad_part [n_pol][n_blocks][aux_len] partial
- * gradients of [w (D) | g.W (G*S) | g.b (G) | h.W (D*G) | h.b (D)] (variant 1: only w).  n_blocks = ceil(B/32).
+ * gradients of [w (D) | g.W (G*S) | g.b (G) | h.W (D*G) | h.b (D)] (variant 1: only w).  n_blocks = sfgpi_td_partials(B)
+ * (one partial per 8-CTA thread-block cluster = 256 transitions).
  */
 typedef struct {
     int32_t variant, n_pol, B, S, A, D, G;
@@ -129,8 +130,14 @@ typedef struct {
     float *loss_part;
     float *aux_grad_part;
     int32_t aux_len;
+    /* optional: instead of next_sel, gather psi^-(s')[a*_b,:] here from the target nets' full output next_psi [B][n_pol][A*D]
+       with a*_b decoded from the packed GPI keys next_keys[p * next_key_stride + b] (sfdqn.py:331) */
+    const float *next_psi;
+    const int64_t *next_keys;
+    int32_t next_key_stride;
 } sfgpi_td_args;
 
+int sfgpi_td_partials(int32_t B);
 int sfgpi_td_step(const sfgpi_td_args *args, void *stream);
 
 /*
@@ -180,6 +187,8 @@ typedef struct {
     const float *loss_part; int32_t n_loss_part; float l1_scale, l2_scale, beta_loss;
     float *losses;
     int32_t sequential_shared;      /* 1: segments with param_stride 0 are stepped by optimizer 0..n_pol-1 in order */
+    double *consts;                 /* optional [n_pol][2]: {1 - beta1^t, sqrt(1 - beta2^t)} for t = step + 1; must be consistent
+                                       with `step` on entry, refreshed on device after the step.  NULL: computed in-kernel */
 } sfgpi_adam_args;
 
 int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
@@ -204,6 +213,19 @@ int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, int32_t polic
                    int32_t w_diag, void *wq_out, float *bq_out, void *stream);
 int sfgpi_mlp_forward_tc(const sfgpi_forward_args *args, const void *params_bf16, int32_t n_policies_total, const void *wq,
                          const float *bq, void *stream);
+/*
+ * Up to 3 independent tensor-core forwards in ONE launch (the train step's online psi(s), GPI on s' and target psi(s') are
+ * each a fraction of a wave at the shipped sizes; together they fill the machine).  Same semantics per job as
+ * sfgpi_mlp_forward_tc.
+ */
+typedef struct {
+    sfgpi_forward_args args;
+    const void *params_bf16;
+    int32_t n_policies_total;
+    const void *wq;
+    const float *bq;
+} sfgpi_forward_tc_job;
+int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32_t n_jobs, void *stream);
 
 /*
  * Tensor-core backward (bf16 operands, fp32 accumulate), the mode-1 twin of sfgpi_mlp_backward: dgrad chain + split-K wgrad of
