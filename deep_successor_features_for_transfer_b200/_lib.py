@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libsfgpi.so')
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -78,6 +78,15 @@ class BackwardTcArgs(C.Structure):
                 ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
 
 
+class Cmd(C.Structure):
+    _fields_ = [('op', C.c_int32), ('p', C.c_void_p * 5), ('i', C.c_int64 * 4)]
+
+
+OP = dict(H2D=1, D2H=2, D2D=3, KEYS_FILL=4, PACK_BF16=5, FOLD_GPI=6, FORWARD=7, FORWARD_TC_JOBS=8, TD=9, BACKWARD=10,
+          BACKWARD_TC=11, ADAM=12)
+OP_LAUNCHES = {0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2}
+
+
 class AdamSegment(C.Structure):
     _fields_ = [('param', C.c_void_p), ('param_stride', C.c_int64), ('m', C.c_void_p), ('m_stride', C.c_int64),
                 ('v', C.c_void_p), ('v_stride', C.c_int64), ('grad_part', C.c_void_p), ('grad_pol_stride', C.c_int64),
@@ -113,6 +122,7 @@ SYMBOLS = {
     'sfgpi_bwd_tc_splits': (C.c_int, [C.c_int32, C.c_int32]),
     'sfgpi_mlp_backward_tc': (C.c_int, [C.POINTER(BackwardTcArgs), C.c_void_p]),
     'sfgpi_mlp_forward_tc_jobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
 }
@@ -143,6 +153,15 @@ def call(name, *args):
     if rc != 0:
         raise RuntimeError(f'{name} failed (rc={rc}): {lib().sfgpi_last_error().decode()}')
     launch_count += LAUNCHES_PER_CALL.get(name, 1)
+
+
+def run(cmds, n, stream, launches):
+    """One foreign call for a whole command list (sfgpi_run); `launches` = kernels it launches, for the bench's count."""
+    global launch_count
+    rc = lib().sfgpi_run(C.byref(cmds), n, stream)
+    if rc != 0:
+        raise RuntimeError(f'sfgpi_run failed (rc={rc}): {lib().sfgpi_last_error().decode()}')
+    launch_count += launches
 
 
 def ptr(t):

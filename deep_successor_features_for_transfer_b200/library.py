@@ -492,7 +492,7 @@ class PackedSFLibrary:
         ad.l1_scale, ad.l2_scale = 1.0 / (B * A * D), 1.0 / B
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
-        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, tc=tc, ring=0, keys=keys, w_all=w_all, sharded=sharded,
+        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, tc=tc, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
     def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
@@ -509,16 +509,22 @@ class PackedSFLibrary:
             rs = None
         else:
             states, actions, rs, phis, next_states, gammas = transitions
-        sp, dev = self.spec, self.device
-        f32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        states, next_states, phis, gammas = self._check_x(states), self._check_x(next_states), f32(phis), f32(gammas).reshape(-1)
-        actions = torch.as_tensor(actions).to(device=dev, dtype=torch.int64, non_blocking=True).reshape(-1).contiguous()
-        B, D = states.shape[0], sp.n_features
+        sp = self.spec
+        S, D = sp.dims[0], sp.n_features
+        states, next_states = self._as_input(states, torch.float32), self._as_input(next_states, torch.float32)
+        phis, gammas = self._as_input(phis, torch.float32), self._as_input(gammas, torch.float32)
+        actions = self._as_input(actions, torch.int64)
+        if states.dim() == 1:
+            states, next_states = states.unsqueeze(0), next_states.unsqueeze(0)
+        B = states.shape[0]
+        if states.dim() != 2 or states.shape[1] != S:
+            raise ValueError(f'expected states of shape [B, {S}], got {tuple(states.shape)}')
         if rs is not None:
-            rs = f32(rs).reshape(-1)
+            rs = self._as_input(rs, torch.float32)
             if rs.numel() != B:
                 raise ValueError('rs must hold one reward per transition')
-        if not (phis.shape == (B, D) and gammas.numel() == B and actions.numel() == B and next_states.shape[0] == B):
+        if not (tuple(next_states.shape) == (B, S) and phis.numel() == B * D and phis.shape[0] == B and gammas.numel() == B
+                and actions.numel() == B):
             raise ValueError('inconsistent transition batch shapes')
         if variant == 2 and self.G is None:
             raise Exception('Affine Function (h) is not initialized')          # tsfdqn.py:592-593
@@ -526,52 +532,122 @@ class PackedSFLibrary:
         plan = self._ws.get(key)
         if plan is None:
             plan = self._ws[key] = self._build_plan(B, policy, use_gpi, variant, beta)
-        ws, a1, a2, a3, t, b, ad = (plan[k] for k in ('ws', 'a1', 'a2', 'a3', 't', 'b', 'ad'))
-        a1.x, a1.sel_actions = states.data_ptr(), actions.data_ptr()
-        a2.x = a3.x = next_states.data_ptr()
-        t.phis, t.gammas, t.states, t.next_states = phis.data_ptr(), gammas.data_ptr(), states.data_ptr(), next_states.data_ptr()
-        t.rs = None if rs is None else rs.data_ptr()
-        b.x, b.actions = states.data_ptr(), actions.data_ptr()
+            self._build_commands(plan)
+        a1, a2, a3, t, b, ad = (plan[k] for k in ('a1', 'a2', 'a3', 't', 'b', 'ad'))
+        # inputs: device tensors are read in place; host tensors are staged by H2D commands at the head of the list
+        ins = plan['inputs']
+        dptr = []
+        for k, src in enumerate((states, actions, rs, phis, next_states, gammas)):
+            cmd = plan['h2d'][k]
+            if src is None:
+                cmd.op = 0
+                dptr.append(None)
+            elif src.is_cuda:
+                cmd.op = 0
+                dptr.append(src.data_ptr())
+            else:
+                cmd.op, cmd.p[1] = _lib.OP['H2D'], src.data_ptr()
+                dptr.append(ins[k].data_ptr())
+        p_states, p_actions, p_rs, p_phis, p_next, p_gammas = dptr
+        a1.x, a1.sel_actions = p_states, p_actions
+        a2.x = a3.x = p_next
+        t.phis, t.gammas, t.states, t.next_states, t.rs = p_phis, p_gammas, p_states, p_next, p_rs
+        b.x, b.actions = p_states, p_actions
         plan['ring'] = (plan['ring'] + 1) % 64
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
+        if plan['tc']:
+            for j, which in enumerate(('online', 'online', 'target')):      # the job array embeds copies of the arg blocks
+                plan['jobs'][j].args = (a1, a2, a3)[j]
         st = _stream()
         keys, sharded = plan['keys'], plan['sharded']
-        if self.precision != 'fp32':
-            self._pack('online', 0, self.n)                     # one refresh of the bf16 shadows per step
-            self._pack('target', a3.policy_lo, a3.n_pol)
-        _lib.call('sfgpi_keys_fill', ptr(keys), keys.numel(), st)
+        segs = plan['segments']
+        run = lambda seg: seg[1] and _lib.run(seg[0], seg[1], st, seg[2])
+        run(segs[0])                                          # [H2D] pack shadows, key fill
         if sharded and plan['w_all'] is not None:
             self._gather_w(plan['w_all'])
-        if plan['tc']:
-            wq, bq = self._fold(a2, 'online')
-            jobs = plan.get('jobs')
-            if jobs is None:
-                jobs = plan['jobs'] = (_lib.ForwardTcJob * 3)()
-            for j, (aj, which) in enumerate(((a1, 'online'), (a2, 'online'), (a3, 'target'))):
-                jobs[j].args, jobs[j].params_bf16, jobs[j].n_policies_total = aj, self._shadow_for(which).data_ptr(), self.cap
-            jobs[1].wq, jobs[1].bq = wq.data_ptr(), bq.data_ptr()
-            self._forward_jobs(jobs, 3)
-            if sharded:
-                from .dist import allreduce_max_keys
-                allreduce_max_keys(keys, self.shard.group)
-        else:
-            self._forward(a1, 'online', fresh=True)
-            self._forward(a2, 'online', fresh=True)
-            if sharded:
-                from .dist import allreduce_max_keys
-                allreduce_max_keys(keys, self.shard.group)
-            self._forward(a3, 'target', fresh=True)
-        _lib.call('sfgpi_td_step', C.byref(t), st)
-        _lib.call('sfgpi_mlp_backward_tc' if plan['tc'] else 'sfgpi_mlp_backward', C.byref(b), st)
+        run(segs[1])                                          # fold + forwards (fp32: online + GPI forwards)
+        if sharded:
+            from .dist import allreduce_max_keys
+            allreduce_max_keys(keys, self.shard.group)        # packed (value,index) MAX over NVLink: global GPI
         h0 = self.h.clone() if (self._sharded and variant == 2) else None
-        _lib.call('sfgpi_adam_step', C.byref(ad), st)
+        run(segs[2])                                          # (fp32: target forward) TD, backward, Adam
         if h0 is not None:                        # every rank applied only its own optimizers' deltas to the shared h
             import torch.distributed as dist
             delta = self.h - h0
             dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.shard.group)
             self.h.copy_(h0 + delta)
         return losses
+
+    def _as_input(self, t, dtype):
+        """Transition field as a contiguous tensor of `dtype` WITHOUT moving it: host inputs are staged by the command list."""
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        if t.is_cuda and t.device != self.device:
+            t = t.to(self.device)
+        return t if t.is_contiguous() else t.contiguous()
+
+    def _build_commands(self, plan):
+        """Command lists of one train step (replayed through sfgpi_run): 3 segments, split only where a collective may sit."""
+        sp, ws = self.spec, plan['ws']
+        B, n_pol = plan['B'], plan['n_pol']
+        S, D = sp.dims[0], sp.n_features
+        OP = _lib.OP
+        dev = self.device
+        plan['inputs'] = [torch.empty(B, S, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.int64, device=dev),
+                          torch.empty(B, dtype=torch.float32, device=dev), torch.empty(B, D, dtype=torch.float32, device=dev),
+                          torch.empty(B, S, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.float32, device=dev)]
+        plan['desc'] = sp.desc()
+        a1, a2, a3, t, b, ad = (plan[k] for k in ('a1', 'a2', 'a3', 't', 'b', 'ad'))
+        keys = plan['keys']
+        seg0, seg1, seg2 = [], [], []
+
+        def cmd(seg, op, p=(), i=()):
+            seg.append((op, list(p), list(i)))
+
+        for k in range(6):
+            cmd(seg0, 'NOP', (plan['inputs'][k].data_ptr(), 0), (plan['inputs'][k].numel() * plan['inputs'][k].element_size(),))
+        if plan['tc']:
+            dref = C.addressof(plan['desc'])
+            cmd(seg0, 'PACK_BF16', (dref, self.online.data_ptr(), self._shadow_for('online').data_ptr()), (0, self.n))
+            cmd(seg0, 'PACK_BF16', (dref, self.target.data_ptr(), self._shadow_for('target').data_ptr()), (a3.policy_lo, a3.n_pol))
+        cmd(seg0, 'KEYS_FILL', (keys.data_ptr(),), (keys.numel(),))
+        if plan['tc']:
+            nw = 1 if a2.w_diag else a2.n_w
+            nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(plan['desc']), nw)
+            plan['wq'] = torch.empty(a2.n_pol * nq * 256, dtype=torch.bfloat16, device=dev)
+            plan['bq'] = self._f(a2.n_pol * nq)
+            cmd(seg1, 'FOLD_GPI', (dref, self.online.data_ptr(), a2.w, plan['wq'].data_ptr(), plan['bq'].data_ptr()),
+                (a2.policy_lo, a2.n_pol, a2.n_w, a2.w_diag))
+            jobs = plan['jobs'] = (_lib.ForwardTcJob * 3)()
+            for j, which in enumerate(('online', 'online', 'target')):
+                jobs[j].params_bf16, jobs[j].n_policies_total = self._shadow_for(which).data_ptr(), self.cap
+            jobs[1].wq, jobs[1].bq = plan['wq'].data_ptr(), plan['bq'].data_ptr()
+            cmd(seg1, 'FORWARD_TC_JOBS', (C.addressof(jobs),), (3,))
+        else:
+            cmd(seg1, 'FORWARD', (C.addressof(a1),))
+            cmd(seg1, 'FORWARD', (C.addressof(a2),))
+            cmd(seg2, 'FORWARD', (C.addressof(a3),))
+        cmd(seg2, 'TD', (C.addressof(t),))
+        cmd(seg2, 'BACKWARD_TC' if plan['tc'] else 'BACKWARD', (C.addressof(b),))
+        cmd(seg2, 'ADAM', (C.addressof(ad),))
+        segs = [seg0, seg1, seg2] if plan['sharded'] else [seg0 + seg1 + seg2, [], []]
+        plan['segments'], plan['h2d'] = [], None
+        for seg in segs:
+            arr = (_lib.Cmd * max(1, len(seg)))()
+            launches = 0
+            for k, (op, p, i) in enumerate(seg):
+                arr[k].op = OP.get(op, 0)
+                for q, v in enumerate(p):
+                    arr[k].p[q] = v
+                for q, v in enumerate(i):
+                    arr[k].i[q] = int(v)
+                launches += _lib.OP_LAUNCHES[arr[k].op]
+            if plan['h2d'] is None:
+                plan['h2d'] = [arr[k] for k in range(6)]
+            plan['segments'].append((arr, len(seg), launches))
 
     def psi_gradients(self, states, actions, d_out, lo=0, n_pol=None):
         """

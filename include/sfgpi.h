@@ -256,6 +256,31 @@ int sfgpi_bwd_tc_out_pad(const sfgpi_net_desc *net);
 int sfgpi_bwd_tc_splits(int32_t B, int32_t want);
 int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 
+/*
+ * Command list: one foreign call runs a whole train step (or any other fixed sequence of the entry points above plus plain
+ * copies) back to back on `stream`.  p[] / i[] carry the operands of op (see csrc/run.cu); argument structs are referenced,
+ * not copied, so the caller patches input pointers in place between replays.
+ */
+#define SFGPI_OP_NOP 0
+#define SFGPI_OP_H2D 1              /* p0 = dst (device), p1 = src (pinned host), i0 = bytes */
+#define SFGPI_OP_D2H 2              /* p0 = dst (host), p1 = src (device), i0 = bytes */
+#define SFGPI_OP_D2D 3
+#define SFGPI_OP_KEYS_FILL 4        /* p0 = keys, i0 = n */
+#define SFGPI_OP_PACK_BF16 5        /* p0 = net desc, p1 = params, p2 = out, i0 = policy_lo, i1 = n_pol */
+#define SFGPI_OP_FOLD_GPI 6         /* p0 = net desc, p1 = params, p2 = w, p3 = wq, p4 = bq, i0 = policy_lo, i1 = n_pol, i2 = n_w, i3 = w_diag */
+#define SFGPI_OP_FORWARD 7          /* p0 = sfgpi_forward_args */
+#define SFGPI_OP_FORWARD_TC_JOBS 8  /* p0 = sfgpi_forward_tc_job[], i0 = n_jobs */
+#define SFGPI_OP_TD 9               /* p0 = sfgpi_td_args */
+#define SFGPI_OP_BACKWARD 10        /* p0 = sfgpi_backward_args */
+#define SFGPI_OP_BACKWARD_TC 11     /* p0 = sfgpi_backward_tc_args */
+#define SFGPI_OP_ADAM 12            /* p0 = sfgpi_adam_args */
+typedef struct {
+    int32_t op;
+    void *p[5];
+    int64_t i[4];
+} sfgpi_cmd;
+int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream);
+
 const char *sfgpi_last_error(void);
 int sfgpi_version(void);
 
