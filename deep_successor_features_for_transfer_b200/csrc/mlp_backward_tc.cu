@@ -53,11 +53,11 @@ __device__ __forceinline__ DgItem dg_item(const DgParams &p, int it) {
 // Expanded dense chunk c of this row's dZ_{L-1}: columns [256c, 256c+256) of a row that is zero except d_out[0..D) at
 // [sel, sel+D).  Written to the A slot (K-major SW128) and, as the wgrad operand, to dzo (row-major bf16).
 __device__ __forceinline__ void build_dzo_chunk(const DgParams &p, int c, uint32_t Arow, int r, bool row_ok, int sel,
-                                                const float *drow, __nv_bfloat16 *dzo_row) {
+                                                const float *drow, __nv_bfloat16 *dzo_row, int j0, int jstep) {
     const int D = p.net.n_features;
     const int cend = min(256, p.ADp - c * 256);
 #pragma unroll 1
-    for (int j = 0; j * 8 < cend; ++j) {
+    for (int j = j0; j * 8 < cend; j += jstep) {
         const int col0 = c * 256 + j * 8;
         float v[8];
 #pragma unroll
@@ -73,25 +73,26 @@ __device__ __forceinline__ void build_dzo_chunk(const DgParams &p, int c, uint32
 }
 
 // dZ_lo = acc * act'(act_lo): 256 accumulator columns of one row -> bf16 -> next A operand (in place) + HBM row.
-template <int ACT>
+// NCH = 32-column chunks handled by this thread starting at column cbase (8 = whole row; 4 = one half, one-tile mode).
+template <int ACT, int NCH>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, int r, bool row_ok, const uint4 *act_row,
-                                               uint4 *dz_row, bool write_a) {
+                                               uint4 *dz_row, bool write_a, int cbase) {
     uint32_t v[2][32];
     uint4 am[2][4] = {};
     if (ACT != SFGPI_ACT_NONE && row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) am[0][g] = __ldg(act_row + g);
+        for (int g = 0; g < 4; ++g) am[0][g] = __ldg(act_row + (cbase >> 3) + g);
     }
-    tmem_ld32(t_lane, v[0]);
+    tmem_ld32(t_lane + cbase, v[0]);
 #pragma unroll
-    for (int cb = 0; cb < kH / 32; ++cb) {
-        const int c0 = cb * 32;
+    for (int cb = 0; cb < NCH; ++cb) {
+        const int c0 = cbase + cb * 32;
         tmem_wait_ld();
-        if (cb + 1 < kH / 32) {
+        if (cb + 1 < NCH) {
             tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
             if (ACT != SFGPI_ACT_NONE && row_ok) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) am[(cb + 1) & 1][g] = __ldg(act_row + (cb + 1) * 4 + g);
+                for (int g = 0; g < 4; ++g) am[(cb + 1) & 1][g] = __ldg(act_row + ((c0 + 32) >> 3) + g);
             }
         }
         const uint32_t(&u)[32] = v[cb & 1];
@@ -128,15 +129,19 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
     const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t W_addr = sbase + 2 * kABytes;
     const uint32_t bar0 = W_addr + kNStage * kStageBytes;
+    // one-tile mode (p.paired == 0): slot Y's 64 KB are 4 more weight stages and both epilogue groups share the tile (see the
+    // forward kernel).  Stage s lives at W_addr + (s < 4 ? s : s - 8) * 16 KB.
+    const int ns_log = p.paired ? 2 : 3, ns_mask = (1 << ns_log) - 1;
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto W_EMPTY = [&](int s) { return bar0 + 8u * (kNStage + s); };
-    auto SLOT_READY = [&](int s) { return bar0 + 8u * (2 * kNStage + s); };
-    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * kNStage + 2 + s); };
-    const uint32_t holder_addr = bar0 + 8u * (2 * kNStage + 4);
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto SLOT_READY = [&](int s) { return bar0 + 8u * (16 + s); };
+    auto ACC_FULL = [&](int s) { return bar0 + 8u * (18 + s); };
+    auto stage_off = [&](int s) { return (s - ((s & 4) << 1)) * kStageBytes; };
+    const uint32_t holder_addr = bar0 + 8u * 20;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kNStage; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 128); mbar_init(ACC_FULL(s), 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), p.paired ? 128 : 256); mbar_init(ACC_FULL(s), 1); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_w);
     }
@@ -164,13 +169,13 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot)
                         for (int kb = 0; kb < n_kb; ++kb)
                             for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
-                                const int s = n % kNStage;
-                                if (s != warp) continue;
-                                mbar_wait_warp(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
+                                const int s = n & ns_mask;
+                                if ((s & 3) != warp) continue;
+                                mbar_wait_warp(W_EMPTY(s), ((n >> ns_log) & 1) ^ 1);
                                 mbar_arrive_expect_tx_e(W_FULL(s), kStageBytes, leader);
                                 const int wrow = row0 + ii.row_base + kb * kKB;       // 64 reduction rows of W
-                                tma_load_2d_e(W_addr + s * kStageBytes, &tmap_w, W_FULL(s), nb * kNB, wrow, leader);
-                                tma_load_2d_e(W_addr + s * kStageBytes + kBoxBytes, &tmap_w, W_FULL(s), nb * kNB + 64, wrow, leader);
+                                tma_load_2d_e(W_addr + stage_off(s), &tmap_w, W_FULL(s), nb * kNB, wrow, leader);
+                                tma_load_2d_e(W_addr + stage_off(s) + kBoxBytes, &tmap_w, W_FULL(s), nb * kNB + 64, wrow, leader);
                             }
                 }
             }
@@ -195,16 +200,39 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                         ++ready_cnt[slot];
                         tc_fence_after();
                         const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
+                        // N = 256 MMAs over a pair of adjacent ring stages (four 64-column blocks, LBO apart): half the instructions
+                        const bool wide = !(n & 1);
+                        const uint32_t idesc_wide = umma_idesc_bf16_major(kTM, 256, 0u, 1u);
                         for (int kb = 0; kb < n_kb; ++kb) {
                             const uint64_t ad = (slot ? adesc_y : adesc_x) + (uint64_t)(kb * ((kTM * 128) >> 4));
                             const int n_k16 = min(4, (ii.K - kb * kKB) >> 4);
-                            for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
-                                const int s = n % kNStage;
-                                mbar_wait_warp(W_FULL(s), (n / kNStage) & 1);
+                            const uint32_t acc0 = (!fresh || kb) ? 1u : 0u;
+                            if (wide) {
+                                const int s = n & ns_mask;
+                                mbar_wait_warp(W_FULL(s), (n >> ns_log) & 1);
+                                mbar_wait_warp(W_FULL(s + 1), (n >> ns_log) & 1);
                                 tc_fence_after();
-                                const uint64_t bd = bdesc0 + (uint64_t)(s * (kStageBytes >> 4));
+                                const uint64_t bd = bdesc0 + (uint64_t)(int64_t)(stage_off(s) >> 4);
+                                if (n_k16 == 4) {
+                                    umma_bf16_e(d_base, ad, bd, idesc_wide, acc0, leader);
+                                    umma_bf16_e(d_base, ad + 2, bd + 128, idesc_wide, 1u, leader);
+                                    umma_bf16_e(d_base, ad + 4, bd + 256, idesc_wide, 1u, leader);
+                                    umma_bf16_e(d_base, ad + 6, bd + 384, idesc_wide, 1u, leader);
+                                } else {
+                                    for (int k16 = 0; k16 < n_k16; ++k16)
+                                        umma_bf16_e(d_base, ad + 2 * k16, bd + 128 * k16, idesc_wide, (acc0 || k16) ? 1u : 0u, leader);
+                                }
+                                umma_commit_e(W_EMPTY(s), leader);
+                                umma_commit_e(W_EMPTY(s + 1), leader);
+                                n += 2;
+                                continue;
+                            }
+                            for (int nb = 0; nb < kH / kNB; ++nb, ++n) {
+                                const int s = n & ns_mask;
+                                mbar_wait_warp(W_FULL(s), (n >> ns_log) & 1);
+                                tc_fence_after();
+                                const uint64_t bd = bdesc0 + (uint64_t)(int64_t)(stage_off(s) >> 4);
                                 const uint32_t d = d_base + nb * kNB;
-                                const uint32_t acc0 = (!fresh || kb) ? 1u : 0u;
                                 if (n_k16 == 4) {
                                     umma_bf16_e(d, ad, bd, idesc, acc0, leader);
                                     umma_bf16_e(d, ad + 2, bd + 128, idesc, 1u, leader);
@@ -224,7 +252,10 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         }
     } else {
         // =========================== epilogue groups ===========================
-        const int slot = (warp - kEpiWarp0) >> 2;
+        const int group = (warp - kEpiWarp0) >> 2;
+        const int slot = p.paired ? group : 0;
+        const int half = p.paired ? -1 : group;              // one-tile mode: group g handles column half g
+        const int j0 = half > 0 ? 1 : 0, jstep = half >= 0 ? 2 : 1;
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * 256u;
@@ -234,7 +265,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
             const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
-            if (slot == 1 && !has_y) continue;
+            if (p.paired && slot == 1 && !has_y) continue;
             const int tile = p.paired ? 2 * pip + slot : pip;
             const int b = tile * kTM + r;
             const bool row_ok = b < B;
@@ -243,7 +274,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
             const float *drow = p.d_out + prow * D;
             __nv_bfloat16 *dzo_row = p.dzo + prow * p.ADp;
 
-            build_dzo_chunk(p, 0, Arow, r, row_ok, sel, drow, dzo_row);
+            build_dzo_chunk(p, 0, Arow, r, row_ok, sel, drow, dzo_row, j0, jstep);
             fence_proxy_async();
             mbar_arrive(SLOT_READY(slot));
 
@@ -252,7 +283,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                 ++full_cnt;
                 tc_fence_after();
                 if (it + 1 < p.n_chunks) {                       // more output-layer chunks: refill the A slot
-                    build_dzo_chunk(p, it + 1, Arow, r, row_ok, sel, drow, dzo_row);
+                    build_dzo_chunk(p, it + 1, Arow, r, row_ok, sel, drow, dzo_row, j0, jstep);
                     fence_proxy_async();
                     mbar_arrive(SLOT_READY(slot));
                     continue;
@@ -263,9 +294,15 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                 const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + off);
                 uint4 *dz_row = reinterpret_cast<uint4 *>(p.dz + off);
                 const bool write_a = lo > 0;
-                if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a);
-                else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a);
-                else dgrad_epilogue<SFGPI_ACT_TANH>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a);
+                if (half < 0) {
+                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 8>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, 0);
+                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 8>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, 0);
+                    else dgrad_epilogue<SFGPI_ACT_TANH, 8>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, 0);
+                } else {
+                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, half * 128);
+                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, half * 128);
+                    else dgrad_epilogue<SFGPI_ACT_TANH, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, half * 128);
+                }
                 tc_fence_before();
                 if (write_a) {
                     fence_proxy_async();

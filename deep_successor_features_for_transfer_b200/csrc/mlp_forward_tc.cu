@@ -66,16 +66,18 @@ __device__ __forceinline__ float act_apply_fast(float v, int act) {
 
 // One hidden-type epilogue for one row: 256 accumulator columns -> bias + activation -> bf16 -> next layer's A operand.
 // The TMEM load of the next 32 columns is in flight while the current 32 are processed.
-template <int ACT>
+// NCH = 32-column chunks handled by this thread (8: the whole row; 4: one half, when both epilogue groups share a tile),
+// starting at column cbase.
+template <int ACT, int NCH>
 __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save,
-                                                uint4 *save_bf16) {
+                                                uint4 *save_bf16, int cbase) {
     uint32_t v[2][32];
-    tmem_ld32(t_lane, v[0]);
+    tmem_ld32(t_lane + cbase, v[0]);
 #pragma unroll
-    for (int cb = 0; cb < kH / 32; ++cb) {
-        const int c0 = cb * 32;
+    for (int cb = 0; cb < NCH; ++cb) {
+        const int c0 = cbase + cb * 32;
         tmem_wait_ld();
-        if (cb + 1 < kH / 32) tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
+        if (cb + 1 < NCH) tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
         const uint32_t(&u)[32] = v[cb & 1];
         uint32_t pk[16];
 #pragma unroll
@@ -112,6 +114,7 @@ constexpr int kMaxJobs = 3;
 struct TcMulti {
     long long *timeline;             // developer aid (env SFGPI_TIMELINE=1): clock64() stamps of CTA 0's roles, else NULL
     int n_jobs, total_pairs;
+    int paired;                      // 1: two tiles ping-pong per CTA; 0: one tile per CTA (small launches), see kernel header
     int pair_start[kMaxJobs + 1];
     TcParams job[kMaxJobs];
 };
@@ -138,15 +141,20 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
     const uint32_t bias_addr = W_addr + kNStage * kStageBytes;
     const uint32_t bar0 = bias_addr + kBiasFloatsMax * 4;
     // barriers: [0,4) w_full, [4,8) w_empty, [8,10) slot_ready, [10,12) acc_full ; then the TMEM base holder
+    // One-tile-per-CTA mode (launches of <= 148 tiles): the idle Y slot's 64 KB become 4 more weight stages (an 8-deep ring holds
+    // a whole 256x256 layer, so the next layer streams in during the current epilogue) and BOTH epilogue groups work on the one
+    // tile, each on half of the columns.  Stage s lives at W_addr + (s < 4 ? s : s - 8) * 16 KB (s >= 4: inside slot Y).
+    const int ns_log = m.paired ? 2 : 3, ns_mask = (1 << ns_log) - 1;
     auto W_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto W_EMPTY = [&](int s) { return bar0 + 8u * (kNStage + s); };
-    auto SLOT_READY = [&](int s) { return bar0 + 8u * (2 * kNStage + s); };
-    auto ACC_FULL = [&](int s) { return bar0 + 8u * (2 * kNStage + 2 + s); };
-    const uint32_t holder_addr = bar0 + 8u * (2 * kNStage + 4);
+    auto W_EMPTY = [&](int s) { return bar0 + 8u * (8 + s); };
+    auto SLOT_READY = [&](int s) { return bar0 + 8u * (16 + s); };
+    auto ACC_FULL = [&](int s) { return bar0 + 8u * (18 + s); };
+    auto stage_off = [&](int s) { return (s - ((s & 4) << 1)) * kStageBytes; };      // signed byte offset from W_addr
+    const uint32_t holder_addr = bar0 + 8u * 20;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kNStage; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 128); mbar_init(ACC_FULL(s), 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), m.paired ? 128 : 256); mbar_init(ACC_FULL(s), 1); }
         fence_mbar_init();
         for (int j = 0; j < m.n_jobs; ++j) {
             tma_prefetch_desc(&maps.w[j]);
@@ -187,12 +195,12 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot)
                         for (int kb = 0; kb < ii.n_kb; ++kb)
                             for (int nb = 0; nb < nblocks; ++nb, ++n) {
-                                const int s = n % kNStage;
-                                if (s != warp) continue;
-                                mbar_wait_warp(W_EMPTY(s), ((n / kNStage) & 1) ^ 1);
+                                const int s = n & ns_mask;
+                                if ((s & 3) != warp) continue;
+                                mbar_wait_warp(W_EMPTY(s), ((n >> ns_log) & 1) ^ 1);
                                 if (warp == 0 && leader) TL_STAMP(2, tlc);
                                 mbar_arrive_expect_tx_e(W_FULL(s), kStageBytes, leader);
-                                tma_load_2d_e(W_addr + s * kStageBytes, tm, W_FULL(s), kb * kKB, rbase + nb * kNB, leader);
+                                tma_load_2d_e(W_addr + stage_off(s), tm, W_FULL(s), kb * kKB, rbase + nb * kNB, leader);
                             }
                 }
             }
@@ -223,15 +231,41 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         tc_fence_after();
                         if (leader) TL_STAMP(1, tlc);                         // slot ready
                         const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
+                        // A full 256-column layer is issued as N=256 MMAs over a PAIR of adjacent ring stages (rows 0-127 | 128-255
+                        // of the weight block are contiguous in shared memory): half as many instructions for the same math --
+                        // the single issuing thread needs ~107 cycles per tcgen05.mma, more than the 64 an N=128 MMA executes.
+                        const bool wide = nblocks == 2 && ii.n_cols == 256 && !(n & 1);
+                        const uint32_t idesc_wide = umma_idesc_bf16(kTM, 256);
                         for (int kb = 0; kb < ii.n_kb; ++kb) {
                             const uint64_t ad = (slot ? adesc_y : adesc_x) + (uint64_t)(kb * ((kTM * 128) >> 4));
+                            if (wide) {
+                                const int s = n & ns_mask;
+                                mbar_wait_warp(W_FULL(s), (n >> ns_log) & 1);
+                                mbar_wait_warp(W_FULL(s + 1), (n >> ns_log) & 1);
+                                tc_fence_after();
+                                if (leader && kb == 0) TL_STAMP(1, tlc);              // first weight stages landed
+                                const uint64_t bd = bdesc0 + (uint64_t)(int64_t)(stage_off(s) >> 4);
+                                if (ii.n_k16 == 4) {
+                                    umma_bf16_e(d_base, ad, bd, idesc_wide, kb ? 1u : 0u, leader);
+                                    umma_bf16_e(d_base, ad + 2, bd + 2, idesc_wide, 1u, leader);
+                                    umma_bf16_e(d_base, ad + 4, bd + 4, idesc_wide, 1u, leader);
+                                    umma_bf16_e(d_base, ad + 6, bd + 6, idesc_wide, 1u, leader);
+                                } else {
+                                    for (int k16 = 0; k16 < ii.n_k16; ++k16)
+                                        umma_bf16_e(d_base, ad + 2 * k16, bd + 2 * k16, idesc_wide, (kb | k16) ? 1u : 0u, leader);
+                                }
+                                umma_commit_e(W_EMPTY(s), leader);
+                                umma_commit_e(W_EMPTY(s + 1), leader);
+                                n += 2;
+                                continue;
+                            }
                             for (int nb = 0; nb < nblocks; ++nb, ++n) {
-                                const int s = n % kNStage;
-                                mbar_wait_warp(W_FULL(s), (n / kNStage) & 1);
+                                const int s = n & ns_mask;
+                                mbar_wait_warp(W_FULL(s), (n >> ns_log) & 1);
                                 tc_fence_after();
                                 if (leader && kb == 0 && nb == 0) TL_STAMP(1, tlc);   // first weight stage landed
                                 const uint32_t idesc = (nb == nblocks - 1) ? idesc_last : idesc_full;
-                                const uint64_t bd = bdesc0 + (uint64_t)(s * (kStageBytes >> 4));
+                                const uint64_t bd = bdesc0 + (uint64_t)(int64_t)(stage_off(s) >> 4);
                                 const uint32_t d = d_base + nb * kNB;
                                 if (ii.n_k16 == 4) {
                                     umma_bf16_e(d, ad, bd, idesc, kb ? 1u : 0u, leader);
@@ -253,7 +287,9 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
         }
     } else {
         // =========================== epilogue groups ===========================
-        const int slot = (warp - kEpiWarp0) >> 2;           // warps 5-8 -> X, 9-12 -> Y
+        const int group = (warp - kEpiWarp0) >> 2;          // warps 5-8 -> group 0, 9-12 -> group 1
+        const int slot = m.paired ? group : 0;              // paired: group g owns tile slot g; else both share slot 0 ...
+        const int half = m.paired ? -1 : group;             // ... and group g handles column half g of every hidden layer
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int r = quad * 32 + lane;                     // row inside the tile == TMEM lane
         const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..255 among epilogue threads
@@ -280,6 +316,26 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const int tile = p.paired ? 2 * pip + slot : pip;
             const float *P = a.params + (size_t)(a.policy_lo + pl) * net.row_stride;
 
+            const bool active = !(m.paired && slot == 1 && !has_y);   // (uniform per group) nothing to do for Y in this pair
+            const int b = tile * kTM + r;                     // global state index of this thread's row
+            const bool row_ok = b < B;
+
+            // ---------------- stage the state tile as the input layer's A operand (bf16, K padded to 16*ks0) ----------------
+            if (active) {
+                const float *xr = a.x + (size_t)b * S;
+                for (int c = 0; c < (half <= 0 ? p.ks0 * 16 : 0); c += 8) {
+                    float xv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) xv[i] = (row_ok && c + i < S) ? xr[c + i] : 0.0f;
+                    sts128(Arow + a_chunk_off(r, c), pack_bf16x2(xv[0], xv[1]), pack_bf16x2(xv[2], xv[3]),
+                           pack_bf16x2(xv[4], xv[5]), pack_bf16x2(xv[6], xv[7]));
+                }
+                fence_proxy_async();                          // generic-proxy smem writes -> visible to the UMMA (async proxy)
+                mbar_arrive(SLOT_READY(slot));
+                TL_EPI();                                     // state tile staged
+            }
+
+            // Biases AFTER the state tile was handed to the MMA warp: their global-load latency hides behind the input layer.
             if (jb * 65536 + pl != cur_policy) {             // per-(job, policy) biases -> smem (all 256 epilogue threads)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int e = et; e < n_bias; e += 256) {
@@ -294,25 +350,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_policy = jb * 65536 + pl;
             }
-            if (slot == 1 && !has_y) continue;               // (uniform per group) nothing to do for Y in this pair
-
-            const int b = tile * kTM + r;                     // global state index of this thread's row
-            const bool row_ok = b < B;
-
-            // ---------------- stage the state tile as the input layer's A operand (bf16, K padded to 16*ks0) ----------------
-            {
-                const float *xr = a.x + (size_t)b * S;
-                for (int c = 0; c < p.ks0 * 16; c += 8) {
-                    float xv[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) xv[i] = (row_ok && c + i < S) ? xr[c + i] : 0.0f;
-                    sts128(Arow + a_chunk_off(r, c), pack_bf16x2(xv[0], xv[1]), pack_bf16x2(xv[2], xv[3]),
-                           pack_bf16x2(xv[4], xv[5]), pack_bf16x2(xv[6], xv[7]));
-                }
-                fence_proxy_async();                          // generic-proxy smem writes -> visible to the UMMA (async proxy)
-                mbar_arrive(SLOT_READY(slot));
-                TL_EPI();                                     // state tile staged
-            }
+            if (!active) continue;
 
             int sel_base = -(1 << 30);
             if (a.sel_out != nullptr && row_ok) {
@@ -339,28 +377,41 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         ? reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.acts_bf16_out) +
                                                     (((size_t)it * a.n_pol + pl) * B + b) * kH)
                         : nullptr;
-                    if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU>(t_lane, bias, Arow, r, save, save16);
-                    else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE>(t_lane, bias, Arow, r, save, save16);
-                    else hidden_epilogue<SFGPI_ACT_TANH>(t_lane, bias, Arow, r, save, save16);
+                    if (half < 0) {
+                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 8>(t_lane, bias, Arow, r, save, save16, 0);
+                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 8>(t_lane, bias, Arow, r, save, save16, 0);
+                        else hidden_epilogue<SFGPI_ACT_TANH, 8>(t_lane, bias, Arow, r, save, save16, 0);
+                    } else {
+                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 4>(t_lane, bias, Arow, r, save, save16, half * 128);
+                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4>(t_lane, bias, Arow, r, save, save16, half * 128);
+                        else hidden_epilogue<SFGPI_ACT_TANH, 4>(t_lane, bias, Arow, r, save, save16, half * 128);
+                    }
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(SLOT_READY(slot));
                 } else {
                     // -------- output layer chunk --------
                     const uint32_t bias = bias_addr + 4u * ((1 + p.Lh) * kH + ii.col0);
+                    // 8 columns per trip in a rolled loop: this code runs once per tile, so it is instruction-fetch bound and
+                    // compact beats wide.  One-tile mode: psi-form column groups alternate between the two epilogue groups;
+                    // the GPI form carries a running (max, argmax) along the columns, so group 0 scans it alone.
+                    const int c_first = (half == 1) ? (p.gpi ? ii.n_cols : 8) : 0;
+                    const int c_step = (half >= 0 && !p.gpi) ? 16 : 8;
+                    const int ncol = p.nw * A_;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < ii.n_cols; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + c0, v);
+                    for (int c0 = c_first; c0 < ii.n_cols; c0 += c_step) {
+                        uint32_t v[8];
+                        tmem_ld8(t_lane + c0, v);
+                        const float4 b0 = lds128(bias + 4u * c0), b1 = lds128(bias + 4u * (c0 + 4));
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         tmem_wait_ld();
                         if (p.gpi) {
                             // folded GPI: column = wi * A + act
-                            const int ncol = p.nw * A_;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
+                            for (int i = 0; i < 8; ++i) {
                                 const int col = ii.col0 + c0 + i;
                                 if (col < ncol) {
-                                    const float q = __uint_as_float(v[i]) + lds32(bias + 4u * (c0 + i));
+                                    const float q = __uint_as_float(v[i]) + bv[i];
                                     if (wi == 0 && a.q_out != nullptr && row_ok)
                                         a.q_out[((size_t)b * a.n_pol + pl) * A_ + act_i] = q;
                                     if (q > best) { best = q; best_a = act_i; }
@@ -379,14 +430,24 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                                 }
                             }
                         } else {
+                            const int colb = ii.col0 + c0;
+                            float val[8];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = ii.col0 + c0 + i;
-                                if (col < AD && row_ok) {
-                                    const float val = __uint_as_float(v[i]) + lds32(bias + 4u * (c0 + i));
-                                    if (a.psi_out != nullptr) a.psi_out[((size_t)b * a.n_pol + pl) * AD + col] = val;
-                                    const unsigned off = (unsigned)(col - sel_base);
-                                    if (off < (unsigned)D) a.sel_out[((size_t)pl * B + b) * D + off] = val;
+                            for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[i]) + bv[i];
+                            if (row_ok) {
+                                if (a.psi_out != nullptr) {
+                                    float *po = a.psi_out + ((size_t)b * a.n_pol + pl) * AD + colb;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (colb + i < AD) po[i] = val[i];
+                                }
+                                if ((unsigned)(colb + 7 - sel_base) < (unsigned)(D + 7)) {       // group overlaps [sel, sel + D)
+                                    float *so = a.sel_out + ((size_t)pl * B + b) * D;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const unsigned off = (unsigned)(colb + i - sel_base);
+                                        if (off < (unsigned)D) so[off] = val[i];
+                                    }
                                 }
                             }
                         }
@@ -584,6 +645,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     m.timeline = tl_on ? tl_buf : nullptr;
     const int paired = total_tiles > 148 ? 1 : 0;                // small launches: one tile per CTA, no ping-pong partner
     m.total_pairs = 0;
+    m.paired = paired;
     for (int j = 0; j < m.n_jobs; ++j) {
         TcParams &p = m.job[j];
         p.paired = paired;

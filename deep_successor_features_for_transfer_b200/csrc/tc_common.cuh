@@ -169,6 +169,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// 32 lanes x 8 consecutive fp32 columns (compact epilogue loops: small code beats wide loads when the loop body is cold)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in the canonical 128B-swizzled layout: row r at byte r*128, 16-byte chunk j stored at j ^ (r & 7);
 // 8-row groups 1024 B apart (SBO).  Bits: [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,

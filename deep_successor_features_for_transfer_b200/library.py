@@ -296,7 +296,7 @@ class PackedSFLibrary:
                 ws['acts16'], ws['dz16'] = bf(L - 1, n_pol, B, 256), bf(L - 1, n_pol, B, 256)
                 ws['dzo16'], ws['xo16'] = bf(n_pol, B, adp), bf(B, 64)
                 items = (sp.dims[-1] + 127) // 128 + 2 * (L - 1)
-                n_split = _lib.lib().sfgpi_bwd_tc_splits(B, max(1, -(-222 // (items * n_pol))))
+                n_split = _lib.lib().sfgpi_bwd_tc_splits(B, max(1, 148 // (items * n_pol)))      # one wave of CTAs
             ws['n_split'] = n_split
             ws['grad_part'] = torch.zeros(n_pol, n_split, sp.row_stride, dtype=torch.float32, device=self.device)
             if self.G is not None:
