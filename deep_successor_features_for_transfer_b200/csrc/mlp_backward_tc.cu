@@ -141,7 +141,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), p.paired ? 128 : 256); mbar_init(ACC_FULL(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 256); mbar_init(ACC_FULL(s), 1); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_w);
     }
@@ -252,61 +252,63 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         }
     } else {
         // =========================== epilogue groups ===========================
+        // Both groups (8 warps) drain ONE accumulator at a time, each half of the columns, alternating between the two tile
+        // slots -- same reasoning as in the forward kernel (a TMEM drain needs 8 warps in flight to run at its 2048-cycle floor).
         const int group = (warp - kEpiWarp0) >> 2;
-        const int slot = p.paired ? group : 0;
-        const int half = p.paired ? -1 : group;              // one-tile mode: group g handles column half g
-        const int j0 = half > 0 ? 1 : 0, jstep = half >= 0 ? 2 : 1;
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * 256u;
-        const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
-        uint32_t full_cnt = 0;
+        const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t full_cnt[2] = {0, 0};
 
         for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
-            const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
-            if (p.paired && slot == 1 && !has_y) continue;
-            const int tile = p.paired ? 2 * pip + slot : pip;
-            const int b = tile * kTM + r;
-            const bool row_ok = b < B;
-            const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
-            const int sel = row_ok ? (int)p.actions[b] * D : 0;
-            const float *drow = p.d_out + prow * D;
-            __nv_bfloat16 *dzo_row = p.dzo + prow * p.ADp;
-
-            build_dzo_chunk(p, 0, Arow, r, row_ok, sel, drow, dzo_row, j0, jstep);
-            fence_proxy_async();
-            mbar_arrive(SLOT_READY(slot));
+            const int n_slots = (p.paired && (2 * pip + 1 < p.tiles_per_policy)) ? 2 : 1;
+            int bs[2];
+#pragma unroll 1
+            for (int slot = 0; slot < n_slots; ++slot) {
+                const int b = (p.paired ? 2 * pip + slot : pip) * kTM + r;
+                bs[slot] = b;
+                const bool row_ok = b < B;
+                const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
+                const int sel = row_ok ? (int)p.actions[b] * D : 0;
+                build_dzo_chunk(p, 0, sbase + (uint32_t)slot * kABytes, r, row_ok, sel, p.d_out + prow * D, p.dzo + prow * p.ADp,
+                                group, 2);
+                fence_proxy_async();
+                mbar_arrive(SLOT_READY(slot));
+            }
 
             for (int it = 0; it < p.n_items; ++it) {
-                mbar_wait(ACC_FULL(slot), full_cnt & 1);
-                ++full_cnt;
-                tc_fence_after();
-                if (it + 1 < p.n_chunks) {                       // more output-layer chunks: refill the A slot
-                    build_dzo_chunk(p, it + 1, Arow, r, row_ok, sel, drow, dzo_row, j0, jstep);
-                    fence_proxy_async();
-                    mbar_arrive(SLOT_READY(slot));
-                    continue;
-                }
-                const int lo = (it < p.n_chunks) ? p.L - 2 : p.L - 3 - (it - p.n_chunks);    // produces dZ_lo
-                const int act = net.acts[lo];
-                const size_t off = (((size_t)lo * p.n_pol + pl) * B + (row_ok ? b : 0)) * kH;
-                const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + off);
-                uint4 *dz_row = reinterpret_cast<uint4 *>(p.dz + off);
-                const bool write_a = lo > 0;
-                if (half < 0) {
-                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 8>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, 0);
-                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 8>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, 0);
-                    else dgrad_epilogue<SFGPI_ACT_TANH, 8>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, 0);
-                } else {
-                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, half * 128);
-                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, half * 128);
-                    else dgrad_epilogue<SFGPI_ACT_TANH, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, half * 128);
-                }
-                tc_fence_before();
-                if (write_a) {
-                    fence_proxy_async();
-                    mbar_arrive(SLOT_READY(slot));
+#pragma unroll 1
+                for (int slot = 0; slot < n_slots; ++slot) {
+                    const int b = bs[slot];
+                    const bool row_ok = b < B;
+                    const uint32_t t_lane = t_lane0 + (uint32_t)slot * 256u;
+                    const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
+                    mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
+                    ++full_cnt[slot];
+                    tc_fence_after();
+                    if (it + 1 < p.n_chunks) {                   // more output-layer chunks: refill the A slot
+                        const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
+                        const int sel = row_ok ? (int)p.actions[b] * D : 0;
+                        build_dzo_chunk(p, it + 1, Arow, r, row_ok, sel, p.d_out + prow * D, p.dzo + prow * p.ADp, group, 2);
+                        fence_proxy_async();
+                        mbar_arrive(SLOT_READY(slot));
+                        continue;
+                    }
+                    const int lo = (it < p.n_chunks) ? p.L - 2 : p.L - 3 - (it - p.n_chunks);    // produces dZ_lo
+                    const int act = net.acts[lo];
+                    const size_t off = (((size_t)lo * p.n_pol + pl) * B + (row_ok ? b : 0)) * kH;
+                    const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + off);
+                    uint4 *dz_row = reinterpret_cast<uint4 *>(p.dz + off);
+                    const bool write_a = lo > 0;
+                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, group * 128);
+                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, group * 128);
+                    else dgrad_epilogue<SFGPI_ACT_TANH, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, group * 128);
+                    tc_fence_before();
+                    if (write_a) {
+                        fence_proxy_async();
+                        mbar_arrive(SLOT_READY(slot));
+                    }
                 }
             }
         }

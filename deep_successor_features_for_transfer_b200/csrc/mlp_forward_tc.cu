@@ -154,7 +154,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), m.paired ? 128 : 256); mbar_init(ACC_FULL(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 256); mbar_init(ACC_FULL(s), 1); }
         fence_mbar_init();
         for (int j = 0; j < m.n_jobs; ++j) {
             tma_prefetch_desc(&maps.w[j]);
@@ -287,15 +287,16 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
         }
     } else {
         // =========================== epilogue groups ===========================
+        // All 8 epilogue warps work on ONE accumulator at a time, each group on half of the columns: draining a 128 x 256 fp32
+        // accumulator is TMEM-read-bound (~2048 cycles, as long as the MMAs that produced it) only with 8 warps in flight;
+        // 4 warps need 3100-4100 cycles (measured, clock64 timeline) and would pace the whole kernel.  With two tiles per
+        // CTA the groups alternate X, Y, X, ... while the tensor core works on the other slot.
         const int group = (warp - kEpiWarp0) >> 2;          // warps 5-8 -> group 0, 9-12 -> group 1
-        const int slot = m.paired ? group : 0;              // paired: group g owns tile slot g; else both share slot 0 ...
-        const int half = m.paired ? -1 : group;             // ... and group g handles column half g of every hidden layer
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int r = quad * 32 + lane;                     // row inside the tile == TMEM lane
         const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..255 among epilogue threads
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * 256u;
-        const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
-        uint32_t full_cnt = 0;
+        const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t full_cnt[2] = {0, 0};
         int cur_policy = -1;
         int tlc = 0;
         const int tl_role = (et == 0) ? 0 : ((et == 128) ? 3 : -1);
@@ -312,150 +313,162 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const int n_bias = (1 + p.Lh) * kH + p.n_final;     // [b_0 | b_1..b_Lh | b_final]
             const int pair = gpair - m.pair_start[jb];
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
-            const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
-            const int tile = p.paired ? 2 * pip + slot : pip;
+            const int n_slots = (p.paired && (2 * pip + 1 < p.tiles_per_policy)) ? 2 : 1;
             const float *P = a.params + (size_t)(a.policy_lo + pl) * net.row_stride;
 
-            const bool active = !(m.paired && slot == 1 && !has_y);   // (uniform per group) nothing to do for Y in this pair
-            const int b = tile * kTM + r;                     // global state index of this thread's row
-            const bool row_ok = b < B;
-
-            // ---------------- stage the state tile as the input layer's A operand (bf16, K padded to 16*ks0) ----------------
-            if (active) {
-                const float *xr = a.x + (size_t)b * S;
-                for (int c = 0; c < (half <= 0 ? p.ks0 * 16 : 0); c += 8) {
-                    float xv[8];
+            int bs[2], sel_base[2];
+            // ---------------- stage the state tiles as the input layer's A operands (bf16, K padded to 16*ks0) ----------------
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) xv[i] = (row_ok && c + i < S) ? xr[c + i] : 0.0f;
-                    sts128(Arow + a_chunk_off(r, c), pack_bf16x2(xv[0], xv[1]), pack_bf16x2(xv[2], xv[3]),
-                           pack_bf16x2(xv[4], xv[5]), pack_bf16x2(xv[6], xv[7]));
+            for (int slot = 0; slot < 2; ++slot) {
+                if (slot >= n_slots) break;
+                const int b = ((p.paired ? 2 * pip + slot : pip)) * kTM + r;     // global state index of this thread's row
+                const bool row_ok = b < B;
+                bs[slot] = b;
+                if (group == 0) {
+                    const float *xr = a.x + (size_t)b * S;
+                    const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
+                    for (int c = 0; c < p.ks0 * 16; c += 8) {
+                        float xv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xv[i] = (row_ok && c + i < S) ? xr[c + i] : 0.0f;
+                        sts128(Arow + a_chunk_off(r, c), pack_bf16x2(xv[0], xv[1]), pack_bf16x2(xv[2], xv[3]),
+                               pack_bf16x2(xv[4], xv[5]), pack_bf16x2(xv[6], xv[7]));
+                    }
+                    fence_proxy_async();                      // generic-proxy smem writes -> visible to the UMMA (async proxy)
                 }
-                fence_proxy_async();                          // generic-proxy smem writes -> visible to the UMMA (async proxy)
                 mbar_arrive(SLOT_READY(slot));
-                TL_EPI();                                     // state tile staged
+                sel_base[slot] = -(1 << 30);
+                if (a.sel_out != nullptr && row_ok) {
+                    const int sidx = a.sel_actions ? (int)a.sel_actions[b]
+                                                   : (int)key_index(a.sel_keys[(size_t)pl * a.sel_key_stride + b]);
+                    sel_base[slot] = sidx * D;
+                }
             }
+            TL_EPI();                                         // state tiles staged
 
-            // Biases AFTER the state tile was handed to the MMA warp: their global-load latency hides behind the input layer.
+            // Biases AFTER the state tiles were handed to the MMA warp: their global-load latency hides behind the input layer.
             if (jb * 65536 + pl != cur_policy) {             // per-(job, policy) biases -> smem (all 256 epilogue threads)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int e = et; e < n_bias; e += 256) {
-                    float v;
-                    if (e < (1 + p.Lh) * kH) v = P[net.b_off[e >> 8] + (e & 255)];
-                    else {
-                        const int c = e - (1 + p.Lh) * kH;
-                        v = p.gpi ? p.bq[(size_t)pl * p.n_final + c] : (c < AD ? P[net.b_off[L - 1] + c] : 0.0f);
+                for (int e0 = et; e0 < n_bias; e0 += 4 * 256) {       // 4 independent loads in flight per thread
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * 256;
+                        v[u] = 0.0f;
+                        if (e < (1 + p.Lh) * kH) v[u] = P[net.b_off[e >> 8] + (e & 255)];
+                        else if (e < n_bias) {
+                            const int c = e - (1 + p.Lh) * kH;
+                            v[u] = p.gpi ? p.bq[(size_t)pl * p.n_final + c] : (c < AD ? P[net.b_off[L - 1] + c] : 0.0f);
+                        }
                     }
-                    sts32(bias_addr + 4u * e, v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (e0 + u * 256 < n_bias) sts32(bias_addr + 4u * (e0 + u * 256), v[u]);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_policy = jb * 65536 + pl;
             }
-            if (!active) continue;
 
-            int sel_base = -(1 << 30);
-            if (a.sel_out != nullptr && row_ok) {
-                const int sidx = a.sel_actions ? (int)a.sel_actions[b]
-                                               : (int)key_index(a.sel_keys[(size_t)pl * a.sel_key_stride + b]);
-                sel_base = sidx * D;
-            }
-            // GPI running state (folded form): columns are (reward vector wi, action act)
+            // GPI running state (folded form): columns are (reward vector wi, action act); group g scans slot g
             float best = -INFINITY;
             int best_a = 0, wi = 0, act_i = 0;
 
             for (int it = 0; it < p.n_items; ++it) {
                 const ItemInfo ii = item_info(p, it);
-                mbar_wait(ACC_FULL(slot), full_cnt & 1);
-                ++full_cnt;
-                tc_fence_after();
-                TL_EPI();                                     // accumulator of item `it` complete
-                if (ii.kind != 2) {
-                    // -------- input / hidden layer: bias + act, bf16, write next A operand (in place), optional save --------
-                    const uint32_t bias = bias_addr + 4u * (it * kH);
-                    const int act = net.acts[it];
-                    float *save = (a.acts_out[it] && row_ok) ? a.acts_out[it] + ((size_t)pl * B + b) * kH : nullptr;
-                    uint4 *save16 = (a.acts_bf16_out && row_ok)
-                        ? reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.acts_bf16_out) +
-                                                    (((size_t)it * a.n_pol + pl) * B + b) * kH)
-                        : nullptr;
-                    if (half < 0) {
-                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 8>(t_lane, bias, Arow, r, save, save16, 0);
-                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 8>(t_lane, bias, Arow, r, save, save16, 0);
-                        else hidden_epilogue<SFGPI_ACT_TANH, 8>(t_lane, bias, Arow, r, save, save16, 0);
-                    } else {
-                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 4>(t_lane, bias, Arow, r, save, save16, half * 128);
-                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4>(t_lane, bias, Arow, r, save, save16, half * 128);
-                        else hidden_epilogue<SFGPI_ACT_TANH, 4>(t_lane, bias, Arow, r, save, save16, half * 128);
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(SLOT_READY(slot));
-                } else {
-                    // -------- output layer chunk --------
-                    const uint32_t bias = bias_addr + 4u * ((1 + p.Lh) * kH + ii.col0);
-                    // 8 columns per trip in a rolled loop: this code runs once per tile, so it is instruction-fetch bound and
-                    // compact beats wide.  One-tile mode: psi-form column groups alternate between the two epilogue groups;
-                    // the GPI form carries a running (max, argmax) along the columns, so group 0 scans it alone.
-                    const int c_first = (half == 1) ? (p.gpi ? ii.n_cols : 8) : 0;
-                    const int c_step = (half >= 0 && !p.gpi) ? 16 : 8;
-                    const int ncol = p.nw * A_;
 #pragma unroll 1
-                    for (int c0 = c_first; c0 < ii.n_cols; c0 += c_step) {
-                        uint32_t v[8];
-                        tmem_ld8(t_lane + c0, v);
-                        const float4 b0 = lds128(bias + 4u * c0), b1 = lds128(bias + 4u * (c0 + 4));
-                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        tmem_wait_ld();
-                        if (p.gpi) {
-                            // folded GPI: column = wi * A + act
+                for (int slot = 0; slot < n_slots; ++slot) {
+                    const int b = bs[slot];
+                    const bool row_ok = b < B;
+                    const uint32_t t_lane = t_lane0 + (uint32_t)slot * 256u;
+                    const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
+                    mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
+                    ++full_cnt[slot];
+                    tc_fence_after();
+                    TL_EPI();                                 // accumulator of (item, slot) complete
+                    if (ii.kind != 2) {
+                        // ------ input / hidden layer: bias + act, bf16, write next A operand (in place), optional save ------
+                        const uint32_t bias = bias_addr + 4u * (it * kH);
+                        const int act = net.acts[it];
+                        float *save = (a.acts_out[it] && row_ok) ? a.acts_out[it] + ((size_t)pl * B + b) * kH : nullptr;
+                        uint4 *save16 = (a.acts_bf16_out && row_ok)
+                            ? reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.acts_bf16_out) +
+                                                        (((size_t)it * a.n_pol + pl) * B + b) * kH)
+                            : nullptr;
+                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 4>(t_lane, bias, Arow, r, save, save16, group * 128);
+                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4>(t_lane, bias, Arow, r, save, save16, group * 128);
+                        else hidden_epilogue<SFGPI_ACT_TANH, 4>(t_lane, bias, Arow, r, save, save16, group * 128);
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(SLOT_READY(slot));
+                    } else {
+                        // ------ output layer chunk ------
+                        const uint32_t bias = bias_addr + 4u * ((1 + p.Lh) * kH + ii.col0);
+                        // 8 columns per trip in a rolled loop: this code runs once per tile, so it is instruction-fetch bound
+                        // and compact beats wide.  psi form: column groups alternate between the two epilogue groups; GPI form:
+                        // a running (max, argmax) is carried along the columns, so ONE group scans a slot (group g: slot g).
+                        const int c_first = p.gpi ? (group == slot ? 0 : ii.n_cols) : group * 8;
+                        const int c_step = p.gpi ? 8 : 16;
+                        const int ncol = p.nw * A_;
+                        const int sb = sel_base[slot];
+#pragma unroll 1
+                        for (int c0 = c_first; c0 < ii.n_cols; c0 += c_step) {
+                            uint32_t v[8];
+                            tmem_ld8(t_lane + c0, v);
+                            const float4 b0 = lds128(bias + 4u * c0), b1 = lds128(bias + 4u * (c0 + 4));
+                            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            tmem_wait_ld();
+                            if (p.gpi) {
+                                // folded GPI: column = wi * A + act
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int col = ii.col0 + c0 + i;
-                                if (col < ncol) {
-                                    const float q = __uint_as_float(v[i]) + bv[i];
-                                    if (wi == 0 && a.q_out != nullptr && row_ok)
-                                        a.q_out[((size_t)b * a.n_pol + pl) * A_ + act_i] = q;
-                                    if (q > best) { best = q; best_a = act_i; }
-                                    if (++act_i == A_) {
-                                        if (row_ok) {
-                                            const int krow = a.w_diag ? pl : wi;
-                                            if (a.key_action)
-                                                atomicMax(reinterpret_cast<long long *>(a.key_action) + (size_t)krow * B + b,
-                                                          pack_key(best, (uint32_t)best_a));
-                                            if (a.key_task)
-                                                atomicMax(reinterpret_cast<long long *>(a.key_task) + (size_t)krow * B + b,
-                                                          pack_key(best, (uint32_t)(a.task_base + pl)));
+                                for (int i = 0; i < 8; ++i) {
+                                    const int col = ii.col0 + c0 + i;
+                                    if (col < ncol) {
+                                        const float q = __uint_as_float(v[i]) + bv[i];
+                                        if (wi == 0 && a.q_out != nullptr && row_ok)
+                                            a.q_out[((size_t)b * a.n_pol + pl) * A_ + act_i] = q;
+                                        if (q > best) { best = q; best_a = act_i; }
+                                        if (++act_i == A_) {
+                                            if (row_ok) {
+                                                const int krow = a.w_diag ? pl : wi;
+                                                if (a.key_action)
+                                                    atomicMax(reinterpret_cast<long long *>(a.key_action) + (size_t)krow * B + b,
+                                                              pack_key(best, (uint32_t)best_a));
+                                                if (a.key_task)
+                                                    atomicMax(reinterpret_cast<long long *>(a.key_task) + (size_t)krow * B + b,
+                                                              pack_key(best, (uint32_t)(a.task_base + pl)));
+                                            }
+                                            act_i = 0; ++wi; best = -INFINITY; best_a = 0;
                                         }
-                                        act_i = 0; ++wi; best = -INFINITY; best_a = 0;
                                     }
                                 }
-                            }
-                        } else {
-                            const int colb = ii.col0 + c0;
-                            float val[8];
+                            } else {
+                                const int colb = ii.col0 + c0;
+                                float val[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[i]) + bv[i];
-                            if (row_ok) {
-                                if (a.psi_out != nullptr) {
-                                    float *po = a.psi_out + ((size_t)b * a.n_pol + pl) * AD + colb;
+                                for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[i]) + bv[i];
+                                if (row_ok) {
+                                    if (a.psi_out != nullptr) {
+                                        float *po = a.psi_out + ((size_t)b * a.n_pol + pl) * AD + colb;
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
-                                        if (colb + i < AD) po[i] = val[i];
-                                }
-                                if ((unsigned)(colb + 7 - sel_base) < (unsigned)(D + 7)) {       // group overlaps [sel, sel + D)
-                                    float *so = a.sel_out + ((size_t)pl * B + b) * D;
+                                        for (int i = 0; i < 8; ++i)
+                                            if (colb + i < AD) po[i] = val[i];
+                                    }
+                                    if ((unsigned)(colb + 7 - sb) < (unsigned)(D + 7)) {         // group overlaps [sel, sel + D)
+                                        float *so = a.sel_out + ((size_t)pl * B + b) * D;
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const unsigned off = (unsigned)(colb + i - sel_base);
-                                        if (off < (unsigned)D) so[off] = val[i];
+                                        for (int i = 0; i < 8; ++i) {
+                                            const unsigned off = (unsigned)(colb + i - sb);
+                                            if (off < (unsigned)D) so[off] = val[i];
+                                        }
                                     }
                                 }
                             }
                         }
+                        tc_fence_before();
+                        if (it + 1 < p.n_items) mbar_arrive(SLOT_READY(slot));     // next chunk may overwrite the accumulator
                     }
-                    tc_fence_before();
-                    if (it + 1 < p.n_items) mbar_arrive(SLOT_READY(slot));     // next chunk may overwrite the accumulator
+                    TL_EPI();                                 // epilogue of (item, slot) done
                 }
-                TL_EPI();                                     // epilogue of item `it` done
             }
         }
     }
