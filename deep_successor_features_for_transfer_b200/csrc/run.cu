@@ -13,6 +13,9 @@ extern "C" int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream) {
         switch (c.op) {
             case SFGPI_OP_NOP:
                 break;
+            case SFGPI_OP_EVENT:
+                if (cudaEventRecord(reinterpret_cast<cudaEvent_t>(c.p[0]), st) != cudaSuccess) rc = check_launch("sfgpi_run(event)");
+                break;
             case SFGPI_OP_H2D:
                 if (cudaMemcpyAsync(c.p[0], c.p[1], (size_t)c.i[0], cudaMemcpyHostToDevice, st) != cudaSuccess) rc = check_launch("sfgpi_run(h2d)");
                 break;

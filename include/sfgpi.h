@@ -274,6 +274,7 @@ int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 #define SFGPI_OP_BACKWARD 10        /* p0 = sfgpi_backward_args */
 #define SFGPI_OP_BACKWARD_TC 11     /* p0 = sfgpi_backward_tc_args */
 #define SFGPI_OP_ADAM 12            /* p0 = sfgpi_adam_args */
+#define SFGPI_OP_EVENT 13           /* p0 = cudaEvent_t: cudaEventRecord on the stream (timing probes around a command) */
 typedef struct {
     int32_t op;
     void *p[5];
