@@ -71,11 +71,21 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
 
     // u = g(s) + g(s') = Wg (s + s') + 2 bg                                   (tsfdqn.py:621-622)
     if (tsf) {
-        for (int e = tid; e < kTdRows * G; e += kTdThreads) {
-            int r = e / G, g = e - r * G;
-            float acc = 2.0f * bg_s[g];
-            for (int s = 0; s < S; ++s) acc = fmaf(Wg_s[g * S + s], ss_s[r * S + s], acc);
-            u_s[e] = acc;
+        // thread = one g column, 4 rows per trip: each weight is read once per 4 FMAs and there is no per-element division
+        for (int g = tid; g < G; g += kTdThreads) {
+            const float b2 = 2.0f * bg_s[g];
+            const float *wg = Wg_s + g * S;
+            for (int r = 0; r < kTdRows; r += 4) {
+                float a0 = b2, a1 = b2, a2 = b2, a3 = b2;
+                for (int s = 0; s < S; ++s) {
+                    const float w = wg[s];
+                    a0 = fmaf(w, ss_s[(r + 0) * S + s], a0);
+                    a1 = fmaf(w, ss_s[(r + 1) * S + s], a1);
+                    a2 = fmaf(w, ss_s[(r + 2) * S + s], a2);
+                    a3 = fmaf(w, ss_s[(r + 3) * S + s], a3);
+                }
+                u_s[(r + 0) * G + g] = a0; u_s[(r + 1) * G + g] = a1; u_s[(r + 2) * G + g] = a2; u_s[(r + 3) * G + g] = a3;
+            }
         }
         __syncthreads();
     }
@@ -157,31 +167,53 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
     __syncthreads();
     float *daff_s = diff_s;
     // du = daff . Wh
-    for (int e = tid; e < kTdRows * G; e += kTdThreads) {
-        int r = e / G, g = e - r * G;
-        float acc = 0.0f;
-        for (int d = 0; d < D; ++d) acc = fmaf(daff_s[r * D + d], Wh_s[d * G + g], acc);
-        du_s[e] = acc;
+    for (int g = tid; g < G; g += kTdThreads) {
+        for (int r = 0; r < kTdRows; r += 4) {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            for (int d = 0; d < D; ++d) {
+                const float w = Wh_s[d * G + g];
+                a0 = fmaf(daff_s[(r + 0) * D + d], w, a0);
+                a1 = fmaf(daff_s[(r + 1) * D + d], w, a1);
+                a2 = fmaf(daff_s[(r + 2) * D + d], w, a2);
+                a3 = fmaf(daff_s[(r + 3) * D + d], w, a3);
+            }
+            du_s[(r + 0) * G + g] = a0; du_s[(r + 1) * G + g] = a1; du_s[(r + 2) * G + g] = a2; du_s[(r + 3) * G + g] = a3;
+        }
     }
     __syncthreads();
     // parameter gradients: g.W [G][S], g.b [G], h.W [D][G], h.b [D]
     float *gW = gpart + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
-    for (int e = tid; e < G * S; e += kTdThreads) {
-        int g = e / S, s = e - g * S;
-        float acc = 0.0f;
-        for (int r = 0; r < kTdRows; ++r) acc = fmaf(du_s[r * G + g], ss_s[r * S + s], acc);
-        gW[e] = acc;
-    }
+    // thread = one g column; 4 outputs (4 s / 4 d) per trip share each du / u load
     for (int g = tid; g < G; g += kTdThreads) {
-        float acc = 0.0f;
-        for (int r = 0; r < kTdRows; ++r) acc += du_s[r * G + g];
-        gb[g] = 2.0f * acc;
-    }
-    for (int e = tid; e < D * G; e += kTdThreads) {
-        int d = e / G, g = e - d * G;
-        float acc = 0.0f;
-        for (int r = 0; r < kTdRows; ++r) acc = fmaf(daff_s[r * D + d], u_s[r * G + g], acc);
-        hW[e] = acc;
+        float accb = 0.0f;
+        for (int r = 0; r < kTdRows; ++r) accb += du_s[r * G + g];
+        gb[g] = 2.0f * accb;
+        for (int s0 = 0; s0 < S; s0 += 4) {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            const int s1 = min(s0 + 1, S - 1), s2 = min(s0 + 2, S - 1), s3 = min(s0 + 3, S - 1);
+            for (int r = 0; r < kTdRows; ++r) {
+                const float v = du_s[r * G + g];
+                const float *sr = ss_s + r * S;
+                a0 = fmaf(v, sr[s0], a0); a1 = fmaf(v, sr[s1], a1); a2 = fmaf(v, sr[s2], a2); a3 = fmaf(v, sr[s3], a3);
+            }
+            gW[g * S + s0] = a0;
+            if (s0 + 1 < S) gW[g * S + s0 + 1] = a1;
+            if (s0 + 2 < S) gW[g * S + s0 + 2] = a2;
+            if (s0 + 3 < S) gW[g * S + s0 + 3] = a3;
+        }
+        for (int d0 = 0; d0 < D; d0 += 4) {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            const int d1 = min(d0 + 1, D - 1), d2 = min(d0 + 2, D - 1), d3 = min(d0 + 3, D - 1);
+            for (int r = 0; r < kTdRows; ++r) {
+                const float v = u_s[r * G + g];
+                const float *dr = daff_s + r * D;
+                a0 = fmaf(dr[d0], v, a0); a1 = fmaf(dr[d1], v, a1); a2 = fmaf(dr[d2], v, a2); a3 = fmaf(dr[d3], v, a3);
+            }
+            hW[d0 * G + g] = a0;
+            if (d0 + 1 < D) hW[(d0 + 1) * G + g] = a1;
+            if (d0 + 2 < D) hW[(d0 + 2) * G + g] = a2;
+            if (d0 + 3 < D) hW[(d0 + 3) * G + g] = a3;
+        }
     }
     for (int d = tid; d < D; d += kTdThreads) {
         float acc = 0.0f;
