@@ -49,6 +49,8 @@ __device__ __forceinline__ float sum_partials(const float *__restrict__ gp, int 
 
 __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constant__ sfgpi_adam_args a, int blocks_per_pol) {
     __shared__ float sqrt_bc2_s, step_size_s[SFGPI_MAX_SEGMENTS];
+    pdl_launch_dependents();
+    pdl_wait();
     const int p = blockIdx.y;                               // optimizer (policy slot)
     // ---- losses (block 0 of each optimizer): fixed-order sum of the TD kernel's per-CTA partials ----
     if (blockIdx.x == 0 && a.loss_part != nullptr && threadIdx.x < 32) {
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
 
 // step += 1 and, when the caller keeps them, the bias corrections of the step after that
 __global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double beta1, double beta2) {
+    pdl_launch_dependents();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const int s = step[i] + 1;
@@ -173,9 +177,9 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     if (blocks > cap) blocks = cap < 1 ? 1 : cap;
     dim3 grid(blocks, a.n_pol);
     cudaStream_t st = (cudaStream_t)stream;
-    adam_kernel<<<grid, kAdamThreads, 0, st>>>(a, blocks);
+    launch_pdl(adam_kernel, grid, dim3(kAdamThreads), 0, st, a, blocks);
     int rc = check_launch("sfgpi_adam_step");
     if (rc) return rc;
-    adam_finish_kernel<<<(a.n_pol + 127) / 128, 128, 0, st>>>(a.step, a.consts, a.n_pol, a.beta1, a.beta2);
+    launch_pdl(adam_finish_kernel, dim3((a.n_pol + 127) / 128), dim3(128), 0, st, a.step, a.consts, a.n_pol, a.beta1, a.beta2);
     return check_launch("sfgpi_adam_step(finish)");
 }

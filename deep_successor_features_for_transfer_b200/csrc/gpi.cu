@@ -1,6 +1,7 @@
 // GPI helpers: packed-key fill / decode, the unfused GPI epilogue on a materialised psi, error plumbing.
 #include <stdarg.h>
 #include <limits.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sfgpi {
@@ -14,6 +15,11 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+bool pdl_enabled() {
+    static const bool on = getenv("SFGPI_NO_PDL") == nullptr;
+    return on;
+}
+
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -24,6 +30,8 @@ int check_launch(const char *what) {
 }
 
 __global__ void keys_fill_kernel(long long *keys, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) keys[i] = LLONG_MIN;
@@ -98,7 +106,7 @@ extern "C" int sfgpi_keys_fill(int64_t *keys, int64_t n, void *stream) {
     if (n <= 0) return SFGPI_OK;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    keys_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(keys), (long long)n);
+    launch_pdl(keys_fill_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<long long *>(keys), (long long)n);
     return check_launch("sfgpi_keys_fill");
 }
 

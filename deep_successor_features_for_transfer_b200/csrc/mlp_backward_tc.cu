@@ -122,6 +122,7 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, i
 __global__ void __launch_bounds__(kThreadsDg, 1)
 mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ CUtensorMap tmap_w) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch_dependents();
     const sfgpi_net_desc &net = p.net;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -151,6 +152,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
+    pdl_wait();
 
     const int B = p.B, D = net.n_features;
 
@@ -346,6 +348,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
                     const __grid_constant__ CUtensorMap tmap_dzo, const __grid_constant__ CUtensorMap tmap_acts,
                     const __grid_constant__ CUtensorMap tmap_xo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch_dependents();
     const sfgpi_net_desc &net = p.net;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem_raw);
@@ -378,6 +381,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
+    pdl_wait();
 
     if (warp < kWgStages) {
         {
@@ -481,6 +485,8 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
 
 // xo[b][c] = x[b][c] for c < S, 1 for c == S, 0 otherwise  (bf16 [B][64])
 __global__ void build_xo_kernel(const float *__restrict__ x, int B, int S, __nv_bfloat16 *__restrict__ xo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * kXoCols) return;
     const int b = i / kXoCols, c = i - b * kXoCols;
@@ -541,7 +547,7 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     cudaStream_t st = (cudaStream_t)stream;
     const int AD = net.n_actions * net.n_features, ADp = sfgpi_bwd_tc_out_pad(&net), S = net.dims[0];
 
-    build_xo_kernel<<<(a.B * kXoCols + 255) / 256, 256, 0, st>>>(a.x, a.B, S, reinterpret_cast<__nv_bfloat16 *>(a.xo_bf16));
+    launch_pdl(build_xo_kernel, dim3((a.B * kXoCols + 255) / 256), dim3(256), 0, st, a.x, a.B, S, reinterpret_cast<__nv_bfloat16 *>(a.xo_bf16));
     int rc = check_launch("sfgpi_mlp_backward_tc(xo)");
     if (rc) return rc;
 
@@ -573,7 +579,7 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     const int dg_smem = 2 * kABytes + kNStage * kStageBytes + 256;
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem); cfg = true; }
-    mlp_dgrad_tc_kernel<<<dp.total_pairs < 148 ? dp.total_pairs : 148, kThreadsDg, dg_smem, st>>>(dp, tmap_w);
+    launch_pdl(mlp_dgrad_tc_kernel, dim3(dp.total_pairs < 148 ? dp.total_pairs : 148), dim3(kThreadsDg), dg_smem, st, dp, tmap_w);
     rc = check_launch("sfgpi_mlp_backward_tc(dgrad)");
     if (rc) return rc;
 
@@ -601,6 +607,6 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     static bool cfg2 = false;
     if (!cfg2) { cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem); cfg2 = true; }
     dim3 grid(wp.items_per_policy * a.n_split, a.n_pol);
-    mlp_wgrad_tc_kernel<<<grid, kWgThreads, wg_smem, st>>>(wp, tm_dz, tm_dzo, tm_acts, tm_xo);
+    launch_pdl(mlp_wgrad_tc_kernel, grid, dim3(kWgThreads), wg_smem, st, wp, tm_dz, tm_dzo, tm_acts, tm_xo);
     return check_launch("sfgpi_mlp_backward_tc(wgrad)");
 }

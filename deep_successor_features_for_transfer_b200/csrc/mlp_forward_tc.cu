@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ TmapSet maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     if (m.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) m.timeline[255] = clock64();      // kernel entry
 
     // ---- carve-up: [A slot X 64K][A slot Y 64K][weight ring 4 x 16K][biases 24K][barriers] ----
@@ -167,6 +168,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
+    pdl_wait();                                              // set-up above overlapped the predecessor's tail
 
 
     if (warp < kNStage) {
@@ -487,6 +489,8 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 //   rows [0,256) W_0 (columns >= S zero), then hidden W_1..W_Lh, then W_out padded to n3pad rows.
 __global__ void pack_bf16_kernel(sfgpi_net_desc net, const float *__restrict__ params, int policy_lo, int n_pol,
                                  __nv_bfloat16 *__restrict__ out, int rows_per_policy, int Lh) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int AD = net.n_actions * net.n_features, L = net.n_layers, S = net.dims[0];
     const size_t total = (size_t)n_pol * rows_per_policy * kH;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -514,6 +518,8 @@ __global__ void pack_bf16_kernel(sfgpi_net_desc net, const float *__restrict__ p
 __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const float *__restrict__ params, int policy_lo,
                                                        const float *__restrict__ w, int nw, int w_diag, int nqpad,
                                                        __nv_bfloat16 *__restrict__ wq, float *__restrict__ bq) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int pl = blockIdx.y, row = blockIdx.x, k = threadIdx.x;
     const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
     const float *P = params + (size_t)(policy_lo + pl) * net.row_stride;
@@ -579,8 +585,8 @@ extern "C" int sfgpi_pack_bf16(const sfgpi_net_desc *net, const float *params, i
     const size_t total = (size_t)n_pol * rpp * kH;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    pack_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*net, params, policy_lo, n_pol,
-                                                               reinterpret_cast<__nv_bfloat16 *>(out_bf16), rpp, Lh);
+    launch_pdl(pack_bf16_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, *net, params, policy_lo, n_pol,
+               reinterpret_cast<__nv_bfloat16 *>(out_bf16), rpp, Lh);
     return check_launch("sfgpi_pack_bf16");
 }
 
@@ -595,8 +601,8 @@ extern "C" int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, in
     if (nw < 1) { set_error("sfgpi_fold_gpi: n_w must be >= 1"); return SFGPI_E_INVALID; }
     const int nqpad = sfgpi_gpi_fold_rows(net, nw);
     dim3 grid(nqpad, n_pol);
-    fold_gpi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*net, params, policy_lo, w, nw, w_diag, nqpad,
-                                                             reinterpret_cast<__nv_bfloat16 *>(wq_out), bq_out);
+    launch_pdl(fold_gpi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *net, params, policy_lo, w, nw, w_diag, nqpad,
+               reinterpret_cast<__nv_bfloat16 *>(wq_out), bq_out);
     return check_launch("sfgpi_fold_gpi");
 }
 
@@ -673,7 +679,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); cfg = true; }
     const int grid = m.total_pairs < 148 ? m.total_pairs : 148;
-    mlp_forward_tc_kernel<<<grid, kThreadsTc, smem_bytes, (cudaStream_t)stream>>>(m, maps);
+    launch_pdl(mlp_forward_tc_kernel, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, m, maps);
     if (tl_on) {                                                 // developer aid: dump CTA 0's role timelines (cycles since t0)
         long long h[256];
         cudaStreamSynchronize((cudaStream_t)stream);

@@ -20,6 +20,8 @@ constexpr int kTdCluster = 8;     // CTAs per cluster (portable maximum)
 __global__ void __cluster_dims__(kTdCluster, 1, 1) __launch_bounds__(kTdThreads)
 td_kernel(const __grid_constant__ sfgpi_td_args a) {
     extern __shared__ __align__(16) float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const int B = a.B, S = a.S, D = a.D, G = a.G;
@@ -262,6 +264,6 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     if (bytes > (size_t)kMaxSmem) { set_error("sfgpi_td_step: D/G too large for shared memory (%zu B)", bytes); return SFGPI_E_SMEM; }
     if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     dim3 grid(sfgpi_td_partials(a.B) * kTdCluster, a.n_pol);
-    td_kernel<<<grid, kTdThreads, bytes, (cudaStream_t)stream>>>(a);
+    launch_pdl(td_kernel, grid, dim3(kTdThreads), bytes, (cudaStream_t)stream, a);
     return check_launch("sfgpi_td_step");
 }
