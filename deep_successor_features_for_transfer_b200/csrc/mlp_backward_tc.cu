@@ -35,6 +35,7 @@ struct DgParams {
     const long long *actions;        // [B]
     const float *d_out;              // [n_pol][B][D]
     const __nv_bfloat16 *acts;       // [L-1][n_pol][B][256]
+    const uint32_t *masks;           // [L-1][n_pol][B][8] ReLU sign bits written by the forward (NULL: derive from acts)
     __nv_bfloat16 *dz;               // [L-1][n_pol][B][256]
     __nv_bfloat16 *dzo;              // [n_pol][B][ADp]
     int rows_per_policy, L, AD, AD16, ADp, n_chunks, n_items;
@@ -67,19 +68,27 @@ __device__ __forceinline__ void build_dzo_chunk(const DgParams &p, int c, uint32
         }
         const uint32_t q0 = pack_bf16x2(v[0], v[1]), q1 = pack_bf16x2(v[2], v[3]), q2 = pack_bf16x2(v[4], v[5]),
                        q3 = pack_bf16x2(v[6], v[7]);
-        sts128(Arow + a_chunk_off(r, j * 8), q0, q1, q2, q3);
-        if (row_ok) *reinterpret_cast<uint4 *>(dzo_row + col0) = make_uint4(q0, q1, q2, q3);
+        sts128(Arow + a_chunk_off(r, j * 8), q0, q1, q2, q3);      // the tile is stored to dzo by TMA (see the epilogue)
     }
 }
 
 // dZ_lo = acc * act'(act_lo): 256 accumulator columns of one row -> bf16 -> next A operand (in place) + HBM row.
-// NCH = 32-column chunks handled by this thread starting at column cbase (8 = whole row; 4 = one half, one-tile mode).
+// dZ_lo = acc * act'(act_lo) for NCH 32-column chunks starting at cbase: bf16 -> A slot (next layer's operand AND the tile that a
+// bulk tensor store writes to dz[lo]).  ReLU: the sign bits come from the forward's mask words (16 bytes per thread);
+// tanh: from the saved activations (slow path: 16-byte loads at a 512-byte pitch).
 template <int ACT, int NCH>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, int r, bool row_ok, const uint4 *act_row,
-                                               uint4 *dz_row, bool write_a, int cbase) {
+                                               const uint32_t *mask_row, int cbase) {
     uint32_t v[2][32];
     uint4 am[2][4] = {};
-    if (ACT != SFGPI_ACT_NONE && row_ok) {
+    uint32_t mw[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    const bool use_mask = (ACT == SFGPI_ACT_RELU) && mask_row != nullptr;
+    if (ACT == SFGPI_ACT_RELU && use_mask && row_ok) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(mask_row + (cbase >> 5)));
+        mw[0] = q.x; mw[1] = q.y; mw[2] = q.z; mw[3] = q.w;
+    }
+    const bool need_vals = (ACT == SFGPI_ACT_TANH) || (ACT == SFGPI_ACT_RELU && !use_mask);
+    if (need_vals && row_ok) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) am[0][g] = __ldg(act_row + (cbase >> 3) + g);
     }
@@ -90,12 +99,13 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, i
         tmem_wait_ld();
         if (cb + 1 < NCH) {
             tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
-            if (ACT != SFGPI_ACT_NONE && row_ok) {
+            if (need_vals && row_ok) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) am[(cb + 1) & 1][g] = __ldg(act_row + ((c0 + 32) >> 3) + g);
             }
         }
         const uint32_t(&u)[32] = v[cb & 1];
+        const uint32_t mword = mw[cb & 3];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const uint4 aq = am[cb & 1][g];
@@ -104,23 +114,24 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, i
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float gv = row_ok ? __uint_as_float(u[8 * g + i]) : 0.0f;
-                if (ACT != SFGPI_ACT_NONE) {
+                if (ACT == SFGPI_ACT_RELU && use_mask) {
+                    gv = ((mword >> (8 * g + i)) & 1u) ? gv : 0.0f;                                   // threshold_backward
+                } else if (ACT != SFGPI_ACT_NONE) {
                     const uint32_t ab = (i & 1) ? (aw[i >> 1] >> 16) : (aw[i >> 1] & 0xFFFFu);      // bf16 bits of act[col]
-                    if (ACT == SFGPI_ACT_RELU) gv = ((short)ab > 0) ? gv : 0.0f;                    // threshold_backward
+                    if (ACT == SFGPI_ACT_RELU) gv = ((short)ab > 0) ? gv : 0.0f;
                     else { const float av = __uint_as_float(ab << 16); gv *= (1.0f - av * av); }      // tanh_backward
                 }
                 h[i] = gv;
             }
-            const uint32_t q0 = pack_bf16x2(h[0], h[1]), q1 = pack_bf16x2(h[2], h[3]), q2 = pack_bf16x2(h[4], h[5]),
-                           q3 = pack_bf16x2(h[6], h[7]);
-            if (write_a) sts128(Arow + a_chunk_off(r, c0 + 8 * g), q0, q1, q2, q3);
-            if (row_ok) dz_row[(c0 >> 3) + g] = make_uint4(q0, q1, q2, q3);
+            sts128(Arow + a_chunk_off(r, c0 + 8 * g), pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
+                   pack_bf16x2(h[6], h[7]));
         }
     }
 }
 
 __global__ void __launch_bounds__(kThreadsDg, 1)
-mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ CUtensorMap tmap_w) {
+mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_dzo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     const sfgpi_net_desc &net = p.net;
@@ -259,13 +270,36 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         const int group = (warp - kEpiWarp0) >> 2;
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
+        const int et = threadIdx.x - kEpiWarp0 * 32;
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t full_cnt[2] = {0, 0};
+        // Every tile this kernel produces (the dense dZ_{L-1} chunk, each dZ_lo) is left in the A slot in TMA's swizzled box
+        // layout and written to HBM by ONE thread with bulk tensor stores; see the forward kernel for the reasoning and the
+        // guard protocol (a slot is rewritten only after its pending store has finished reading it).
+        bool store_pending[2] = {false, false};
+        auto a_slot_guard = [&](bool all) {
+            if (et == 0) { if (all) bulk_wait_read0(); else bulk_wait_read1(); }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
+        auto guard_slot = [&](int slot) {
+            if (store_pending[slot]) { a_slot_guard(!store_pending[slot ^ 1]); store_pending[slot] = false; }
+        };
 
         for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
             const int n_slots = (p.paired && (2 * pip + 1 < p.tiles_per_policy)) ? 2 : 1;
             int bs[2];
+            // tile complete in shared memory (fenced by its writers) -> barrier, one thread stores nbox 64-column boxes
+            auto store_tile = [&](const CUtensorMap *tm, int slot, int nbox, int col0, int slab) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) {
+                    const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
+                    const int row0 = (p.paired ? 2 * pip + slot : pip) * kTM;
+                    for (int j = 0; j < nbox; ++j) tma_store_3d(tm, Arow + j * (kTM * 128), col0 + j * kKB, row0, slab);
+                    bulk_commit();
+                }
+                store_pending[slot] = true;
+            };
 #pragma unroll 1
             for (int slot = 0; slot < n_slots; ++slot) {
                 const int b = (p.paired ? 2 * pip + slot : pip) * kTM + r;
@@ -273,10 +307,12 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                 const bool row_ok = b < B;
                 const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
                 const int sel = row_ok ? (int)p.actions[b] * D : 0;
+                guard_slot(slot);
                 build_dzo_chunk(p, 0, sbase + (uint32_t)slot * kABytes, r, row_ok, sel, p.d_out + prow * D, p.dzo + prow * p.ADp,
                                 group, 2);
                 fence_proxy_async();
                 mbar_arrive(SLOT_READY(slot));
+                store_tile(&tmap_dzo, slot, (min(256, p.ADp) + kKB - 1) / kKB, 0, pl);
             }
 
             for (int it = 0; it < p.n_items; ++it) {
@@ -289,31 +325,32 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
                     ++full_cnt[slot];
                     tc_fence_after();
+                    guard_slot(slot);
                     if (it + 1 < p.n_chunks) {                   // more output-layer chunks: refill the A slot
                         const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
                         const int sel = row_ok ? (int)p.actions[b] * D : 0;
                         build_dzo_chunk(p, it + 1, Arow, r, row_ok, sel, p.d_out + prow * D, p.dzo + prow * p.ADp, group, 2);
                         fence_proxy_async();
                         mbar_arrive(SLOT_READY(slot));
+                        store_tile(&tmap_dzo, slot, (min(256, p.ADp - (it + 1) * 256) + kKB - 1) / kKB, (it + 1) * 256, pl);
                         continue;
                     }
                     const int lo = (it < p.n_chunks) ? p.L - 2 : p.L - 3 - (it - p.n_chunks);    // produces dZ_lo
                     const int act = net.acts[lo];
-                    const size_t off = (((size_t)lo * p.n_pol + pl) * B + (row_ok ? b : 0)) * kH;
-                    const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + off);
-                    uint4 *dz_row = reinterpret_cast<uint4 *>(p.dz + off);
-                    const bool write_a = lo > 0;
-                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, group * 128);
-                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, group * 128);
-                    else dgrad_epilogue<SFGPI_ACT_TANH, 4>(t_lane, Arow, r, row_ok, act_row, dz_row, write_a, group * 128);
+                    const size_t rowi = ((size_t)lo * p.n_pol + pl) * B + (row_ok ? b : 0);
+                    const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + rowi * kH);
+                    const uint32_t *mask_row = p.masks ? p.masks + rowi * 8 : nullptr;
+                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
+                    else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
+                    else dgrad_epilogue<SFGPI_ACT_TANH, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
                     tc_fence_before();
-                    if (write_a) {
-                        fence_proxy_async();
-                        mbar_arrive(SLOT_READY(slot));
-                    }
+                    fence_proxy_async();
+                    if (lo > 0) mbar_arrive(SLOT_READY(slot));   // dZ_lo is the next MMA's A operand
+                    store_tile(&tmap_dz, slot, kH / kKB, 0, lo * p.n_pol + pl);
                 }
             }
         }
+        if (et == 0) bulk_wait0();                               // outstanding stores complete before the CTA retires
     }
 
     tc_fence_before();
@@ -558,6 +595,7 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     dp.actions = reinterpret_cast<const long long *>(a.actions);
     dp.d_out = a.d_out;
     dp.acts = reinterpret_cast<const __nv_bfloat16 *>(a.acts_bf16);
+    dp.masks = reinterpret_cast<const uint32_t *>(a.relu_masks);
     dp.dz = reinterpret_cast<__nv_bfloat16 *>(a.dz_bf16);
     dp.dzo = reinterpret_cast<__nv_bfloat16 *>(a.dzo_bf16);
     dp.rows_per_policy = sfgpi_bf16_rows_per_policy(&net);
@@ -576,10 +614,18 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
         rc = make_tmap_bf16(&tmap_w, a.params_bf16, 2, dims, box);
         if (rc) return rc;
     }
+    CUtensorMap tm_dz_st, tm_dzo_st;                                 // store maps: box = {64 columns, 128 rows, 1 slab}
+    {
+        const uint64_t d3[3] = {(uint64_t)kH, (uint64_t)a.B, (uint64_t)(L - 1) * a.n_pol};
+        const uint64_t do3[3] = {(uint64_t)ADp, (uint64_t)a.B, (uint64_t)a.n_pol};
+        const uint32_t box[3] = {64, 128, 1};
+        if ((rc = make_tmap_bf16(&tm_dz_st, a.dz_bf16, 3, d3, box))) return rc;
+        if ((rc = make_tmap_bf16(&tm_dzo_st, a.dzo_bf16, 3, do3, box))) return rc;
+    }
     const int dg_smem = 2 * kABytes + kNStage * kStageBytes + 256;
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem); cfg = true; }
-    launch_pdl(mlp_dgrad_tc_kernel, dim3(dp.total_pairs < 148 ? dp.total_pairs : 148), dim3(kThreadsDg), dg_smem, st, dp, tmap_w);
+    launch_pdl(mlp_dgrad_tc_kernel, dim3(dp.total_pairs < 148 ? dp.total_pairs : 148), dim3(kThreadsDg), dg_smem, st, dp, tmap_w, tm_dz_st, tm_dzo_st);
     rc = check_launch("sfgpi_mlp_backward_tc(dgrad)");
     if (rc) return rc;
 

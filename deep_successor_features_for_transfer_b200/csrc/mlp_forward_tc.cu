@@ -70,8 +70,9 @@ __device__ __forceinline__ float act_apply_fast(float v, int act) {
 // starting at column cbase.
 template <int ACT, int NCH>
 __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save,
-                                                uint4 *save_bf16, int cbase) {
+                                                uint32_t *mask_out, int cbase) {
     uint32_t v[2][32];
+    uint32_t mbits[NCH];                               // bit i of word cb: activation (cbase + 32 cb + i) > 0
     tmem_ld32(t_lane + cbase, v[0]);
 #pragma unroll
     for (int cb = 0; cb < NCH; ++cb) {
@@ -80,12 +81,17 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
         if (cb + 1 < NCH) tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
         const uint32_t(&u)[32] = v[cb & 1];
         uint32_t pk[16];
+        uint32_t mb = 0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const float4 bv = lds128(bias + 4u * (c0 + 4 * g));
             float h0 = __uint_as_float(u[4 * g]) + bv.x, h1 = __uint_as_float(u[4 * g + 1]) + bv.y;
             float h2 = __uint_as_float(u[4 * g + 2]) + bv.z, h3 = __uint_as_float(u[4 * g + 3]) + bv.w;
-            if (ACT == SFGPI_ACT_RELU) { h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f); }
+            if (ACT == SFGPI_ACT_RELU) {
+                mb |= (h0 > 0.f ? 1u : 0u) << (4 * g) | (h1 > 0.f ? 2u : 0u) << (4 * g) | (h2 > 0.f ? 4u : 0u) << (4 * g) |
+                      (h3 > 0.f ? 8u : 0u) << (4 * g);
+                h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f);
+            }
             if (ACT == SFGPI_ACT_TANH) { h0 = tanhf(h0); h1 = tanhf(h1); h2 = tanhf(h2); h3 = tanhf(h3); }
             pk[2 * g] = pack_bf16x2(h0, h1);
             pk[2 * g + 1] = pack_bf16x2(h2, h3);
@@ -93,10 +99,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
 #pragma unroll
         for (int g = 0; g < 4; ++g)
             sts128(Arow + a_chunk_off(r, c0 + 8 * g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        if (save_bf16) {                               // row-major bf16 copy for the tensor-core backward pass
-#pragma unroll
-            for (int g = 0; g < 4; ++g) save_bf16[(c0 >> 3) + g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        }
+        mbits[cb] = mb;
         if (save) {                                    // the bf16-rounded values the next layer really consumed
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -104,6 +107,10 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
                     make_float4(__uint_as_float(pk[2 * g] << 16), __uint_as_float(pk[2 * g] & 0xFFFF0000u),
                                 __uint_as_float(pk[2 * g + 1] << 16), __uint_as_float(pk[2 * g + 1] & 0xFFFF0000u));
         }
+    }
+    if (ACT == SFGPI_ACT_RELU && mask_out != nullptr) {    // 1 bit per activation: all the backward pass needs of a ReLU layer
+        static_assert(NCH == 4, "mask row layout: 8 words per row, 4 per column half");
+        *reinterpret_cast<uint4 *>(mask_out + (cbase >> 5)) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
     }
 }
 
@@ -118,7 +125,7 @@ struct TcMulti {
     int pair_start[kMaxJobs + 1];
     TcParams job[kMaxJobs];
 };
-struct TmapSet { CUtensorMap w[kMaxJobs]; CUtensorMap q[kMaxJobs]; };
+struct TmapSet { CUtensorMap w[kMaxJobs]; CUtensorMap q[kMaxJobs]; CUtensorMap acts[kMaxJobs]; };
 
 // role 0 = epilogue X (thread 0), 1 = MMA issuer, 2 = producer warp 0, 3 = epilogue Y (thread 0); 64 slots each
 #define TL_STAMP(role, cnt) do { if (m.timeline != nullptr && blockIdx.x == 0 && (cnt) < 64) m.timeline[(role) * 64 + (cnt)++] = clock64(); } while (0)
@@ -300,6 +307,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t full_cnt[2] = {0, 0};
         int cur_policy = -1;
+        bool store_pending[2] = {false, false};              // (uniform over the 256 epilogue threads)
         int tlc = 0;
         const int tl_role = (et == 0) ? 0 : ((et == 128) ? 3 : -1);
 #define TL_EPI() do { if (tl_role >= 0) TL_STAMP(tl_role, tlc); } while (0)
@@ -317,6 +325,19 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
             const int n_slots = (p.paired && (2 * pip + 1 < p.tiles_per_policy)) ? 2 : 1;
             const float *P = a.params + (size_t)(a.policy_lo + pl) * net.row_stride;
+
+            // Saved activations (training forward): the bf16 tile a hidden epilogue leaves in the A slot IS the row-major
+            // activation block in TMA's 128B-swizzled box layout, so one thread stores it with 4 bulk tensor copies while the
+            // next layer's MMAs read the same tile -- per-thread 16-byte stores at a 512-byte row pitch cost one L1 wavefront per
+            // lane (~8000 cycles per tile-layer, measured) against ~2000 for everything else in the epilogue.
+            const bool saving = a.acts_bf16_out != nullptr;
+            // before a write to A slot s: its pending bulk store has finished READING it.  Stores are issued in (item, slot)
+            // order, so with two slots in flight the newest group belongs to the other slot and may stay pending.
+            auto a_slot_guard = [&](bool all) {
+                if (et == 0) { if (all) bulk_wait_read0(); else bulk_wait_read1(); }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            };
+            if (store_pending[0] || store_pending[1]) { a_slot_guard(true); store_pending[0] = store_pending[1] = false; }
 
             int bs[2], sel_base[2];
             // ---------------- stage the state tiles as the input layer's A operands (bf16, K padded to 16*ks0) ----------------
@@ -392,16 +413,27 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         const uint32_t bias = bias_addr + 4u * (it * kH);
                         const int act = net.acts[it];
                         float *save = (a.acts_out[it] && row_ok) ? a.acts_out[it] + ((size_t)pl * B + b) * kH : nullptr;
-                        uint4 *save16 = (a.acts_bf16_out && row_ok)
-                            ? reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.acts_bf16_out) +
-                                                        (((size_t)it * a.n_pol + pl) * B + b) * kH)
+                        uint32_t *mask_out = (a.relu_mask_out && row_ok)
+                            ? reinterpret_cast<uint32_t *>(a.relu_mask_out) + (((size_t)it * a.n_pol + pl) * B + b) * 8
                             : nullptr;
-                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 4>(t_lane, bias, Arow, r, save, save16, group * 128);
-                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4>(t_lane, bias, Arow, r, save, save16, group * 128);
-                        else hidden_epilogue<SFGPI_ACT_TANH, 4>(t_lane, bias, Arow, r, save, save16, group * 128);
+                        if (store_pending[slot]) { a_slot_guard(!store_pending[slot ^ 1]); store_pending[slot] = false; }
+                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 4>(t_lane, bias, Arow, r, save, mask_out, group * 128);
+                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4>(t_lane, bias, Arow, r, save, mask_out, group * 128);
+                        else hidden_epilogue<SFGPI_ACT_TANH, 4>(t_lane, bias, Arow, r, save, mask_out, group * 128);
                         tc_fence_before();
                         fence_proxy_async();
                         mbar_arrive(SLOT_READY(slot));
+                        if (saving) {                         // tile complete in shared memory -> one thread stores it
+                            asm volatile("bar.sync 1, 256;" ::: "memory");
+                            if (et == 0) {
+                                const int row0 = (p.paired ? 2 * pip + slot : pip) * kTM;
+#pragma unroll
+                                for (int kb = 0; kb < kH / kKB; ++kb)
+                                    tma_store_3d(&maps.acts[jb], Arow + kb * (kTM * 128), kb * kKB, row0, it * a.n_pol + pl);
+                                bulk_commit();
+                            }
+                            store_pending[slot] = true;
+                        }
                     } else {
                         // ------ output layer chunk ------
                         const uint32_t bias = bias_addr + 4u * ((1 + p.Lh) * kH + ii.col0);
@@ -473,6 +505,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                 }
             }
         }
+        if (et == 0) bulk_wait0();                           // outstanding activation stores complete before the CTA retires
     }
 
     // ---- teardown ----
@@ -550,6 +583,21 @@ static int make_tmap(CUtensorMap *tm, const void *base, uint64_t rows) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return SFGPI_E_CUDA; }
+    return SFGPI_OK;
+}
+
+// 3-D map of a [slabs][rows][256] bf16 tensor, box = {64 columns, 128 rows, 1 slab}: rows past the end of a slab are clipped
+static int make_tmap_acts(CUtensorMap *tm, const void *base, uint64_t slabs, uint64_t rows) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return SFGPI_E_CUDA; }
+    const cuuint64_t gdim[3] = {(cuuint64_t)kH, (cuuint64_t)rows, (cuuint64_t)slabs};
+    const cuuint64_t gstride[2] = {(cuuint64_t)kH * 2, (cuuint64_t)kH * 2 * rows};
+    const cuuint32_t box[3] = {(cuuint32_t)kKB, (cuuint32_t)kTM, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult cr = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), gdim, gstride, box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(acts) failed (%d)", (int)cr); return SFGPI_E_CUDA; }
     return SFGPI_OK;
 }
 
@@ -654,6 +702,11 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         } else {
             maps.q[m.n_jobs] = maps.w[m.n_jobs];
         }
+        maps.acts[m.n_jobs] = maps.w[m.n_jobs];
+        if (a.acts_bf16_out != nullptr) {                        // [L-1][n_pol][B][256] bf16, stored tile by tile with TMA
+            rc = make_tmap_acts(&maps.acts[m.n_jobs], a.acts_bf16_out, (uint64_t)(net.n_layers - 1) * a.n_pol, (uint64_t)a.B);
+            if (rc) return rc;
+        }
         ++m.n_jobs;
     }
     if (m.n_jobs == 0) return SFGPI_OK;
@@ -674,7 +727,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         m.total_pairs += p.total_pairs;
     }
     for (int j = m.n_jobs; j <= kMaxJobs; ++j) m.pair_start[j] = m.total_pairs;
-    for (int j = m.n_jobs; j < kMaxJobs; ++j) { m.job[j] = m.job[0]; maps.w[j] = maps.w[0]; maps.q[j] = maps.q[0]; }
+    for (int j = m.n_jobs; j < kMaxJobs; ++j) { m.job[j] = m.job[0]; maps.w[j] = maps.w[0]; maps.q[j] = maps.q[0]; maps.acts[j] = maps.acts[0]; }
     const int smem_bytes = 2 * kABytes + kNStage * kStageBytes + kBiasFloatsMax * 4 + 256;
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); cfg = true; }

@@ -63,6 +63,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void *tmap,
         : "memory");
 }
 
+// Tiled store shared -> global (bulk async-group completion).  The source tile must be visible to the async proxy
+// (fence.proxy.async by its writers + a barrier) and must not be overwritten before bulk_wait_read0() returns in the issuer.
+__device__ __forceinline__ void tma_store_3d(const void *tmap, uint32_t smem_src, int crd0, int crd1, int crd2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(crd0), "r"(crd1), "r"(crd2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMEM / tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {      // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols) : "memory");

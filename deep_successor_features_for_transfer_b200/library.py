@@ -295,6 +295,7 @@ class PackedSFLibrary:
                 adp = _lib.lib().sfgpi_bwd_tc_out_pad(C.byref(desc))
                 ws['acts16'], ws['dz16'] = bf(L - 1, n_pol, B, 256), bf(L - 1, n_pol, B, 256)
                 ws['dzo16'], ws['xo16'] = bf(n_pol, B, adp), bf(B, 64)
+                ws['masks'] = torch.zeros(L - 1, n_pol, B, 8, dtype=torch.int32, device=self.device)   # ReLU sign bits
                 items = (sp.dims[-1] + 127) // 128 + 2 * (L - 1)
                 n_split = _lib.lib().sfgpi_bwd_tc_splits(B, max(1, 148 // (items * n_pol)))      # one wave of CTAs
             ws['n_split'] = n_split
@@ -396,7 +397,7 @@ class PackedSFLibrary:
         a1 = self._fwd_args(self.online, lo, n_pol, None, B)
         tc = self.precision != 'fp32'
         if tc:
-            a1.acts_bf16_out = ws['acts16'].data_ptr()
+            a1.acts_bf16_out, a1.relu_mask_out = ws['acts16'].data_ptr(), ws['masks'].data_ptr()
         else:
             for l in range(L - 1):
                 a1.acts_out[l] = ws['acts'][l].data_ptr()
@@ -452,6 +453,7 @@ class PackedSFLibrary:
             b.net, b.params_bf16, b.n_policies_total = sp.desc(), ptr(self._shadow_for('online')), self.cap
             b.policy_lo, b.n_pol, b.B, b.d_out = lo, n_pol, B, ptr(ws['d_out'])
             b.acts_bf16, b.dz_bf16, b.dzo_bf16, b.xo_bf16 = (ptr(ws[k]) for k in ('acts16', 'dz16', 'dzo16', 'xo16'))
+            b.relu_masks = ptr(ws['masks'])
         else:
             b = _lib.BackwardArgs()
             b.net, b.params, b.policy_lo, b.n_pol = sp.desc(), ptr(self.online), lo, n_pol
@@ -689,11 +691,12 @@ class PackedSFLibrary:
         a1.sel_actions, a1.sel_out = actions.data_ptr(), ptr(ws['cur_sel'])
         if self.precision != 'fp32':
             self._pack('online', lo, n_pol)
-            a1.acts_bf16_out = ws['acts16'].data_ptr()
+            a1.acts_bf16_out, a1.relu_mask_out = ws['acts16'].data_ptr(), ws['masks'].data_ptr()
             self._forward(a1, 'online', fresh=True)
             b = _lib.BackwardTcArgs()
             b.net, b.params_bf16, b.n_policies_total = sp.desc(), ptr(self._shadow_for('online')), self.cap
             b.acts_bf16, b.dz_bf16, b.dzo_bf16, b.xo_bf16 = (ptr(ws[k]) for k in ('acts16', 'dz16', 'dzo16', 'xo16'))
+            b.relu_masks = ptr(ws['masks'])
             name = 'sfgpi_mlp_backward_tc'
         else:
             for l in range(L - 1):

@@ -84,6 +84,8 @@ typedef struct {
     int32_t mode;
     void *acts_bf16_out;            /* tensor-core mode only: [L-1][n_pol][B][256] bf16 post-activation outputs (row-major),
                                        the operands of sfgpi_mlp_backward_tc */
+    void *relu_mask_out;            /* tensor-core mode only: [L-1][n_pol][B][8] uint32, bit c%32 of word c/32 = (activation c > 0)
+                                       for ReLU layers: all the dgrad chain needs of them */
 } sfgpi_forward_args;
 
 int sfgpi_mlp_forward(const sfgpi_forward_args *args, void *stream);
@@ -243,6 +245,7 @@ typedef struct {
     const float *x;                 /* [B][S] */
     int32_t B;
     const void *acts_bf16;          /* [L-1][n_pol][B][256] */
+    const void *relu_masks;         /* [L-1][n_pol][B][8] uint32 from sfgpi_mlp_forward_tc (relu_mask_out); NULL: signs from acts */
     const int64_t *actions;         /* [B] */
     const float *d_out;             /* [n_pol][B][D] */
     void *dz_bf16;
