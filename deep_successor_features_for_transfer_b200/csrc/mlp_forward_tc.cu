@@ -483,9 +483,14 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                                 if (row_ok) {
                                     if (a.psi_out != nullptr) {
                                         float *po = a.psi_out + ((size_t)b * a.n_pol + pl) * AD + colb;
+                                        if ((AD & 3) == 0) {                  // rows are 16-byte aligned: 128-bit stores
+                                            if (colb < AD) *reinterpret_cast<float4 *>(po) = make_float4(val[0], val[1], val[2], val[3]);
+                                            if (colb + 4 < AD) *reinterpret_cast<float4 *>(po + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                                        } else {
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i)
-                                            if (colb + i < AD) po[i] = val[i];
+                                            for (int i = 0; i < 8; ++i)
+                                                if (colb + i < AD) po[i] = val[i];
+                                        }
                                     }
                                     if ((unsigned)(colb + 7 - sb) < (unsigned)(D + 7)) {         // group overlaps [sel, sel + D)
                                         float *so = a.sel_out + ((size_t)pl * B + b) * D;
