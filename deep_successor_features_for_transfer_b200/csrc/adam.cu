@@ -47,6 +47,25 @@ __device__ __forceinline__ float sum_partials(const float *__restrict__ gp, int 
     return (g0 + g1) + (g2 + g3);
 }
 
+__device__ __forceinline__ float4 sum_partials4(const float4 *__restrict__ gp, int n_part, size_t stride4) {
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
+    int k = 0;
+    for (; k + 4 <= n_part; k += 4) {
+        const float4 t0 = __ldg(gp + (size_t)k * stride4), t1 = __ldg(gp + (size_t)(k + 1) * stride4),
+                     t2 = __ldg(gp + (size_t)(k + 2) * stride4), t3 = __ldg(gp + (size_t)(k + 3) * stride4);
+        g0.x += t0.x; g0.y += t0.y; g0.z += t0.z; g0.w += t0.w;
+        g1.x += t1.x; g1.y += t1.y; g1.z += t1.z; g1.w += t1.w;
+        g2.x += t2.x; g2.y += t2.y; g2.z += t2.z; g2.w += t2.w;
+        g3.x += t3.x; g3.y += t3.y; g3.z += t3.z; g3.w += t3.w;
+    }
+    for (; k < n_part; ++k) {
+        const float4 t = __ldg(gp + (size_t)k * stride4);
+        g0.x += t.x; g0.y += t.y; g0.z += t.z; g0.w += t.w;
+    }
+    return make_float4((g0.x + g1.x) + (g2.x + g3.x), (g0.y + g1.y) + (g2.y + g3.y), (g0.z + g1.z) + (g2.z + g3.z),
+                       (g0.w + g1.w) + (g2.w + g3.w));
+}
+
 __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constant__ sfgpi_adam_args a, int blocks_per_pol) {
     __shared__ float sqrt_bc2_s, step_size_s[SFGPI_MAX_SEGMENTS];
     pdl_launch_dependents();
@@ -79,7 +98,6 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
     for (int s = 0; s < a.n_seg; ++s) {
         const sfgpi_adam_segment &sg = a.seg[s];
         const bool shared = (sg.param_stride == 0 && a.n_pol > 1);
-        if (shared && p != 0) continue;
         const float step_size = step_size_s[s];
         if (!shared) {
             const float *gp0 = sg.grad_part + (size_t)p * sg.grad_pol_stride;
@@ -92,11 +110,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             if (vec) {                                        // 128-bit path: 4 parameters per thread per trip
                 const int n4 = sg.len >> 2;
                 for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < n4; i += blocks_per_pol * kAdamThreads) {
-                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k = 0; k < sg.n_part; ++k) {
-                        const float4 t = __ldg(reinterpret_cast<const float4 *>(gp0 + (size_t)k * sg.grad_part_stride) + i);
-                        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-                    }
+                    float4 g = sum_partials4(reinterpret_cast<const float4 *>(gp0) + i, sg.n_part, (size_t)(sg.grad_part_stride >> 2));
                     float4 pw = reinterpret_cast<float4 *>(pp0)[i], m = reinterpret_cast<float4 *>(pm0)[i],
                            v = reinterpret_cast<float4 *>(pv0)[i];
                     adam_elem(pw.x, m.x, v.x, g.x, step_size, sqrt_bc2, sg.weight_decay, kc);
@@ -116,25 +130,36 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
                 }
             }
         } else {
-            // shared tensor (TSF's h) stepped by every optimizer from the SAME pre-step value; deltas added in
-            // optimizer order (frozen-snapshot ensemble semantics).  Each optimizer has its own step.
-            for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.len; i += blocks_per_pol * kAdamThreads) {
+            // shared tensor (TSF's h) stepped by every optimizer from the SAME pre-step value (frozen-snapshot ensemble semantics,
+            // see DESIGN.md); each optimizer has its own moments and step.  One WARP per element, lane = optimizer: the per-optimizer
+            // work (partial sums, moments, delta) runs in parallel and the deltas are summed by a fixed butterfly.  Every block of
+            // the grid takes part.
+            const int lane = threadIdx.x & 31;
+            const int warps_total = gridDim.x * gridDim.y * (kAdamThreads / 32);
+            const int wg = (blockIdx.y * gridDim.x + blockIdx.x) * (kAdamThreads / 32) + (threadIdx.x >> 5);
+            for (int i = wg; i < sg.len; i += warps_total) {
                 const float p0 = sg.param[i];
-                float pacc = p0;
-                for (int q = 0; q < a.n_pol; ++q) {
-                    double qbc1;
-                    float qsb2;
-                    bias_corrections(a, q, qbc1, qsb2);
-                    const float g = sum_partials(sg.grad_part + (size_t)q * sg.grad_pol_stride + i, sg.n_part,
-                                                 (size_t)sg.grad_part_stride);
-                    float *pm = sg.m + (size_t)q * sg.m_stride + i;
-                    float *pv = sg.v + (size_t)q * sg.v_stride + i;
-                    float pw = p0, m = *pm, v = *pv;
-                    adam_elem(pw, m, v, g, (float)((double)sg.lr / qbc1), qsb2, sg.weight_decay, kc);
-                    *pm = m; *pv = v;
-                    pacc += pw - p0;
+                float dsum = 0.0f;
+                for (int q0 = 0; q0 < a.n_pol; q0 += 32) {
+                    const int q = q0 + lane;
+                    float delta = 0.0f;
+                    if (q < a.n_pol) {
+                        double qbc1;
+                        float qsb2;
+                        bias_corrections(a, q, qbc1, qsb2);
+                        const float g = sum_partials(sg.grad_part + (size_t)q * sg.grad_pol_stride + i, sg.n_part,
+                                                     (size_t)sg.grad_part_stride);
+                        float *pm = sg.m + (size_t)q * sg.m_stride + i;
+                        float *pv = sg.v + (size_t)q * sg.v_stride + i;
+                        float pw = p0, m = *pm, v = *pv;
+                        adam_elem(pw, m, v, g, (float)((double)sg.lr / qbc1), qsb2, sg.weight_decay, kc);
+                        *pm = m; *pv = v;
+                        delta = pw - p0;
+                    }
+                    dsum += warp_sum(delta);
                 }
-                sg.param[i] = pacc;
+                __syncwarp();
+                if (lane == 0) sg.param[i] = p0 + dsum;
             }
         }
     }
