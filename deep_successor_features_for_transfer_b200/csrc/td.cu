@@ -1,10 +1,18 @@
 // TD target, the two MSE losses and every gradient that does not flow through the psi MLP, fused in one kernel
-// (sfdqn.py:330-345; tsfdqn.py:621-645; features/deep.py:112-121).  Elementwise / tiny-GEMM work: HBM-bound on the
-// [B][D] operands, deterministic two-stage reductions (per-CTA partials, summed by the Adam kernel).
+// (sfdqn.py:330-345; tsfdqn.py:621-645; features/deep.py:112-121).  Elementwise work per transition plus small reductions:
+// HBM-bound on the [B][D] operands, deterministic reductions.
 //
-// Thread-block clusters: 8 CTAs (8 x 32 transitions) form a cluster and sum their gradient / loss partials through
-// distributed shared memory in a fixed rank order before anything is written, so the Adam kernel reads ceil(B/256) partials
-// per parameter instead of ceil(B/32) (that read loop was the longest latency chain of the whole train step).
+// TSF (variant 2): g_i = Linear(S,G) and h = Linear(G,D) are applied back to back with NO nonlinearity between them
+// (tsfdqn.py:621-623), so aff = h(g(s)) + h(g(s')) = M (s + s') + c with M = Wh Wg [D][S], c = 2 (Wh bg + bh), and every g / h
+// gradient is a linear image of two tiny per-policy sums over the batch,
+//     T[d][s] = sum_b daff[b][d] (s + s')[b][s]        t[d] = sum_b daff[b][d]        (daff = dLoss/daff)
+//     dWh = T Wg^T + 2 t bg^T     dbh = 2 t     dWg = Wh^T T     dbg = 2 Wh^T t
+// The TD kernel therefore reduces only D*S + 2D numbers per policy (not G*S + G + D*G + D), and tsf_expand_kernel applies the
+// linear maps once per policy after the reduction.  Same mathematics as autograd through u = g(s)+g(s'), different summation
+// order (within the 1e-5 parity bound; tests/test_gpu_parity.py).
+//
+// Thread-block clusters: 8 CTAs (8 x 32 transitions) form a cluster and sum their partials through distributed shared memory in
+// a fixed rank order before anything is written: ceil(B/256) partials per policy reach global memory.
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -16,7 +24,8 @@ constexpr int kTdRows = 32;       // transitions per CTA
 constexpr int kTdThreads = 128;
 constexpr int kTdCluster = 8;     // CTAs per cluster (portable maximum)
 
-// smem layout (floats): see carve-up below
+__host__ __device__ inline int tsf_red_len(int D, int S) { return D + D * S + D; }      // [dw | T | t]
+
 __global__ void __cluster_dims__(kTdCluster, 1, 1) __launch_bounds__(kTdThreads)
 td_kernel(const __grid_constant__ sfgpi_td_args a) {
     extern __shared__ __align__(16) float sm[];
@@ -30,7 +39,8 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
     const int row0 = blk * kTdRows;
     const int rows = max(0, min(kTdRows, B - row0));         // the grid is padded to whole clusters: trailing CTAs add zeros
     const bool tsf = a.variant == 2, reward = a.variant >= 1;
-    const int n_acc = a.aux_len + 2;                         // [aux gradient partials | sum diff^2 | sum e^2]
+    const int n_red = tsf ? tsf_red_len(D, S) : (reward ? D : 0);      // gradient partials of this variant
+    const int n_acc = n_red + 2;                             // [partials | sum diff^2 | sum e^2]
 
     // carve-up
     float *w_s = sm;                              // [D]
@@ -39,14 +49,13 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
     float *diff_s = tphi_s + kTdRows * D;         // [32][D]  then reused as daff
     float *e_s = diff_s + kTdRows * D;            // [32]
     float *red_s = e_s + kTdRows;                 // [8] block-reduction scratch
-    float *Wg_s = red_s + 8;                      // [G][S]   (tsf only from here)
-    float *bg_s = Wg_s + G * S;                   // [G]
-    float *Wh_s = bg_s + G;                       // [D][G]
-    float *bh_s = Wh_s + D * G;                   // [D]
-    float *ss_s = bh_s + D;                       // [32][S]  s + s'
-    float *u_s = ss_s + kTdRows * S;              // [32][G]  g(s) + g(s')
-    float *du_s = u_s + kTdRows * G;              // [32][G]
-    float *gacc_s = tsf ? du_s + kTdRows * G : Wg_s;      // [aux_len + 2] this CTA's partials, summed across the cluster
+    float *gacc_s = red_s + 8;                    // [n_acc] this CTA's partials, summed across the cluster
+    float *M_s = gacc_s + n_acc;                  // [D][S]   (tsf only from here)
+    float *c_s = M_s + D * S;                     // [D]
+    float *ss_s = c_s + D;                        // [32][S]  s + s'
+    float *Wg_s = ss_s + kTdRows * S;             // [G][S] | bg [G] | Wh [D][G] | bh [D]   staging for M, c
+    float *bg_s = Wg_s + G * S, *Wh_s = bg_s + G, *bh_s = Wh_s + D * G;
+
     for (int e = tid; e < n_acc; e += kTdThreads) gacc_s[e] = 0.0f;
 
     const float *cur = a.cur_sel + (size_t)pl * B * D;
@@ -54,39 +63,28 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
     float *dout = a.d_out + (size_t)pl * B * D;
 
     if (reward) for (int d = tid; d < D; d += kTdThreads) w_s[d] = a.w[(size_t)pl * a.w_stride + d];
-    for (int e = tid; e < kTdRows * D; e += kTdThreads) {
-        int r = e / D;
-        phi_s[e] = r < rows ? a.phis[(size_t)row0 * D + e] : 0.0f;
-    }
+    for (int e = tid; e < kTdRows * D; e += kTdThreads) phi_s[e] = e < rows * D ? a.phis[(size_t)row0 * D + e] : 0.0f;
     if (tsf) {
         const float *gp = a.g + (size_t)pl * a.g_stride;
-        for (int e = tid; e < G * S; e += kTdThreads) Wg_s[e] = gp[e];
-        for (int e = tid; e < G; e += kTdThreads) bg_s[e] = gp[G * S + e];
-        for (int e = tid; e < D * G; e += kTdThreads) Wh_s[e] = a.h[e];
-        for (int e = tid; e < D; e += kTdThreads) bh_s[e] = a.h[D * G + e];
-        for (int e = tid; e < kTdRows * S; e += kTdThreads) {
-            int r = e / S;
-            ss_s[e] = r < rows ? a.states[(size_t)row0 * S + e] + a.next_states[(size_t)row0 * S + e] : 0.0f;
-        }
+        for (int e = tid; e < G * S + G; e += kTdThreads) Wg_s[e] = gp[e];                 // Wg | bg (contiguous in the row)
+        for (int e = tid; e < D * G + D; e += kTdThreads) Wh_s[e] = a.h[e];                // Wh | bh
+        for (int e = tid; e < kTdRows * S; e += kTdThreads)
+            ss_s[e] = e < rows * S ? a.states[(size_t)row0 * S + e] + a.next_states[(size_t)row0 * S + e] : 0.0f;
     }
     __syncthreads();
 
-    // u = g(s) + g(s') = Wg (s + s') + 2 bg                                   (tsfdqn.py:621-622)
     if (tsf) {
-        // thread = one g column, 4 rows per trip: each weight is read once per 4 FMAs and there is no per-element division
-        for (int g = tid; g < G; g += kTdThreads) {
-            const float b2 = 2.0f * bg_s[g];
-            const float *wg = Wg_s + g * S;
-            for (int r = 0; r < kTdRows; r += 4) {
-                float a0 = b2, a1 = b2, a2 = b2, a3 = b2;
-                for (int s = 0; s < S; ++s) {
-                    const float w = wg[s];
-                    a0 = fmaf(w, ss_s[(r + 0) * S + s], a0);
-                    a1 = fmaf(w, ss_s[(r + 1) * S + s], a1);
-                    a2 = fmaf(w, ss_s[(r + 2) * S + s], a2);
-                    a3 = fmaf(w, ss_s[(r + 3) * S + s], a3);
-                }
-                u_s[(r + 0) * G + g] = a0; u_s[(r + 1) * G + g] = a1; u_s[(r + 2) * G + g] = a2; u_s[(r + 3) * G + g] = a3;
+        // M = Wh Wg, c = 2 (Wh bg + bh): D*(S+1) dot products of length G
+        for (int o = tid; o < D * (S + 1); o += kTdThreads) {
+            const int d = o / (S + 1), s = o - d * (S + 1);
+            const float *wh = Wh_s + d * G;
+            float acc = 0.0f;
+            if (s < S) {
+                for (int g = 0; g < G; ++g) acc = fmaf(wh[g], Wg_s[g * S + s], acc);
+                M_s[d * S + s] = acc;
+            } else {
+                for (int g = 0; g < G; ++g) acc = fmaf(wh[g], bg_s[g], acc);
+                c_s[d] = 2.0f * (acc + bh_s[d]);
             }
         }
         __syncthreads();
@@ -96,11 +94,11 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
     const float c1 = 2.0f / ((float)B * (float)a.A * (float)D);
     float l1_acc = 0.0f;
     for (int e = tid; e < kTdRows * D; e += kTdThreads) {
-        int r = e / D, d = e - r * D;
+        const int r = e / D, d = e - r * D;
         float tphi = phi_s[e], df = 0.0f;
         if (tsf) {
-            float aff = 2.0f * bh_s[d];
-            for (int g = 0; g < G; ++g) aff = fmaf(Wh_s[d * G + g], u_s[r * G + g], aff);
+            float aff = c_s[d];
+            for (int s = 0; s < S; ++s) aff = fmaf(M_s[d * S + s], ss_s[r * S + s], aff);
             tphi *= aff;
         }
         if (r < rows) {
@@ -137,17 +135,16 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
         __syncthreads();
     }
 
-    // loss partials (deterministic tree inside the CTA, one slot per CTA)
+    // loss partials (deterministic tree inside the CTA)
     {
         float s1 = warp_sum(l1_acc), s2 = warp_sum(l2_acc);
         if ((tid & 31) == 0) { red_s[tid >> 5] = s1; red_s[4 + (tid >> 5)] = s2; }
         __syncthreads();
         if (tid == 0) {
-            gacc_s[a.aux_len] = (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
-            gacc_s[a.aux_len + 1] = (red_s[4] + red_s[5]) + (red_s[6] + red_s[7]);
+            gacc_s[n_red] = (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
+            gacc_s[n_red + 1] = (red_s[4] + red_s[5]) + (red_s[6] + red_s[7]);
         }
     }
-    float *gpart = gacc_s;
     const float c2 = 2.0f * a.beta / (float)B;           // variant 1: beta == 1
 
     if (reward) {
@@ -155,76 +152,35 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
         for (int d = tid; d < D; d += kTdThreads) {
             float acc = 0.0f;
             for (int r = 0; r < kTdRows; ++r) acc = fmaf(e_s[r], tphi_s[r * D + d], acc);
-            gpart[d] = c2 * acc;
+            gacc_s[d] = c2 * acc;
         }
     }
     if (tsf) {
-
-    // daff = (dL/dphi~) * phi,  dL/dphi~ = -c1*diff + c2*e*w                   (targets carry grad, tsfdqn.py:629)
-    __syncthreads();
-    for (int e = tid; e < kTdRows * D; e += kTdThreads) {
-        int r = e / D, d = e - r * D;
-        diff_s[e] = (c2 * e_s[r] * w_s[d] - c1 * diff_s[e]) * phi_s[e];
-    }
-    __syncthreads();
-    float *daff_s = diff_s;
-    // du = daff . Wh
-    for (int g = tid; g < G; g += kTdThreads) {
-        for (int r = 0; r < kTdRows; r += 4) {
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            for (int d = 0; d < D; ++d) {
-                const float w = Wh_s[d * G + g];
-                a0 = fmaf(daff_s[(r + 0) * D + d], w, a0);
-                a1 = fmaf(daff_s[(r + 1) * D + d], w, a1);
-                a2 = fmaf(daff_s[(r + 2) * D + d], w, a2);
-                a3 = fmaf(daff_s[(r + 3) * D + d], w, a3);
+        // daff = (dL/dphi~) * phi,  dL/dphi~ = -c1*diff + c2*e*w                   (targets carry grad, tsfdqn.py:629)
+        __syncthreads();
+        for (int e = tid; e < kTdRows * D; e += kTdThreads) {
+            const int r = e / D, d = e - r * D;
+            diff_s[e] = (c2 * e_s[r] * w_s[d] - c1 * diff_s[e]) * phi_s[e];
+        }
+        __syncthreads();
+        const float *daff_s = diff_s;
+        float *T = gacc_s + D, *tv = T + D * S;
+        for (int o = tid; o < D * (S + 1); o += kTdThreads) {
+            const int d = o / (S + 1), s = o - d * (S + 1);
+            float acc = 0.0f;
+            if (s < S) {
+                for (int r = 0; r < kTdRows; ++r) acc = fmaf(daff_s[r * D + d], ss_s[r * S + s], acc);
+                T[d * S + s] = acc;
+            } else {
+                for (int r = 0; r < kTdRows; ++r) acc += daff_s[r * D + d];
+                tv[d] = acc;
             }
-            du_s[(r + 0) * G + g] = a0; du_s[(r + 1) * G + g] = a1; du_s[(r + 2) * G + g] = a2; du_s[(r + 3) * G + g] = a3;
         }
     }
-    __syncthreads();
-    // parameter gradients: g.W [G][S], g.b [G], h.W [D][G], h.b [D]
-    float *gW = gpart + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
-    // thread = one g column; 4 outputs (4 s / 4 d) per trip share each du / u load
-    for (int g = tid; g < G; g += kTdThreads) {
-        float accb = 0.0f;
-        for (int r = 0; r < kTdRows; ++r) accb += du_s[r * G + g];
-        gb[g] = 2.0f * accb;
-        for (int s0 = 0; s0 < S; s0 += 4) {
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            const int s1 = min(s0 + 1, S - 1), s2 = min(s0 + 2, S - 1), s3 = min(s0 + 3, S - 1);
-            for (int r = 0; r < kTdRows; ++r) {
-                const float v = du_s[r * G + g];
-                const float *sr = ss_s + r * S;
-                a0 = fmaf(v, sr[s0], a0); a1 = fmaf(v, sr[s1], a1); a2 = fmaf(v, sr[s2], a2); a3 = fmaf(v, sr[s3], a3);
-            }
-            gW[g * S + s0] = a0;
-            if (s0 + 1 < S) gW[g * S + s0 + 1] = a1;
-            if (s0 + 2 < S) gW[g * S + s0 + 2] = a2;
-            if (s0 + 3 < S) gW[g * S + s0 + 3] = a3;
-        }
-        for (int d0 = 0; d0 < D; d0 += 4) {
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            const int d1 = min(d0 + 1, D - 1), d2 = min(d0 + 2, D - 1), d3 = min(d0 + 3, D - 1);
-            for (int r = 0; r < kTdRows; ++r) {
-                const float v = u_s[r * G + g];
-                const float *dr = daff_s + r * D;
-                a0 = fmaf(dr[d0], v, a0); a1 = fmaf(dr[d1], v, a1); a2 = fmaf(dr[d2], v, a2); a3 = fmaf(dr[d3], v, a3);
-            }
-            hW[d0 * G + g] = a0;
-            if (d0 + 1 < D) hW[(d0 + 1) * G + g] = a1;
-            if (d0 + 2 < D) hW[(d0 + 2) * G + g] = a2;
-            if (d0 + 3 < D) hW[(d0 + 3) * G + g] = a3;
-        }
-    }
-    for (int d = tid; d < D; d += kTdThreads) {
-        float acc = 0.0f;
-        for (int r = 0; r < kTdRows; ++r) acc += daff_s[r * D + d];
-        hb[d] = 2.0f * acc;
-    }
-    }   // tsf
 
     // ---- cluster reduction through distributed shared memory: rank r sums slice r of the 8 CTAs' partials, rank order ----
+    float *out_part = tsf ? a.tsf_part + ((size_t)pl * nclu + clu) * n_red
+                          : a.aux_grad_part + ((size_t)pl * nclu + clu) * a.aux_len;
     cluster.sync();
     {
         const unsigned rk = cluster.block_rank();
@@ -238,11 +194,56 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
 #pragma unroll
             for (int q = 0; q < kTdCluster; ++q) v[q] = remote[q][e];
             const float sum = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-            if (e < a.aux_len) a.aux_grad_part[((size_t)pl * nclu + clu) * a.aux_len + e] = sum;
-            else a.loss_part[((size_t)pl * nclu + clu) * 2 + (e - a.aux_len)] = sum;
+            if (e < n_red) out_part[e] = sum;
+            else a.loss_part[((size_t)pl * nclu + clu) * 2 + (e - n_red)] = sum;
         }
     }
     cluster.sync();                                          // nobody leaves while its shared memory is still being read
+}
+
+// TSF: (dw, T, t) partials [n_pol][nclu][2D + D*S] -> the full reduced gradient row [dw | dWg | dbg | dWh | dbh] of each
+// policy (written to partial slot 0 of aux_grad_part; the Adam kernel reads it with n_part = 1).
+__global__ void __launch_bounds__(256) tsf_expand_kernel(const __grid_constant__ sfgpi_td_args a, int nclu) {
+    extern __shared__ __align__(16) float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, pl = blockIdx.x;
+    const int S = a.S, D = a.D, G = a.G;
+    const int n_red = tsf_red_len(D, S);
+    float *red = sm;                              // [dw | T | t]
+    float *Wg_s = red + n_red;                    // [G][S] | bg [G]
+    float *Wh_s = Wg_s + G * S + G;               // [D][G]
+    const float *part = a.tsf_part + (size_t)pl * nclu * n_red;
+    for (int e = tid; e < n_red; e += 256) {
+        float acc = 0.0f;
+        for (int k = 0; k < nclu; ++k) acc += part[(size_t)k * n_red + e];
+        red[e] = acc;
+    }
+    const float *gp = a.g + (size_t)pl * a.g_stride;
+    for (int e = tid; e < G * S + G; e += 256) Wg_s[e] = gp[e];
+    for (int e = tid; e < D * G; e += 256) Wh_s[e] = a.h[e];
+    __syncthreads();
+    const float *T = red + D, *tv = T + D * S, *bg_s = Wg_s + G * S;
+    float *out = a.aux_grad_part + (size_t)pl * nclu * a.aux_len;        // slot 0 of this policy
+    float *gW = out + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
+    for (int d = tid; d < D; d += 256) { out[d] = red[d]; hb[d] = 2.0f * tv[d]; }
+    for (int e = tid; e < G * S; e += 256) {                 // dWg[g][s] = sum_d Wh[d][g] T[d][s]
+        const int g = e / S, s = e - g * S;
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = fmaf(Wh_s[d * G + g], T[d * S + s], acc);
+        gW[e] = acc;
+    }
+    for (int g = tid; g < G; g += 256) {                     // dbg[g] = 2 sum_d Wh[d][g] t[d]
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = fmaf(Wh_s[d * G + g], tv[d], acc);
+        gb[g] = 2.0f * acc;
+    }
+    for (int e = tid; e < D * G; e += 256) {                 // dWh[d][g] = sum_s T[d][s] Wg[g][s] + 2 bg[g] t[d]
+        const int d = e / G, g = e - d * G;
+        float acc = 2.0f * bg_s[g] * tv[d];
+        for (int s = 0; s < S; ++s) acc = fmaf(T[d * S + s], Wg_s[g * S + s], acc);
+        hW[e] = acc;
+    }
 }
 
 }  // namespace sfgpi
@@ -258,12 +259,20 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     const bool tsf = a.variant == 2;
     const int want_aux = a.variant == 0 ? 0 : (tsf ? a.D + a.G * a.S + a.G + a.D * a.G + a.D : a.D);
     if (a.aux_len < want_aux) { set_error("sfgpi_td_step: aux_len %d < %d", a.aux_len, want_aux); return SFGPI_E_INVALID; }
-    size_t fl = a.D + 3 * (size_t)kTdRows * a.D + kTdRows + 8 + (size_t)a.aux_len + 2;
-    if (tsf) fl += (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D + (size_t)kTdRows * a.S + 2 * (size_t)kTdRows * a.G;
+    if (tsf && a.tsf_part == nullptr) { set_error("sfgpi_td_step: variant 2 needs the tsf_part scratch buffer"); return SFGPI_E_INVALID; }
+    const int n_red = tsf ? tsf_red_len(a.D, a.S) : a.D;
+    size_t fl = a.D + 3 * (size_t)kTdRows * a.D + kTdRows + 8 + (size_t)n_red + 2;
+    if (tsf) fl += (size_t)a.D * a.S + a.D + (size_t)kTdRows * a.S + (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D;
     const size_t bytes = fl * sizeof(float);
     if (bytes > (size_t)kMaxSmem) { set_error("sfgpi_td_step: D/G too large for shared memory (%zu B)", bytes); return SFGPI_E_SMEM; }
     if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    dim3 grid(sfgpi_td_partials(a.B) * kTdCluster, a.n_pol);
+    const int nclu = sfgpi_td_partials(a.B);
+    dim3 grid(nclu * kTdCluster, a.n_pol);
     launch_pdl(td_kernel, grid, dim3(kTdThreads), bytes, (cudaStream_t)stream, a);
-    return check_launch("sfgpi_td_step");
+    int rc = check_launch("sfgpi_td_step");
+    if (rc || !tsf) return rc;
+    const size_t ebytes = ((size_t)n_red + (size_t)a.G * a.S + a.G + (size_t)a.D * a.G) * sizeof(float);
+    if (ebytes > 48 * 1024) cudaFuncSetAttribute(tsf_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    launch_pdl(tsf_expand_kernel, dim3(a.n_pol), dim3(256), ebytes, (cudaStream_t)stream, a, nclu);
+    return check_launch("sfgpi_td_step(expand)");
 }

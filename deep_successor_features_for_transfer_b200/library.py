@@ -306,6 +306,8 @@ class PackedSFLibrary:
             else:
                 ws['aux_len'] = D
             ws['aux_part'] = self._f(n_pol, nblk, ws['aux_len'])
+            if self.G is not None:
+                ws['tsf_part'] = self._f(n_pol, nblk, 2 * D + D * sp.dims[0])
             self._ws[key] = ws
         return ws
 
@@ -447,6 +449,8 @@ class PackedSFLibrary:
         if variant == 2:
             t.g, t.g_stride, t.h = P(self.g), self.g.shape[1], ptr(self.h)
         t.d_out, t.loss_part, t.aux_grad_part, t.aux_len = ptr(ws['d_out']), ptr(ws['loss_part']), ptr(ws['aux_part']), ws['aux_len']
+        if variant == 2:
+            t.tsf_part = ptr(ws['tsf_part'])
         # (5) backward through psi: dgrad chain + split-K wgrad
         if tc:
             b = _lib.BackwardTcArgs()
@@ -468,6 +472,7 @@ class PackedSFLibrary:
         ad.consts = C.c_void_p(self.adam_consts[lo:].data_ptr())
         ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
         rs_, nblk, al = sp.row_stride, ws['nblk'], ws['aux_len']
+        npa = 1 if variant == 2 else nblk          # variant 2: the TD step leaves ONE reduced aux-gradient row per policy
 
         def seg(k, param, pstride, m, v, mstride, grad, gpol, gpart, npart, length, lr, wd):
             s = ad.seg[k]
@@ -480,13 +485,13 @@ class PackedSFLibrary:
         nseg = 1
         aux = ws['aux_part']
         if variant >= 1:
-            seg(1, P(self.w), D, P(self.w_m), P(self.w_v), D, ptr(aux), nblk * al, al, nblk, D, self.lr['w'], self.wd['w'])
+            seg(1, P(self.w), D, P(self.w_m), P(self.w_v), D, ptr(aux), nblk * al, al, npa, D, self.lr['w'], self.wd['w'])
             nseg = 2
         if variant == 2:
             gl, hl = self.g.shape[1], self.h.numel()
-            seg(2, P(self.g), gl, P(self.g_m), P(self.g_v), gl, C.c_void_p(aux.data_ptr() + 4 * D), nblk * al, al, nblk, gl,
+            seg(2, P(self.g), gl, P(self.g_m), P(self.g_v), gl, C.c_void_p(aux.data_ptr() + 4 * D), nblk * al, al, npa, gl,
                 self.lr['g'], self.wd['g'])
-            seg(3, ptr(self.h), 0, P(self.h_m), P(self.h_v), hl, C.c_void_p(aux.data_ptr() + 4 * (D + gl)), nblk * al, al, nblk,
+            seg(3, ptr(self.h), 0, P(self.h_m), P(self.h_v), hl, C.c_void_p(aux.data_ptr() + 4 * (D + gl)), nblk * al, al, npa,
                 hl, self.lr['h'], self.wd['h'])
             nseg = 4
         ad.n_seg = nseg

@@ -137,6 +137,10 @@ typedef struct {
     const float *next_psi;
     const int64_t *next_keys;
     int32_t next_key_stride;
+    /* variant 2 scratch: [n_pol][n_blocks][2*D + D*S] partial sums (dw | T | t), see csrc/td.cu.  In variant 2 the g / h
+       gradients are linear images of T and t; sfgpi_td_step reduces those and writes ONE complete gradient row per policy into
+       partial slot 0 of aux_grad_part (read it with n_part = 1); loss_part keeps n_blocks partials */
+    float *tsf_part;
 } sfgpi_td_args;
 
 int sfgpi_td_partials(int32_t B);
