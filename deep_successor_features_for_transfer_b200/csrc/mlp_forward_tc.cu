@@ -720,7 +720,8 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     if (tl_on && !tl_buf) cudaMalloc(&tl_buf, 256 * sizeof(long long));
     if (tl_on) cudaMemsetAsync(tl_buf, 0, 256 * sizeof(long long), (cudaStream_t)stream);
     m.timeline = tl_on ? tl_buf : nullptr;
-    const int paired = total_tiles > 148 ? 1 : 0;                // small launches: one tile per CTA, no ping-pong partner
+    static const int pair_min = getenv("SFGPI_PAIR_MIN") ? atoi(getenv("SFGPI_PAIR_MIN")) : 148;
+    const int paired = total_tiles > pair_min ? 1 : 0;           // small launches: one tile per CTA, no ping-pong partner
     m.total_pairs = 0;
     m.paired = paired;
     for (int j = 0; j < m.n_jobs; ++j) {
