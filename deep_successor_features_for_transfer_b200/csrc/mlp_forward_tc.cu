@@ -68,7 +68,7 @@ __device__ __forceinline__ float act_apply_fast(float v, int act) {
 // The TMEM load of the next 32 columns is in flight while the current 32 are processed.
 // NCH = 32-column chunks handled by this thread (8: the whole row; 4: one half, when both epilogue groups share a tile),
 // starting at column cbase.
-template <int ACT, int NCH>
+template <int ACT, int NCH, bool MASK>
 __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save,
                                                 uint32_t *mask_out, int cbase) {
     uint32_t v[2][32];
@@ -88,8 +88,9 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
             float h0 = __uint_as_float(u[4 * g]) + bv.x, h1 = __uint_as_float(u[4 * g + 1]) + bv.y;
             float h2 = __uint_as_float(u[4 * g + 2]) + bv.z, h3 = __uint_as_float(u[4 * g + 3]) + bv.w;
             if (ACT == SFGPI_ACT_RELU) {
-                mb |= (h0 > 0.f ? 1u : 0u) << (4 * g) | (h1 > 0.f ? 2u : 0u) << (4 * g) | (h2 > 0.f ? 4u : 0u) << (4 * g) |
-                      (h3 > 0.f ? 8u : 0u) << (4 * g);
+                if (MASK)
+                    mb |= (h0 > 0.f ? 1u : 0u) << (4 * g) | (h1 > 0.f ? 2u : 0u) << (4 * g) | (h2 > 0.f ? 4u : 0u) << (4 * g) |
+                          (h3 > 0.f ? 8u : 0u) << (4 * g);
                 h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f);
             }
             if (ACT == SFGPI_ACT_TANH) { h0 = tanhf(h0); h1 = tanhf(h1); h2 = tanhf(h2); h3 = tanhf(h3); }
@@ -108,7 +109,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
                                 __uint_as_float(pk[2 * g + 1] << 16), __uint_as_float(pk[2 * g + 1] & 0xFFFF0000u));
         }
     }
-    if (ACT == SFGPI_ACT_RELU && mask_out != nullptr) {    // 1 bit per activation: all the backward pass needs of a ReLU layer
+    if (MASK && ACT == SFGPI_ACT_RELU && mask_out != nullptr) {    // 1 bit per activation: all the backward pass needs of a ReLU layer
         static_assert(NCH == 4, "mask row layout: 8 words per row, 4 per column half");
         *reinterpret_cast<uint4 *>(mask_out + (cbase >> 5)) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
     }
@@ -417,9 +418,11 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                             ? reinterpret_cast<uint32_t *>(a.relu_mask_out) + (((size_t)it * a.n_pol + pl) * B + b) * 8
                             : nullptr;
                         if (store_pending[slot]) { a_slot_guard(!store_pending[slot ^ 1]); store_pending[slot] = false; }
-                        if (act == SFGPI_ACT_RELU) hidden_epilogue<SFGPI_ACT_RELU, 4>(t_lane, bias, Arow, r, save, mask_out, group * 128);
-                        else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4>(t_lane, bias, Arow, r, save, mask_out, group * 128);
-                        else hidden_epilogue<SFGPI_ACT_TANH, 4>(t_lane, bias, Arow, r, save, mask_out, group * 128);
+                        if (act == SFGPI_ACT_RELU) {
+                            if (a.relu_mask_out) hidden_epilogue<SFGPI_ACT_RELU, 4, true>(t_lane, bias, Arow, r, save, mask_out, group * 128);
+                            else hidden_epilogue<SFGPI_ACT_RELU, 4, false>(t_lane, bias, Arow, r, save, nullptr, group * 128);
+                        } else if (act == SFGPI_ACT_NONE) hidden_epilogue<SFGPI_ACT_NONE, 4, false>(t_lane, bias, Arow, r, save, nullptr, group * 128);
+                        else hidden_epilogue<SFGPI_ACT_TANH, 4, false>(t_lane, bias, Arow, r, save, nullptr, group * 128);
                         tc_fence_before();
                         fence_proxy_async();
                         mbar_arrive(SLOT_READY(slot));
