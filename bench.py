@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -220,11 +220,16 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- value: HBM-resident inputs, CUDA events per step ----------------
-    for k in range(args.warmup):
-        ag.update_successor_all(resident[k % n_res], use_gpi=True)
-    barrier()
+    # nvidia-smi needs ~0.1 s to start and the timed regions last milliseconds: it samples every 20 ms from here (before the
+    # warm-up) to the end of the e2e loop, i.e. throughout both timed regions and the loaded phases around them.
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_w = time.perf_counter()
+    k = 0
+    while k < args.warmup or time.perf_counter() - t_w < 0.3:      # >= W warm-up steps, >= 0.3 s under load
+        ag.update_successor_all(resident[k % n_res], use_gpi=True)
+        k += 1
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     # probes around the dominant kernel (the one-launch fused forward: online psi(s) + GPI(s') + target psi(s')), recorded by
     # the command list itself inside every timed step
@@ -242,7 +247,6 @@ def main():
     barrier()
     lib.set_probe(plan_key, None, None)
     launches = _lib.launch_count - l0
-    clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -263,6 +267,7 @@ def main():
         losses_host = losses.cpu()                                  # D2H read of the step's result (syncs)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)

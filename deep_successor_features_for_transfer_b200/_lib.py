@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libsfgpi.so')
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -78,6 +78,12 @@ class BackwardTcArgs(C.Structure):
                 ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
 
 
+class ReplayArgs(C.Structure):
+    _fields_ = [('ring', C.c_void_p), ('row_stride', C.c_int64), ('S', C.c_int32), ('D', C.c_int32), ('B', C.c_int32),
+                ('picks', C.c_void_p), ('states', C.c_void_p), ('actions', C.c_void_p), ('rewards', C.c_void_p),
+                ('phis', C.c_void_p), ('next_states', C.c_void_p), ('gammas', C.c_void_p)]
+
+
 class Cmd(C.Structure):
     _fields_ = [('op', C.c_int32), ('p', C.c_void_p * 5), ('i', C.c_int64 * 4)]
 
@@ -122,6 +128,7 @@ SYMBOLS = {
     'sfgpi_bwd_tc_splits': (C.c_int, [C.c_int32, C.c_int32]),
     'sfgpi_mlp_backward_tc': (C.c_int, [C.POINTER(BackwardTcArgs), C.c_void_p]),
     'sfgpi_mlp_forward_tc_jobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'sfgpi_replay_gather': (C.c_int, [C.POINTER(ReplayArgs), C.c_void_p]),
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),

@@ -54,6 +54,65 @@ class ReplayBuffer:
         self.index = (self.index + 1) % self.n_samples
 
 
+class DeviceReplayBuffer:
+    """
+    Same interface and sampling stream as ReplayBuffer (sfdqn.py:12-89), but the ring lives in HBM as packed fp32 rows
+    [s | s' | phi | r | gamma | action] and replay() is ONE gather kernel (csrc/replay.cu) instead of python loops + vstack +
+    .to(device) (66 ms per B=4096 batch in the reference).  Picks come from np.random.randint exactly like the
+    reference's, so under the same numpy seed both buffers return the same transitions.
+    """
+
+    def __init__(self, n_samples=1000000, n_batch=32):
+        self.n_samples = int(n_samples)
+        self.n_batch = int(n_batch)
+        self.reset()
+
+    def reset(self):
+        self.ring = None
+        self.index = 0
+        self.size = 0
+        self._out = None
+
+    def _alloc(self, S, D):
+        import ctypes as C
+        from . import _lib
+        dev = _device()
+        self.S, self.D = S, D
+        self.row = 2 * S + D + 3
+        self.ring = torch.zeros(self.n_samples, self.row, dtype=torch.float32, device=dev)
+        B = self.n_batch
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        self._out = (f32(B, S), torch.empty(B, dtype=torch.int64, device=dev), f32(B, 1), f32(B, D), f32(B, S), f32(B))
+        self._picks = torch.empty(B, dtype=torch.int64, device=dev)
+        self._picks_host = torch.empty(B, dtype=torch.int64).pin_memory()
+        a = self._args = _lib.ReplayArgs()
+        a.ring, a.row_stride, a.S, a.D, a.B, a.picks = self.ring.data_ptr(), self.row, S, D, B, self._picks.data_ptr()
+        a.states, a.actions, a.rewards, a.phis, a.next_states, a.gammas = (t.data_ptr() for t in self._out)
+
+    def append(self, state, action, reward, phi, next_state, gamma):
+        dev = _device()
+        flat = lambda v: torch.as_tensor(v, dtype=torch.float32).reshape(-1).to(dev, non_blocking=True)
+        s, s1, p = flat(state), flat(next_state), flat(phi)
+        if self.ring is None:
+            self._alloc(s.numel(), p.numel())
+        if int(torch.as_tensor(action).reshape(-1)[0]) >= (1 << 24):
+            raise ValueError('action index too large for the packed fp32 row')
+        self.ring[self.index].copy_(torch.cat([s, s1, p, flat(reward), flat(gamma), flat(action)]))
+        self.size = min(self.size + 1, self.n_samples)
+        self.index = (self.index + 1) % self.n_samples
+
+    def replay(self):
+        """None until n_batch samples exist (sfdqn.py:57); else (states, actions, rewards, phis, next_states, gammas)."""
+        if self.size < self.n_batch:
+            return None
+        import ctypes as C
+        from . import _lib
+        self._picks_host.copy_(torch.from_numpy(np.random.randint(low=0, high=self.size, size=(self.n_batch,))))
+        self._picks.copy_(self._picks_host, non_blocking=True)
+        _lib.call('sfgpi_replay_gather', C.byref(self._args), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return self._out
+
+
 class PackedPsi(torch.nn.Module):
     """
     The per-task psi module handed to callers in `sf.psi[i]`.  Its Linear parameters are views of row i of the packed

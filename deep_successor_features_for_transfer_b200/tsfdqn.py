@@ -9,7 +9,7 @@ import random
 import numpy as np
 import torch
 
-from .sfdqn import DeepSF, ReplayBuffer, SFDQN, _device  # noqa: F401  (ReplayBuffer re-exported like the reference file)
+from .sfdqn import DeepSF, DeviceReplayBuffer, ReplayBuffer, SFDQN, _device  # noqa: F401  (re-exported like the reference file)
 
 
 class DeepTSF(DeepSF):

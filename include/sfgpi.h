@@ -264,6 +264,26 @@ int sfgpi_bwd_tc_splits(int32_t B, int32_t want);
 int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 
 /*
+ * Device-resident replay ring (ReplayBuffer.replay, sfdqn.py:54-80): gathers B picked transitions out of the packed ring
+ *   ring [capacity][row_stride] fp32, row = [ s (S) | s' (S) | phi (D) | r | gamma | action ]
+ * into the six tensors of a replay batch: states [B][S], actions [B] int64, rewards [B], phis [B][D], next_states [B][S],
+ * gammas [B].  picks [B] int64 (device) are ring indices.
+ */
+typedef struct {
+    const float *ring;
+    int64_t row_stride;
+    int32_t S, D, B;
+    const int64_t *picks;
+    float *states;
+    int64_t *actions;
+    float *rewards;
+    float *phis;
+    float *next_states;
+    float *gammas;
+} sfgpi_replay_args;
+int sfgpi_replay_gather(const sfgpi_replay_args *args, void *stream);
+
+/*
  * Command list: one foreign call runs a whole train step (or any other fixed sequence of the entry points above plus plain
  * copies) back to back on `stream`.  p[] / i[] carry the operands of op (see csrc/run.cu); argument structs are referenced,
  * not copied, so the caller patches input pointers in place between replays.

@@ -52,7 +52,7 @@ def c_struct_fields(name):
 
 @pytest.mark.parametrize('cname,pyname', [('sfgpi_net_desc', 'NetDesc'), ('sfgpi_forward_args', 'ForwardArgs'),
                                           ('sfgpi_td_args', 'TdArgs'), ('sfgpi_backward_args', 'BackwardArgs'),
-                                          ('sfgpi_backward_tc_args', 'BackwardTcArgs'), ('sfgpi_forward_tc_job', 'ForwardTcJob'), ('sfgpi_cmd', 'Cmd'),
+                                          ('sfgpi_backward_tc_args', 'BackwardTcArgs'), ('sfgpi_forward_tc_job', 'ForwardTcJob'), ('sfgpi_cmd', 'Cmd'), ('sfgpi_replay_args', 'ReplayArgs'),
                                           ('sfgpi_adam_segment', 'AdamSegment'), ('sfgpi_adam_args', 'AdamArgs')])
 def test_ctypes_structs_mirror_header(cname, pyname):
     assert c_struct_fields(cname) == [f[0] for f in getattr(_lib, pyname)._fields_]

@@ -278,3 +278,28 @@ def test_full_size_properties_hopper_gpi():
     idx = torch.randperm(B, generator=gen)[:512]
     q_ref, _ = o.GPI(x.cpu()[idx], 0)
     assert rel_err(q.cpu()[idx], q_ref) < FWD_TOL
+
+
+def test_device_replay_buffer_matches_host_ring():
+    """the HBM ring + gather kernel return exactly what the reference-style host ring returns (same numpy stream)."""
+    from deep_successor_features_for_transfer_b200.sfdqn import ReplayBuffer, DeviceReplayBuffer
+    S, D, A, n_batch, cap = 4, 12, 9, 64, 300
+    host, dev = ReplayBuffer(n_samples=cap, n_batch=n_batch), DeviceReplayBuffer(n_samples=cap, n_batch=n_batch)
+    gen = torch.Generator().manual_seed(9)
+    assert dev.replay() is None
+    for k in range(cap + 57):                                     # wraps around the ring
+        s, s1 = torch.randn(1, S, generator=gen), torch.randn(1, S, generator=gen)
+        a = torch.randint(0, A, (), generator=gen)
+        r, phi, gamma = float(torch.randn((), generator=gen)), torch.rand(D, generator=gen), 0.0 if k % 17 == 0 else 0.9
+        host.append(s, a, r, phi, s1, gamma)
+        dev.append(s.cuda() if k % 2 else s, a, r, phi, s1, gamma)      # host and device inputs both accepted
+        if k == n_batch // 2:
+            assert dev.replay() is None and host.replay() is None
+    for seed in (1, 2):
+        np.random.seed(seed)
+        ref = host.replay()
+        np.random.seed(seed)
+        got = dev.replay()
+        for name, x, y in zip(('states', 'actions', 'rewards', 'phis', 'next_states', 'gammas'), ref, got):
+            assert x.shape == y.shape and x.dtype == y.dtype, (name, x.shape, y.shape, x.dtype, y.dtype)
+            assert torch.equal(x.cpu(), y.cpu()), name
