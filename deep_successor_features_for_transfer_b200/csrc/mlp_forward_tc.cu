@@ -19,6 +19,7 @@
 //               psi[B,N,A,D] is never formed, not even on chip.  (GPI_w, sfdqn.py:215-240.)
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace sfgpi {
 namespace tc {
@@ -137,10 +138,24 @@ __device__ __forceinline__ int job_of_pair(const TcMulti &m, int pair) {
     return j;
 }
 
+// TWO = true: 2-CTA pairs (cluster of 2, tcgen05 cta_group::2).  The pair runs ONE MMA stream with M = 256 (128 rows from each
+// CTA) and each CTA stores only its half of every weight block, so per SM the weight traffic (TMA in, MMA read) halves and a
+// 16 KB ring stage feeds a whole 256-column k-block.  Work unit = 4 row tiles of one policy: CTA r handles tile 4q + r in slot
+// X and tile 4q + 2 + r in slot Y.  Rank 0 issues all MMAs; producers and epilogues run in both CTAs.
+template <bool TWO>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ TmapSet maps) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+    const int unit0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // tile handled by this CTA in slot `slot` of work unit `pip` (of its policy), and whether the unit has a Y slot
+    auto tile_of = [&](const TcParams &p, int pip, int slot) {
+        return TWO ? 4 * pip + 2 * slot + (int)cta_rank : (p.paired ? 2 * pip + slot : pip);
+    };
+    auto has_y_of = [&](const TcParams &p, int pip) {
+        return TWO ? (4 * pip + 2 < p.tiles_per_policy) : (p.paired && (2 * pip + 1 < p.tiles_per_policy));
+    };
     pdl_launch_dependents();
     if (m.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) m.timeline[255] = clock64();      // kernel entry
 
@@ -163,16 +178,16 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), 256); mbar_init(ACC_FULL(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SLOT_READY(s), TWO ? 2 : 256); mbar_init(ACC_FULL(s), 1); }
         fence_mbar_init();
         for (int j = 0; j < m.n_jobs; ++j) {
             tma_prefetch_desc(&maps.w[j]);
             if (m.job[j].gpi) tma_prefetch_desc(&maps.q[j]);
         }
     }
-    if (warp == kMmaWarp) tmem_alloc(holder_addr, 512);
+    if (warp == kMmaWarp) { if (TWO) tmem_alloc2(holder_addr, 512); else tmem_alloc(holder_addr, 512); }
     tc_fence_before();
-    __syncthreads();
+    if (TWO) cluster_sync_all(); else __syncthreads();       // (pair: the peer's barriers must exist before anything arrives on them)
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
@@ -188,20 +203,21 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const uint32_t leader = elect_one();
             uint32_t n = 0;
             int tlc = 0;
-            for (int gpair = blockIdx.x; gpair < m.total_pairs; gpair += gridDim.x) {
+            for (int gpair = unit0; gpair < m.total_pairs; gpair += unit_stride) {
                 const int jb = job_of_pair(m, gpair);
                 const TcParams &p = m.job[jb];
                 const sfgpi_forward_args &a = p.a;
                 const int pair = gpair - m.pair_start[jb];
                 const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
                 const int row0 = (a.policy_lo + pl) * p.rows_per_policy;
-                const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
+                const bool has_y = has_y_of(p, pip);
                 for (int it = 0; it < p.n_items; ++it) {
                     const ItemInfo ii = item_info(p, it);
-                    const int nblocks = (ii.n_cols + kNB - 1) / kNB;
+                    const int nblocks = TWO ? 1 : (ii.n_cols + kNB - 1) / kNB;
                     const bool folded = ii.kind == 2 && p.gpi;
                     const void *tm = folded ? (const void *)&maps.q[jb] : (const void *)&maps.w[jb];
-                    const int rbase = folded ? pl * p.n_final + ii.row_base : row0 + ii.row_base;
+                    // pair: this CTA stores weight rows [rank * n_cols / 2, ...) of the block (its half of the B operand)
+                    const int rbase = (folded ? pl * p.n_final + ii.row_base : row0 + ii.row_base) + (TWO ? (int)cta_rank * (ii.n_cols >> 1) : 0);
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot)
                         for (int kb = 0; kb < ii.n_kb; ++kb)
                             for (int nb = 0; nb < nblocks; ++nb, ++n) {
@@ -209,8 +225,13 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                                 if ((s & 3) != warp) continue;
                                 mbar_wait_warp(W_EMPTY(s), ((n >> ns_log) & 1) ^ 1);
                                 if (warp == 0 && leader) TL_STAMP(2, tlc);
-                                mbar_arrive_expect_tx_e(W_FULL(s), kStageBytes, leader);
-                                tma_load_2d_e(W_addr + stage_off(s), tm, W_FULL(s), kb * kKB, rbase + nb * kNB, leader);
+                                if (TWO) {                       // both halves are counted on the pair leader's barrier
+                                    if (cta_rank == 0) mbar_arrive_expect_tx_e(W_FULL(s), 2 * kStageBytes, leader);
+                                    tma_load_2d_2cta_e(W_addr + stage_off(s), tm, W_FULL(s), kb * kKB, rbase, leader);
+                                } else {
+                                    mbar_arrive_expect_tx_e(W_FULL(s), kStageBytes, leader);
+                                    tma_load_2d_e(W_addr + stage_off(s), tm, W_FULL(s), kb * kKB, rbase + nb * kNB, leader);
+                                }
                             }
                 }
             }
@@ -218,29 +239,48 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
     } else if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
         // Whole warp runs the loop (operands stay in uniform registers), the elected lane issues: see tc_common.cuh.
-        {
+        if (!TWO || cta_rank == 0) {
             const uint32_t leader = elect_one();
             uint32_t n = 0, ready_cnt[2] = {0, 0};
             int tlc = 0;
             const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
             const uint64_t bdesc0 = umma_desc_k_sw128(W_addr);
-            for (int gpair = blockIdx.x; gpair < m.total_pairs; gpair += gridDim.x) {
+            for (int gpair = unit0; gpair < m.total_pairs; gpair += unit_stride) {
                 const int jb = job_of_pair(m, gpair);
                 const TcParams &p = m.job[jb];
                 const int pair = gpair - m.pair_start[jb];
                 const int pip = pair % p.pairs_per_policy;
-                const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
+                const bool has_y = has_y_of(p, pip);
                 for (int it = 0; it < p.n_items; ++it) {
                     const ItemInfo ii = item_info(p, it);
                     const int nblocks = (ii.n_cols + kNB - 1) / kNB;
                     const uint32_t idesc_full = umma_idesc_bf16(kTM, kNB);
                     const uint32_t idesc_last = umma_idesc_bf16(kTM, (uint32_t)(ii.n_cols - (nblocks - 1) * kNB));
                     for (int slot = 0; slot < (has_y ? 2 : 1); ++slot) {
-                        mbar_wait_warp(SLOT_READY(slot), ready_cnt[slot] & 1);
+                        if (TWO) mbar_wait_warp_cluster(SLOT_READY(slot), ready_cnt[slot] & 1);
+                        else mbar_wait_warp(SLOT_READY(slot), ready_cnt[slot] & 1);
                         ++ready_cnt[slot];
                         tc_fence_after();
                         if (leader) TL_STAMP(1, tlc);                         // slot ready
                         const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
+                        if (TWO) {
+                            // pair: one ring stage (this CTA's half of the weight block) per k-block, M = 256, N = n_cols
+                            const uint32_t idesc2 = umma_idesc_bf16(256, (uint32_t)ii.n_cols);
+                            for (int kb = 0; kb < ii.n_kb; ++kb, ++n) {
+                                const uint64_t ad = (slot ? adesc_y : adesc_x) + (uint64_t)(kb * ((kTM * 128) >> 4));
+                                const int s = n & ns_mask;
+                                mbar_wait_warp(W_FULL(s), (n >> ns_log) & 1);
+                                tc_fence_after();
+                                if (leader && kb == 0) TL_STAMP(1, tlc);
+                                const uint64_t bd = bdesc0 + (uint64_t)(int64_t)(stage_off(s) >> 4);
+                                for (int k16 = 0; k16 < ii.n_k16; ++k16)
+                                    umma_bf16_2cta_e(d_base, ad + 2 * k16, bd + 2 * k16, idesc2, (kb | k16) ? 1u : 0u, leader);
+                                umma_commit_2cta_e(W_EMPTY(s), leader);
+                            }
+                            umma_commit_2cta_e(ACC_FULL(slot), leader);
+                            if (leader) TL_STAMP(1, tlc);
+                            continue;
+                        }
                         // A full 256-column layer is issued as N=256 MMAs over a PAIR of adjacent ring stages (rows 0-127 | 128-255
                         // of the weight block are contiguous in shared memory): half as many instructions for the same math --
                         // the single issuing thread needs ~107 cycles per tcgen05.mma, more than the 64 an N=128 MMA executes.
@@ -314,7 +354,17 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 #define TL_EPI() do { if (tl_role >= 0) TL_STAMP(tl_role, tlc); } while (0)
         TL_EPI();                                            // set-up done
 
-        for (int gpair = blockIdx.x; gpair < m.total_pairs; gpair += gridDim.x) {
+        // pair: SLOT_READY lives in the leader CTA and takes ONE cluster-scope release arrive per CTA -- 256 per-thread
+        // release.cluster arrives cost ~1000 cycles per epilogue (measured); a CTA barrier orders the others' writes before it.
+        auto slot_ready = [&](int slot) {
+            if (TWO) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) mbar_arrive_leader(SLOT_READY(slot));
+            } else {
+                mbar_arrive(SLOT_READY(slot));
+            }
+        };
+        for (int gpair = unit0; gpair < m.total_pairs; gpair += unit_stride) {
             const int jb = job_of_pair(m, gpair);
             const TcParams &p = m.job[jb];
             const sfgpi_forward_args &a = p.a;
@@ -324,7 +374,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const int n_bias = (1 + p.Lh) * kH + p.n_final;     // [b_0 | b_1..b_Lh | b_final]
             const int pair = gpair - m.pair_start[jb];
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
-            const int n_slots = (p.paired && (2 * pip + 1 < p.tiles_per_policy)) ? 2 : 1;
+            const int n_slots = has_y_of(p, pip) ? 2 : 1;
             const float *P = a.params + (size_t)(a.policy_lo + pl) * net.row_stride;
 
             // Saved activations (training forward): the bf16 tile a hidden epilogue leaves in the A slot IS the row-major
@@ -345,7 +395,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 #pragma unroll
             for (int slot = 0; slot < 2; ++slot) {
                 if (slot >= n_slots) break;
-                const int b = ((p.paired ? 2 * pip + slot : pip)) * kTM + r;     // global state index of this thread's row
+                const int b = tile_of(p, pip, slot) * kTM + r;                   // global state index of this thread's row
                 const bool row_ok = b < B;
                 bs[slot] = b;
                 if (group == 0) {
@@ -360,7 +410,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                     }
                     fence_proxy_async();                      // generic-proxy smem writes -> visible to the UMMA (async proxy)
                 }
-                mbar_arrive(SLOT_READY(slot));
+                slot_ready(slot);
                 sel_base[slot] = -(1 << 30);
                 if (a.sel_out != nullptr && row_ok) {
                     const int sidx = a.sel_actions ? (int)a.sel_actions[b]
@@ -425,11 +475,11 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         else hidden_epilogue<SFGPI_ACT_TANH, 4, false>(t_lane, bias, Arow, r, save, nullptr, group * 128);
                         tc_fence_before();
                         fence_proxy_async();
-                        mbar_arrive(SLOT_READY(slot));
+                        slot_ready(slot);
                         if (saving) {                         // tile complete in shared memory -> one thread stores it
-                            asm volatile("bar.sync 1, 256;" ::: "memory");
+                            if (!TWO) asm volatile("bar.sync 1, 256;" ::: "memory");      // (pair: slot_ready just did)
                             if (et == 0) {
-                                const int row0 = (p.paired ? 2 * pip + slot : pip) * kTM;
+                                const int row0 = tile_of(p, pip, slot) * kTM;
 #pragma unroll
                                 for (int kb = 0; kb < kH / kKB; ++kb)
                                     tma_store_3d(&maps.acts[jb], Arow + kb * (kTM * 128), kb * kKB, row0, it * a.n_pol + pl);
@@ -507,7 +557,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                             }
                         }
                         tc_fence_before();
-                        if (it + 1 < p.n_items) mbar_arrive(SLOT_READY(slot));     // next chunk may overwrite the accumulator
+                        if (it + 1 < p.n_items) slot_ready(slot);                  // next chunk may overwrite the accumulator
                     }
                     TL_EPI();                                 // epilogue of (item, slot) done
                 }
@@ -518,11 +568,11 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 
     // ---- teardown ----
     tc_fence_before();
-    __syncthreads();
+    if (TWO) cluster_sync_all(); else __syncthreads();       // (pair: nobody retires while the peer may still touch it)
     if (warp == kMmaWarp) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (TWO) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -609,6 +659,8 @@ static int make_tmap_acts(CUtensorMap *tm, const void *base, uint64_t slabs, uin
     return SFGPI_OK;
 }
 
+static int g_two_cta_min = getenv("SFGPI_2CTA_MIN") ? atoi(getenv("SFGPI_2CTA_MIN")) : 0x7fffffff;
+
 static bool tc_shape_ok(const sfgpi_net_desc &net, const char **why) {
     if (net.n_layers < 3) { *why = "needs >= 3 Linear layers"; return false; }
     for (int l = 1; l < net.n_layers; ++l)
@@ -623,6 +675,18 @@ static bool tc_shape_ok(const sfgpi_net_desc &net, const char **why) {
 
 using namespace sfgpi;
 using namespace sfgpi::tc;
+
+// Runtime options of the tensor-core path.  "2cta_min_tiles": launches with more row tiles than this use 2-CTA pairs
+// (default: never); returns the previous value, or -1 for an unknown option.
+extern "C" int sfgpi_set_option(const char *name, int32_t value) {
+    if (name != nullptr && strcmp(name, "2cta_min_tiles") == 0) {
+        const int old = g_two_cta_min;
+        g_two_cta_min = value;
+        return old;
+    }
+    set_error("sfgpi_set_option: unknown option");
+    return -1;
+}
 
 extern "C" int sfgpi_bf16_rows_per_policy(const sfgpi_net_desc *net) {
     const int AD = net->n_actions * net->n_features;
@@ -724,13 +788,18 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     if (tl_on) cudaMemsetAsync(tl_buf, 0, 256 * sizeof(long long), (cudaStream_t)stream);
     m.timeline = tl_on ? tl_buf : nullptr;
     static const int pair_min = getenv("SFGPI_PAIR_MIN") ? atoi(getenv("SFGPI_PAIR_MIN")) : 148;
+    // 2-CTA pairs are opt-in (sfgpi_set_option("2cta_min_tiles", n) or env SFGPI_2CTA_MIN): measured on B200 they remove the
+    // shared-memory bound of the MMA phase (3100-3300 -> 2300-2600 cycles per tile-layer) but the cluster-scope hand-off makes
+    // every epilogue ~500 cycles longer, and the epilogue chain is then the critical path: 0.506 ms vs 0.448 ms at N=64, B=16384.
+    const int two_min = g_two_cta_min;
     const int paired = total_tiles > pair_min ? 1 : 0;           // small launches: one tile per CTA, no ping-pong partner
+    const bool two = paired && total_tiles > two_min;            // >= 2 row tiles per SM: 2-CTA pairs (4 tiles per work unit)
     m.total_pairs = 0;
     m.paired = paired;
     for (int j = 0; j < m.n_jobs; ++j) {
         TcParams &p = m.job[j];
         p.paired = paired;
-        p.pairs_per_policy = paired ? (p.tiles_per_policy + 1) / 2 : p.tiles_per_policy;
+        p.pairs_per_policy = two ? (p.tiles_per_policy + 3) / 4 : (paired ? (p.tiles_per_policy + 1) / 2 : p.tiles_per_policy);
         p.total_pairs = p.pairs_per_policy * p.a.n_pol;
         m.pair_start[j] = m.total_pairs;
         m.total_pairs += p.total_pairs;
@@ -739,9 +808,14 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     for (int j = m.n_jobs; j < kMaxJobs; ++j) { m.job[j] = m.job[0]; maps.w[j] = maps.w[0]; maps.q[j] = maps.q[0]; maps.acts[j] = maps.acts[0]; }
     const int smem_bytes = 2 * kABytes + kNStage * kStageBytes + kBiasFloatsMax * 4 + 256;
     static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); cfg = true; }
-    const int grid = m.total_pairs < 148 ? m.total_pairs : 148;
-    launch_pdl(mlp_forward_tc_kernel, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, m, maps);
+    if (!cfg) {
+        cudaFuncSetAttribute(mlp_forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaFuncSetAttribute(mlp_forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cfg = true;
+    }
+    const int grid = two ? (m.total_pairs < 74 ? 2 * m.total_pairs : 148) : (m.total_pairs < 148 ? m.total_pairs : 148);
+    if (two) launch_pdl_cluster(mlp_forward_tc_kernel<true>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, 2, m, maps);
+    else launch_pdl(mlp_forward_tc_kernel<false>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, m, maps);
     if (tl_on) {                                                 // developer aid: dump CTA 0's role timelines (cycles since t0)
         long long h[256];
         cudaStreamSynchronize((cudaStream_t)stream);
@@ -749,7 +823,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         long long t0 = 0;
         for (int i = 0; i < 256; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
         static const char *role[4] = {"epiX", "mma", "tma0", "epiY"};
-        fprintf(stderr, "[sfgpi timeline] jobs=%d pairs=%d grid=%d\n", m.n_jobs, m.total_pairs, grid);
+        fprintf(stderr, "[sfgpi timeline] jobs=%d units=%d grid=%d %s\n", m.n_jobs, m.total_pairs, grid, two ? "2-CTA pairs" : (paired ? "paired" : "one-tile"));
         for (int r = 0; r < 4; ++r) {
             fprintf(stderr, "  %-4s:", role[r]);
             for (int i = 0; i < 64 && h[r * 64 + i]; ++i) fprintf(stderr, " %lld", h[r * 64 + i] - t0);

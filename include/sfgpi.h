@@ -309,6 +309,10 @@ typedef struct {
 } sfgpi_cmd;
 int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream);
 
+/* Runtime options: "2cta_min_tiles" = tensor-core forward launches with more 128-row tiles than this run as 2-CTA pairs
+ * (tcgen05 cta_group::2, each CTA holds half of every weight block); default: never.  Returns the previous value or -1. */
+int sfgpi_set_option(const char *name, int32_t value);
+
 const char *sfgpi_last_error(void);
 int sfgpi_version(void);
 

@@ -33,10 +33,21 @@ def make(S, A, D, N, seed, tsf_dim=None, beta=1):
 @pytest.mark.parametrize('S,A,D,N,B,hopper', [
     (4, 9, 12, 4, 4096, False),          # 128 tiles: one tile per CTA (no ping-pong partner)
     (4, 9, 12, 6, 33 * 128 - 5, False),  # 198 tiles: paired mode, odd tile count per policy, ragged last tile
+    (4, 9, 12, 10, 33 * 128 - 5, False), # 330 tiles: 2-CTA pairs, 33 tiles per policy (last work unit has one tile)
+    (11, 27, 50, 5, 8192, True),         # Hopper on 2-CTA pairs: output layer in 6 chunks, 64 tiles per policy
     (11, 27, 50, 3, 1000, True),         # Hopper: output layer in 6 chunks of <= 256 columns, S = 11
     (4, 2, 20, 3, 32, False),            # CartPole, a single partial tile
 ])
 def test_bf16_forward_gpi_vs_oracle(S, A, D, N, B, hopper):
+    from deep_successor_features_for_transfer_b200 import _lib
+    old = _lib.lib().sfgpi_set_option(b'2cta_min_tiles', 296)           # the two big cases run as 2-CTA pairs
+    try:
+        _bf16_forward_gpi_vs_oracle(S, A, D, N, B, hopper)
+    finally:
+        _lib.lib().sfgpi_set_option(b'2cta_min_tiles', old)
+
+
+def _bf16_forward_gpi_vs_oracle(S, A, D, N, B, hopper):
     meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
     o, gen = make(S, A, D, N, seed=21)
     sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
