@@ -224,11 +224,9 @@ def main():
     # warm-up) to the end of the e2e loop, i.e. throughout both timed regions and the loaded phases around them.
     sampler = ClockSampler(local_rank)
     sampler.start()
-    t_w = time.perf_counter()
-    k = 0
-    while k < args.warmup or time.perf_counter() - t_w < 0.3:      # >= W warm-up steps, >= 0.3 s under load
+    n_warm = max(args.warmup, 1000)                     # a FIXED count (identical on every rank): >= W steps, ~0.3 s under load
+    for k in range(n_warm):
         ag.update_successor_all(resident[k % n_res], use_gpi=True)
-        k += 1
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     # probes around the dominant kernel (the one-launch fused forward: online psi(s) + GPI(s') + target psi(s')), recorded by
@@ -242,7 +240,7 @@ def main():
             flush.fill_(k & 0xFF)
         lib.set_probe(plan_key, *kev[k])
         ev[k][0].record()
-        ag.update_successor_all(resident[(args.warmup + k) % n_res], use_gpi=True)
+        ag.update_successor_all(resident[(n_warm + k) % n_res], use_gpi=True)
         ev[k][1].record()
     barrier()
     lib.set_probe(plan_key, None, None)

@@ -130,6 +130,8 @@ SYMBOLS = {
     'sfgpi_mlp_forward_tc_jobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_replay_gather': (C.c_int, [C.POINTER(ReplayArgs), C.c_void_p]),
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'sfgpi_shard_unpack': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_set_option': (C.c_int, [C.c_char_p, C.c_int32]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),

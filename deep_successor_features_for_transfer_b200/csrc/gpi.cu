@@ -129,3 +129,53 @@ extern "C" int sfgpi_gpi_from_psi(const float *psi, const float *w, int32_t B, i
         psi, w, B, N, A, D, task_base, q_out, reinterpret_cast<long long *>(key_action), reinterpret_cast<long long *>(key_task));
     return check_launch("sfgpi_gpi_from_psi");
 }
+
+// ---- policy sharding: ONE all-gather per train step carries everything the ranks exchange besides the GPI keys --------------
+// x_local = [ w of the local policies (nw floats) | delta of the shared h applied by the local optimizers (nh floats) ]
+namespace sfgpi {
+__global__ void shard_pack_kernel(const float *__restrict__ w, int nw, const float *__restrict__ h, const float *__restrict__ h_prev,
+                                  int nh, float *__restrict__ x_local) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nw) x_local[i] = w[i];
+    else if (i < nw + nh) x_local[i] = h[i - nw] - h_prev[i - nw];
+}
+// x_all [world][nw + nh] -> w_all [world * nw] (reward vectors of ALL policies, rank-major = global policy order),
+// h = h_prev + sum_r delta_r (rank order: identical on every rank), h_prev = h
+__global__ void shard_unpack_kernel(const float *__restrict__ x_all, int world, int nw, int nh, float *__restrict__ w_all,
+                                    float *__restrict__ h, float *__restrict__ h_prev) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = nw + nh;
+    if (i < world * nw) {
+        const int r = i / nw, k = i - r * nw;
+        w_all[i] = x_all[(size_t)r * stride + k];
+    } else if (i < world * nw + nh) {
+        const int k = i - world * nw;
+        float acc = h_prev[k];
+        for (int r = 0; r < world; ++r) acc += x_all[(size_t)r * stride + nw + k];
+        h[k] = acc;
+        h_prev[k] = acc;
+    }
+}
+}  // namespace sfgpi
+
+extern "C" int sfgpi_shard_pack(const float *w, int32_t nw, const float *h, const float *h_prev, int32_t nh, float *x_local,
+                                void *stream) {
+    if (nw < 0 || nh < 0 || (nh > 0 && (!h || !h_prev)) || !x_local) { set_error("sfgpi_shard_pack: invalid arguments"); return SFGPI_E_INVALID; }
+    if (nw + nh == 0) return SFGPI_OK;
+    launch_pdl(shard_pack_kernel, dim3((nw + nh + 255) / 256), dim3(256), 0, (cudaStream_t)stream, w, (int)nw, h, h_prev, (int)nh, x_local);
+    return check_launch("sfgpi_shard_pack");
+}
+
+extern "C" int sfgpi_shard_unpack(const float *x_all, int32_t world, int32_t nw, int32_t nh, float *w_all, float *h, float *h_prev,
+                                  void *stream) {
+    if (world < 1 || nw < 0 || nh < 0 || !x_all) { set_error("sfgpi_shard_unpack: invalid arguments"); return SFGPI_E_INVALID; }
+    const int n = world * nw + nh;
+    if (n == 0) return SFGPI_OK;
+    launch_pdl(shard_unpack_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x_all, (int)world, (int)nw, (int)nh, w_all,
+               h, h_prev);
+    return check_launch("sfgpi_shard_unpack");
+}

@@ -119,6 +119,7 @@ class PackedSFLibrary:
         self._ws = {}
         self.h = None
         self.shard = None           # dist.ShardContext once enable_sharding() was called
+        self._xchg = None
         self.set_precision(precision)
 
     def set_precision(self, precision):
@@ -182,6 +183,15 @@ class PackedSFLibrary:
         from .dist import ShardContext
         self.shard = ShardContext(self.n, group)
         self._ws = {k: v for k, v in self._ws.items() if not (isinstance(k, tuple) and k and k[0] == 'plan')}
+        self._xchg = None
+        if self.shard.world > 1:
+            D, sh = self.spec.n_features, self.shard
+            nh = self.h.numel() if self.h is not None else 0
+            x = dict(w_all=self._f(sh.n_total, D), nh=nh, ok=False)
+            if sh.uniform:                                   # fused exchange: one all-gather per step (see _exchange)
+                x.update(local=self._f(self.n * D + nh), all=self._f(sh.world, self.n * D + nh),
+                         h_prev=self.h.clone() if nh else None)
+            self._xchg = x
         return self.shard
 
     @property
@@ -209,6 +219,7 @@ class PackedSFLibrary:
             setattr(self, k, t)
         self.cap = cap
         self._ws = {}
+        self.invalidate_exchange()
         for i, mods in enumerate(self._views):
             self._point_views(i, mods)
 
@@ -260,6 +271,7 @@ class PackedSFLibrary:
         self._views.append(mods)
         self._point_views(i, mods)
         self.n += 1
+        self.invalidate_exchange()
         return i
 
     def reset(self):
@@ -418,7 +430,7 @@ class PackedSFLibrary:
             if sharded and ensemble:
                 nt = self.shard.n_total
                 keys = ws['keys_all'] = ws.get('keys_all', torch.empty(nt, B, dtype=torch.int64, device=self.device))
-                w_all = ws['w_all'] = ws.get('w_all', self._f(nt, D))
+                w_all = self._xchg['w_all']
                 a2.w, a2.n_w, a2.w_diag, key_row0 = ptr(w_all), nt, 0, self.shard.lo
             else:
                 a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 0
@@ -571,21 +583,55 @@ class PackedSFLibrary:
         keys, sharded = plan['keys'], plan['sharded']
         segs = plan['segments']
         run = lambda seg: seg[1] and _lib.run(seg[0], seg[1], st, seg[2])
+        xc = self._xchg if self._sharded else None
+        fused = xc is not None and 'local' in xc              # uniform shards: ONE all-gather per step carries w and h's deltas
+        need_h = xc is not None and variant == 2
         run(segs[0])                                          # [H2D] pack shadows, key fill
-        if sharded and plan['w_all'] is not None:
-            self._gather_w(plan['w_all'])
+        if sharded and plan['w_all'] is not None and not (fused and xc['ok']):
+            self._gather_w(plan['w_all'])                     # first step (or after outside changes): plain gather of w
         run(segs[1])                                          # fold + forwards (fp32: online + GPI forwards)
         if sharded:
             from .dist import allreduce_max_keys
             allreduce_max_keys(keys, self.shard.group)        # packed (value,index) MAX over NVLink: global GPI
-        h0 = self.h.clone() if (self._sharded and variant == 2) else None
+        h0 = None
+        if need_h:
+            if not fused:
+                h0 = self.h.clone()
+            elif not xc['ok']:
+                xc['h_prev'].copy_(self.h)
         run(segs[2])                                          # (fp32: target forward) TD, backward, Adam
-        if h0 is not None:                        # every rank applied only its own optimizers' deltas to the shared h
+        if fused:
+            self._exchange(xc, need_h)
+        elif h0 is not None:                      # every rank applied only its own optimizers' deltas to the shared h
             import torch.distributed as dist
             delta = self.h - h0
             dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.shard.group)
             self.h.copy_(h0 + delta)
         return losses
+
+    def _exchange(self, xc, with_h):
+        """
+        End-of-step exchange of a sharded library: x_local = [w_local | h - h_prev] -> all-gather -> w_all (the reward vectors
+        the NEXT step's GPI scores against), h = h_prev + sum of every rank's delta, h_prev = h.  Two small kernels around one
+        NCCL all-gather replace the w all-gather, the h clone and the delta all-reduce of the unfused path.
+        """
+        import torch.distributed as dist
+        st, D = _stream(), self.spec.n_features
+        nw, nh = self.n * D, (xc['nh'] if with_h else 0)
+        local, allx = (xc['local'], xc['all']) if nh == xc['nh'] else (xc['local'][:nw], None)
+        if allx is None:                                      # TSF library stepped without h (variants 0/1): w only
+            allx = xc.setdefault('all_w', self._f(self.shard.world, nw))
+        _lib.call('sfgpi_shard_pack', ptr(self.w), nw, ptr(self.h) if nh else None, ptr(xc['h_prev']) if nh else None, nh,
+                  ptr(local), st)
+        dist.all_gather_into_tensor(allx, local, group=self.shard.group)
+        _lib.call('sfgpi_shard_unpack', ptr(allx), self.shard.world, nw, nh, ptr(xc['w_all']), ptr(self.h) if nh else None,
+                  ptr(xc['h_prev']) if nh else None, st)
+        xc['ok'] = True
+
+    def invalidate_exchange(self):
+        """Call after changing w or h of a sharded library from outside train_step (e.g. through the nn.Module views)."""
+        if getattr(self, '_xchg', None) is not None:
+            self._xchg['ok'] = False
 
     def _as_input(self, t, dtype):
         """Transition field as a contiguous tensor of `dtype` WITHOUT moving it: host inputs are staged by the command list."""

@@ -309,6 +309,16 @@ typedef struct {
 } sfgpi_cmd;
 int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream);
 
+/*
+ * Policy sharding (one process per GPU): everything the ranks exchange per train step besides the GPI keys travels in ONE
+ * all-gather of x_local = [ w of the local policies (nw) | delta of the shared TSF h applied by the local optimizers (nh) ].
+ * pack builds x_local (delta = h - h_prev); unpack turns the gathered x_all [world][nw + nh] into w_all [world * nw] (global
+ * policy order), h = h_prev + sum_r delta_r (rank order, identical everywhere) and h_prev = h.  nh = 0 without TSF.
+ */
+int sfgpi_shard_pack(const float *w, int32_t nw, const float *h, const float *h_prev, int32_t nh, float *x_local, void *stream);
+int sfgpi_shard_unpack(const float *x_all, int32_t world, int32_t nw, int32_t nh, float *w_all, float *h, float *h_prev,
+                       void *stream);
+
 /* Runtime options: "2cta_min_tiles" = tensor-core forward launches with more 128-row tiles than this run as 2-CTA pairs
  * (tcgen05 cta_group::2, each CTA holds half of every weight block); default: never.  Returns the previous value or -1. */
 int sfgpi_set_option(const char *name, int32_t value);

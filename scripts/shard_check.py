@@ -21,7 +21,8 @@ rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int
 torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 S, A, D, B, K = 4, 9, 12, 1000, 3
-N = 2 * world + 1                                             # uneven shards on purpose
+# uneven shards (plain gather / all-reduce path) by default; 'even' exercises the fused one-all-gather exchange
+N = 2 * world + (0 if (len(sys.argv) > 2 and sys.argv[2] == 'even') else 1)
 gen = torch.Generator().manual_seed(5)
 o = OracleSF(S, A, D, (256, 256), ('relu', 'relu'), tsf_dim=100, beta=1)
 for _ in range(N):
