@@ -139,3 +139,142 @@ class TSFDQN(SFDQN):
         for i in range(self.sf.n_tasks):
             self.sf._after_update(i)
         return losses
+
+    # ---- target tasks: omega-weighted transfer (tsfdqn.py:784-1011) -----------------------------------------
+    # Host loop as in the reference; every psi evaluation (get_successors / get_next_successors: N nets per call) runs on the
+    # fused ensemble kernels, the (w, omega) update is a handful of [1, N, A, D]-sized torch ops.
+    def _epsilon_greedy(self, q):
+        q = q.flatten()
+        assert q.size()[0] == self.n_actions
+        if random.random() <= self.epsilon:
+            a = torch.tensor(random.randrange(self.n_actions)).to(self.device)
+        else:
+            a = torch.argmax(q)
+        self.epsilon = max(self.epsilon * self.epsilon_decay, self.epsilon_min)
+        return a
+
+    def _new_target_task(self, feature_dim, omegas_init):
+        """(w_approx, Adam over {w, omega}, LambdaLR decaying only omega's lr) for one target task (tsfdqn.py:803-832)."""
+        hp = self.hyperparameters
+        omegas = omegas_init.clone().detach().requires_grad_(True)
+        w_approx = torch.nn.Linear(feature_dim, 1, bias=False, device=self.device)
+        with torch.no_grad():
+            w_approx.weight.uniform_(-0.01, 0.01)
+        optim = torch.optim.Adam([
+            {'params': w_approx.parameters(), 'lr': hp['learning_rate_w'], 'weight_decay': hp['weight_decay_w']},
+            {'params': omegas, 'lr': hp['learning_rate_omega'], 'weight_decay': hp['weight_decay_omega']}])
+        decay = hp['learning_rate_omega_decay']
+        scheduler = torch.optim.lr_scheduler.LambdaLR(optim, [lambda epoch: 1.0, lambda epoch: (1 - decay) ** epoch])
+        return w_approx, optim, scheduler, omegas
+
+    def train(self, train_tasks, n_samples, viewers=None, n_view_ev=None, test_tasks=[], n_test_ev=1000, cycles_per_task=1):
+        if viewers is None:
+            viewers = [None] * len(train_tasks)
+        self.reset()
+        for train_task in train_tasks:
+            self.add_training_task(train_task)
+        with torch.no_grad():
+            omegas0 = self._init_omega(len(train_tasks))
+            omegas0 = omegas0 / torch.sum(omegas0, axis=1, keepdim=True)          # sum_i omega_i = 1 at the start
+        self.test_tasks_weights, self.omegas = [], []
+        for test_task in test_tasks:
+            w_approx, optim, scheduler, omegas = self._new_target_task(test_task.feature_dim(), omegas0)
+            self.test_tasks_weights.append((w_approx, optim, scheduler))
+            self.omegas.append(omegas)
+        return_data = []
+        for _ in range(cycles_per_task):
+            for index, (train_task, viewer) in enumerate(zip(train_tasks, viewers)):
+                self.set_active_training_task(index)
+                for t in range(n_samples):
+                    self.next_sample(viewer, n_view_ev)
+                    if t % n_test_ev == 0 and len(test_tasks) > 0:
+                        Rs = [self.test_agent(task, k) for k, task in enumerate(test_tasks)]
+                        avg_R = torch.mean(torch.Tensor(Rs).to(self.device))
+                        return_data.append(avg_R)
+                        if self.logger is not None:
+                            self.logger.log_progress(self.get_progress_dict())
+                            self.logger.log_average_reward(avg_R, self.total_training_steps)
+                            self.logger.log_accumulative_reward(torch.sum(torch.Tensor(return_data).to(self.device)),
+                                                                self.total_training_steps)
+                    self.total_training_steps += 1
+        return return_data
+
+    @staticmethod
+    def _normalized(omegas):
+        return omegas / torch.sum(omegas, axis=1, keepdim=True)
+
+    def get_test_action(self, s_enc, w, omegas=None):
+        if omegas is None:                                    # SFDQN-style call (GPI over the library under w)
+            return super().get_test_action(s_enc, w)
+        with torch.no_grad():
+            if random.random() <= self.test_epsilon:
+                return torch.tensor(random.randrange(self.n_actions)).to(self.device)
+            tsf = torch.sum(self.sf.get_successors(s_enc) * self._normalized(omegas), axis=1)      # [1, A, D]
+            return torch.argmax(w(tsf))                       # the target task acts by Q-learning on the mixed psi
+
+    def test_agent(self, task, test_index):
+        R = 0.0
+        w, optim, scheduler = self.test_tasks_weights[test_index]
+        omegas = self.omegas[test_index]
+        s_enc = self.encoding(task.initialize())
+        accum = [0.0, 0.0, 0.0]
+        for _ in range(self.T):
+            a = self.get_test_action(s_enc, w, omegas)
+            s1, r, done = task.transition(a)
+            s1_enc = self.encoding(s1)
+            a1 = self.get_test_action(s1_enc, w, omegas)
+            losses = self.update_test_reward_mapper(w, omegas, optim, task, r, s_enc, a, s1_enc, a1)
+            accum = [acc + float(x) for acc, x in zip(accum, losses)]
+            scheduler.step()
+            s_enc = s1_enc
+            R += r
+            if done:
+                break
+        if self.total_training_steps % 5000 == 0 and self.logger is not None:
+            beta = self.hyperparameters['beta_loss_coefficient']
+            self.logger.log_target_error_progress(
+                self.get_target_reward_mapper_error(R, accum[0], accum[1], accum[2], test_index, beta, self.T))
+            self.logger.log_omegas_learning_rate(optim.param_groups[1]['lr'], test_index, self.total_training_steps)
+        self.omegas[test_index] = omegas
+        return R
+
+    def update_test_reward_mapper(self, w_approx, omegas, optim, task, r, s, a, s1, a1=None):
+        """One (w, omega) step on a target task: returns (loss, reward loss, psi loss)  [tsfdqn.py:917-997]."""
+        if self.h_function is None:
+            raise Exception('Affine Function (h) is not initialized')
+        hp = self.hyperparameters
+        s, s1 = torch.as_tensor(s).float().to(self.device), torch.as_tensor(s1).float().to(self.device)
+        phi = torch.as_tensor(task.features(s, a, s1)).float().to(self.device)
+        norm = self._normalized(omegas)
+        with torch.no_grad():
+            ts = torch.vstack([g(s) for g in self.g_functions]).unsqueeze(1)          # [N, 1, G] -> broadcasts with [1, N, 1, 1]
+            ts1 = torch.vstack([g(s1) for g in self.g_functions]).unsqueeze(1)
+            psi = self.sf.get_successors(s)                                           # [1, N, A, D]  (ensemble kernel)
+            next_psi = self.sf.get_next_successors(s1)                                # target nets
+            r_tensor = torch.tensor(r).float().unsqueeze(0).to(self.device)
+        affine = self.h_function(torch.sum(ts * norm, axis=1)) + self.h_function(torch.sum(ts1 * norm, axis=1))
+        tphi = phi * affine.squeeze(0)
+        next_tsf = tphi + self.gamma * torch.sum(next_psi * norm, axis=1)[:, a1, :]
+        tsf = torch.sum(psi * norm, axis=1)[:, a, :]
+        l1 = torch.nn.functional.mse_loss(tsf, next_tsf)
+        l2 = torch.mean((w_approx(tphi) - r_tensor) ** 2)
+        loss = l1 + hp['beta_loss_coefficient'] * l2 + hp['omegas_l1_coefficient'] * torch.norm(omegas, 1)
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        with torch.no_grad():
+            omegas.clamp_(1e-7)
+        return loss, l2, l1
+
+    def get_target_reward_mapper_error(self, r, loss, phi_loss, psi_loss, task_index, target_loss_coefficient, ts):
+        return {'task': task_index, 'reward': r, 'steps': (500 * (self.total_training_steps // 1000)) + ts, 'w_error': loss,
+                'psi_loss': psi_loss, 'phi_loss': phi_loss, 'target_loss_coefficient': target_loss_coefficient}
+
+    def get_progress_strings(self):
+        sample_str = 'task \t {} \t steps \t {} \t episodes \t {} \t eps \t {:.4f}'.format(
+            self.task_index, self.steps, self.episode, self.epsilon)
+        reward_str = 'ep_reward \t {:.4f} \t reward \t {:.4f}'.format(self.episode_reward, self.reward)
+        w_error = torch.linalg.norm(self.sf.fit_w[self.task_index].weight.T -
+                                    torch.as_tensor(self.sf.true_w[self.task_index]).to(self.device))
+        gpi_str = 'GPI% \t {:.4f} \t w_err \t {:.4f}'.format(self.sf.GPI_usage_percent(self.task_index), w_error)
+        return sample_str, reward_str, gpi_str

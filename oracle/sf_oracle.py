@@ -255,6 +255,45 @@ class OracleSF:
             self._target_sync(i)
         return loss.detach(), l1.detach(), l2.detach()
 
+    # ---------------- N1: TSF target-task adaptation, tsfdqn.py:859-997 ----------------
+    def new_target_task(self, w_target, omegas, lr_omega, wd_omega=0.0, lr_omega_decay=0.0, l1_coef=0.0, gamma=0.9):
+        """State of one target task as TSFDQN.train builds it (tsfdqn.py:797-832): w [1,D], omegas [1,N,1,1], one Adam."""
+        return dict(w=w_target.clone(), omegas=omegas.clone(), lr_omega=lr_omega, wd_omega=wd_omega, decay=lr_omega_decay,
+                    l1=l1_coef, gamma=gamma, epoch=0, step=0,
+                    m=[torch.zeros_like(w_target), torch.zeros_like(omegas)], v=[torch.zeros_like(w_target), torch.zeros_like(omegas)])
+
+    def target_q(self, s, tt):
+        """Greedy branch of get_test_action (tsfdqn.py:864-871): q = w(sum_j omega_j psi_j(s)) -> [1, A, 1]."""
+        norm = tt['omegas'] / torch.sum(tt['omegas'], dim=1, keepdim=True)
+        tsf = torch.sum(self.get_successors(s) * norm, dim=1)
+        return torch.nn.functional.linear(tsf, tt['w'])
+
+    def target_adapt_step(self, tt, s, a, r, s1, a1, phi):
+        """update_test_reward_mapper (tsfdqn.py:917-997) + scheduler.step() (:895): returns (loss, l2, l1)."""
+        lin = torch.nn.functional.linear
+        w_leaf, om_leaf = tt['w'].detach().requires_grad_(True), tt['omegas'].detach().requires_grad_(True)
+        norm = om_leaf / torch.sum(om_leaf, dim=1, keepdim=True)                               # :929
+        with torch.no_grad():
+            ts = torch.vstack([lin(s, *g) for g in self.g]).unsqueeze(1)                      # :931-940
+            ts1 = torch.vstack([lin(s1, *g) for g in self.g]).unsqueeze(1)
+            psi, next_psi = self.get_successors(s), self.get_next_successors(s1)               # :948-950
+        aff = lin(torch.sum(ts * norm, dim=1), *self.h) + lin(torch.sum(ts1 * norm, dim=1), *self.h)     # :942-944
+        tphi = phi * aff.squeeze(0)                                                          # :945
+        next_tsf = tphi + tt['gamma'] * torch.sum(next_psi * norm, dim=1)[:, a1, :]          # :953
+        tsf = torch.sum(psi * norm, dim=1)[:, a, :]                                          # :955
+        l1 = torch.nn.functional.mse_loss(tsf, next_tsf)
+        l2 = torch.mean((lin(tphi, w_leaf) - torch.tensor([r], dtype=torch.float32)) ** 2)   # [1,1] vs [1] broadcast, :958-969
+        loss = l1 + torch.tensor(self.beta) * l2 + torch.tensor(tt['l1']) * torch.norm(om_leaf, 1)   # :962-971
+        gw, go = torch.autograd.grad(loss, [w_leaf, om_leaf])
+        with torch.no_grad():
+            tt['step'] += 1
+            lr_o = tt['lr_omega'] * (1 - tt['decay']) ** tt['epoch']                         # LambdaLR on the omega group (:822-826)
+            self._adam_tensor(tt['w'], gw, tt['m'][0], tt['v'][0], tt['step'], self.lr['w'], self.wd['w'])
+            self._adam_tensor(tt['omegas'], go, tt['m'][1], tt['v'][1], tt['step'], lr_o, tt['wd_omega'])
+            tt['omegas'].clamp_(1e-7)                                                        # :977-979
+            tt['epoch'] += 1
+        return loss.detach(), l2.detach(), l1.detach()
+
     # ---------------- A6'': G1 ensemble step, agents/sfdqn.py:57-60 ----------------
     def ensemble_update_sequential(self, transitions5):
         """Literal reference loop (Gauss-Seidel: task k's GPI sees psi_0..psi_{k-1} already stepped)."""

@@ -218,6 +218,76 @@ def case_g3(name, S, A, D, hidden, acts, N, B, K, policy, use_gpi, seed, gdim, b
     print('wrote', name, 'losses', losses[-1])
 
 
+class FeatTask(FakeTask):
+    """FakeTask with a deterministic, non-trivial feature map (the target-task loop multiplies phi into the loss)."""
+
+    def features(self, s, a, s1):
+        base = torch.arange(self.D, dtype=torch.float32)
+        return torch.sin(base * 0.7 + float(torch.as_tensor(s).sum()) + 0.3 * float(a)) - 0.25 * float(torch.as_tensor(s1).sum())
+
+
+TARGET_HYPER = dict(learning_rate_omega=1e-2, weight_decay_omega=0.0, learning_rate_omega_decay=1e-3, omegas_l1_coefficient=0.1)
+
+
+def case_g3_target(name, S, A, D, hidden, acts, N, K, seed, gdim, beta):
+    """TSFDQN target-task adaptation (tsfdqn.py:859-997): get_test_action + update_test_reward_mapper."""
+    torch.manual_seed(seed)
+    hyper = dict(HYPER, g_h_function_dims=gdim, beta_loss_coefficient=beta, **TARGET_HYPER)
+    with contextlib.redirect_stdout(io.StringIO()):
+        dsf = ref_tsfdqn.DeepTSF(pytorch_model_handle=make_model_lambda(hidden, acts), use_true_reward=False,
+                                 target_update_ev=1000, hyperparameters=hyper)
+        ag = ref_tsfdqn.TSFDQN(deep_sf=dsf, buffer_handle=lambda: ref_tsfdqn.ReplayBuffer(), gamma=0.9, T=500,
+                               encoding=None, use_gpi=True, test_epsilon=0.0, hyperparameters=hyper)
+        ag.reset()
+        for i in range(N):
+            ag.add_training_task(FakeTask(S, A, D, i))
+    ag.total_training_steps = 1                                           # keeps the reference's debug print silent
+    out = {'meta': np.array(repr(dict(kind='g3_target', S=S, A=A, D=D, hidden=list(hidden), acts=list(acts), N=N, K=K,
+                                       gdim=gdim, beta=beta, gamma=0.9, **TARGET_HYPER)))}
+    for i in range(N):
+        dump_net(out, f'init.psi{i}', dsf.psi[i][0][0])
+        out[f'init.w{i}'] = dsf.fit_w[i].weight.detach().numpy().copy()
+        out[f'init.g{i}.W'] = ag.g_functions[i].weight.detach().numpy().copy()
+        out[f'init.g{i}.b'] = ag.g_functions[i].bias.detach().numpy().copy()
+    out['init.h.W'] = ag.h_function.weight.detach().numpy().copy()
+    out['init.h.b'] = ag.h_function.bias.detach().numpy().copy()
+    # what TSFDQN.train does for one test task (tsfdqn.py:797-832)
+    task = FeatTask(S, A, D, 0)
+    omegas = ag._init_omega(N)
+    with torch.no_grad():
+        omegas = omegas / torch.sum(omegas, axis=1, keepdim=True)
+    omegas = omegas.clone().detach().requires_grad_(True)
+    w_approx = torch.nn.Linear(D, 1, bias=False)
+    with torch.no_grad():
+        w_approx.weight = torch.nn.Parameter(torch.Tensor(1, D).uniform_(-0.01, 0.01))
+    optim = torch.optim.Adam([
+        {'params': w_approx.parameters(), 'lr': hyper['learning_rate_w'], 'weight_decay': hyper['weight_decay_w']},
+        {'params': omegas, 'lr': hyper['learning_rate_omega'], 'weight_decay': hyper['weight_decay_omega']}])
+    sched = torch.optim.lr_scheduler.LambdaLR(optim, [lambda e: 1 ** e, lambda e: (1 - hyper['learning_rate_omega_decay']) ** e])
+    out['init.omegas'] = omegas.detach().numpy().copy()
+    out['init.w_target'] = w_approx.weight.detach().numpy().copy()
+    gen = torch.Generator().manual_seed(seed + 1)
+    losses = []
+    for k in range(K):
+        s, s1 = torch.randn(1, S, generator=gen), torch.randn(1, S, generator=gen)
+        r = float(torch.randn((), generator=gen))
+        with torch.no_grad():
+            a = ag.get_test_action(s, w_approx, omegas)
+            a1 = ag.get_test_action(s1, w_approx, omegas)
+        out[f'step{k}.s'], out[f'step{k}.s1'] = s.numpy().copy(), s1.numpy().copy()
+        out[f'step{k}.r'], out[f'step{k}.a'], out[f'step{k}.a1'] = np.array(r), np.array(int(a)), np.array(int(a1))
+        out[f'step{k}.phi'] = task.features(s, a, s1).numpy().copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            l = ag.update_test_reward_mapper(w_approx, omegas, optim, task, r, s, a, s1, a1)
+        sched.step()
+        losses.append([float(x) for x in l])
+        out[f'step{k}.omegas'] = omegas.detach().numpy().copy()
+        out[f'step{k}.w_target'] = w_approx.weight.detach().numpy().copy()
+    out['out.losses'] = np.array(losses, dtype=np.float64)                # (loss, l2 = reward loss, l1 = psi loss)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print('wrote', name, 'losses', losses[-1])
+
+
 def case_g1(name, S, A, D, hidden, acts, N, B, seed, lr=1e-3):
     """G1 ensemble (features/deep.py + agents/sfdqn.py:57-60): literal sequential loop AND frozen-snapshot variant."""
     torch.manual_seed(seed)
@@ -263,4 +333,5 @@ if __name__ == '__main__':
             gdim=100, beta=1)
     case_g3('g3_reacher_beta30', 4, 9, 12, (64, 64), ('relu', 'relu'), N=3, B=32, K=4, policy=0, use_gpi=False, seed=2025,
             gdim=100, beta=30, policies=[0, 2, 0, 2])                    # shared h stepped by two different optimizers
+    case_g3_target('g3_reacher_target_adapt', 4, 9, 12, (64, 64), ('relu', 'relu'), N=3, K=5, seed=2026, gdim=100, beta=30)
     case_g1('g1_reacher_ensemble', 4, 9, 12, (64, 64), ('relu', 'relu'), N=3, B=32, seed=3024)

@@ -29,7 +29,7 @@ def net_layers(z, prefix, meta):
 
 
 def oracle_from_golden(meta, z, **kw):
-    tsf = meta['kind'] == 'g3'
+    tsf = meta['kind'] in ('g3', 'g3_target')
     o = OracleSF(meta['S'], meta['A'], meta['D'], meta['hidden'], meta['acts'],
                  tsf_dim=meta.get('gdim') if tsf else None, beta=meta.get('beta', 1),
                  target_update_ev=meta.get('target_update_ev', 1000), **kw)

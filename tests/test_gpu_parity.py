@@ -303,3 +303,35 @@ def test_device_replay_buffer_matches_host_ring():
         for name, x, y in zip(('states', 'actions', 'rewards', 'phis', 'next_states', 'gammas'), ref, got):
             assert x.shape == y.shape and x.dtype == y.dtype, (name, x.shape, y.shape, x.dtype, y.dtype)
             assert torch.equal(x.cpu(), y.cpu()), name
+
+
+def test_g3_target_task_adaptation_vs_golden():
+    """TSFDQN.get_test_action / update_test_reward_mapper on the kernel-backed library == the reference."""
+    meta, z = load('g3_reacher_target_adapt')
+    dsf, ag = gu.build_g3(dict(meta, use_gpi=True), z=z)
+    ag.hyperparameters.update({k: meta[k] for k in ('learning_rate_omega', 'weight_decay_omega', 'learning_rate_omega_decay',
+                                                     'omegas_l1_coefficient')})
+    ag.test_epsilon = 0.0
+    ag.n_actions = meta['A']
+
+    class Task:
+        def __init__(self):
+            self.k = 0
+
+        def features(self, s, a, s1):
+            return t(z[f'step{self.k}.phi'])
+
+    task = Task()
+    w_approx, optim, sched, omegas = ag._new_target_task(meta['D'], t(z['init.omegas']).cuda())
+    with torch.no_grad():
+        w_approx.weight.copy_(t(z['init.w_target']))
+    for k in range(meta['K']):
+        task.k = k
+        s, s1 = t(z[f'step{k}.s']).cuda(), t(z[f'step{k}.s1']).cuda()
+        a, a1, r = int(z[f'step{k}.a']), int(z[f'step{k}.a1']), float(z[f'step{k}.r'])
+        assert int(ag.get_test_action(s, w_approx, omegas)) == a and int(ag.get_test_action(s1, w_approx, omegas)) == a1
+        losses = ag.update_test_reward_mapper(w_approx, omegas, optim, task, r, s, a, s1, a1)
+        sched.step()
+        assert np.allclose([float(x) for x in losses], z['out.losses'][k], rtol=2e-5, atol=1e-7)
+        assert rel_err(omegas.detach().cpu(), z[f'step{k}.omegas']) < 2e-5
+        assert rel_err(w_approx.weight.detach().cpu(), z[f'step{k}.w_target']) < 2e-5
