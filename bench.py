@@ -143,8 +143,9 @@ def run_reference(args, cfg, rank, world):
     }))
 
 
-def workload_config(name, cfg, n_total, world, precision='fp32', l2='flush'):
-    return {'workload': f'{name}: TSFDQN Reacher S4/A9/D12 MLP 256-256 relu, g 4->100, h 100->12, beta=1, B={cfg["B"]}, '
+def workload_config(name, cfg, n_total, world, precision='fp32', l2='flush', exchange=None):
+    extra = {'exchange': exchange} if exchange else {}
+    return {**extra, 'workload': f'{name}: TSFDQN Reacher S4/A9/D12 MLP 256-256 relu, g 4->100, h 100->12, beta=1, B={cfg["B"]}, '
                         f'{cfg["n_local"]} policies/GPU ({n_total} total), all-task fused TD update with GPI next actions',
             'batch': cfg['B'], 'policies_total': n_total, 'policies_per_gpu': cfg['n_local'],
             'parallelism': f'policy-sharded x{world}' if world > 1 else 'single GPU',
@@ -303,7 +304,10 @@ def main():
             'metric': 'SF TD updates (transitions x tasks)/s', 'value': value, 'unit': 'updates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-            'config': workload_config(args.workload, cfg, n_total, world, args.precision, args.l2),
+            'config': workload_config(args.workload, cfg, n_total, world, args.precision, args.l2,
+                                      None if world == 1 else ('peer-memory kernels in the step\'s launch chain (CUDA IPC arenas, signal/wait '
+                                      'flags, 128-bit pulls over NVLink): GPI keys MAX reduce-scatter + [w | delta h] all-gather, no NCCL call '
+                                      'inside a step' if lib._peer is not None else 'NCCL: all-reduce(MAX) of packed keys + one all-gather')),
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_t) / e2e_steps * 1e3},

@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libsfgpi.so')
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -89,8 +89,25 @@ class Cmd(C.Structure):
 
 
 OP = dict(H2D=1, D2H=2, D2D=3, KEYS_FILL=4, PACK_BF16=5, FOLD_GPI=6, FORWARD=7, FORWARD_TC_JOBS=8, TD=9, BACKWARD=10,
-          BACKWARD_TC=11, ADAM=12, EVENT=13)
-OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2}
+          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16)
+OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1}
+MAX_PEERS = 16
+PEER_CHANNELS = 4
+IPC_HANDLE_BYTES = 64
+
+
+class PeerCtx(C.Structure):
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('flags', C.c_void_p * MAX_PEERS)]
+
+
+class PeerKeysArgs(C.Structure):
+    _fields_ = [('ctx', PeerCtx), ('epoch', C.c_int64), ('keys_all', C.c_void_p * MAX_PEERS), ('row_lo', C.c_int32),
+                ('n_rows', C.c_int32), ('B', C.c_int32), ('keys_out', C.c_void_p)]
+
+
+class PeerUnpackArgs(C.Structure):
+    _fields_ = [('ctx', PeerCtx), ('epoch', C.c_int64), ('x', C.c_void_p * MAX_PEERS), ('nw', C.c_int32), ('nh', C.c_int32),
+                ('w_all', C.c_void_p), ('h', C.c_void_p), ('h_prev', C.c_void_p)]
 
 
 class AdamSegment(C.Structure):
@@ -132,6 +149,12 @@ SYMBOLS = {
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'sfgpi_shard_unpack': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    'sfgpi_peer_open': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'sfgpi_peer_close': (C.c_int, [C.c_void_p]),
+    'sfgpi_peer_free': (C.c_int, [C.c_void_p]),
+    'sfgpi_peer_reduce_keys': (C.c_int, [C.POINTER(PeerKeysArgs), C.c_void_p]),
+    'sfgpi_peer_unpack': (C.c_int, [C.POINTER(PeerUnpackArgs), C.c_void_p]),
     'sfgpi_set_option': (C.c_int, [C.c_char_p, C.c_int32]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
@@ -140,7 +163,8 @@ SYMBOLS = {
 _lib = None
 launch_count = 0          # kernels launched through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES_PER_CALL = {'sfgpi_pack_bf16': 1, 'sfgpi_fold_gpi': 1, 'sfgpi_mlp_forward_tc': 1, 'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
-                     'sfgpi_td_step': 2, 'sfgpi_mlp_backward': 2, 'sfgpi_mlp_backward_tc': 3, 'sfgpi_adam_step': 2}
+                     'sfgpi_td_step': 2, 'sfgpi_mlp_backward': 2, 'sfgpi_mlp_backward_tc': 3, 'sfgpi_adam_step': 2,
+                     'sfgpi_peer_alloc': 0, 'sfgpi_peer_open': 0, 'sfgpi_peer_close': 0, 'sfgpi_peer_free': 0}
 
 
 def lib():

@@ -55,6 +55,16 @@ extern "C" int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream) {
             case SFGPI_OP_ADAM:
                 rc = sfgpi_adam_step(reinterpret_cast<const sfgpi_adam_args *>(c.p[0]), stream);
                 break;
+            case SFGPI_OP_PEER_KEYS:
+                rc = sfgpi_peer_reduce_keys(reinterpret_cast<const sfgpi_peer_keys_args *>(c.p[0]), stream);
+                break;
+            case SFGPI_OP_SHARD_PACK:
+                rc = sfgpi_shard_pack(reinterpret_cast<const float *>(c.p[0]), (int32_t)c.i[0], reinterpret_cast<const float *>(c.p[1]),
+                                      reinterpret_cast<const float *>(c.p[2]), (int32_t)c.i[1], reinterpret_cast<float *>(c.p[3]), stream);
+                break;
+            case SFGPI_OP_PEER_UNPACK:
+                rc = sfgpi_peer_unpack(reinterpret_cast<const sfgpi_peer_unpack_args *>(c.p[0]), stream);
+                break;
             default:
                 set_error("sfgpi_run: unknown op %d at command %d", c.op, i);
                 return SFGPI_E_INVALID;

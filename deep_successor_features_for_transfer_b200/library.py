@@ -98,6 +98,15 @@ class NetSpec:
         return out
 
 
+def _peer_flag_bytes():
+    from .peer import FLAG_BYTES
+    return FLAG_BYTES
+
+
+def _peer_mode_ok(peer_mod):
+    return peer_mod.peer_mode_wanted()
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -120,6 +129,7 @@ class PackedSFLibrary:
         self.h = None
         self.shard = None           # dist.ShardContext once enable_sharding() was called
         self._xchg = None
+        self._peer = None           # peer-memory exchange state (enable_sharding on an NVLink node)
         self.set_precision(precision)
 
     def set_precision(self, precision):
@@ -192,6 +202,18 @@ class PackedSFLibrary:
                 x.update(local=self._f(self.n * D + nh), all=self._f(sh.world, self.n * D + nh),
                          h_prev=self.h.clone() if nh else None)
             self._xchg = x
+            self._peer = None
+            import torch.distributed as dist
+            from . import peer as _peer
+            if sh.uniform and sh.world <= _lib.MAX_PEERS and dist.get_backend(group) == 'nccl' and _peer_mode_ok(_peer):
+                # peer-memory exchange (csrc/peer.cu): flag block + double-buffered x_local in an arena every rank maps
+                xb = (4 * (self.n * D + nh) + 15) // 16 * 16
+                try:
+                    arena = _peer.PeerArena(_peer.FLAG_BYTES + 2 * xb, group)
+                    self._peer = dict(base=arena, xb=xb, ep=[0, 0], keys={})
+                except RuntimeError as e:
+                    import warnings
+                    warnings.warn(f'peer-memory exchange unavailable, using NCCL collectives: {e}')
         return self.shard
 
     @property
@@ -425,13 +447,26 @@ class PackedSFLibrary:
                                       'step with cross-GPU GPI is train_step_owner()/gpi_assist()')
         key_row0 = 0
         w_all = None
+        peer = None
         if use_gpi:
             a2 = self._fwd_args(self.online, 0, self.n, None, B)
             if sharded and ensemble:
                 nt = self.shard.n_total
-                keys = ws['keys_all'] = ws.get('keys_all', torch.empty(nt, B, dtype=torch.int64, device=self.device))
                 w_all = self._xchg['w_all']
                 a2.w, a2.n_w, a2.w_diag, key_row0 = ptr(w_all), nt, 0, self.shard.lo
+                if getattr(self, '_peer', None) is not None:
+                    # peer mode: this rank's keys [nt][B] live in a mapped arena (double-buffered on epoch parity); the
+                    # exchange kernel leaves the MAX over ranks of this rank's own rows in keys_own
+                    from .peer import PeerArena
+                    kb = nt * B * 8
+                    karena = self._peer['keys'].get(B)
+                    if karena is None:
+                        karena = self._peer['keys'][B] = PeerArena(2 * kb, self.shard.group)
+                    peer = dict(karena=karena, kb=kb, lo=self.shard.lo)
+                    keys = ws['keys_own'] = ws.get('keys_own', torch.empty(n_pol, B, dtype=torch.int64, device=self.device))
+                    key_row0 = 0
+                else:
+                    keys = ws['keys_all'] = ws.get('keys_all', torch.empty(nt, B, dtype=torch.int64, device=self.device))
             else:
                 a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 0
             a2.task_base = self.shard.lo if self.shard is not None else 0
@@ -512,6 +547,7 @@ class PackedSFLibrary:
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
         return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, tc=tc, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
+                    peer=peer, variant=variant,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
     def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
@@ -576,6 +612,22 @@ class PackedSFLibrary:
         plan['ring'] = (plan['ring'] + 1) % 64
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
+        peer = plan.get('peer')
+        if peer is not None:
+            # peer-memory exchange: epoch numbers (identical on every rank) pick the arena halves this step writes / pulls
+            pa = self._peer
+            pa['ep'][0] += 1
+            pa['ep'][1] += 1
+            ek, ex = pa['ep']
+            koff, xoff = (ek & 1) * peer['kb'], _peer_flag_bytes() + (ex & 1) * pa['xb']
+            ka, ua, karena, base = peer['ka'], peer['ua'], peer['karena'], pa['base']
+            ka.epoch, ua.epoch = ek, ex
+            for r in range(base.world):
+                ka.keys_all[r] = karena.ptrs[r] + koff
+                ua.x[r] = base.ptrs[r] + xoff
+            a2.key_action = karena.local + koff
+            peer['fill_cmd'].p[0] = karena.local + koff
+            peer['pack_cmd'].p[3] = base.local + xoff
         if plan['tc']:
             for j, which in enumerate(('online', 'online', 'target')):      # the job array embeds copies of the arg blocks
                 plan['jobs'][j].args = (a1, a2, a3)[j]
@@ -586,6 +638,14 @@ class PackedSFLibrary:
         xc = self._xchg if self._sharded else None
         fused = xc is not None and 'local' in xc              # uniform shards: ONE all-gather per step carries w and h's deltas
         need_h = xc is not None and variant == 2
+        if peer is not None:
+            if not xc['ok']:                                  # first step (or after outside changes): NCCL gather of w
+                self._gather_w(plan['w_all'])
+                if peer['nh']:
+                    xc['h_prev'].copy_(self.h)
+            run(segs[0])                                      # the whole step, exchanges included: one foreign call
+            xc['ok'] = True
+            return losses
         run(segs[0])                                          # [H2D] pack shadows, key fill
         if sharded and plan['w_all'] is not None and not (fused and xc['ok']):
             self._gather_w(plan['w_all'])                     # first step (or after outside changes): plain gather of w
@@ -667,7 +727,11 @@ class PackedSFLibrary:
             dref = C.addressof(plan['desc'])
             cmd(seg0, 'PACK_BF16', (dref, self.online.data_ptr(), self._shadow_for('online').data_ptr()), (0, self.n))
             cmd(seg0, 'PACK_BF16', (dref, self.target.data_ptr(), self._shadow_for('target').data_ptr()), (a3.policy_lo, a3.n_pol))
-        cmd(seg0, 'KEYS_FILL', (keys.data_ptr(),), (keys.numel(),))
+        peer = plan.get('peer')
+        if peer is None:
+            cmd(seg0, 'KEYS_FILL', (keys.data_ptr(),), (keys.numel(),))
+        else:                                                 # pointer patched per step (epoch parity)
+            cmd(seg0, 'KEYS_FILL', (peer['karena'].local,), (peer['kb'] // 8,))
         if plan['tc']:
             nw = 1 if a2.w_diag else a2.n_w
             nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(plan['desc']), nw)
@@ -691,7 +755,26 @@ class PackedSFLibrary:
         cmd(seg2, 'TD', (C.addressof(t),))
         cmd(seg2, 'BACKWARD_TC' if plan['tc'] else 'BACKWARD', (C.addressof(b),))
         cmd(seg2, 'ADAM', (C.addressof(ad),))
-        segs = [seg0, seg1, seg2] if plan['sharded'] else [seg0 + seg1 + seg2, [], []]
+        if peer is not None:
+            # peer mode: the exchanges are kernels of the chain -> the sharded step is ONE command list again
+            pa, xc = self._peer, self._xchg
+            nw, nh = self.n * D, (xc['nh'] if plan['variant'] == 2 else 0)
+            ka, ua = _lib.PeerKeysArgs(), _lib.PeerUnpackArgs()
+            ka.ctx = ua.ctx = pa['base'].ctx()
+            ka.row_lo, ka.n_rows, ka.B, ka.keys_out = peer['lo'], n_pol, B, keys.data_ptr()
+            ua.nw, ua.nh, ua.w_all = nw, nh, xc['w_all'].data_ptr()
+            if nh:
+                ua.h, ua.h_prev = self.h.data_ptr(), xc['h_prev'].data_ptr()
+            peer.update(ka=ka, ua=ua, nh=nh)
+            n_fill = len(seg0) - 1
+            n_keys = len(seg0) + len(seg1)
+            cmd(seg1, 'PEER_KEYS', (C.addressof(ka),))
+            cmd(seg2, 'SHARD_PACK', (self.w.data_ptr(), self.h.data_ptr() if nh else 0, xc['h_prev'].data_ptr() if nh else 0,
+                                     pa['base'].local), (nw, nh))
+            cmd(seg2, 'PEER_UNPACK', (C.addressof(ua),))
+            segs = [seg0 + seg1 + seg2, [], []]
+        else:
+            segs = [seg0, seg1, seg2] if plan['sharded'] else [seg0 + seg1 + seg2, [], []]
         plan['segments'], plan['h2d'], plan['probe'] = [], None, []
         for seg in segs:
             arr = (_lib.Cmd * max(1, len(seg)))()
@@ -707,6 +790,9 @@ class PackedSFLibrary:
                 plan['h2d'] = [arr[k] for k in range(6)]
             plan['probe'] += [arr[k] for k, (op, p, i) in enumerate(seg) if op == 'NOP' and not p]
             plan['segments'].append((arr, len(seg), launches))
+        if peer is not None:
+            arr = plan['segments'][0][0]
+            peer['fill_cmd'], peer['pack_cmd'] = arr[n_fill], arr[len(segs[0]) - 2]
 
     def set_probe(self, plan_key, start_event=None, end_event=None):
         """

@@ -302,6 +302,9 @@ int sfgpi_replay_gather(const sfgpi_replay_args *args, void *stream);
 #define SFGPI_OP_BACKWARD_TC 11     /* p0 = sfgpi_backward_tc_args */
 #define SFGPI_OP_ADAM 12            /* p0 = sfgpi_adam_args */
 #define SFGPI_OP_EVENT 13           /* p0 = cudaEvent_t: cudaEventRecord on the stream (timing probes around a command) */
+#define SFGPI_OP_PEER_KEYS 14       /* p0 = sfgpi_peer_keys_args */
+#define SFGPI_OP_SHARD_PACK 15      /* p0 = w, p1 = h, p2 = h_prev, p3 = x_local, i0 = nw, i1 = nh */
+#define SFGPI_OP_PEER_UNPACK 16     /* p0 = sfgpi_peer_unpack_args */
 typedef struct {
     int32_t op;
     void *p[5];
@@ -318,6 +321,48 @@ int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream);
 int sfgpi_shard_pack(const float *w, int32_t nw, const float *h, const float *h_prev, int32_t nh, float *x_local, void *stream);
 int sfgpi_shard_unpack(const float *x_all, int32_t world, int32_t nw, int32_t nh, float *w_all, float *h, float *h_prev,
                        void *stream);
+
+/*
+ * Peer-memory exchange (policy sharding on one NVSwitch node, one process per GPU): the two per-step exchanges of the sharded
+ * train step -- the MAX reduce-scatter of the packed GPI keys (replaces dist.all_reduce(keys, MAX), SURVEY 8e "Collective --
+ * training with GPI") and the all-gather of x_local = [w | delta h] (sfgpi_shard_pack / _unpack above) -- as kernels inside the
+ * step's launch chain that signal, wait and PULL over NVLink from arenas every rank has mapped with CUDA IPC.
+ *   sfgpi_peer_alloc   cudaMalloc + zero + cudaIpcGetMemHandle: the 64-byte handle is what ranks exchange (any transport)
+ *   sfgpi_peer_open    cudaIpcOpenMemHandle with lazy peer access; sfgpi_peer_close / sfgpi_peer_free undo the two
+ * flags[r] = rank r's flag block, uint64 [SFGPI_PEER_CHANNELS][SFGPI_MAX_PEERS], zero-initialised; flags[r][ch][q] is written by
+ * rank q only.  `epoch` must be > 0, identical on every rank for the same exchange and strictly increasing per channel; data
+ * buffers are double-buffered by the caller on epoch parity.  A rank that waits 20 s for a peer traps (the CUDA context fails
+ * loudly instead of hanging).
+ */
+#define SFGPI_MAX_PEERS 16
+#define SFGPI_PEER_CHANNELS 4
+#define SFGPI_PEER_CH_KEYS 0
+#define SFGPI_PEER_CH_X 1
+#define SFGPI_IPC_HANDLE_BYTES 64
+typedef struct {
+    int32_t world, rank;
+    void *flags[SFGPI_MAX_PEERS];
+} sfgpi_peer_ctx;
+typedef struct {
+    sfgpi_peer_ctx ctx;
+    int64_t epoch;
+    const int64_t *keys_all[SFGPI_MAX_PEERS];   /* rank r's keys [n_total][B] of this epoch (keys_all[rank] is local) */
+    int32_t row_lo, n_rows, B;                  /* this rank's rows: keys_out[row][b] = max_r keys_all[r][row_lo + row][b] */
+    int64_t *keys_out;                          /* [n_rows][B], local */
+} sfgpi_peer_keys_args;
+typedef struct {
+    sfgpi_peer_ctx ctx;
+    int64_t epoch;
+    const float *x[SFGPI_MAX_PEERS];            /* rank r's x_local [nw + nh] of this epoch */
+    int32_t nw, nh;
+    float *w_all, *h, *h_prev;                  /* as sfgpi_shard_unpack */
+} sfgpi_peer_unpack_args;
+int sfgpi_peer_alloc(int64_t bytes, void **dptr, void *ipc_handle_out);
+int sfgpi_peer_open(const void *ipc_handle, void **dptr);
+int sfgpi_peer_close(void *dptr);
+int sfgpi_peer_free(void *dptr);
+int sfgpi_peer_reduce_keys(const sfgpi_peer_keys_args *args, void *stream);
+int sfgpi_peer_unpack(const sfgpi_peer_unpack_args *args, void *stream);
 
 /* Runtime options: "2cta_min_tiles" = tensor-core forward launches with more 128-row tiles than this run as 2-CTA pairs
  * (tcgen05 cta_group::2, each CTA holds half of every weight block); default: never.  Returns the previous value or -1. */

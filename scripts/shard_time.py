@@ -1,5 +1,6 @@
 """torchrun script: per-phase CUDA-event timing of the sharded train step (which collective / segment costs what)."""
 import os, sys, time
+os.environ["SFGPI_PEER"] = "0"      # this script times the NCCL-collective variant of the sharded step phase by phase
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from oracle.sf_oracle import synthetic_transitions
