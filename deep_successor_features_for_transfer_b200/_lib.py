@@ -75,7 +75,14 @@ class BackwardTcArgs(C.Structure):
     _fields_ = [('net', NetDesc), ('params_bf16', C.c_void_p), ('n_policies_total', C.c_int32), ('policy_lo', C.c_int32),
                 ('n_pol', C.c_int32), ('x', C.c_void_p), ('B', C.c_int32), ('acts_bf16', C.c_void_p), ('relu_masks', C.c_void_p), ('actions', C.c_void_p),
                 ('d_out', C.c_void_p), ('dz_bf16', C.c_void_p), ('dzo_bf16', C.c_void_p), ('xo_bf16', C.c_void_p),
-                ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
+                ('grad_part', C.c_void_p), ('n_split', C.c_int32), ('xo_ready', C.c_int32)]
+
+
+class StepPrepArgs(C.Structure):
+    _fields_ = [('net', NetDesc), ('pack_params', C.c_void_p * 2), ('pack_out', C.c_void_p * 2), ('pack_lo', C.c_int32 * 2),
+                ('pack_n', C.c_int32 * 2), ('keys', C.c_void_p), ('n_keys', C.c_int64), ('fold_params', C.c_void_p),
+                ('fold_lo', C.c_int32), ('fold_n', C.c_int32), ('w', C.c_void_p), ('n_w', C.c_int32), ('w_diag', C.c_int32),
+                ('wq', C.c_void_p), ('bq', C.c_void_p), ('x', C.c_void_p), ('B', C.c_int32), ('xo_bf16', C.c_void_p)]
 
 
 class ReplayArgs(C.Structure):
@@ -89,8 +96,8 @@ class Cmd(C.Structure):
 
 
 OP = dict(H2D=1, D2H=2, D2D=3, KEYS_FILL=4, PACK_BF16=5, FOLD_GPI=6, FORWARD=7, FORWARD_TC_JOBS=8, TD=9, BACKWARD=10,
-          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16)
-OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1}
+          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16, STEP_PREP=17)
+OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1, 17: 1}
 MAX_PEERS = 16
 PEER_CHANNELS = 4
 IPC_HANDLE_BYTES = 64
@@ -121,7 +128,7 @@ class AdamArgs(C.Structure):
     _fields_ = [('n_seg', C.c_int32), ('n_pol', C.c_int32), ('seg', AdamSegment * MAX_SEGMENTS), ('step', C.c_void_p),
                 ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
                 ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
-                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p)]
+                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p), ('finish_counter', C.c_void_p)]
 
 
 # every symbol include/sfgpi.h declares: name -> (restype, argtypes)
@@ -149,6 +156,7 @@ SYMBOLS = {
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'sfgpi_shard_unpack': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_step_prep': (C.c_int, [C.POINTER(StepPrepArgs), C.c_void_p]),
     'sfgpi_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     'sfgpi_peer_open': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'sfgpi_peer_close': (C.c_int, [C.c_void_p]),
@@ -164,7 +172,8 @@ _lib = None
 launch_count = 0          # kernels launched through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES_PER_CALL = {'sfgpi_pack_bf16': 1, 'sfgpi_fold_gpi': 1, 'sfgpi_mlp_forward_tc': 1, 'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
                      'sfgpi_td_step': 2, 'sfgpi_mlp_backward': 2, 'sfgpi_mlp_backward_tc': 3, 'sfgpi_adam_step': 2,
-                     'sfgpi_peer_alloc': 0, 'sfgpi_peer_open': 0, 'sfgpi_peer_close': 0, 'sfgpi_peer_free': 0}
+                     'sfgpi_step_prep': 1,
+    'sfgpi_peer_alloc': 0, 'sfgpi_peer_open': 0, 'sfgpi_peer_close': 0, 'sfgpi_peer_free': 0}
 
 
 def lib():

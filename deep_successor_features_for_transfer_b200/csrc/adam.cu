@@ -66,6 +66,17 @@ __device__ __forceinline__ float4 sum_partials4(const float4 *__restrict__ gp, i
                        (g0.w + g1.w) + (g2.w + g3.w));
 }
 
+// step += 1 and, when the caller keeps them, the bias corrections of the step after that
+__device__ __forceinline__ void adam_finish_one(int32_t *step, double *consts, int i, double beta1, double beta2) {
+    const int s = step[i] + 1;
+    step[i] = s;
+    if (consts != nullptr) {
+        const double t = (double)(s + 1);
+        consts[2 * i] = 1.0 - pow(beta1, t);
+        consts[2 * i + 1] = sqrt(1.0 - pow(beta2, t));
+    }
+}
+
 __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constant__ sfgpi_adam_args a, int blocks_per_pol) {
     __shared__ float sqrt_bc2_s, step_size_s[SFGPI_MAX_SEGMENTS];
     pdl_launch_dependents();
@@ -163,22 +174,27 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             }
         }
     }
+    // ---- fused finish: the LAST CTA to get here advances step / bias corrections (every CTA read them before arriving) ----
+    if (a.finish_counter != nullptr) {
+        __shared__ unsigned last_s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_s = atomicAdd(a.finish_counter, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last_s) {
+            for (int i = threadIdx.x; i < a.n_pol; i += kAdamThreads) adam_finish_one(a.step, a.consts, i, a.beta1, a.beta2);
+            if (threadIdx.x == 0) *a.finish_counter = 0u;
+        }
+    }
 }
 
-// step += 1 and, when the caller keeps them, the bias corrections of the step after that
 __global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double beta1, double beta2) {
     pdl_launch_dependents();
     pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int s = step[i] + 1;
-        step[i] = s;
-        if (consts != nullptr) {
-            const double t = (double)(s + 1);
-            consts[2 * i] = 1.0 - pow(beta1, t);
-            consts[2 * i + 1] = sqrt(1.0 - pow(beta2, t));
-        }
-    }
+    if (i < n) adam_finish_one(step, consts, i, beta1, beta2);
 }
 
 }  // namespace sfgpi
@@ -204,7 +220,7 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     launch_pdl(adam_kernel, grid, dim3(kAdamThreads), 0, st, a, blocks);
     int rc = check_launch("sfgpi_adam_step");
-    if (rc) return rc;
+    if (rc || a.finish_counter != nullptr) return rc;
     launch_pdl(adam_finish_kernel, dim3((a.n_pol + 127) / 128), dim3(128), 0, st, a.step, a.consts, a.n_pol, a.beta1, a.beta2);
     return check_launch("sfgpi_adam_step(finish)");
 }

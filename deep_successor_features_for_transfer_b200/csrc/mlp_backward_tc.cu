@@ -585,9 +585,12 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     cudaStream_t st = (cudaStream_t)stream;
     const int AD = net.n_actions * net.n_features, ADp = sfgpi_bwd_tc_out_pad(&net), S = net.dims[0];
 
-    launch_pdl(build_xo_kernel, dim3((a.B * kXoCols + 255) / 256), dim3(256), 0, st, a.x, a.B, S, reinterpret_cast<__nv_bfloat16 *>(a.xo_bf16));
-    int rc = check_launch("sfgpi_mlp_backward_tc(xo)");
-    if (rc) return rc;
+    int rc = SFGPI_OK;
+    if (!a.xo_ready) {
+        launch_pdl(build_xo_kernel, dim3((a.B * kXoCols + 255) / 256), dim3(256), 0, st, a.x, a.B, S, reinterpret_cast<__nv_bfloat16 *>(a.xo_bf16));
+        rc = check_launch("sfgpi_mlp_backward_tc(xo)");
+        if (rc) return rc;
+    }
 
     // ---------------- dgrad chain ----------------
     DgParams dp;

@@ -18,6 +18,7 @@
 //               so the layer has only n_w * A columns and the epilogue is a running (max, argmax) per reward vector --
 //               psi[B,N,A,D] is never formed, not even on chip.  (GPI_w, sfdqn.py:215-240.)
 #include "tc_common.cuh"
+#include <limits.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -123,11 +124,20 @@ constexpr int kMaxJobs = 3;
 struct TcMulti {
     long long *timeline;             // developer aid (env SFGPI_TIMELINE=1): clock64() stamps of CTA 0's roles, else NULL
     int n_jobs, total_pairs;
+    int sched;                       // 1: work units come from the UnitTable (see below)
     int paired;                      // 1: two tiles ping-pong per CTA; 0: one tile per CTA (small launches), see kernel header
     int pair_start[kMaxJobs + 1];
     TcParams job[kMaxJobs];
 };
 struct TmapSet { CUtensorMap w[kMaxJobs]; CUtensorMap q[kMaxJobs]; CUtensorMap acts[kMaxJobs]; };
+
+// Balanced schedule for mid-size launches (m.sched = 1): the host lists the work units explicitly -- ping-pong PAIRS of row
+// tiles for the full rounds, then SINGLE tiles for the remainder -- so that no CTA is left with a whole extra pair while
+// others idle (384 tiles on 148 SMs: pair + single everywhere instead of 2 pairs on 44 CTAs and 1 on 104).
+// entry = job << 30 | has_y << 29 | policy << 16 | first tile.
+constexpr int kMaxUnits = 1024;
+struct UnitTable { uint32_t u[kMaxUnits]; };
+struct Unit { int jb, pl, pip, tile0, tstep; bool has_y; };
 
 // role 0 = epilogue X (thread 0), 1 = MMA issuer, 2 = producer warp 0, 3 = epilogue Y (thread 0); 64 slots each
 #define TL_STAMP(role, cnt) do { if (m.timeline != nullptr && blockIdx.x == 0 && (cnt) < 64) m.timeline[(role) * 64 + (cnt)++] = clock64(); } while (0)
@@ -144,17 +154,28 @@ __device__ __forceinline__ int job_of_pair(const TcMulti &m, int pair) {
 // X and tile 4q + 2 + r in slot Y.  Rank 0 issues all MMAs; producers and epilogues run in both CTAs.
 template <bool TWO>
 __global__ void __launch_bounds__(kThreadsTc, 1)
-mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ TmapSet maps) {
+mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ TmapSet maps, const __grid_constant__ UnitTable ut) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
     const int unit0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    // tile handled by this CTA in slot `slot` of work unit `pip` (of its policy), and whether the unit has a Y slot
-    auto tile_of = [&](const TcParams &p, int pip, int slot) {
-        return TWO ? 4 * pip + 2 * slot + (int)cta_rank : (p.paired ? 2 * pip + slot : pip);
-    };
-    auto has_y_of = [&](const TcParams &p, int pip) {
-        return TWO ? (4 * pip + 2 < p.tiles_per_policy) : (p.paired && (2 * pip + 1 < p.tiles_per_policy));
+    // work unit g -> job, policy slot, the tile this CTA handles in slot X (slot Y: tile0 + tstep), whether it has a Y slot
+    auto unit_at = [&](int g) {
+        Unit u;
+        if (!TWO && m.sched) {
+            const uint32_t e = ut.u[g];
+            u.jb = (int)(e >> 30); u.has_y = (e >> 29) & 1u; u.pl = (int)((e >> 16) & 0x1FFFu); u.tile0 = (int)(e & 0xFFFFu);
+            u.pip = 0; u.tstep = 1;
+            return u;
+        }
+        u.jb = job_of_pair(m, g);
+        const TcParams &p = m.job[u.jb];
+        const int pair = g - m.pair_start[u.jb];
+        u.pl = pair / p.pairs_per_policy;
+        u.pip = pair - u.pl * p.pairs_per_policy;
+        if (TWO) { u.tile0 = 4 * u.pip + (int)cta_rank; u.tstep = 2; u.has_y = 4 * u.pip + 2 < p.tiles_per_policy; }
+        else { u.tile0 = p.paired ? 2 * u.pip : u.pip; u.tstep = 1; u.has_y = p.paired && (2 * u.pip + 1 < p.tiles_per_policy); }
+        return u;
     };
     pdl_launch_dependents();
     if (m.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) m.timeline[255] = clock64();      // kernel entry
@@ -204,13 +225,12 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             uint32_t n = 0;
             int tlc = 0;
             for (int gpair = unit0; gpair < m.total_pairs; gpair += unit_stride) {
-                const int jb = job_of_pair(m, gpair);
+                const Unit un = unit_at(gpair);
+                const int jb = un.jb, pl = un.pl;
                 const TcParams &p = m.job[jb];
                 const sfgpi_forward_args &a = p.a;
-                const int pair = gpair - m.pair_start[jb];
-                const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
                 const int row0 = (a.policy_lo + pl) * p.rows_per_policy;
-                const bool has_y = has_y_of(p, pip);
+                const bool has_y = un.has_y;
                 for (int it = 0; it < p.n_items; ++it) {
                     const ItemInfo ii = item_info(p, it);
                     const int nblocks = TWO ? 1 : (ii.n_cols + kNB - 1) / kNB;
@@ -246,11 +266,10 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
             const uint64_t bdesc0 = umma_desc_k_sw128(W_addr);
             for (int gpair = unit0; gpair < m.total_pairs; gpair += unit_stride) {
-                const int jb = job_of_pair(m, gpair);
+                const Unit un = unit_at(gpair);
+                const int jb = un.jb;
                 const TcParams &p = m.job[jb];
-                const int pair = gpair - m.pair_start[jb];
-                const int pip = pair % p.pairs_per_policy;
-                const bool has_y = has_y_of(p, pip);
+                const bool has_y = un.has_y;
                 for (int it = 0; it < p.n_items; ++it) {
                     const ItemInfo ii = item_info(p, it);
                     const int nblocks = (ii.n_cols + kNB - 1) / kNB;
@@ -365,16 +384,16 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             }
         };
         for (int gpair = unit0; gpair < m.total_pairs; gpair += unit_stride) {
-            const int jb = job_of_pair(m, gpair);
+            const Unit un = unit_at(gpair);
+            const int jb = un.jb;
             const TcParams &p = m.job[jb];
             const sfgpi_forward_args &a = p.a;
             const sfgpi_net_desc &net = a.net;
             const int B = a.B, L = net.n_layers, A_ = net.n_actions, D = net.n_features, AD = A_ * D;
             const int S = net.dims[0];
             const int n_bias = (1 + p.Lh) * kH + p.n_final;     // [b_0 | b_1..b_Lh | b_final]
-            const int pair = gpair - m.pair_start[jb];
-            const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
-            const int n_slots = has_y_of(p, pip) ? 2 : 1;
+            const int pl = un.pl;
+            const int n_slots = un.has_y ? 2 : 1;
             const float *P = a.params + (size_t)(a.policy_lo + pl) * net.row_stride;
 
             // Saved activations (training forward): the bf16 tile a hidden epilogue leaves in the A slot IS the row-major
@@ -395,7 +414,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 #pragma unroll
             for (int slot = 0; slot < 2; ++slot) {
                 if (slot >= n_slots) break;
-                const int b = tile_of(p, pip, slot) * kTM + r;                   // global state index of this thread's row
+                const int b = (un.tile0 + slot * un.tstep) * kTM + r;                   // global state index of this thread's row
                 const bool row_ok = b < B;
                 bs[slot] = b;
                 if (group == 0) {
@@ -479,7 +498,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         if (saving) {                         // tile complete in shared memory -> one thread stores it
                             if (!TWO) asm volatile("bar.sync 1, 256;" ::: "memory");      // (pair: slot_ready just did)
                             if (et == 0) {
-                                const int row0 = tile_of(p, pip, slot) * kTM;
+                                const int row0 = (un.tile0 + slot * un.tstep) * kTM;
 #pragma unroll
                                 for (int kb = 0; kb < kH / kKB; ++kb)
                                     tma_store_3d(&maps.acts[jb], Arow + kb * (kTM * 128), kb * kKB, row0, it * a.n_pol + pl);
@@ -630,6 +649,100 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
     if (k == 0) bq[(size_t)pl * nqpad + row] = bacc;
 }
 
+// ---- step prologue in ONE launch ---------------------------------------------------------------------------------------------
+// Everything a tensor-core train step needs before its first GEMM is independent elementwise work on different buffers: the two
+// bf16 shadow packs (online, target), the GPI key fill, the GPI fold and the backward pass's [x | 1 | 0] operand.  As five
+// launches they cost five launch latencies on the step's dependent chain (~2-6 us each); here they are block ranges of one
+// grid.  Same arithmetic as pack_bf16_kernel / keys_fill_kernel / fold_gpi_kernel / build_xo_kernel (bit-identical outputs),
+// with 128-bit loads and stores in the packs.
+struct PrepParams {
+    sfgpi_step_prep_args a;
+    int rows_per_policy, Lh, nqpad;
+    int blk_end[5];                  // exclusive prefix ends of the block ranges: pack 0, pack 1, keys, fold, xo
+};
+
+__device__ __forceinline__ void prep_pack8(const sfgpi_net_desc &net, const float *__restrict__ params, int policy_lo, long long item,
+                                           __nv_bfloat16 *__restrict__ out, int rpp, int Lh) {
+    const int AD = net.n_actions * net.n_features, L = net.n_layers, S = net.dims[0];
+    const int k0 = (int)(item & 31) * 8;
+    const long long rr = item >> 5;
+    const int row = (int)(rr % rpp), pl = (int)(rr / rpp);
+    const float *P = params + (size_t)(policy_lo + pl) * net.row_stride;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (row < kH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (k0 + i < S) v[i] = P[net.w_off[0] + row * S + k0 + i];
+    } else {
+        const float *src = nullptr;
+        if (row < (1 + Lh) * kH) src = P + net.w_off[row / kH] + (size_t)(row % kH) * kH + k0;
+        else if (row - (1 + Lh) * kH < AD) src = P + net.w_off[L - 1] + (size_t)(row - (1 + Lh) * kH) * kH + k0;
+        if (src != nullptr) {
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const float4 lo = *reinterpret_cast<const float4 *>(src), hi = *reinterpret_cast<const float4 *>(src + 4);
+                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = src[i];
+            }
+        }
+    }
+    *reinterpret_cast<uint4 *>(out + ((size_t)(policy_lo + pl) * rpp + row) * kH + k0) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ PrepParams pp) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const sfgpi_step_prep_args &a = pp.a;
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    if (bid < pp.blk_end[1]) {                                // ---- bf16 shadow packs: 8 consecutive k per thread ----
+        const int j = bid < pp.blk_end[0] ? 0 : 1;
+        const long long item = (long long)(bid - (j ? pp.blk_end[0] : 0)) * 256 + tid;
+        if (item < (long long)a.pack_n[j] * pp.rows_per_policy * 32)
+            prep_pack8(a.net, a.pack_params[j], a.pack_lo[j], item, reinterpret_cast<__nv_bfloat16 *>(a.pack_out[j]), pp.rows_per_policy, pp.Lh);
+    } else if (bid < pp.blk_end[2]) {                         // ---- GPI keys <- INT64_MIN, 2 per thread ----
+        const long long i = ((long long)(bid - pp.blk_end[1]) * 256 + tid) * 2;
+        long long *k = reinterpret_cast<long long *>(a.keys);
+        if (i + 1 < a.n_keys && (reinterpret_cast<uintptr_t>(k) & 15) == 0) *reinterpret_cast<longlong2 *>(k + i) = make_longlong2(LLONG_MIN, LLONG_MIN);
+        else {
+            if (i < a.n_keys) k[i] = LLONG_MIN;
+            if (i + 1 < a.n_keys) k[i + 1] = LLONG_MIN;
+        }
+    } else if (bid < pp.blk_end[3]) {                         // ---- GPI fold: one block per (policy, folded row), thread = k ----
+        const sfgpi_net_desc &net = a.net;
+        const int u = bid - pp.blk_end[2];
+        const int pl = u / pp.nqpad, row = u - pl * pp.nqpad, k = tid;
+        const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
+        const int nw = a.w_diag ? 1 : a.n_w;
+        const float *P = a.fold_params + (size_t)(a.fold_lo + pl) * net.row_stride;
+        float acc = 0.0f, bacc = 0.0f;
+        if (row < nw * A_) {
+            const int wi = row / A_, act = row - wi * A_;
+            const float *wv = a.w + (size_t)(a.w_diag ? pl : wi) * D;
+            const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH;
+            const float *bo = P + net.b_off[L - 1] + act * D;
+            for (int d = 0; d < D; ++d) {
+                const float wd = wv[d];
+                acc = fmaf(wd, Wo[d * kH + k], acc);
+                bacc = fmaf(wd, bo[d], bacc);
+            }
+        }
+        reinterpret_cast<__nv_bfloat16 *>(a.wq)[((size_t)pl * pp.nqpad + row) * kH + k] = __float2bfloat16_rn(acc);
+        if (k == 0) a.bq[(size_t)pl * pp.nqpad + row] = bacc;
+    } else {                                                  // ---- xo[b] = [x[b] | 1 | 0 ...] bf16 [B][64], 8 columns per thread ----
+        const int i = (bid - pp.blk_end[3]) * 256 + tid;
+        const int b = i >> 3, c0 = (i & 7) * 8, S = a.net.dims[0];
+        if (b < a.B) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (c0 + q < S) ? a.x[(size_t)b * S + c0 + q] : ((c0 + q == S) ? 1.0f : 0.0f);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(a.xo_bf16) + (size_t)b * 64 + c0) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+    }
+}
+
 static int make_tmap(CUtensorMap *tm, const void *base, uint64_t rows) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return SFGPI_E_CUDA; }
@@ -726,6 +839,37 @@ extern "C" int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, in
     return check_launch("sfgpi_fold_gpi");
 }
 
+extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
+    if (!args) { set_error("sfgpi_step_prep: null args"); return SFGPI_E_INVALID; }
+    PrepParams pp;
+    pp.a = *args;
+    const sfgpi_step_prep_args &a = pp.a;
+    const char *why = "";
+    if (!tc_shape_ok(a.net, &why)) { set_error("sfgpi_step_prep: tensor-core path %s", why); return SFGPI_E_INVALID; }
+    pp.Lh = a.net.n_layers - 2;
+    pp.rows_per_policy = sfgpi_bf16_rows_per_policy(&a.net);
+    const int nw = a.w_diag ? 1 : a.n_w;
+    pp.nqpad = a.fold_n > 0 ? sfgpi_gpi_fold_rows(&a.net, nw) : 0;
+    if (a.fold_n > 0 && (nw < 1 || !a.fold_params || !a.w || !a.wq || !a.bq)) { set_error("sfgpi_step_prep: incomplete fold arguments"); return SFGPI_E_INVALID; }
+    if (a.x != nullptr && (a.B < 0 || !a.xo_bf16 || a.net.dims[0] > 63)) { set_error("sfgpi_step_prep: invalid xo arguments"); return SFGPI_E_INVALID; }
+    long long n = 0;
+    for (int j = 0; j < 2; ++j) {
+        if (a.pack_n[j] > 0 && (!a.pack_params[j] || !a.pack_out[j])) { set_error("sfgpi_step_prep: incomplete pack arguments"); return SFGPI_E_INVALID; }
+        if (a.pack_n[j] > 0) n += ((long long)a.pack_n[j] * pp.rows_per_policy * 32 + 255) / 256;
+        pp.blk_end[j] = (int)n;
+    }
+    if (a.keys != nullptr && a.n_keys > 0) n += ((a.n_keys + 1) / 2 + 255) / 256;
+    pp.blk_end[2] = (int)n;
+    if (a.fold_n > 0) n += (long long)pp.nqpad * a.fold_n;
+    pp.blk_end[3] = (int)n;
+    if (a.x != nullptr && a.B > 0) n += ((long long)a.B * 8 + 255) / 256;
+    pp.blk_end[4] = (int)n;
+    if (n == 0) return SFGPI_OK;
+    if (n > 0x7fffffffLL) { set_error("sfgpi_step_prep: too many blocks"); return SFGPI_E_INVALID; }
+    launch_pdl(step_prep_kernel, dim3((unsigned)n), dim3(256), 0, (cudaStream_t)stream, pp);
+    return check_launch("sfgpi_step_prep");
+}
+
 // mode-1 forward, up to 3 independent jobs in one launch.  Per job: `params_bf16` = shadow produced by sfgpi_pack_bf16 for
 // the same `params` (n_policies_total row sets); GPI form (args.w != NULL) additionally needs wq / bq from sfgpi_fold_gpi for
 // the same (policy_lo, n_pol, w).
@@ -805,6 +949,62 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         m.total_pairs += p.total_pairs;
     }
     for (int j = m.n_jobs; j <= kMaxJobs; ++j) m.pair_start[j] = m.total_pairs;
+    // Balanced schedule (see UnitTable): r = floor(tiles / 2G) full rounds of pairs, and when the remainder fits in ONE more
+    // round of single tiles (<= G) it runs as singles instead of as pairs on a few CTAs.  Pairs are listed cheapest first
+    // and singles dearest first (jobs that save activations have the longer epilogues), so CTA c -- which takes units
+    // c, c + G, ... -- combines a cheap pair with a single, and the dear pairs at the end of the round get no second unit.
+    static UnitTable ut;                                         // (host scratch; the launch copies it into the kernel parameters)
+    static const bool sched_off = getenv("SFGPI_SCHED_OFF") != nullptr;
+    m.sched = 0;
+    {
+        const int G = 148, rounds = total_tiles / (2 * G), left = total_tiles - 2 * rounds * G;
+        int q_total = 0;
+        for (int j = 0; j < m.n_jobs; ++j) q_total += m.job[j].a.n_pol;
+        if (!sched_off && paired && !two && rounds >= 1 && left > 0 && left <= G && q_total <= 0x1FFF) {
+            const int p_target = rounds * G;
+            int order[kMaxJobs], nj = m.n_jobs;
+            for (int j = 0; j < nj; ++j) order[j] = j;
+            auto dear = [&](int j) { return m.job[j].a.acts_bf16_out != nullptr ? 1 : 0; };
+            for (int i = 0; i < nj; ++i)                      // cheapest jobs first (stable)
+                for (int k = i + 1; k < nj; ++k)
+                    if (dear(order[k]) < dear(order[i])) { int t = order[i]; order[i] = order[k]; order[k] = t; }
+            int n_units = 0;
+            bool ok = true;
+            // pairs: policy-job q gets an even share of p_target (clipped to the pairs it has)
+            static int np_buf[0x2000];
+            int qi = 0, given = 0;
+            for (int oi = 0; oi < nj && ok; ++oi) {
+                const TcParams &p = m.job[order[oi]];
+                if (p.tiles_per_policy > 0xFFFF) { ok = false; break; }
+                for (int pl = 0; pl < p.a.n_pol; ++pl, ++qi) {
+                    int share = (int)((long long)p_target * (qi + 1) / q_total - (long long)p_target * qi / q_total);
+                    if (share > p.tiles_per_policy / 2) share = p.tiles_per_policy / 2;
+                    np_buf[qi] = share;
+                    given += share;
+                }
+            }
+            const int singles = total_tiles - 2 * given;
+            if (ok && given + singles <= kMaxUnits) {
+                qi = 0;
+                for (int oi = 0; oi < nj; ++oi) {             // pairs, cheapest job first
+                    const int j = order[oi];
+                    for (int pl = 0; pl < m.job[j].a.n_pol; ++pl, ++qi)
+                        for (int k = 0; k < np_buf[qi]; ++k)
+                            ut.u[n_units++] = ((uint32_t)j << 30) | (1u << 29) | ((uint32_t)pl << 16) | (uint32_t)(2 * k);
+                }
+                for (int oi = nj - 1; oi >= 0; --oi) {        // singles, dearest job first
+                    const int j = order[oi];
+                    int qj = 0;
+                    for (int o2 = 0; o2 < oi; ++o2) qj += m.job[order[o2]].a.n_pol;
+                    for (int pl = 0; pl < m.job[j].a.n_pol; ++pl)
+                        for (int t = 2 * np_buf[qj + pl]; t < m.job[j].tiles_per_policy; ++t)
+                            ut.u[n_units++] = ((uint32_t)j << 30) | ((uint32_t)pl << 16) | (uint32_t)t;
+                }
+                m.sched = 1;
+                m.total_pairs = n_units;
+            }
+        }
+    }
     for (int j = m.n_jobs; j < kMaxJobs; ++j) { m.job[j] = m.job[0]; maps.w[j] = maps.w[0]; maps.q[j] = maps.q[0]; maps.acts[j] = maps.acts[0]; }
     const int smem_bytes = 2 * kABytes + kNStage * kStageBytes + kBiasFloatsMax * 4 + 256;
     static bool cfg = false;
@@ -814,8 +1014,8 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         cfg = true;
     }
     const int grid = two ? (m.total_pairs < 74 ? 2 * m.total_pairs : 148) : (m.total_pairs < 148 ? m.total_pairs : 148);
-    if (two) launch_pdl_cluster(mlp_forward_tc_kernel<true>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, 2, m, maps);
-    else launch_pdl(mlp_forward_tc_kernel<false>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, m, maps);
+    if (two) launch_pdl_cluster(mlp_forward_tc_kernel<true>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, 2, m, maps, ut);
+    else launch_pdl(mlp_forward_tc_kernel<false>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, m, maps, ut);
     if (tl_on) {                                                 // developer aid: dump CTA 0's role timelines (cycles since t0)
         long long h[256];
         cudaStreamSynchronize((cudaStream_t)stream);
@@ -823,7 +1023,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         long long t0 = 0;
         for (int i = 0; i < 256; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
         static const char *role[4] = {"epiX", "mma", "tma0", "epiY"};
-        fprintf(stderr, "[sfgpi timeline] jobs=%d units=%d grid=%d %s\n", m.n_jobs, m.total_pairs, grid, two ? "2-CTA pairs" : (paired ? "paired" : "one-tile"));
+        fprintf(stderr, "[sfgpi timeline] jobs=%d units=%d grid=%d %s\n", m.n_jobs, m.total_pairs, grid, two ? "2-CTA pairs" : (m.sched ? "pairs + singles (unit table)" : (paired ? "paired" : "one-tile")));
         for (int r = 0; r < 4; ++r) {
             fprintf(stderr, "  %-4s:", role[r]);
             for (int i = 0; i < 64 && h[r * 64 + i]; ++i) fprintf(stderr, " %lld", h[r * 64 + i] - t0);

@@ -517,6 +517,9 @@ class PackedSFLibrary:
         ad = _lib.AdamArgs()
         ad.n_pol, ad.step = n_pol, C.c_void_p(self.step[lo:].data_ptr())
         ad.consts = C.c_void_p(self.adam_consts[lo:].data_ptr())
+        if getattr(self, '_adam_counter', None) is None:
+            self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ad.finish_counter = self._adam_counter.data_ptr()      # the update kernel's last CTA advances step / consts
         ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
         rs_, nblk, al = sp.row_stride, ws['nblk'], ws['aux_len']
         npa = 1 if variant == 2 else nblk          # variant 2: the TD step leaves ONE reduced aux-gradient row per policy
@@ -609,6 +612,8 @@ class PackedSFLibrary:
         a2.x = a3.x = p_next
         t.phis, t.gammas, t.states, t.next_states, t.rs = p_phis, p_gammas, p_states, p_next, p_rs
         b.x, b.actions = p_states, p_actions
+        if plan.get('prep') is not None:
+            plan['prep'].x = p_states
         plan['ring'] = (plan['ring'] + 1) % 64
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
@@ -626,7 +631,10 @@ class PackedSFLibrary:
                 ka.keys_all[r] = karena.ptrs[r] + koff
                 ua.x[r] = base.ptrs[r] + xoff
             a2.key_action = karena.local + koff
-            peer['fill_cmd'].p[0] = karena.local + koff
+            if plan['prep'] is not None:
+                plan['prep'].keys = karena.local + koff
+            else:
+                peer['fill_cmd'].p[0] = karena.local + koff
             peer['pack_cmd'].p[3] = base.local + xoff
         if plan['tc']:
             for j, which in enumerate(('online', 'online', 'target')):      # the job array embeds copies of the arg blocks
@@ -723,22 +731,42 @@ class PackedSFLibrary:
 
         for k in range(6):
             cmd(seg0, 'NOP', (plan['inputs'][k].data_ptr(), 0), (plan['inputs'][k].numel() * plan['inputs'][k].element_size(),))
+        peer = plan.get('peer')
+        n_keys = keys.numel() if peer is None else peer['kb'] // 8
+        keys_ptr = keys.data_ptr() if peer is None else peer['karena'].local      # peer: patched per step (epoch parity)
+        # one-launch prologue (sfgpi_step_prep) whenever nothing has to happen between the packs and the fold, i.e. always
+        # except on the NCCL-collective sharded path, whose first steps gather w between them
+        merged = plan['tc'] and not (plan['sharded'] and peer is None)
+        plan['prep'] = None
         if plan['tc']:
             dref = C.addressof(plan['desc'])
-            cmd(seg0, 'PACK_BF16', (dref, self.online.data_ptr(), self._shadow_for('online').data_ptr()), (0, self.n))
-            cmd(seg0, 'PACK_BF16', (dref, self.target.data_ptr(), self._shadow_for('target').data_ptr()), (a3.policy_lo, a3.n_pol))
-        peer = plan.get('peer')
-        if peer is None:
-            cmd(seg0, 'KEYS_FILL', (keys.data_ptr(),), (keys.numel(),))
-        else:                                                 # pointer patched per step (epoch parity)
-            cmd(seg0, 'KEYS_FILL', (peer['karena'].local,), (peer['kb'] // 8,))
-        if plan['tc']:
             nw = 1 if a2.w_diag else a2.n_w
             nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(plan['desc']), nw)
             plan['wq'] = torch.empty(a2.n_pol * nq * 256, dtype=torch.bfloat16, device=dev)
             plan['bq'] = self._f(a2.n_pol * nq)
-            cmd(seg1, 'FOLD_GPI', (dref, self.online.data_ptr(), a2.w, plan['wq'].data_ptr(), plan['bq'].data_ptr()),
-                (a2.policy_lo, a2.n_pol, a2.n_w, a2.w_diag))
+        if merged:
+            pr = plan['prep'] = _lib.StepPrepArgs()
+            pr.net = sp.desc()
+            pr.pack_params[0], pr.pack_out[0] = self.online.data_ptr(), self._shadow_for('online').data_ptr()
+            pr.pack_lo[0], pr.pack_n[0] = 0, self.n
+            pr.pack_params[1], pr.pack_out[1] = self.target.data_ptr(), self._shadow_for('target').data_ptr()
+            pr.pack_lo[1], pr.pack_n[1] = a3.policy_lo, a3.n_pol
+            pr.keys, pr.n_keys = keys_ptr, n_keys
+            pr.fold_params, pr.fold_lo, pr.fold_n = self.online.data_ptr(), a2.policy_lo, a2.n_pol
+            pr.w, pr.n_w, pr.w_diag = a2.w, a2.n_w, a2.w_diag
+            pr.wq, pr.bq = plan['wq'].data_ptr(), plan['bq'].data_ptr()
+            pr.B, pr.xo_bf16 = B, ws['xo16'].data_ptr()       # pr.x = this step's states, patched per step
+            b.xo_ready = 1
+            cmd(seg0, 'STEP_PREP', (C.addressof(pr),))
+        else:
+            if plan['tc']:
+                cmd(seg0, 'PACK_BF16', (dref, self.online.data_ptr(), self._shadow_for('online').data_ptr()), (0, self.n))
+                cmd(seg0, 'PACK_BF16', (dref, self.target.data_ptr(), self._shadow_for('target').data_ptr()), (a3.policy_lo, a3.n_pol))
+            cmd(seg0, 'KEYS_FILL', (keys_ptr,), (n_keys,))
+            if plan['tc']:
+                cmd(seg1, 'FOLD_GPI', (dref, self.online.data_ptr(), a2.w, plan['wq'].data_ptr(), plan['bq'].data_ptr()),
+                    (a2.policy_lo, a2.n_pol, a2.n_w, a2.w_diag))
+        if plan['tc']:
             jobs = plan['jobs'] = (_lib.ForwardTcJob * 3)()
             for j, which in enumerate(('online', 'online', 'target')):
                 jobs[j].params_bf16, jobs[j].n_policies_total = self._shadow_for(which).data_ptr(), self.cap
@@ -785,7 +813,8 @@ class PackedSFLibrary:
                     arr[k].p[q] = v
                 for q, v in enumerate(i):
                     arr[k].i[q] = int(v)
-                launches += _lib.OP_LAUNCHES[arr[k].op]
+                launches += _lib.OP_LAUNCHES[arr[k].op] - (1 if op == 'BACKWARD_TC' and b.xo_ready else 0) \
+                    - (1 if op == 'ADAM' and ad.finish_counter else 0)
             if plan['h2d'] is None:
                 plan['h2d'] = [arr[k] for k in range(6)]
             plan['probe'] += [arr[k] for k, (op, p, i) in enumerate(seg) if op == 'NOP' and not p]

@@ -195,6 +195,9 @@ typedef struct {
     int32_t sequential_shared;      /* 1: segments with param_stride 0 are stepped by optimizer 0..n_pol-1 in order */
     double *consts;                 /* optional [n_pol][2]: {1 - beta1^t, sqrt(1 - beta2^t)} for t = step + 1; must be consistent
                                        with `step` on entry, refreshed on device after the step.  NULL: computed in-kernel */
+    uint32_t *finish_counter;       /* optional: one zero-initialised device word owned by this optimizer group.  Given it, the
+                                       last CTA of the update kernel advances step / consts itself (the word returns to 0) and the
+                                       separate one-block finishing launch drops out of the step's dependent chain */
 } sfgpi_adam_args;
 
 int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
@@ -257,11 +260,37 @@ typedef struct {
     void *xo_bf16;
     float *grad_part;               /* [n_pol][n_split][row_stride] */
     int32_t n_split;
+    int32_t xo_ready;               /* nonzero: xo_bf16 already holds [x | 1 | 0] (sfgpi_step_prep built it) -> one launch fewer */
 } sfgpi_backward_tc_args;
 
 int sfgpi_bwd_tc_out_pad(const sfgpi_net_desc *net);
 int sfgpi_bwd_tc_splits(int32_t B, int32_t want);
 int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
+
+/*
+ * Step prologue of a tensor-core train step in ONE launch: sfgpi_pack_bf16 for up to two row sets (online, target),
+ * sfgpi_keys_fill, sfgpi_fold_gpi and the backward pass's xo = [x | 1 | 0] operand (bf16 [B][64]) -- five independent
+ * elementwise passes that would otherwise be five launches on the step's dependent chain.  A part is skipped when its count is
+ * 0 / its pointer NULL.  Outputs are bit-identical to the separate entry points.
+ */
+typedef struct {
+    sfgpi_net_desc net;
+    const float *pack_params[2];    /* library rows to pack ...                  */
+    void *pack_out[2];              /* ... into these bf16 shadows               */
+    int32_t pack_lo[2], pack_n[2];  /* policy range of each pack (n = 0: skip)   */
+    int64_t *keys;                  /* GPI keys to reset to INT64_MIN (NULL: skip) */
+    int64_t n_keys;
+    const float *fold_params;       /* sfgpi_fold_gpi arguments (fold_n = 0: skip) */
+    int32_t fold_lo, fold_n;
+    const float *w;
+    int32_t n_w, w_diag;
+    void *wq;
+    float *bq;
+    const float *x;                 /* [B][S] states of the online forward (NULL: skip) */
+    int32_t B;
+    void *xo_bf16;                  /* [B][64] */
+} sfgpi_step_prep_args;
+int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream);
 
 /*
  * Device-resident replay ring (ReplayBuffer.replay, sfdqn.py:54-80): gathers B picked transitions out of the packed ring
@@ -305,6 +334,7 @@ int sfgpi_replay_gather(const sfgpi_replay_args *args, void *stream);
 #define SFGPI_OP_PEER_KEYS 14       /* p0 = sfgpi_peer_keys_args */
 #define SFGPI_OP_SHARD_PACK 15      /* p0 = w, p1 = h, p2 = h_prev, p3 = x_local, i0 = nw, i1 = nh */
 #define SFGPI_OP_PEER_UNPACK 16     /* p0 = sfgpi_peer_unpack_args */
+#define SFGPI_OP_STEP_PREP 17       /* p0 = sfgpi_step_prep_args */
 typedef struct {
     int32_t op;
     void *p[5];

@@ -155,3 +155,60 @@ def test_psi_backward_vs_autograd(precision, tol, S, A, D, N, B, hopper):
         for l, ((W, b), (gW, gb)) in enumerate(zip(lib.spec.views(got[p]), ref[p])):
             assert fro_err(W, gW) < tol, f'policy {p} layer {l}: dW error {fro_err(W, gW)}'
             assert fro_err(b, gb) < tol, f'policy {p} layer {l}: db error {fro_err(b, gb)}'
+
+
+def test_bf16_forward_unit_table_schedule():
+    """380 row tiles on 148 SMs: the balanced pairs + singles schedule (unit table) of the one-CTA-per-SM kernel."""
+    _bf16_forward_gpi_vs_oracle(4, 9, 12, 10, 38 * 128 - 5, False)
+
+
+@pytest.mark.parametrize('S,A,D,N,B', [(4, 9, 12, 3, 1000), (11, 27, 50, 2, 333)])
+def test_step_prep_equals_separate_passes(S, A, D, N, B):
+    """sfgpi_step_prep (one launch) == sfgpi_pack_bf16 x2 + sfgpi_keys_fill + sfgpi_fold_gpi + build_xo, bit for bit."""
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    from deep_successor_features_for_transfer_b200.library import _stream
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=31)
+    sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+    lib = sf._library
+    lib.target[:N].mul_(1.5)                                    # online != target
+    desc = lib.spec.desc()
+    x = synthetic_transitions(B, S, A, D, gen)[0].cuda()
+    nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(desc), N)
+    st = _stream()
+    # separate passes
+    lib._pack('online', 0, N)
+    lib._pack('target', 1, N - 1)
+    ref_on, ref_tg = lib._shadow_for('online').clone(), lib._shadow_for('target').clone()
+    keys_ref = torch.zeros(5, B, dtype=torch.int64, device='cuda')
+    _lib.call('sfgpi_keys_fill', keys_ref.data_ptr(), keys_ref.numel() - 1, st)
+    wq_ref = torch.zeros(N * nq * 256, dtype=torch.bfloat16, device='cuda')
+    bq_ref = torch.zeros(N * nq, device='cuda')
+    _lib.call('sfgpi_fold_gpi', C.byref(desc), lib.online.data_ptr(), 0, N, lib.w.data_ptr(), N, 0, wq_ref.data_ptr(),
+              bq_ref.data_ptr(), st)
+    xo_ref = torch.zeros(B, 64, device='cuda')
+    xo_ref[:, :S] = x
+    xo_ref[:, S] = 1.0
+    xo_ref = xo_ref.to(torch.bfloat16)
+    # one launch
+    lib._shadow_for('online').zero_()
+    lib._shadow_for('target').zero_()
+    keys = torch.zeros(5, B, dtype=torch.int64, device='cuda')
+    wq, bq = torch.zeros_like(wq_ref), torch.zeros_like(bq_ref)
+    xo = torch.zeros(B, 64, dtype=torch.bfloat16, device='cuda')
+    pr = _lib.StepPrepArgs()
+    pr.net = desc
+    pr.pack_params[0], pr.pack_out[0], pr.pack_lo[0], pr.pack_n[0] = lib.online.data_ptr(), lib._shadow_for('online').data_ptr(), 0, N
+    pr.pack_params[1], pr.pack_out[1], pr.pack_lo[1], pr.pack_n[1] = lib.target.data_ptr(), lib._shadow_for('target').data_ptr(), 1, N - 1
+    pr.keys, pr.n_keys = keys.data_ptr(), keys.numel() - 1
+    pr.fold_params, pr.fold_lo, pr.fold_n = lib.online.data_ptr(), 0, N
+    pr.w, pr.n_w, pr.w_diag, pr.wq, pr.bq = lib.w.data_ptr(), N, 0, wq.data_ptr(), bq.data_ptr()
+    pr.x, pr.B, pr.xo_bf16 = x.data_ptr(), B, xo.data_ptr()
+    _lib.call('sfgpi_step_prep', C.byref(pr), st)
+    torch.cuda.synchronize()
+    assert torch.equal(lib._shadow_for('online').view(torch.int16), ref_on.view(torch.int16))
+    assert torch.equal(lib._shadow_for('target').view(torch.int16), ref_tg.view(torch.int16))
+    assert torch.equal(keys, keys_ref) and int(keys.view(-1)[-1]) == 0          # the element past n_keys is untouched
+    assert torch.equal(wq.view(torch.int16), wq_ref.view(torch.int16)) and torch.equal(bq, bq_ref)
+    assert torch.equal(xo.view(torch.int16), xo_ref.view(torch.int16))
