@@ -659,6 +659,8 @@ struct PrepParams {
     sfgpi_step_prep_args a;
     int rows_per_policy, Lh, nqpad;
     int blk_end[5];                  // exclusive prefix ends of the block ranges: pack 0, pack 1, keys, fold, xo
+    int copy_end[SFGPI_PREP_COPIES]; // ... preceded by the staging copies' ranges (blocks [0, copy_end[5]))
+    const void *copy_src_dev[SFGPI_PREP_COPIES];      // device-visible addresses of the (pinned host) sources
 };
 
 __device__ __forceinline__ void prep_pack8(const sfgpi_net_desc &net, const float *__restrict__ params, int policy_lo, long long item,
@@ -695,7 +697,22 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
     pdl_launch_dependents();
     pdl_wait();
     const sfgpi_step_prep_args &a = pp.a;
-    const int bid = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    if (bid < pp.copy_end[SFGPI_PREP_COPIES - 1]) {           // ---- staging copies (pinned host -> HBM over PCIe), first in the grid ----
+        int j = 0;
+        while (bid >= pp.copy_end[j]) ++j;
+        const long long off = ((long long)(bid - (j ? pp.copy_end[j - 1] : 0)) * 256 + tid) * 16;
+        const char *src = reinterpret_cast<const char *>(pp.copy_src_dev[j]);
+        char *dst = reinterpret_cast<char *>(a.copy_dst[j]);
+        const long long n = a.copy_bytes[j];
+        if (off + 16 <= n && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
+            *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(src + off);
+        else
+            for (long long q = off; q < min(off + 16, n); ++q) dst[q] = src[q];
+        return;
+    }
+    bid -= pp.copy_end[SFGPI_PREP_COPIES - 1];
     if (bid < pp.blk_end[1]) {                                // ---- bf16 shadow packs: 8 consecutive k per thread ----
         const int j = bid < pp.blk_end[0] ? 0 : 1;
         const long long item = (long long)(bid - (j ? pp.blk_end[0] : 0)) * 256 + tid;
@@ -852,6 +869,26 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     pp.nqpad = a.fold_n > 0 ? sfgpi_gpi_fold_rows(&a.net, nw) : 0;
     if (a.fold_n > 0 && (nw < 1 || !a.fold_params || !a.w || !a.wq || !a.bq)) { set_error("sfgpi_step_prep: incomplete fold arguments"); return SFGPI_E_INVALID; }
     if (a.x != nullptr && (a.B < 0 || !a.xo_bf16 || a.net.dims[0] > 63)) { set_error("sfgpi_step_prep: invalid xo arguments"); return SFGPI_E_INVALID; }
+    long long nc = 0;
+    for (int j = 0; j < SFGPI_PREP_COPIES; ++j) {
+        pp.copy_src_dev[j] = nullptr;
+        if (a.copy_bytes[j] > 0) {
+            if (!a.copy_src[j] || !a.copy_dst[j]) { set_error("sfgpi_step_prep: incomplete staging copy %d", j); return SFGPI_E_INVALID; }
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, a.copy_src[j]) != cudaSuccess || at.type == cudaMemoryTypeUnregistered || !at.devicePointer) {
+                // pageable host memory: the kernel cannot read it -> a plain stream-ordered copy ahead of the launch
+                cudaGetLastError();
+                if (cudaMemcpyAsync(a.copy_dst[j], a.copy_src[j], (size_t)a.copy_bytes[j], cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess)
+                    return check_launch("sfgpi_step_prep(pageable staging copy)");
+                if (a.x == a.copy_src[j]) pp.a.x = reinterpret_cast<const float *>(a.copy_dst[j]);
+            } else {
+                pp.copy_src_dev[j] = at.devicePointer;
+                if (a.x == a.copy_src[j]) pp.a.x = reinterpret_cast<const float *>(at.devicePointer);
+                nc += ((a.copy_bytes[j] + 15) / 16 + 255) / 256;
+            }
+        }
+        pp.copy_end[j] = (int)nc;
+    }
     long long n = 0;
     for (int j = 0; j < 2; ++j) {
         if (a.pack_n[j] > 0 && (!a.pack_params[j] || !a.pack_out[j])) { set_error("sfgpi_step_prep: incomplete pack arguments"); return SFGPI_E_INVALID; }
@@ -864,6 +901,7 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     pp.blk_end[3] = (int)n;
     if (a.x != nullptr && a.B > 0) n += ((long long)a.B * 8 + 255) / 256;
     pp.blk_end[4] = (int)n;
+    n += nc;
     if (n == 0) return SFGPI_OK;
     if (n > 0x7fffffffLL) { set_error("sfgpi_step_prep: too many blocks"); return SFGPI_E_INVALID; }
     launch_pdl(step_prep_kernel, dim3((unsigned)n), dim3(256), 0, (cudaStream_t)stream, pp);

@@ -270,9 +270,11 @@ int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 /*
  * Step prologue of a tensor-core train step in ONE launch: sfgpi_pack_bf16 for up to two row sets (online, target),
  * sfgpi_keys_fill, sfgpi_fold_gpi and the backward pass's xo = [x | 1 | 0] operand (bf16 [B][64]) -- five independent
- * elementwise passes that would otherwise be five launches on the step's dependent chain.  A part is skipped when its count is
- * 0 / its pointer NULL.  Outputs are bit-identical to the separate entry points.
+ * elementwise passes that would otherwise be five launches on the step's dependent chain -- plus, optionally, the staging of the
+ * step's host-resident inputs.  A part is skipped when its count is 0 / its pointer NULL.  Outputs are bit-identical to the
+ * separate entry points.
  */
+#define SFGPI_PREP_COPIES 6
 typedef struct {
     sfgpi_net_desc net;
     const float *pack_params[2];    /* library rows to pack ...                  */
@@ -286,9 +288,15 @@ typedef struct {
     int32_t n_w, w_diag;
     void *wq;
     float *bq;
-    const float *x;                 /* [B][S] states of the online forward (NULL: skip) */
+    const float *x;                 /* [B][S] states of the online forward (NULL: skip); may be a pinned host address */
     int32_t B;
     void *xo_bf16;                  /* [B][64] */
+    /* input staging: up to 6 plain copies src -> dst run as the first blocks of the same grid.  src may be PINNED HOST memory
+     * (the kernel reads it over PCIe: a replay batch arriving from the host costs no cudaMemcpyAsync calls) or pageable host
+     * memory (copied with cudaMemcpyAsync ahead of the launch); `x` may alias a copy_src; bytes = 0: skip */
+    const void *copy_src[SFGPI_PREP_COPIES];
+    void *copy_dst[SFGPI_PREP_COPIES];
+    int64_t copy_bytes[SFGPI_PREP_COPIES];
 } sfgpi_step_prep_args;
 int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream);
 

@@ -212,3 +212,26 @@ def test_step_prep_equals_separate_passes(S, A, D, N, B):
     assert torch.equal(keys, keys_ref) and int(keys.view(-1)[-1]) == 0          # the element past n_keys is untouched
     assert torch.equal(wq.view(torch.int16), wq_ref.view(torch.int16)) and torch.equal(bq, bq_ref)
     assert torch.equal(xo.view(torch.int16), xo_ref.view(torch.int16))
+
+
+@pytest.mark.parametrize('kind', ['pinned', 'pageable'])
+def test_train_step_from_host_batches_equals_device_batches(kind):
+    """Host-resident replay batches (pinned: pulled over PCIe by the prologue kernel itself; pageable: cudaMemcpyAsync
+    commands) must give bit-identical steps to device-resident batches."""
+    S, A, D, N, B = 4, 9, 12, 3, 1000
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True)
+    o, gen = make(S, A, D, N, seed=41, tsf_dim=100)
+    batches = [synthetic_transitions(B, S, A, D, gen) for _ in range(3)]
+    sf_d, ag_d = gu.build_g3(meta, oracle=o)
+    sf_h, ag_h = gu.build_g3(meta, oracle=o)
+    sf_d._library.set_precision('bf16')
+    sf_h._library.set_precision('bf16')
+    for tr in batches:
+        host = tuple(t.pin_memory() for t in tr) if kind == 'pinned' else tr
+        ld = ag_d.update_successor_all(tuple(t.cuda() for t in tr), use_gpi=True)
+        lh = ag_h.update_successor_all(host, use_gpi=True)
+        torch.cuda.synchronize()
+        assert torch.equal(ld, lh)
+    n = N
+    assert torch.equal(sf_d._library.online[:n], sf_h._library.online[:n])
+    assert torch.equal(sf_d._library.g[:n], sf_h._library.g[:n]) and torch.equal(sf_d._library.h, sf_h._library.h)
