@@ -57,7 +57,7 @@ class TdArgs(C.Structure):
                 ('next_states', C.c_void_p), ('w', C.c_void_p), ('g', C.c_void_p), ('h', C.c_void_p),
                 ('w_stride', C.c_int32), ('g_stride', C.c_int32), ('d_out', C.c_void_p), ('loss_part', C.c_void_p),
                 ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32), ('next_psi', C.c_void_p), ('next_keys', C.c_void_p),
-                ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p)]
+                ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p), ('defer_expand', C.c_int32)]
 
 
 class ForwardTcJob(C.Structure):
@@ -75,7 +75,7 @@ class BackwardTcArgs(C.Structure):
     _fields_ = [('net', NetDesc), ('params_bf16', C.c_void_p), ('n_policies_total', C.c_int32), ('policy_lo', C.c_int32),
                 ('n_pol', C.c_int32), ('x', C.c_void_p), ('B', C.c_int32), ('acts_bf16', C.c_void_p), ('relu_masks', C.c_void_p), ('actions', C.c_void_p),
                 ('d_out', C.c_void_p), ('dz_bf16', C.c_void_p), ('dzo_bf16', C.c_void_p), ('xo_bf16', C.c_void_p),
-                ('grad_part', C.c_void_p), ('n_split', C.c_int32), ('xo_ready', C.c_int32)]
+                ('grad_part', C.c_void_p), ('n_split', C.c_int32), ('xo_ready', C.c_int32), ('expand_td', C.c_void_p)]
 
 
 class StepPrepArgs(C.Structure):
@@ -129,7 +129,7 @@ class AdamArgs(C.Structure):
     _fields_ = [('n_seg', C.c_int32), ('n_pol', C.c_int32), ('seg', AdamSegment * MAX_SEGMENTS), ('step', C.c_void_p),
                 ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
                 ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
-                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p), ('finish_counter', C.c_void_p)]
+                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p)]
 
 
 # every symbol include/sfgpi.h declares: name -> (restype, argtypes)

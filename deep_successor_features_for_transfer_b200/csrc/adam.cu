@@ -174,20 +174,6 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             }
         }
     }
-    // ---- fused finish: the LAST CTA to get here advances step / bias corrections (every CTA read them before arriving) ----
-    if (a.finish_counter != nullptr) {
-        __shared__ unsigned last_s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            last_s = atomicAdd(a.finish_counter, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
-        }
-        __syncthreads();
-        if (last_s) {
-            for (int i = threadIdx.x; i < a.n_pol; i += kAdamThreads) adam_finish_one(a.step, a.consts, i, a.beta1, a.beta2);
-            if (threadIdx.x == 0) *a.finish_counter = 0u;
-        }
-    }
 }
 
 __global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double beta1, double beta2) {
@@ -220,7 +206,7 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     launch_pdl(adam_kernel, grid, dim3(kAdamThreads), 0, st, a, blocks);
     int rc = check_launch("sfgpi_adam_step");
-    if (rc || a.finish_counter != nullptr) return rc;
+    if (rc) return rc;
     launch_pdl(adam_finish_kernel, dim3((a.n_pol + 127) / 128), dim3(128), 0, st, a.step, a.consts, a.n_pol, a.beta1, a.beta2);
     return check_launch("sfgpi_adam_step(finish)");
 }

@@ -207,4 +207,65 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- TSF expand (csrc/td.cu explains the mathematics) ---------------------------------------------------------------------
+__host__ __device__ inline int tsf_red_len(int D, int S) { return D + D * S + D; }      // [dw | T | t]
+
+// TSF: (dw, T, t) partials [n_pol][nclu][2D + D*S] -> the full reduced gradient row [dw | dWg | dbg | dWh | dbh] of each
+// policy (written to partial slot 0 of aux_grad_part; the Adam kernel reads it with n_part = 1).  red: [n_red] shared scratch,
+// Wg_s: [G][S] | bg [G], Wh_s: [D][G] already staged in shared memory; nt threads of one CTA take part.
+__device__ __forceinline__ void tsf_expand_policy(const sfgpi_td_args &a, int pl, int nclu, float *red, const float *Wg_s,
+                                                  const float *Wh_s, int tid, int nt) {
+    const int S = a.S, D = a.D, G = a.G;
+    const int n_red = tsf_red_len(D, S);
+    const float *part = a.tsf_part + (size_t)pl * nclu * n_red;
+    for (int e = tid; e < n_red; e += nt) {                  // fixed order k = 0, 1, ...; 8 loads in flight at a time
+        float acc = 0.0f;
+        int k = 0;
+        for (; k + 8 <= nclu; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = part[(size_t)(k + q) * n_red + e];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[q];
+        }
+        for (; k < nclu; ++k) acc += part[(size_t)k * n_red + e];
+        red[e] = acc;
+    }
+    __syncthreads();
+    const float *T = red + D, *tv = T + D * S, *bg_s = Wg_s + G * S;
+    float *out = a.aux_grad_part + (size_t)pl * nclu * a.aux_len;        // slot 0 of this policy
+    float *gW = out + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
+    for (int d = tid; d < D; d += nt) { out[d] = red[d]; hb[d] = 2.0f * tv[d]; }
+    for (int e = tid; e < G * S; e += nt) {                  // dWg[g][s] = sum_d Wh[d][g] T[d][s]
+        const int g = e / S, s = e - g * S;
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = fmaf(Wh_s[d * G + g], T[d * S + s], acc);
+        gW[e] = acc;
+    }
+    for (int g = tid; g < G; g += nt) {                      // dbg[g] = 2 sum_d Wh[d][g] t[d]
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) acc = fmaf(Wh_s[d * G + g], tv[d], acc);
+        gb[g] = 2.0f * acc;
+    }
+    for (int e = tid; e < D * G; e += nt) {                  // dWh[d][g] = sum_s T[d][s] Wg[g][s] + 2 bg[g] t[d]
+        const int d = e / G, g = e - d * G;
+        float acc = 2.0f * bg_s[g] * tv[d];
+        for (int s = 0; s < S; ++s) acc = fmaf(T[d * S + s], Wg_s[g * S + s], acc);
+        hW[e] = acc;
+    }
+}
+
+// whole expand of policy pl by one CTA of nt threads; sm: dynamic shared memory of >= tsf_expand_smem_floats() floats
+__host__ __device__ inline int tsf_expand_smem_floats(int D, int S, int G) { return tsf_red_len(D, S) + G * S + G + D * G; }
+__device__ __forceinline__ void tsf_expand_cta(const sfgpi_td_args &a, int pl, int nclu, float *sm, int tid, int nt) {
+    const int S = a.S, D = a.D, G = a.G;
+    float *red = sm;                              // [dw | T | t]
+    float *Wg_s = red + tsf_red_len(D, S);        // [G][S] | bg [G]
+    float *Wh_s = Wg_s + G * S + G;               // [D][G]
+    const float *gp = a.g + (size_t)pl * a.g_stride;
+    for (int e = tid; e < G * S + G; e += nt) Wg_s[e] = gp[e];
+    for (int e = tid; e < D * G; e += nt) Wh_s[e] = a.h[e];
+    tsf_expand_policy(a, pl, nclu, red, Wg_s, Wh_s, tid, nt);
+}
+
 }  // namespace sfgpi

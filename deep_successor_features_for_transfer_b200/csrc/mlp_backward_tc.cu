@@ -41,6 +41,7 @@ struct DgParams {
     __nv_bfloat16 *dzo;              // [n_pol][B][ADp]
     int rows_per_policy, L, AD, AD16, ADp, n_chunks, n_items;
     int tiles_per_policy, pairs_per_policy, total_pairs, paired;
+    int n_main;                      // CTAs running the dgrad tile loop; CTAs [n_main, gridDim.x) are riders (see ex)
 };
 
 struct DgItem { int row_base, K; };                 // shadow row of the first reduction index, reduction length (mult. of 16)
@@ -132,9 +133,18 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t t_lane, uint32_t Arow, i
 
 __global__ void __launch_bounds__(kThreadsDg, 1)
 mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_dzo) {
+                    const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_dzo,
+                    const __grid_constant__ sfgpi_td_args ex, int ex_nclu) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
+    if ((int)blockIdx.x >= p.n_main) {
+        // Rider CTAs: the TSF expand of the TD step (one policy each).  It depends only on the TD kernel -- this launch's
+        // predecessor -- and only the Adam kernel consumes it, so instead of a launch of its own on the step's dependent chain
+        // it runs here, on SMs the dgrad tile loop leaves idle, concurrently with the dgrad CTAs.
+        pdl_wait();
+        tsf_expand_cta(ex, (int)blockIdx.x - p.n_main, ex_nclu, reinterpret_cast<float *>(smem_raw), threadIdx.x, kThreadsDg);
+        return;
+    }
     const sfgpi_net_desc &net = p.net;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -173,7 +183,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         {
             const uint32_t leader = elect_one();             // whole-warp loop, elected issue (tc_common.cuh)
             uint32_t n = 0;
-            for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+            for (int pair = blockIdx.x; pair < p.total_pairs; pair += p.n_main) {
                 const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
                 const int row0 = (p.policy_lo + pl) * p.rows_per_policy;
                 const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
@@ -202,7 +212,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
             const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
             const uint64_t bdesc0 = umma_desc_mn_sw128(W_addr, kBoxBytes);
             const uint32_t idesc = umma_idesc_bf16_major(kTM, kNB, 0u, 1u);
-            for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+            for (int pair = blockIdx.x; pair < p.total_pairs; pair += p.n_main) {
                 const int pip = pair % p.pairs_per_policy;
                 const bool has_y = p.paired && (2 * pip + 1 < p.tiles_per_policy);
                 for (int it = 0; it < p.n_items; ++it) {
@@ -286,7 +296,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
             if (store_pending[slot]) { a_slot_guard(!store_pending[slot ^ 1]); store_pending[slot] = false; }
         };
 
-        for (int pair = blockIdx.x; pair < p.total_pairs; pair += gridDim.x) {
+        for (int pair = blockIdx.x; pair < p.total_pairs; pair += p.n_main) {
             const int pl = pair / p.pairs_per_policy, pip = pair - pl * p.pairs_per_policy;
             const int n_slots = (p.paired && (2 * pip + 1 < p.tiles_per_policy)) ? 2 : 1;
             int bs[2];
@@ -630,7 +640,20 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     const int dg_smem = 2 * kABytes + kNStage * kStageBytes + 256;
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg_smem); cfg = true; }
-    launch_pdl(mlp_dgrad_tc_kernel, dim3(dp.total_pairs < 148 ? dp.total_pairs : 148), dim3(kThreadsDg), dg_smem, st, dp, tmap_w, tm_dz_st, tm_dzo_st);
+    dp.n_main = dp.total_pairs < 148 ? dp.total_pairs : 148;
+    sfgpi_td_args ex = {};
+    int ex_nclu = 0, riders = 0;
+    if (a.expand_td != nullptr) {                                    // deferred TSF expand (sfgpi_td_args.defer_expand)
+        ex = *reinterpret_cast<const sfgpi_td_args *>(a.expand_td);
+        if (ex.variant != 2 || ex.n_pol < 1 || !ex.tsf_part || !ex.aux_grad_part || !ex.g || !ex.h ||
+            (size_t)tsf_expand_smem_floats(ex.D, ex.S, ex.G) * sizeof(float) > (size_t)dg_smem) {
+            set_error("sfgpi_mlp_backward_tc: expand_td is not a variant-2 TD step that fits the dgrad launch");
+            return SFGPI_E_INVALID;
+        }
+        ex_nclu = sfgpi_td_partials(ex.B);
+        riders = ex.n_pol;
+    }
+    launch_pdl(mlp_dgrad_tc_kernel, dim3(dp.n_main + riders), dim3(kThreadsDg), dg_smem, st, dp, tmap_w, tm_dz_st, tm_dzo_st, ex, ex_nclu);
     rc = check_launch("sfgpi_mlp_backward_tc(dgrad)");
     if (rc) return rc;
 

@@ -24,7 +24,6 @@ constexpr int kTdRows = 32;       // transitions per CTA
 constexpr int kTdThreads = 128;
 constexpr int kTdCluster = 8;     // CTAs per cluster (portable maximum)
 
-__host__ __device__ inline int tsf_red_len(int D, int S) { return D + D * S + D; }      // [dw | T | t]
 
 __global__ void __cluster_dims__(kTdCluster, 1, 1) __launch_bounds__(kTdThreads)
 td_kernel(const __grid_constant__ sfgpi_td_args a) {
@@ -199,51 +198,14 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
         }
     }
     cluster.sync();                                          // nobody leaves while its shared memory is still being read
+
 }
 
-// TSF: (dw, T, t) partials [n_pol][nclu][2D + D*S] -> the full reduced gradient row [dw | dWg | dbg | dWh | dbh] of each
-// policy (written to partial slot 0 of aux_grad_part; the Adam kernel reads it with n_part = 1).
 __global__ void __launch_bounds__(256) tsf_expand_kernel(const __grid_constant__ sfgpi_td_args a, int nclu) {
     extern __shared__ __align__(16) float sm[];
     pdl_launch_dependents();
     pdl_wait();
-    const int tid = threadIdx.x, pl = blockIdx.x;
-    const int S = a.S, D = a.D, G = a.G;
-    const int n_red = tsf_red_len(D, S);
-    float *red = sm;                              // [dw | T | t]
-    float *Wg_s = red + n_red;                    // [G][S] | bg [G]
-    float *Wh_s = Wg_s + G * S + G;               // [D][G]
-    const float *part = a.tsf_part + (size_t)pl * nclu * n_red;
-    for (int e = tid; e < n_red; e += 256) {
-        float acc = 0.0f;
-        for (int k = 0; k < nclu; ++k) acc += part[(size_t)k * n_red + e];
-        red[e] = acc;
-    }
-    const float *gp = a.g + (size_t)pl * a.g_stride;
-    for (int e = tid; e < G * S + G; e += 256) Wg_s[e] = gp[e];
-    for (int e = tid; e < D * G; e += 256) Wh_s[e] = a.h[e];
-    __syncthreads();
-    const float *T = red + D, *tv = T + D * S, *bg_s = Wg_s + G * S;
-    float *out = a.aux_grad_part + (size_t)pl * nclu * a.aux_len;        // slot 0 of this policy
-    float *gW = out + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
-    for (int d = tid; d < D; d += 256) { out[d] = red[d]; hb[d] = 2.0f * tv[d]; }
-    for (int e = tid; e < G * S; e += 256) {                 // dWg[g][s] = sum_d Wh[d][g] T[d][s]
-        const int g = e / S, s = e - g * S;
-        float acc = 0.0f;
-        for (int d = 0; d < D; ++d) acc = fmaf(Wh_s[d * G + g], T[d * S + s], acc);
-        gW[e] = acc;
-    }
-    for (int g = tid; g < G; g += 256) {                     // dbg[g] = 2 sum_d Wh[d][g] t[d]
-        float acc = 0.0f;
-        for (int d = 0; d < D; ++d) acc = fmaf(Wh_s[d * G + g], tv[d], acc);
-        gb[g] = 2.0f * acc;
-    }
-    for (int e = tid; e < D * G; e += 256) {                 // dWh[d][g] = sum_s T[d][s] Wg[g][s] + 2 bg[g] t[d]
-        const int d = e / G, g = e - d * G;
-        float acc = 2.0f * bg_s[g] * tv[d];
-        for (int s = 0; s < S; ++s) acc = fmaf(T[d * S + s], Wg_s[g * S + s], acc);
-        hW[e] = acc;
-    }
+    tsf_expand_cta(a, blockIdx.x, nclu, sm, threadIdx.x, 256);
 }
 
 }  // namespace sfgpi
@@ -270,7 +232,7 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     dim3 grid(nclu * kTdCluster, a.n_pol);
     launch_pdl(td_kernel, grid, dim3(kTdThreads), bytes, (cudaStream_t)stream, a);
     int rc = check_launch("sfgpi_td_step");
-    if (rc || !tsf) return rc;
+    if (rc || !tsf || a.defer_expand) return rc;              // deferred: the expand rides in sfgpi_mlp_backward_tc's dgrad launch
     const size_t ebytes = ((size_t)n_red + (size_t)a.G * a.S + a.G + (size_t)a.D * a.G) * sizeof(float);
     if (ebytes > 48 * 1024) cudaFuncSetAttribute(tsf_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     launch_pdl(tsf_expand_kernel, dim3(a.n_pol), dim3(256), ebytes, (cudaStream_t)stream, a, nclu);

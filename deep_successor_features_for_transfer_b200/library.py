@@ -16,6 +16,7 @@ the agents hold VIEWS of row i, so `.parameters()`, `state_dict()`, `update_mode
 working.  No torch op is on the compute path; torch only owns the memory and the stream.
 """
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -511,6 +512,8 @@ class PackedSFLibrary:
             b.policy_lo, b.n_pol, b.B, b.d_out = lo, n_pol, B, ptr(ws['d_out'])
             b.acts_bf16, b.dz_bf16, b.dzo_bf16, b.xo_bf16 = (ptr(ws[k]) for k in ('acts16', 'dz16', 'dzo16', 'xo16'))
             b.relu_masks = ptr(ws['masks'])
+            if variant == 2 and os.environ.get('SFGPI_RIDE_EXPAND', '1') != '0':
+                t.defer_expand, b.expand_td = 1, C.addressof(t)        # TSF expand rides in the dgrad launch (idle SMs)
         else:
             b = _lib.BackwardArgs()
             b.net, b.params, b.policy_lo, b.n_pol = sp.desc(), ptr(self.online), lo, n_pol
@@ -523,9 +526,6 @@ class PackedSFLibrary:
         ad = _lib.AdamArgs()
         ad.n_pol, ad.step = n_pol, C.c_void_p(self.step[lo:].data_ptr())
         ad.consts = C.c_void_p(self.adam_consts[lo:].data_ptr())
-        if getattr(self, '_adam_counter', None) is None:
-            self._adam_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
-        ad.finish_counter = self._adam_counter.data_ptr()      # the update kernel's last CTA advances step / consts
         ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
         rs_, nblk, al = sp.row_stride, ws['nblk'], ws['aux_len']
         npa = 1 if variant == 2 else nblk          # variant 2: the TD step leaves ONE reduced aux-gradient row per policy
@@ -827,7 +827,7 @@ class PackedSFLibrary:
                 for q, v in enumerate(i):
                     arr[k].i[q] = int(v)
                 launches += _lib.OP_LAUNCHES[arr[k].op] - (1 if op == 'BACKWARD_TC' and b.xo_ready else 0) \
-                    - (1 if op == 'ADAM' and ad.finish_counter else 0)
+                    + (1 if op == 'TD' and t.variant == 2 and not t.defer_expand else 0)
             if plan['h2d'] is None:
                 plan['h2d'] = [arr[k] for k in range(6)]
             plan['probe'] += [arr[k] for k, (op, p, i) in enumerate(seg) if op == 'NOP' and not p]

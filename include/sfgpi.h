@@ -141,6 +141,8 @@ typedef struct {
        gradients are linear images of T and t; sfgpi_td_step reduces those and writes ONE complete gradient row per policy into
        partial slot 0 of aux_grad_part (read it with n_part = 1); loss_part keeps n_blocks partials */
     float *tsf_part;
+    int32_t defer_expand;           /* variant 2, nonzero: skip the expand launch here; the caller hands this struct to
+                                       sfgpi_mlp_backward_tc (expand_td), whose dgrad launch runs it on otherwise idle SMs */
 } sfgpi_td_args;
 
 int sfgpi_td_partials(int32_t B);
@@ -195,9 +197,6 @@ typedef struct {
     int32_t sequential_shared;      /* 1: segments with param_stride 0 are stepped by optimizer 0..n_pol-1 in order */
     double *consts;                 /* optional [n_pol][2]: {1 - beta1^t, sqrt(1 - beta2^t)} for t = step + 1; must be consistent
                                        with `step` on entry, refreshed on device after the step.  NULL: computed in-kernel */
-    uint32_t *finish_counter;       /* optional: one zero-initialised device word owned by this optimizer group.  Given it, the
-                                       last CTA of the update kernel advances step / consts itself (the word returns to 0) and the
-                                       separate one-block finishing launch drops out of the step's dependent chain */
 } sfgpi_adam_args;
 
 int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
@@ -261,6 +260,8 @@ typedef struct {
     float *grad_part;               /* [n_pol][n_split][row_stride] */
     int32_t n_split;
     int32_t xo_ready;               /* nonzero: xo_bf16 already holds [x | 1 | 0] (sfgpi_step_prep built it) -> one launch fewer */
+    const void *expand_td;          /* optional sfgpi_td_args of the preceding variant-2 TD step run with defer_expand: its TSF
+                                       expand (independent of the psi backward, consumed only by Adam) rides in the dgrad launch */
 } sfgpi_backward_tc_args;
 
 int sfgpi_bwd_tc_out_pad(const sfgpi_net_desc *net);
