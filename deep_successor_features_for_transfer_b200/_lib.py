@@ -57,7 +57,7 @@ class TdArgs(C.Structure):
                 ('next_states', C.c_void_p), ('w', C.c_void_p), ('g', C.c_void_p), ('h', C.c_void_p),
                 ('w_stride', C.c_int32), ('g_stride', C.c_int32), ('d_out', C.c_void_p), ('loss_part', C.c_void_p),
                 ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32), ('next_psi', C.c_void_p), ('next_keys', C.c_void_p),
-                ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p), ('defer_expand', C.c_int32)]
+                ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p), ('peer_keys', C.c_void_p), ('defer_expand', C.c_int32)]
 
 
 class ForwardTcJob(C.Structure):
@@ -115,7 +115,7 @@ class PeerKeysArgs(C.Structure):
 
 class PeerUnpackArgs(C.Structure):
     _fields_ = [('ctx', PeerCtx), ('epoch', C.c_int64), ('x', C.c_void_p * MAX_PEERS), ('nw', C.c_int32), ('nh', C.c_int32),
-                ('w_all', C.c_void_p), ('h', C.c_void_p), ('h_prev', C.c_void_p)]
+                ('w_all', C.c_void_p), ('h', C.c_void_p), ('h_prev', C.c_void_p), ('pack_w', C.c_void_p)]
 
 
 class AdamSegment(C.Structure):

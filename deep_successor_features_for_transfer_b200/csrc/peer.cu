@@ -10,69 +10,17 @@
 //   * pull:   128-bit loads straight from the peers' HBM over NVLink, reduced (MAX of keys / sum of h deltas) in registers.
 // Arenas are double-buffered by epoch parity: a buffer of epoch e is rewritten at epoch e+2, after this rank has seen every
 // peer's signal of epoch e+1, which a peer sends only after its pull of epoch e has finished (stream order).
-#include "common.cuh"
+#include "peer.cuh"
 
 using namespace sfgpi;
 
 namespace sfgpi {
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// peer loads must not be served from this SM's L1 (the line may hold the previous epoch): relaxed.sys goes to the owner's L2
-__device__ __forceinline__ longlong2 ld_peer_i64x2(const long long *p) {
-    longlong2 v;
-    asm volatile("ld.relaxed.sys.global.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ long long ld_peer_i64(const long long *p) {
-    long long v;
-    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_peer_f32(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Block 0 signals every peer; every block waits until all peers have signalled `epoch` on `channel`.
-__device__ __forceinline__ void peer_signal_and_wait(const sfgpi_peer_ctx &c, int channel, unsigned long long epoch) {
-    const int t = threadIdx.x;
-    if (t < c.world && t != c.rank) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            st_release_sys(reinterpret_cast<unsigned long long *>(c.flags[t]) + channel * SFGPI_MAX_PEERS + c.rank, epoch);
-        }
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(c.flags[c.rank]) + channel * SFGPI_MAX_PEERS + t;
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(mine) < epoch) {
-            if (globaltimer_ns() - t0 > 20ull * 1000000000ull) {
-                printf("sfgpi peer exchange: rank %d waited 20 s for rank %d (channel %d, epoch %llu) -- aborting\n", c.rank, t, channel,
-                       epoch);
-                __trap();
-            }
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
-}
-
 // keys_out[row][b] = max_r keys_all_r[(row_lo + row)][b]: the MAX reduce-scatter of the packed GPI keys, pulled from the peers.
 __global__ void __launch_bounds__(256) peer_reduce_keys_kernel(const __grid_constant__ sfgpi_peer_keys_args a) {
     pdl_launch_dependents();
     pdl_wait();                                               // the forward kernel's atomicMax results are complete and visible
-    peer_signal_and_wait(a.ctx, SFGPI_PEER_CH_KEYS, (unsigned long long)a.epoch);
+    peer_signal_and_wait(a.ctx, SFGPI_PEER_CH_KEYS, (unsigned long long)a.epoch, blockIdx.x == 0);
     const int64_t n = (int64_t)a.n_rows * a.B, off = (int64_t)a.row_lo * a.B;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i >= n) return;
@@ -101,7 +49,14 @@ __global__ void __launch_bounds__(256) peer_reduce_keys_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) peer_unpack_kernel(const __grid_constant__ sfgpi_peer_unpack_args a) {
     pdl_launch_dependents();
     pdl_wait();
-    peer_signal_and_wait(a.ctx, SFGPI_PEER_CH_X, (unsigned long long)a.epoch);
+    if (blockIdx.x == 0 && a.pack_w != nullptr) {
+        // fused sfgpi_shard_pack: this rank's x_local = [w | h - h_prev] is written by the signalling CTA before it signals (the
+        // local flag slot keeps this kernel's other CTAs, which overwrite h and h_prev, behind it)
+        float *xl = const_cast<float *>(a.x[a.ctx.rank]);
+        for (int e = threadIdx.x; e < a.nw + a.nh; e += blockDim.x) xl[e] = e < a.nw ? a.pack_w[e] : a.h[e - a.nw] - a.h_prev[e - a.nw];
+        __syncthreads();
+    }
+    peer_signal_and_wait(a.ctx, SFGPI_PEER_CH_X, (unsigned long long)a.epoch, blockIdx.x == 0);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int world = a.ctx.world;
     if (i < world * a.nw) {

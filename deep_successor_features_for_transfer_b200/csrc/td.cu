@@ -14,7 +14,7 @@
 // Thread-block clusters: 8 CTAs (8 x 32 transitions) form a cluster and sum their partials through distributed shared memory in
 // a fixed rank order before anything is written: ceil(B/256) partials per policy reach global memory.
 #include <cooperative_groups.h>
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -26,8 +26,9 @@ constexpr int kTdCluster = 8;     // CTAs per cluster (portable maximum)
 
 
 __global__ void __cluster_dims__(kTdCluster, 1, 1) __launch_bounds__(kTdThreads)
-td_kernel(const __grid_constant__ sfgpi_td_args a) {
+td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi_peer_keys_args pk) {
     extern __shared__ __align__(16) float sm[];
+    __shared__ int astar_s[kTdRows];                        // a*_b of this CTA's rows, decoded from the GPI keys
     pdl_launch_dependents();
     pdl_wait();
     cg::cluster_group cluster = cg::this_cluster();
@@ -56,6 +57,23 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
     float *bg_s = Wg_s + G * S, *Wh_s = bg_s + G, *bh_s = Wh_s + D * G;
 
     for (int e = tid; e < n_acc; e += kTdThreads) gacc_s[e] = 0.0f;
+
+    if (a.next_psi != nullptr) {
+        // next actions: one key per row.  Sharded over peer memory, the key is the MAX over ranks of the rows this rank owns,
+        // pulled here from the peers' arenas (csrc/peer.cu) once every rank has signalled that its forward pass is complete.
+        if (pk.ctx.world > 0) {
+            peer_signal_and_wait(pk.ctx, SFGPI_PEER_CH_KEYS, (unsigned long long)pk.epoch, blockIdx.x == 0 && blockIdx.y == 0);
+            if (tid < rows) {
+                const size_t off = (size_t)(pk.row_lo + pl) * B + row0 + tid;
+                long long k = ld_peer_i64(reinterpret_cast<const long long *>(pk.keys_all[0]) + off);
+                for (int r = 1; r < pk.ctx.world; ++r) k = max(k, ld_peer_i64(reinterpret_cast<const long long *>(pk.keys_all[r]) + off));
+                astar_s[tid] = (int)key_index(k);
+                if (pk.keys_out != nullptr) pk.keys_out[(size_t)pl * B + row0 + tid] = k;
+            }
+        } else if (tid < rows) {
+            astar_s[tid] = (int)key_index(a.next_keys[(size_t)pl * a.next_key_stride + row0 + tid]);
+        }
+    }
 
     const float *cur = a.cur_sel + (size_t)pl * B * D;
     const float *nxt = a.next_sel + (size_t)pl * B * D;
@@ -104,7 +122,7 @@ td_kernel(const __grid_constant__ sfgpi_td_args a) {
             const size_t gi = (size_t)row0 * D + e;
             float nv;
             if (a.next_psi != nullptr) {                 // gather psi^-(s')[a*] from the full target output by the GPI key
-                const int astar = (int)key_index(a.next_keys[(size_t)pl * a.next_key_stride + row0 + r]);
+                const int astar = astar_s[r];
                 nv = a.next_psi[((size_t)(row0 + r) * a.n_pol + pl) * ((size_t)a.A * D) + (size_t)astar * D + d];
             } else {
                 nv = nxt[gi];
@@ -230,7 +248,18 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     const int nclu = sfgpi_td_partials(a.B);
     dim3 grid(nclu * kTdCluster, a.n_pol);
-    launch_pdl(td_kernel, grid, dim3(kTdThreads), bytes, (cudaStream_t)stream, a);
+    sfgpi_peer_keys_args pk = {};
+    if (a.peer_keys != nullptr) {
+        pk = *reinterpret_cast<const sfgpi_peer_keys_args *>(a.peer_keys);
+        if (a.next_psi == nullptr || pk.ctx.world < 1 || pk.ctx.world > SFGPI_MAX_PEERS || pk.ctx.rank < 0 || pk.ctx.rank >= pk.ctx.world ||
+            pk.epoch <= 0 || pk.B != a.B || pk.n_rows < a.n_pol) {
+            set_error("sfgpi_td_step: peer_keys does not describe this step (needs next_psi, same B, n_rows >= n_pol, epoch > 0)");
+            return SFGPI_E_INVALID;
+        }
+        for (int r = 0; r < pk.ctx.world; ++r)
+            if (!pk.ctx.flags[r] || !pk.keys_all[r]) { set_error("sfgpi_td_step: peer arena of rank %d not mapped", r); return SFGPI_E_INVALID; }
+    }
+    launch_pdl(td_kernel, grid, dim3(kTdThreads), bytes, (cudaStream_t)stream, a, pk);
     int rc = check_launch("sfgpi_td_step");
     if (rc || !tsf || a.defer_expand) return rc;              // deferred: the expand rides in sfgpi_mlp_backward_tc's dgrad launch
     const size_t ebytes = ((size_t)n_red + (size_t)a.G * a.S + a.G + (size_t)a.D * a.G) * sizeof(float);

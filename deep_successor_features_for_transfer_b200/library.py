@@ -648,7 +648,6 @@ class PackedSFLibrary:
                 plan['prep'].keys = karena.local + koff
             else:
                 peer['fill_cmd'].p[0] = karena.local + koff
-            peer['pack_cmd'].p[3] = base.local + xoff
         if plan['tc']:
             for j, which in enumerate(('online', 'online', 'target')):      # the job array embeds copies of the arg blocks
                 plan['jobs'][j].args = (a1, a2, a3)[j]
@@ -809,9 +808,11 @@ class PackedSFLibrary:
             peer.update(ka=ka, ua=ua, nh=nh)
             n_fill = len(seg0) - 1
             n_keys = len(seg0) + len(seg1)
-            cmd(seg1, 'PEER_KEYS', (C.addressof(ka),))
-            cmd(seg2, 'SHARD_PACK', (self.w.data_ptr(), self.h.data_ptr() if nh else 0, xc['h_prev'].data_ptr() if nh else 0,
-                                     pa['base'].local), (nw, nh))
+            if plan['tc']:
+                t.peer_keys = C.addressof(ka)                 # the TD kernel pulls the keys of its rows from the peers itself
+            else:
+                cmd(seg1, 'PEER_KEYS', (C.addressof(ka),))    # fp32 mode: the target forward reads the reduced keys
+            ua.pack_w = self.w.data_ptr()                     # x_local is packed by the unpack launch's signalling CTA
             cmd(seg2, 'PEER_UNPACK', (C.addressof(ua),))
             segs = [seg0 + seg1 + seg2, [], []]
         else:
@@ -834,7 +835,7 @@ class PackedSFLibrary:
             plan['segments'].append((arr, len(seg), launches))
         if peer is not None:
             arr = plan['segments'][0][0]
-            peer['fill_cmd'], peer['pack_cmd'] = arr[n_fill], arr[len(segs[0]) - 2]
+            peer['fill_cmd'] = arr[n_fill]
 
     def set_probe(self, plan_key, start_event=None, end_event=None):
         """

@@ -141,6 +141,9 @@ typedef struct {
        gradients are linear images of T and t; sfgpi_td_step reduces those and writes ONE complete gradient row per policy into
        partial slot 0 of aux_grad_part (read it with n_part = 1); loss_part keeps n_blocks partials */
     float *tsf_part;
+    const void *peer_keys;          /* optional sfgpi_peer_keys_args (policy sharding over peer memory): the kernel signals, waits
+                                       and pulls the MAX over ranks of the keys of its own rows itself (next_keys is not read) --
+                                       the MAX reduce-scatter of the GPI keys fused into the TD step */
     int32_t defer_expand;           /* variant 2, nonzero: skip the expand launch here; the caller hands this struct to
                                        sfgpi_mlp_backward_tc (expand_td), whose dgrad launch runs it on otherwise idle SMs */
 } sfgpi_td_args;
@@ -369,7 +372,7 @@ int sfgpi_shard_unpack(const float *x_all, int32_t world, int32_t nw, int32_t nh
  *   sfgpi_peer_alloc   cudaMalloc + zero + cudaIpcGetMemHandle: the 64-byte handle is what ranks exchange (any transport)
  *   sfgpi_peer_open    cudaIpcOpenMemHandle with lazy peer access; sfgpi_peer_close / sfgpi_peer_free undo the two
  * flags[r] = rank r's flag block, uint64 [SFGPI_PEER_CHANNELS][SFGPI_MAX_PEERS], zero-initialised; flags[r][ch][q] is written by
- * rank q only.  `epoch` must be > 0, identical on every rank for the same exchange and strictly increasing per channel; data
+ * rank q only (q = r: by the rank itself, ordering its own CTAs).  `epoch` must be > 0, identical on every rank for the same exchange and strictly increasing per channel; data
  * buffers are double-buffered by the caller on epoch parity.  A rank that waits 20 s for a peer traps (the CUDA context fails
  * loudly instead of hanging).
  */
@@ -395,6 +398,8 @@ typedef struct {
     const float *x[SFGPI_MAX_PEERS];            /* rank r's x_local [nw + nh] of this epoch */
     int32_t nw, nh;
     float *w_all, *h, *h_prev;                  /* as sfgpi_shard_unpack */
+    const float *pack_w;                        /* optional [nw]: fused sfgpi_shard_pack -- x[rank] = [pack_w | h - h_prev] is
+                                                   written by this launch itself before it signals */
 } sfgpi_peer_unpack_args;
 int sfgpi_peer_alloc(int64_t bytes, void **dptr, void *ipc_handle_out);
 int sfgpi_peer_open(const void *ipc_handle, void **dptr);
