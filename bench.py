@@ -34,7 +34,7 @@ WORKLOADS = {
 SEED = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the ncu --set full capture of this
 # command (profiles/): cold-cache replay, so it is an upper bound of the in-step traffic
-KERNEL_DRAM_BYTES = {'bf16': 3932160, 'fp32': None}      # profiles/r01_step_kernels_full.md: 3.789 MB read + 0.143 MB written
+KERNEL_DRAM_BYTES = {'bf16': 4256000, 'fp32': None}      # profiles/r01_step_kernels_full_v2.md: 3.940 MB read + 0.316 MB written
 
 
 def flops_per_net_pass(S, hidden, AD):
