@@ -170,6 +170,54 @@ def build_agent(cfg, n_local, precision='fp32'):
     return dsf, ag
 
 
+GPI_EVAL = dict(S=11, A=27, D=50, hidden=[256, 256], acts=['relu', 'relu'], N=64, B=65536)
+
+
+def time_gpi_eval(world, rank, dev, precision, barrier, reps=10):
+    from tests.gpu_util import FakeTask, model_lambda, HYPER
+    from deep_successor_features_for_transfer_b200.sfdqn import DeepSF
+    import torch.distributed as dist
+    c = GPI_EVAL
+    if c['N'] % world:
+        return {'skipped': f'{c["N"]} policies do not split over {world} ranks'}
+    n_local = c['N'] // world
+    torch.manual_seed(SEED + 100 + rank)
+    sf = DeepSF(pytorch_model_handle=model_lambda(c['hidden'], c['acts']), hyperparameters=dict(HYPER, precision=precision))
+    sf.reset()
+    for i in range(n_local):
+        sf.add_training_task(FakeTask(c['S'], c['A'], c['D'], rank * n_local + i))
+    lib = sf._library
+    if world > 1:
+        lib.enable_sharding()
+    gen = torch.Generator().manual_seed(SEED + 7)
+    x = torch.sigmoid(torch.randn(c['B'], c['S'], generator=gen)).to(dev)          # tasks/hopper_phi.py:59
+    w = torch.empty(c['D']).uniform_(-0.01, 0.01, generator=gen).to(dev)           # sfdqn.py:197
+    for _ in range(3):
+        lib.gpi(x, w, want_q=False)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        _, ka, kt = lib.gpi(x, w, want_q=False)
+        b.record()
+    barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    best_action = lib.decode_keys(ka)                                             # the result a caller reads
+    F = flops_per_net_pass(c['S'], c['hidden'], c['A'] * c['D']) + 2 * c['A'] * c['D']      # the reference's arithmetic
+    F_exec = flops_per_net_pass(c['S'], c['hidden'], (c['A'] + 15) // 16 * 16)               # with w folded into the output layer
+    return {'metric': 'GPI action evals/s', 'value': c['B'] / (ms * 1e-3), 'unit': 'states/s (each over all 64 policies)',
+            'ms_per_eval': ms, 'algorithmic_tflops_per_gpu': n_local * c['B'] * F / (ms * 1e-3) / 1e12,
+            'executed_tflops_per_gpu': n_local * c['B'] * F_exec / (ms * 1e-3) / 1e12, 'scaling': 'strong',
+            'note': 'algorithmic = N*F per state as the reference computes it (psi[B,N,A,D] then .w); executed = what the kernel '
+                    'runs after folding w into the output layer (A columns instead of A*D), so algorithmic can exceed the bf16 peak',
+            'config': f'SFDQN Hopper S11/A27/D50, {c["N"]} policies ({n_local}/GPU), B={c["B"]} resident states, pack + fold + fused '
+                      f'forward/GPI kernel + key all-reduce per eval, {precision}',
+            'check': int(best_action.min()) >= 0 and int(best_action.max()) < c['A']}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -194,7 +242,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     import torch.distributed as dist
-    from oracle.sf_oracle import synthetic_transitions
+    from tests.synthetic import synthetic_transitions
     from deep_successor_features_for_transfer_b200 import _lib
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -298,6 +346,16 @@ def main():
     step_flops = 5 * F * B * n_local                               # N GPI + N online + N target + 2N backward = 5N passes
     step_tflops = step_flops * args.steps / (total_ms * 1e-3) / 1e12
 
+    # ---------------- M2: GPI action evals/s (BASELINE config 3) ----------------
+    # Hopper shapes (S=11, A=27, D=50), 64 source policies sharded over the ranks (strong scaling: 64 / world per GPU), 65 536
+    # states = sigmoid(N(0,1)) resident in HBM; one eval = fused ensemble forward + GPI epilogue for every state over ALL 64
+    # policies, packed (value, index) keys MAX-all-reduced across ranks (NCCL).  CUDA events, max over ranks.
+    gpi_eval = None
+    try:
+        gpi_eval = time_gpi_eval(world, rank, dev, args.precision, barrier)
+    except Exception as e:                                          # the headline line must not depend on the secondary metric
+        gpi_eval = {'error': f'{type(e).__name__}: {e}'}
+
     out = None
     if rank == 0:
         out = {
@@ -314,6 +372,7 @@ def main():
             'gpu_launches': launches,
             'roofline': roofline,
             'step_tflops_per_gpu': step_tflops,
+            'gpi_eval': gpi_eval,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -272,6 +272,18 @@ int sfgpi_bwd_tc_splits(int32_t B, int32_t want);
 int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 
 /*
+ * Learned features (phi), SURVEY 8f N3: the reward-regression head of SFDQN.pre_train (sfdqn_phi.py:850-862).
+ *   phi [B][D] = output of the PhiFunction MLP (sfdqn_phi.py:90-123; run it with sfgpi_mlp_forward, n_actions = 1),
+ *   e_b = w . phi_b - r_b ;  loss = mean_b e_b^2 (= mse_loss(reward_batch, fit_w(phis)))
+ *   d_out [B][D] = dLoss/dphi = (2/B) e_b w   -> feed to sfgpi_mlp_backward (actions all 0)
+ *   dw_part [n_blocks][D] = per-CTA partials of dLoss/dw, loss_part [n_blocks][2] = {0, sum e^2} -> sfgpi_adam_step (segment
+ *   with n_part = n_blocks; l2_scale = 1/B, beta_loss = 1 reduces the loss).  n_blocks = sfgpi_phi_head_partials(B).
+ */
+int sfgpi_phi_head_partials(int32_t B);
+int sfgpi_phi_head(const float *phi, const float *w, const float *r, int32_t B, int32_t D, float *d_out, float *dw_part,
+                   float *loss_part, void *stream);
+
+/*
  * Step prologue of a tensor-core train step in ONE launch: sfgpi_pack_bf16 for up to two row sets (online, target),
  * sfgpi_keys_fill, sfgpi_fold_gpi and the backward pass's xo = [x | 1 | 0] operand (bf16 [B][64]) -- five independent
  * elementwise passes that would otherwise be five launches on the step's dependent chain -- plus, optionally, the staging of the

@@ -327,6 +327,85 @@ class OracleSF:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# N3: learned features -- PhiFunction (sfdqn_phi.py:90-123) and SFDQN.pre_train (sfdqn_phi.py:800-873)
+# ----------------------------------------------------------------------------------------------------------------
+class OraclePhi:
+    """phi_theta = Linear(2S + action_dim, 128) - ReLU - Linear(128, 256) - ReLU - Linear(256, D), one Adam(lr = 1e-3)."""
+
+    ACTS = ('relu', 'relu', 'none')
+
+    def __init__(self, layers, alpha_phi=1e-3):
+        self.layers = [(W.clone().float(), b.clone().float()) for W, b in layers]
+        self.alpha_phi = alpha_phi
+        self.adam = {'step': 0, 'm': [torch.zeros_like(t) for Wb in self.layers for t in Wb],
+                     'v': [torch.zeros_like(t) for Wb in self.layers for t in Wb]}
+
+    @staticmethod
+    def inputs(state, action, next_state):                               # PhiFunction.forward, sfdqn_phi.py:106-117
+        if action.ndim == 0:
+            action = action.unsqueeze(0)
+        if action.ndim == 1:
+            action = action.unsqueeze(1)
+        if state.ndim == 1:
+            state = state.unsqueeze(0)
+        if next_state.ndim == 1:
+            next_state = next_state.unsqueeze(0)
+        return torch.cat([state, action, next_state], axis=1)
+
+    def forward(self, state, action, next_state):
+        return mlp_forward(self.layers, self.ACTS, self.inputs(state, action, next_state))
+
+    def regression_step(self, state, action, reward, next_state, head):
+        """Body of pre_train's inner loop (sfdqn_phi.py:850-866); head = {'w': [1,D], 'm', 'v', 'step'} (fit_w + its Adam)."""
+        flat = [t for Wb in self.layers for t in Wb]
+        leaves = [t.detach().requires_grad_(True) for t in flat]
+        layers = [(leaves[2 * l], leaves[2 * l + 1]) for l in range(len(self.layers))]
+        w_leaf = head['w'].detach().requires_grad_(True)
+        phis = mlp_forward(layers, self.ACTS, self.inputs(state, action, next_state))
+        lin = torch.nn.functional.linear(phis, w_leaf)
+        loss = torch.nn.functional.mse_loss(reward, lin)                 # :859 (reward [B,1], lin [B,1])
+        grads = torch.autograd.grad(loss, leaves + [w_leaf])
+        with torch.no_grad():
+            self.adam['step'] += 1
+            for p, g, m, v in zip(flat, grads[:-1], self.adam['m'], self.adam['v']):
+                OracleSF._adam_tensor(p, g, m, v, self.adam['step'], self.alpha_phi, 0.0)
+            head['step'] += 1
+            OracleSF._adam_tensor(head['w'], grads[-1], head['m'], head['v'], head['step'], 1e-3, 0.0)
+        return float(loss.detach())
+
+
+def oracle_phi_pre_train(phi, head_ws, train_tasks, n_samples_pre_train, n_cycles=5, n_batch=32):
+    """
+    SFDQN.pre_train (sfdqn_phi.py:800-873) with the initial weights handed in (phi: OraclePhi, head_ws: list of [1,D]).
+    Restates the loop and the replay ring (ReplayBuffer, sfdqn_phi.py:9-86: picks = np.random.randint(0, size, n_batch) once
+    per update; actions from random.randrange) with plain lists / tensors.  Returns the list of losses.
+    """
+    import random
+    import numpy as np
+    heads = [dict(w=w.clone().float(), m=torch.zeros_like(w), v=torch.zeros_like(w), step=0) for w in head_ws]
+    ring, losses = [], []
+    n_actions = train_tasks[0].action_count()
+    for cycle in range(n_cycles):
+        for task_id, task in enumerate(train_tasks):
+            s_enc = task.encode(task.initialize())
+            for sample in range(n_samples_pre_train):
+                a = random.randrange(n_actions)
+                s1, r, terminal = task.transition(a)
+                s1_enc = task.encode(s1)
+                ring.append((s_enc, torch.tensor(a), torch.tensor(r, dtype=torch.float32).float(), s1_enc))
+                s_enc = s1_enc
+                if terminal:
+                    s_enc = task.encode(task.initialize())
+                if len(ring) >= n_batch:
+                    picks = np.random.randint(low=0, high=len(ring), size=(n_batch,))
+                    st, ac, rw, ns = zip(*[ring[k] for k in picks])
+                    losses.append(phi.regression_step(torch.vstack(st), torch.tensor(ac), torch.vstack(rw), torch.vstack(ns),
+                                                      heads[task_id]))
+    phi.heads = heads
+    return losses
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Synthetic replay batches (SURVEY.md section 8d "Synthetic inputs")
 # ----------------------------------------------------------------------------------------------------------------
 def synthetic_transitions(B, S, A, D, gen, hopper=False, five_tuple=False):

@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle.sf_oracle import synthetic_transitions
+from tests.synthetic import synthetic_transitions
 from tests import gpu_util as gu
 from tests.test_gpu_bf16 import make, fro_err, torch_psi_grads
 

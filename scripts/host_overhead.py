@@ -3,7 +3,7 @@ import os, sys, time, cProfile, pstats
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from oracle.sf_oracle import synthetic_transitions
+from tests.synthetic import synthetic_transitions
 
 cfg = bench.WORKLOADS['tsfdqn_reacher_b4096']
 torch.cuda.set_device(0)

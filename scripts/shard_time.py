@@ -3,7 +3,7 @@ import os, sys, time
 os.environ["SFGPI_PEER"] = "0"      # this script times the NCCL-collective variant of the sharded step phase by phase
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
-from oracle.sf_oracle import synthetic_transitions
+from tests.synthetic import synthetic_transitions
 import bench
 from deep_successor_features_for_transfer_b200 import _lib
 from deep_successor_features_for_transfer_b200.library import _stream

@@ -335,3 +335,81 @@ def test_g3_target_task_adaptation_vs_golden():
         assert np.allclose([float(x) for x in losses], z['out.losses'][k], rtol=2e-5, atol=1e-7)
         assert rel_err(omegas.detach().cpu(), z[f'step{k}.omegas']) < 2e-5
         assert rel_err(w_approx.weight.detach().cpu(), z[f'step{k}.w_target']) < 2e-5
+
+
+# ---------------- learned features (PhiFunction + SFDQN.pre_train, sfdqn_phi.py:90-123, 800-873) ----------------
+def _phi_fixture():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'phi_pretrain_cartpole.npz'))
+
+
+def _seed_all(seed):
+    import random
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+def test_phi_function_forward_and_init_vs_golden():
+    from deep_successor_features_for_transfer_b200.sfdqn_phi import PhiFunction
+    z = _phi_fixture()
+    S, D, seed = int(z['S']), int(z['D']), int(z['seed'])
+    _seed_all(seed)
+    phi = PhiFunction(S, 1, D)
+    lin = [m for m in phi._model if isinstance(m, torch.nn.Linear)]
+    for l, m in enumerate(lin):                                  # same draws as the reference's PhiFunction under the same seed
+        assert np.array_equal(m.weight.data.cpu().numpy(), z[f'init.phi.W{l}'])
+        assert np.array_equal(m.bias.data.cpu().numpy(), z[f'init.phi.b{l}'])
+    with torch.no_grad():                                        # load the reference's trained weights through the module views
+        for l, m in enumerate(lin):
+            m.weight.data.copy_(torch.from_numpy(z[f'out.phi.W{l}']))
+            m.bias.data.copy_(torch.from_numpy(z[f'out.phi.b{l}']))
+    out = phi(torch.from_numpy(z['probe.s']), torch.from_numpy(z['probe.a']), torch.from_numpy(z['probe.s1']))
+    assert out.shape == (16, D)
+    assert np.allclose(out.cpu().numpy(), z['probe.phi'], rtol=1e-5, atol=1e-6)
+    one = phi(torch.from_numpy(z['probe.s'][0]), torch.tensor(int(z['probe.a'][0])), torch.from_numpy(z['probe.s1'][0]))
+    assert one.shape == (1, D) and np.allclose(one.cpu().numpy()[0], z['probe.phi'][0], rtol=1e-5, atol=1e-6)
+
+
+def test_phi_regression_step_vs_oracle():
+    """One update on a fixed batch: loss, dL/dtheta via the post-step weights, and both Adam states against OraclePhi."""
+    from oracle.sf_oracle import OraclePhi
+    from deep_successor_features_for_transfer_b200.sfdqn_phi import PhiFunction, _RewardHead
+    z = _phi_fixture()
+    S, A, D, seed = int(z['S']), int(z['A']), int(z['D']), int(z['seed'])
+    _seed_all(seed)
+    phi = PhiFunction(S, 1, D)
+    head = _RewardHead(D, phi.device)
+    o = OraclePhi([(torch.from_numpy(z[f'init.phi.W{l}']), torch.from_numpy(z[f'init.phi.b{l}'])) for l in range(3)])
+    oh = dict(w=head.weight.cpu().reshape(1, D).clone(), m=torch.zeros(1, D), v=torch.zeros(1, D), step=0)
+    g = torch.Generator().manual_seed(5)
+    for B in (32, 300):                                          # 300: two CTAs of the head kernel (partials)
+        s, a, s1 = torch.randn(B, S, generator=g), torch.randint(0, A, (B,), generator=g), torch.randn(B, S, generator=g)
+        r = torch.tanh(torch.randn(B, 1, generator=g))
+        for k in range(3):
+            lo = o.regression_step(s, a, r, s1, oh)
+            lg = float(phi.regression_step(s, a, r, s1, head))
+            assert abs(lg - lo) <= 2e-5 * max(1.0, abs(lo))
+    lin = [m for m in phi._model if isinstance(m, torch.nn.Linear)]
+    for l, m in enumerate(lin):
+        assert rel_err(m.weight.data.cpu(), o.layers[l][0]) < 2e-5
+        assert rel_err(m.bias.data.cpu(), o.layers[l][1]) < 2e-5
+    assert rel_err(head.weight.cpu().reshape(1, D), oh['w']) < 2e-5
+    assert int(head.step) == oh['step'] == 6 and int(phi._library.step[0]) == 6
+
+
+def test_phi_pre_train_vs_golden():
+    """The whole pre_train loop under the reference's seeds: same replay picks, same random actions, losses along the way."""
+    from deep_successor_features_for_transfer_b200.sfdqn_phi import pre_train
+    from tests.phi_util import FakePhiTask
+    z = _phi_fixture()
+    S, A, D, n_tasks, seed = (int(z[k]) for k in ('S', 'A', 'D', 'n_tasks', 'seed'))
+    _seed_all(seed)
+    tasks = [FakePhiTask(S, A, D, i) for i in range(n_tasks)]
+    model, losses = pre_train(tasks, int(z['n_samples']), int(z['n_cycles']))
+    ref = z['out.losses']
+    assert len(losses) == len(ref)
+    assert np.allclose(losses[:20], ref[:20], rtol=1e-4, atol=1e-7)
+    assert np.allclose(losses, ref, rtol=2e-2, atol=1e-4)           # 149 chained Adam updates: fp32 summation-order drift
+    out = model(torch.from_numpy(z['probe.s']), torch.from_numpy(z['probe.a']), torch.from_numpy(z['probe.s1']))
+    assert rel_err(out.cpu(), torch.from_numpy(z['probe.phi'])) < 2e-2
