@@ -65,8 +65,14 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
             peer_signal_and_wait(pk.ctx, SFGPI_PEER_CH_KEYS, (unsigned long long)pk.epoch, blockIdx.x == 0 && blockIdx.y == 0);
             if (tid < rows) {
                 const size_t off = (size_t)(pk.row_lo + pl) * B + row0 + tid;
-                long long k = ld_peer_i64(reinterpret_cast<const long long *>(pk.keys_all[0]) + off);
-                for (int r = 1; r < pk.ctx.world; ++r) k = max(k, ld_peer_i64(reinterpret_cast<const long long *>(pk.keys_all[r]) + off));
+                long long kv[SFGPI_MAX_PEERS];                 // all peers' loads in flight at once (one NVLink round trip, not world)
+#pragma unroll
+                for (int r = 0; r < SFGPI_MAX_PEERS; ++r)
+                    if (r < pk.ctx.world) kv[r] = ld_peer_i64(reinterpret_cast<const long long *>(pk.keys_all[r]) + off);
+                long long k = kv[0];
+#pragma unroll
+                for (int r = 1; r < SFGPI_MAX_PEERS; ++r)
+                    if (r < pk.ctx.world) k = max(k, kv[r]);
                 astar_s[tid] = (int)key_index(k);
                 if (pk.keys_out != nullptr) pk.keys_out[(size_t)pl * B + row0 + tid] = k;
             }

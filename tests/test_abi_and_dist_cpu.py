@@ -53,7 +53,9 @@ def c_struct_fields(name):
 @pytest.mark.parametrize('cname,pyname', [('sfgpi_net_desc', 'NetDesc'), ('sfgpi_forward_args', 'ForwardArgs'),
                                           ('sfgpi_td_args', 'TdArgs'), ('sfgpi_backward_args', 'BackwardArgs'),
                                           ('sfgpi_backward_tc_args', 'BackwardTcArgs'), ('sfgpi_forward_tc_job', 'ForwardTcJob'), ('sfgpi_cmd', 'Cmd'), ('sfgpi_replay_args', 'ReplayArgs'),
-                                          ('sfgpi_adam_segment', 'AdamSegment'), ('sfgpi_adam_args', 'AdamArgs')])
+                                          ('sfgpi_adam_segment', 'AdamSegment'), ('sfgpi_adam_args', 'AdamArgs'),
+                                          ('sfgpi_step_prep_args', 'StepPrepArgs'), ('sfgpi_peer_ctx', 'PeerCtx'),
+                                          ('sfgpi_peer_keys_args', 'PeerKeysArgs'), ('sfgpi_peer_unpack_args', 'PeerUnpackArgs')])
 def test_ctypes_structs_mirror_header(cname, pyname):
     assert c_struct_fields(cname) == [f[0] for f in getattr(_lib, pyname)._fields_]
 
@@ -64,6 +66,28 @@ def test_negative_sizes_are_rejected_without_a_gpu():
     a.net.n_layers = 0
     rc = _lib.lib().sfgpi_mlp_forward(a, None)
     assert rc < 0 and len(_lib.lib().sfgpi_last_error()) > 0
+
+
+def test_new_entry_points_validate_before_touching_cuda():
+    """sfgpi_step_prep / sfgpi_phi_head / peer exchange: bad arguments -> rc < 0 with an error text, no CUDA call needed."""
+    import ctypes as C
+    L = _lib.lib()
+    pr = _lib.StepPrepArgs()                                        # zeroed descriptor: not a tensor-core shape
+    assert L.sfgpi_step_prep(C.byref(pr), None) < 0 and b'sfgpi_step_prep' in L.sfgpi_last_error()
+    assert L.sfgpi_phi_head(None, None, None, 32, 20, None, None, None, None) < 0 and b'sfgpi_phi_head' in L.sfgpi_last_error()
+    assert L.sfgpi_phi_head_partials(32) == 1 and L.sfgpi_phi_head_partials(300) == 2 and L.sfgpi_phi_head_partials(0) == 1
+    ka = _lib.PeerKeysArgs()
+    ka.ctx.world, ka.ctx.rank = 99, 0                               # more than SFGPI_MAX_PEERS
+    assert L.sfgpi_peer_reduce_keys(C.byref(ka), None) < 0 and b'peers' in L.sfgpi_last_error()
+    ua = _lib.PeerUnpackArgs()
+    ua.ctx.world, ua.ctx.rank = 2, 0                                # flag blocks not mapped
+    assert L.sfgpi_peer_unpack(C.byref(ua), None) < 0 and b'not mapped' in L.sfgpi_last_error()
+    t = _lib.TdArgs()
+    t.variant, t.B, t.n_pol, t.D, t.aux_len = 1, 8, 1, 4, 4
+    ka2 = _lib.PeerKeysArgs()
+    t.peer_keys = C.addressof(ka2)                                  # peer keys without next_psi / a valid context
+    assert L.sfgpi_td_step(C.byref(t), None) < 0 and b'peer_keys' in L.sfgpi_last_error()
+    assert _lib.MAX_PEERS == 16 and C.sizeof(_lib.Cmd) == 80
 
 
 def test_shard_range_partitions_exactly():
