@@ -30,6 +30,10 @@ import torch  # noqa: E402
 WORKLOADS = {
     'tsfdqn_reacher_b4096': dict(S=4, A=9, D=12, hidden=[256, 256], acts=['relu', 'relu'], gdim=100, beta=1, B=4096,
                                  n_local=4, hopper=False),
+    # BASELINE config 4 (ii): TSFDQN dissimilar-task sequence, 256 policies in total split over the GPUs (strong scaling),
+    # beta = 30 (reacher_dissimilar.cfg:40), every policy stepped on every batch with GPI over all 256
+    'tsfdqn_dissimilar_n256': dict(S=4, A=9, D=12, hidden=[256, 256], acts=['relu', 'relu'], gdim=100, beta=30, B=4096,
+                                   n_total=256, hopper=False),
 }
 SEED = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the ncu --set full capture of this
@@ -145,10 +149,12 @@ def run_reference(args, cfg, rank, world):
 
 def workload_config(name, cfg, n_total, world, precision='fp32', l2='flush', exchange=None):
     extra = {'exchange': exchange} if exchange else {}
-    return {**extra, 'workload': f'{name}: TSFDQN Reacher S4/A9/D12 MLP 256-256 relu, g 4->100, h 100->12, beta=1, B={cfg["B"]}, '
+    return {**extra, 'workload': f'{name}: TSFDQN Reacher S4/A9/D12 MLP 256-256 relu, g 4->100, h 100->12, beta={cfg["beta"]}, B={cfg["B"]}, '
                         f'{cfg["n_local"]} policies/GPU ({n_total} total), all-task fused TD update with GPI next actions',
             'batch': cfg['B'], 'policies_total': n_total, 'policies_per_gpu': cfg['n_local'],
             'parallelism': f'policy-sharded x{world}' if world > 1 else 'single GPU',
+            'warmup_note': 'at least 1000 untimed steps are run before the timed region whatever --warmup says (clocks under load, '
+                           'identical count on every rank)',
             'l2': ('flushed between timed steps (256 MiB write), flush excluded from the per-step CUDA-event time' if l2 == 'flush'
                    else 'inputs larger than L2: >160 MB of distinct resident batches cycled, weights / optimizer state stay '
                         'L2-resident as in a real training loop'),
@@ -232,9 +238,14 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='bf16: tcgen05 tensor-core forwards (stated tolerance 2e-2); fp32: CUDA-core 1e-5 parity mode')
     args = ap.parse_args()
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+    strong = 'n_total' in cfg
+    if strong:
+        if cfg['n_total'] % world:
+            raise SystemExit(f'{cfg["n_total"]} policies do not split over {world} ranks')
+        cfg['n_local'] = cfg['n_total'] // world
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
         run_reference(args, cfg, rank, world)
@@ -361,7 +372,7 @@ def main():
         out = {
             'metric': 'SF TD updates (transitions x tasks)/s', 'value': value, 'unit': 'updates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': workload_config(args.workload, cfg, n_total, world, args.precision, args.l2,
                                       None if world == 1 else ('peer-memory kernels in the step\'s launch chain (CUDA IPC arenas, signal/wait '
                                       'flags, 128-bit pulls over NVLink): GPI keys MAX reduce-scatter + [w | delta h] all-gather, no NCCL call '
@@ -376,7 +387,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cval, cper = time_cpu(cfg, n_total, 10, 2, cores)
+            cval, cper = time_cpu(cfg, n_total, 10 if n_total <= 8 else 1, 2 if n_total <= 8 else 0, cores)
             out['cpu_baseline'] = {'value': cval, 'unit': 'updates/s', 'cores': cores, 'kind': 'port',
                                    'sample': f'10 all-task steps ({n_total} update_successor calls each), B={B}, '
                                              f'{cper * 1e3:.1f} ms/step, oracle port on torch CPU fp32'}

@@ -9,7 +9,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB_PATH = os.path.join(HERE, 'libsfgpi.so')
+LIB_PATH = os.environ.get('SFGPI_LIB_PATH') or os.path.join(HERE, 'libsfgpi.so')      # (override: A/B runs of two builds)
 SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
@@ -47,7 +47,7 @@ class ForwardArgs(C.Structure):
                 ('sel_actions', C.c_void_p), ('sel_keys', C.c_void_p), ('sel_key_stride', C.c_int32),
                 ('sel_out', C.c_void_p), ('w', C.c_void_p), ('n_w', C.c_int32), ('w_diag', C.c_int32),
                 ('key_action', C.c_void_p), ('key_task', C.c_void_p), ('task_base', C.c_int32), ('q_out', C.c_void_p),
-                ('mode', C.c_int32), ('acts_bf16_out', C.c_void_p), ('relu_mask_out', C.c_void_p)]
+                ('mode', C.c_int32), ('acts_bf16_out', C.c_void_p), ('relu_mask_out', C.c_void_p), ('key_stage', C.c_void_p)]
 
 
 class TdArgs(C.Structure):
@@ -97,8 +97,8 @@ class Cmd(C.Structure):
 
 
 OP = dict(H2D=1, D2H=2, D2D=3, KEYS_FILL=4, PACK_BF16=5, FOLD_GPI=6, FORWARD=7, FORWARD_TC_JOBS=8, TD=9, BACKWARD=10,
-          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16, STEP_PREP=17)
-OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1, 17: 1}
+          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16, STEP_PREP=17, KEYS_REDUCE=18)
+OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1, 17: 1, 18: 1}
 MAX_PEERS = 16
 PEER_CHANNELS = 4
 IPC_HANDLE_BYTES = 64
@@ -136,6 +136,7 @@ class AdamArgs(C.Structure):
 SYMBOLS = {
     'sfgpi_mlp_forward': (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
     'sfgpi_keys_fill': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    'sfgpi_keys_reduce': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'sfgpi_keys_decode': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_gpi_from_psi': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -465,7 +465,6 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             // GPI running state (folded form): columns are (reward vector wi, action act); group g scans slot g
             float best = -INFINITY;
             int best_a = 0, wi = 0, act_i = 0;
-
             for (int it = 0; it < p.n_items; ++it) {
                 const ItemInfo ii = item_info(p, it);
 #pragma unroll 1
@@ -516,45 +515,77 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         const int c_step = p.gpi ? 8 : 16;
                         const int ncol = p.nw * A_;
                         const int sb = sel_base[slot];
+                        // Everything the column loop needs of the job's arguments, in REGISTERS: `p` / `a` are slices of the kernel
+                        // parameters selected by a runtime job index, so each field read is a register-indexed constant load
+                        // (LDC c[0][R+off], ~100 cycles) that the "memory"-clobbering tcgen05 waits force the compiler to repeat
+                        // per column -- ~1600 cycles per 8-column trip (measured: 8.3 ms forward at 256 reward vectors).
+                        const bool gpi_form = p.gpi != 0;
+                        const int n_cols_it = ii.n_cols, col0_it = ii.col0, n_pol_job = a.n_pol, task_base = a.task_base;
+                        float *const q_out = a.q_out, *const psi_out = a.psi_out, *const sel_out = a.sel_out;
+                        // where this row emits the key of reward vector wi: destination pointers that advance by a fixed step per
+                        // vector (no 64-bit index arithmetic in the column loop); rebuilt from wi at every chunk so that they are
+                        // not live across the hidden-layer epilogues.  kp: staged store / action-key atomic, tp: task-key atomic.
+                        uint32_t kstep = 0;
+                        bool k_staged = false, k_has = false, t_has = false;
+                        long long *kp = nullptr, *tp = nullptr;
+                        if (gpi_form) {
+                            kstep = a.w_diag ? 0u : (uint32_t)B;
+                            k_staged = a.key_stage != nullptr;
+                            k_has = k_staged || a.key_action != nullptr;
+                            t_has = a.key_task != nullptr;
+                            kp = k_staged ? reinterpret_cast<long long *>(a.key_stage) + (size_t)pl * (a.w_diag ? 1 : p.nw) * B
+                                          : reinterpret_cast<long long *>(a.key_action) + (a.w_diag ? (size_t)pl * B : 0);
+                            tp = reinterpret_cast<long long *>(a.key_task) + (a.w_diag ? (size_t)pl * B : 0);
+                            kp += (size_t)wi * kstep + b;
+                            tp += (size_t)wi * kstep + b;
+                        }
 #pragma unroll 1
-                        for (int c0 = c_first; c0 < ii.n_cols; c0 += c_step) {
+                        for (int c0 = c_first; c0 < n_cols_it; c0 += c_step) {
                             uint32_t v[8];
                             tmem_ld8(t_lane + c0, v);
                             const float4 b0 = lds128(bias + 4u * c0), b1 = lds128(bias + 4u * (c0 + 4));
                             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                             tmem_wait_ld();
-                            if (p.gpi) {
-                                // folded GPI: column = wi * A + act
+                            if (gpi_form) {
+                                // folded GPI: column = wi * A + act.  The scan is instruction-bound (one thread per row walks every
+                                // column), so the per-column work is kept to add / compare / two selects / count; the key of a
+                                // finished reward vector goes out through the pre-computed pointers.
+                                auto emit = [&]() {
+                                    if (row_ok) {
+                                        if (k_staged) *kp = pack_key(best, (uint32_t)best_a);
+                                        else if (k_has) atomicMax(kp, pack_key(best, (uint32_t)best_a));
+                                        if (t_has) atomicMax(tp, pack_key(best, (uint32_t)(task_base + pl)));
+                                    }
+                                    kp += kstep; tp += kstep;
+                                    act_i = 0; ++wi; best = -INFINITY; best_a = 0;
+                                };
+                                if (col0_it + c0 + 8 <= ncol && !(wi == 0 && q_out != nullptr)) {        // fast path: whole trip valid
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int col = ii.col0 + c0 + i;
-                                    if (col < ncol) {
+                                    for (int i = 0; i < 8; ++i) {
                                         const float q = __uint_as_float(v[i]) + bv[i];
-                                        if (wi == 0 && a.q_out != nullptr && row_ok)
-                                            a.q_out[((size_t)b * a.n_pol + pl) * A_ + act_i] = q;
                                         if (q > best) { best = q; best_a = act_i; }
-                                        if (++act_i == A_) {
-                                            if (row_ok) {
-                                                const int krow = a.w_diag ? pl : wi;
-                                                if (a.key_action)
-                                                    atomicMax(reinterpret_cast<long long *>(a.key_action) + (size_t)krow * B + b,
-                                                              pack_key(best, (uint32_t)best_a));
-                                                if (a.key_task)
-                                                    atomicMax(reinterpret_cast<long long *>(a.key_task) + (size_t)krow * B + b,
-                                                              pack_key(best, (uint32_t)(a.task_base + pl)));
-                                            }
-                                            act_i = 0; ++wi; best = -INFINITY; best_a = 0;
+                                        if (++act_i == A_) emit();
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        if (col0_it + c0 + i < ncol) {
+                                            const float q = __uint_as_float(v[i]) + bv[i];
+                                            if (wi == 0 && q_out != nullptr && row_ok)
+                                                q_out[((size_t)b * n_pol_job + pl) * A_ + act_i] = q;
+                                            if (q > best) { best = q; best_a = act_i; }
+                                            if (++act_i == A_) emit();
                                         }
                                     }
                                 }
                             } else {
-                                const int colb = ii.col0 + c0;
+                                const int colb = col0_it + c0;
                                 float val[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[i]) + bv[i];
                                 if (row_ok) {
-                                    if (a.psi_out != nullptr) {
-                                        float *po = a.psi_out + ((size_t)b * a.n_pol + pl) * AD + colb;
+                                    if (psi_out != nullptr) {
+                                        float *po = psi_out + ((size_t)b * n_pol_job + pl) * AD + colb;
                                         if ((AD & 3) == 0) {                  // rows are 16-byte aligned: 128-bit stores
                                             if (colb < AD) *reinterpret_cast<float4 *>(po) = make_float4(val[0], val[1], val[2], val[3]);
                                             if (colb + 4 < AD) *reinterpret_cast<float4 *>(po + 4) = make_float4(val[4], val[5], val[6], val[7]);
@@ -565,7 +596,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                                         }
                                     }
                                     if ((unsigned)(colb + 7 - sb) < (unsigned)(D + 7)) {         // group overlaps [sel, sel + D)
-                                        float *so = a.sel_out + ((size_t)pl * B + b) * D;
+                                        float *so = sel_out + ((size_t)pl * B + b) * D;
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) {
                                             const unsigned off = (unsigned)(colb + i - sb);

@@ -58,6 +58,9 @@ extern "C" int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream) {
             case SFGPI_OP_STEP_PREP:
                 rc = sfgpi_step_prep(reinterpret_cast<const sfgpi_step_prep_args *>(c.p[0]), stream);
                 break;
+            case SFGPI_OP_KEYS_REDUCE:
+                rc = sfgpi_keys_reduce(reinterpret_cast<const int64_t *>(c.p[0]), (int32_t)c.i[0], c.i[1], reinterpret_cast<int64_t *>(c.p[1]), stream);
+                break;
             case SFGPI_OP_PEER_KEYS:
                 rc = sfgpi_peer_reduce_keys(reinterpret_cast<const sfgpi_peer_keys_args *>(c.p[0]), stream);
                 break;

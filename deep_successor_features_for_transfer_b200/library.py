@@ -481,6 +481,13 @@ class PackedSFLibrary:
             a2 = self._fwd_args(self.online, lo, n_pol, None, B)
             a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 1
         a2.key_action = ptr(keys)
+        # Staged keys (tensor-core mode, GPI over the library): with many (policy, reward vector) pairs the int64 atomicMax per
+        # (policy, vector, state) bounds the forward kernel; the epilogue then stores per-policy keys and one streaming pass
+        # (sfgpi_keys_reduce) takes the MAX over the local policies -- which also replaces the key fill.
+        stage = None
+        if tc and use_gpi and not a2.w_diag and a2.n_w * a2.n_pol >= int(os.environ.get('SFGPI_STAGE_MIN', '64')):
+            stage = ws.setdefault(('key_stage', a2.n_w), torch.empty(a2.n_pol, a2.n_w, B, dtype=torch.int64, device=self.device))
+            a2.key_stage = stage.data_ptr()
         # (3) target forward on s', gather psi^-(s')[a*]                                sfdqn.py:330-331
         a3 = self._fwd_args(self.target, lo, n_pol, None, B)
         if tc:
@@ -556,7 +563,7 @@ class PackedSFLibrary:
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
         return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, tc=tc, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
-                    peer=peer, variant=variant,
+                    peer=peer, variant=variant, stage=stage,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
     def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
@@ -644,7 +651,9 @@ class PackedSFLibrary:
                 ka.keys_all[r] = karena.ptrs[r] + koff
                 ua.x[r] = base.ptrs[r] + xoff
             a2.key_action = karena.local + koff
-            if plan['prep'] is not None:
+            if peer['reduce_cmd'] is not None:
+                peer['reduce_cmd'].p[1] = karena.local + koff
+            elif plan['prep'] is not None:
                 plan['prep'].keys = karena.local + koff
             else:
                 peer['fill_cmd'].p[0] = karena.local + koff
@@ -750,6 +759,9 @@ class PackedSFLibrary:
         # except on the NCCL-collective sharded path, whose first steps gather w between them
         merged = plan['tc'] and not (plan['sharded'] and peer is None)
         plan['prep'] = None
+        stage = plan.get('stage')
+        if stage is not None:
+            n_keys = 0                                        # every key is written by the reduction: no fill
         if plan['tc']:
             dref = C.addressof(plan['desc'])
             nw = 1 if a2.w_diag else a2.n_w
@@ -774,7 +786,8 @@ class PackedSFLibrary:
             if plan['tc']:
                 cmd(seg0, 'PACK_BF16', (dref, self.online.data_ptr(), self._shadow_for('online').data_ptr()), (0, self.n))
                 cmd(seg0, 'PACK_BF16', (dref, self.target.data_ptr(), self._shadow_for('target').data_ptr()), (a3.policy_lo, a3.n_pol))
-            cmd(seg0, 'KEYS_FILL', (keys_ptr,), (n_keys,))
+            if stage is None:
+                cmd(seg0, 'KEYS_FILL', (keys_ptr,), (n_keys,))
             if plan['tc']:
                 cmd(seg1, 'FOLD_GPI', (dref, self.online.data_ptr(), a2.w, plan['wq'].data_ptr(), plan['bq'].data_ptr()),
                     (a2.policy_lo, a2.n_pol, a2.n_w, a2.w_diag))
@@ -786,6 +799,9 @@ class PackedSFLibrary:
             cmd(seg1, 'NOP')                                  # probe slot (set_probe): event before the dominant kernel
             cmd(seg1, 'FORWARD_TC_JOBS', (C.addressof(jobs),), (3,))
             cmd(seg1, 'NOP')                                  # probe slot: event after it
+            if stage is not None:
+                cmd(seg1, 'KEYS_REDUCE', (stage.data_ptr(), keys_ptr), (a2.n_pol, a2.n_w * B))
+                n_reduce = len(seg0) + len(seg1) - 1
         else:
             cmd(seg1, 'FORWARD', (C.addressof(a1),))
             cmd(seg1, 'NOP')
@@ -836,6 +852,7 @@ class PackedSFLibrary:
         if peer is not None:
             arr = plan['segments'][0][0]
             peer['fill_cmd'] = arr[n_fill]
+            peer['reduce_cmd'] = arr[n_reduce] if stage is not None else None
 
     def set_probe(self, plan_key, start_event=None, end_event=None):
         """

@@ -86,6 +86,11 @@ typedef struct {
                                        the operands of sfgpi_mlp_backward_tc */
     void *relu_mask_out;            /* tensor-core mode only: [L-1][n_pol][B][8] uint32, bit c%32 of word c/32 = (activation c > 0)
                                        for ReLU layers: all the dgrad chain needs of them */
+    int64_t *key_stage;             /* tensor-core mode only, optional: [n_pol][n_rows][B] (n_rows = 1 if w_diag else n_w).  Given it,
+                                       the GPI epilogue STORES policy p's per-vector action keys here instead of doing an int64
+                                       atomicMax per (policy, vector, state) into key_action; sfgpi_keys_reduce then takes the MAX
+                                       over policies.  The atomics are the bound once n_pol * n_w is large (33 M per step at 32
+                                       policies x 256 reward vectors); plain coalesced stores + one streaming pass are not */
 } sfgpi_forward_args;
 
 int sfgpi_mlp_forward(const sfgpi_forward_args *args, void *stream);
@@ -97,6 +102,8 @@ int sfgpi_mlp_forward(const sfgpi_forward_args *args, void *stream);
  */
 int sfgpi_keys_fill(int64_t *keys, int64_t n, void *stream);
 int sfgpi_keys_decode(const int64_t *keys, int64_t n, int64_t *index_out, float *value_out, void *stream);
+/* keys_out[i] = max over p < n_pol of stage[p * n + i], i < n: the reduction over policies of staged keys (key_stage above) */
+int sfgpi_keys_reduce(const int64_t *stage, int32_t n_pol, int64_t n, int64_t *keys_out, void *stream);
 
 /*
  * Unfused GPI epilogue on a materialised psi [B][N][A][D] (GPI_w, sfdqn.py:236-239): q_out [B][N][A] (nullable),
@@ -359,6 +366,7 @@ int sfgpi_replay_gather(const sfgpi_replay_args *args, void *stream);
 #define SFGPI_OP_SHARD_PACK 15      /* p0 = w, p1 = h, p2 = h_prev, p3 = x_local, i0 = nw, i1 = nh */
 #define SFGPI_OP_PEER_UNPACK 16     /* p0 = sfgpi_peer_unpack_args */
 #define SFGPI_OP_STEP_PREP 17       /* p0 = sfgpi_step_prep_args */
+#define SFGPI_OP_KEYS_REDUCE 18     /* p0 = stage, p1 = keys_out, i0 = n_pol, i1 = n */
 typedef struct {
     int32_t op;
     void *p[5];

@@ -235,3 +235,33 @@ def test_train_step_from_host_batches_equals_device_batches(kind):
     n = N
     assert torch.equal(sf_d._library.online[:n], sf_h._library.online[:n])
     assert torch.equal(sf_d._library.g[:n], sf_h._library.g[:n]) and torch.equal(sf_d._library.h, sf_h._library.h)
+
+
+def test_staged_keys_equal_atomic_keys(monkeypatch):
+    """GPI keys staged per policy + sfgpi_keys_reduce == the int64 atomicMax path, bit for bit (3 train steps, TSF, GPI)."""
+    S, A, D, N, B = 4, 9, 12, 5, 1000
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True)
+    o, gen = make(S, A, D, N, seed=43, tsf_dim=100)
+    batches = [tuple(t.cuda() for t in synthetic_transitions(B, S, A, D, gen)) for _ in range(3)]
+    monkeypatch.setenv('SFGPI_STAGE_MIN', '1000000')
+    sf_a, ag_a = gu.build_g3(meta, oracle=o)
+    sf_a._library.set_precision('bf16')
+    la = [ag_a.update_successor_all(tr, use_gpi=True).clone() for tr in batches]
+    monkeypatch.setenv('SFGPI_STAGE_MIN', '1')
+    sf_s, ag_s = gu.build_g3(meta, oracle=o)
+    sf_s._library.set_precision('bf16')
+    ls = [ag_s.update_successor_all(tr, use_gpi=True).clone() for tr in batches]
+    plan = sf_s._library._ws[sf_s._library.last_plan_key]
+    assert plan['stage'] is not None and sf_a._library._ws[sf_a._library.last_plan_key]['stage'] is None
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(la, ls))
+    assert torch.equal(sf_a._library.online[:N], sf_s._library.online[:N]) and torch.equal(sf_a._library.h, sf_s._library.h)
+    # the reduction kernel on its own, odd sizes included
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    from deep_successor_features_for_transfer_b200.library import _stream
+    for n_pol, n in ((1, 7), (5, 1001), (9, 4096)):
+        st = torch.randint(-2 ** 62, 2 ** 62, (n_pol, n), dtype=torch.int64, device='cuda')
+        out = torch.empty(n, dtype=torch.int64, device='cuda')
+        _lib.call('sfgpi_keys_reduce', st.data_ptr(), n_pol, n, out.data_ptr(), _stream())
+        assert torch.equal(out, st.max(dim=0).values)
