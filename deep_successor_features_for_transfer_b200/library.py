@@ -481,11 +481,13 @@ class PackedSFLibrary:
             a2 = self._fwd_args(self.online, lo, n_pol, None, B)
             a2.w, a2.n_w, a2.w_diag = P(self.w), n_pol, 1
         a2.key_action = ptr(keys)
-        # Staged keys (tensor-core mode, GPI over the library): with many (policy, reward vector) pairs the int64 atomicMax per
-        # (policy, vector, state) bounds the forward kernel; the epilogue then stores per-policy keys and one streaming pass
-        # (sfgpi_keys_reduce) takes the MAX over the local policies -- which also replaces the key fill.
+        # Staged keys (tensor-core mode, GPI over the library; opt-in through SFGPI_STAGE_MIN = smallest n_w * n_pol that uses it):
+        # the epilogue stores per-policy keys and one streaming pass (sfgpi_keys_reduce) takes the MAX over the local policies,
+        # instead of one int64 atomicMax per (policy, vector, state).  Measured on B200 the atomics are NOT the bound even at
+        # 32 policies x 256 reward vectors (33 M atomics per step: 5.48 ms forward with atomics, 5.55 ms staged), and the extra
+        # launch costs ~4 us on the small configurations, so the default keeps the atomics.
         stage = None
-        if tc and use_gpi and not a2.w_diag and a2.n_w * a2.n_pol >= int(os.environ.get('SFGPI_STAGE_MIN', '64')):
+        if tc and use_gpi and not a2.w_diag and a2.n_w * a2.n_pol >= int(os.environ.get('SFGPI_STAGE_MIN', str(1 << 62))):
             stage = ws.setdefault(('key_stage', a2.n_w), torch.empty(a2.n_pol, a2.n_w, B, dtype=torch.int64, device=self.device))
             a2.key_stage = stage.data_ptr()
         # (3) target forward on s', gather psi^-(s')[a*]                                sfdqn.py:330-331

@@ -89,8 +89,8 @@ typedef struct {
     int64_t *key_stage;             /* tensor-core mode only, optional: [n_pol][n_rows][B] (n_rows = 1 if w_diag else n_w).  Given it,
                                        the GPI epilogue STORES policy p's per-vector action keys here instead of doing an int64
                                        atomicMax per (policy, vector, state) into key_action; sfgpi_keys_reduce then takes the MAX
-                                       over policies.  The atomics are the bound once n_pol * n_w is large (33 M per step at 32
-                                       policies x 256 reward vectors); plain coalesced stores + one streaming pass are not */
+                                       over policies.  (Measured on B200: the atomics are not the bound even at 33 M per launch, so
+                                       the host mirror keeps this opt-in.) */
 } sfgpi_forward_args;
 
 int sfgpi_mlp_forward(const sfgpi_forward_args *args, void *stream);
