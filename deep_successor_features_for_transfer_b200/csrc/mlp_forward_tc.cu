@@ -48,6 +48,56 @@ struct TcParams {
 
 struct ItemInfo { int row_base, n_cols, col0, kind, n_kb, n_k16; };   // kind: 0 input layer, 1 hidden, 2 final
 
+// Column order of the folded GPI output layer.  The epilogue scans the columns with ONE thread per state, so a running
+// (max, argmax) per reward vector is a dependent compare/select chain; with the plain order column = wi * A + act a trip of 8
+// columns belongs to one or two vectors and runs at the chain's latency (~66 cycles per column measured).  Reward vectors are
+// therefore interleaved in blocks of WB = 8 (4 for 4..7 vectors): column = (block * A + act) * WB + w_in_block, so one 8-column
+// trip feeds WB INDEPENDENT chains.  Vectors are padded to a multiple of WB (zero columns, never emitted).  WB = 1: plain order.
+__host__ __device__ inline int gpi_wblock(int nw) { return nw >= 8 ? 8 : (nw >= 4 ? 4 : 1); }
+__host__ __device__ inline int gpi_ncols(int nw, int A) { const int wb = gpi_wblock(nw); return (nw + wb - 1) / wb * wb * A; }
+// folded row -> (reward vector, action); wi >= nw: padding
+__device__ __forceinline__ void gpi_row_to_wa(int row, int nw, int A, int &wi, int &act) {
+    const int wb = gpi_wblock(nw);
+    const int blk = row / (wb * A), rem = row - blk * (wb * A);
+    act = rem / wb;
+    wi = blk * wb + (rem - act * wb);
+}
+
+// 8 columns (registers OFF .. OFF+7 of a 32-column TMEM load) of the blocked scan: 8 / WB actions x WB reward vectors
+template <int WB, int OFF>
+__device__ __forceinline__ void gpi_scan_blocked(const uint32_t (&v)[32], const float (&bv)[8], int col, int ncol, int A_, int nw, float (&bb)[8],
+                                                 int (&ba)[8], int &act_i, int &g, long long *&kp, long long *&tp, uint32_t kstep,
+                                                 bool k_staged, bool k_has, bool t_has, bool row_ok, uint32_t task_id, float *q_row) {
+#pragma unroll
+    for (int j = 0; j < 8 / WB; ++j) {
+        if (col + j * WB < ncol) {                           // (ncol is a multiple of WB)
+#pragma unroll
+            for (int ws = 0; ws < WB; ++ws) {
+                const float q = __uint_as_float(v[OFF + j * WB + ws]) + bv[j * WB + ws];
+                if (q > bb[ws]) { bb[ws] = q; ba[ws] = act_i; }
+            }
+            if (q_row != nullptr && g == 0) q_row[act_i] = __uint_as_float(v[OFF + j * WB]) + bv[j * WB];       // reward vector 0
+            if (++act_i == A_) {                             // block complete: WB keys out, state reset
+#pragma unroll
+                for (int ws = 0; ws < WB; ++ws) {
+                    if (row_ok && g * WB + ws < nw) {
+                        const long long key = pack_key(bb[ws], (uint32_t)ba[ws]);
+                        if (k_staged) kp[(size_t)ws * kstep] = key;
+                        else if (k_has) atomicMax(kp + (size_t)ws * kstep, key);
+                        if (t_has) atomicMax(tp + (size_t)ws * kstep, pack_key(bb[ws], task_id));
+                    }
+                    bb[ws] = -INFINITY;
+                    ba[ws] = 0;
+                }
+                kp += (size_t)WB * kstep;
+                tp += (size_t)WB * kstep;
+                act_i = 0;
+                ++g;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ ItemInfo item_info(const TcParams &p, int it) {
     ItemInfo r;
     if (it == 0) { r.row_base = 0; r.n_cols = kH; r.col0 = 0; r.kind = 0; r.n_kb = 1; r.n_k16 = p.ks0; }
@@ -464,7 +514,11 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 
             // GPI running state (folded form): columns are (reward vector wi, action act); group g scans slot g
             float best = -INFINITY;
-            int best_a = 0, wi = 0, act_i = 0;
+            int best_a = 0, wi = 0, act_i = 0;               // (blocked order: wi counts blocks of WB reward vectors)
+            float bb[8];
+            int ba[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
             for (int it = 0; it < p.n_items; ++it) {
                 const ItemInfo ii = item_info(p, it);
 #pragma unroll 1
@@ -513,7 +567,8 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         // a running (max, argmax) is carried along the columns, so ONE group scans a slot (group g: slot g).
                         const int c_first = p.gpi ? (group == slot ? 0 : ii.n_cols) : group * 8;
                         const int c_step = p.gpi ? 8 : 16;
-                        const int ncol = p.nw * A_;
+                        const int ncol = p.gpi ? gpi_ncols(p.nw, A_) : 0;
+                        const int wblk = p.gpi ? gpi_wblock(p.nw) : 1;
                         const int sb = sel_base[slot];
                         // Everything the column loop needs of the job's arguments, in REGISTERS: `p` / `a` are slices of the kernel
                         // parameters selected by a runtime job index, so each field read is a register-indexed constant load
@@ -536,9 +591,35 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                             kp = k_staged ? reinterpret_cast<long long *>(a.key_stage) + (size_t)pl * (a.w_diag ? 1 : p.nw) * B
                                           : reinterpret_cast<long long *>(a.key_action) + (a.w_diag ? (size_t)pl * B : 0);
                             tp = reinterpret_cast<long long *>(a.key_task) + (a.w_diag ? (size_t)pl * B : 0);
-                            kp += (size_t)wi * kstep + b;
-                            tp += (size_t)wi * kstep + b;
+                            kp += (size_t)(wi * wblk) * kstep + b;
+                            tp += (size_t)(wi * wblk) * kstep + b;
                         }
+                        const int nw_job = p.nw;
+                        float *const q_row = (q_out != nullptr && row_ok) ? q_out + ((size_t)b * n_pol_job + pl) * A_ : nullptr;
+                        if (gpi_form && wblk > 1) {
+                            // blocked GPI scan: 32 columns per TMEM load, then four 8-column sub-trips out of registers.  (Double-
+                            // buffering the loads was tried: no gain at 256 reward vectors and the extra 32 live registers cost the
+                            // hidden-layer epilogues ~5 us per launch in spills.)
+                            if (group == slot) {
+                                const uint32_t tid_ = (uint32_t)(task_base + pl);
+#pragma unroll 1
+                                for (int c0 = 0; c0 < n_cols_it; c0 += 32) {
+                                    uint32_t v[32];
+                                    tmem_ld32(t_lane + c0, v);
+                                    tmem_wait_ld();
+#define SFGPI_SCAN(WB, OFF)                                                                                                            \
+    do {                                                                                                                                \
+        const float4 b0_ = lds128(bias + 4u * (c0 + OFF)), b1_ = lds128(bias + 4u * (c0 + OFF + 4));                                    \
+        const float bv_[8] = {b0_.x, b0_.y, b0_.z, b0_.w, b1_.x, b1_.y, b1_.z, b1_.w};                                                  \
+        gpi_scan_blocked<WB, OFF>(v, bv_, col0_it + c0 + OFF, ncol, A_, nw_job, bb, ba, act_i, wi, kp, tp, kstep, k_staged, k_has,      \
+                                  t_has, row_ok, tid_, q_row);                                                                          \
+    } while (0)
+                                    if (wblk == 8) { SFGPI_SCAN(8, 0); SFGPI_SCAN(8, 8); SFGPI_SCAN(8, 16); SFGPI_SCAN(8, 24); }
+                                    else { SFGPI_SCAN(4, 0); SFGPI_SCAN(4, 8); SFGPI_SCAN(4, 16); SFGPI_SCAN(4, 24); }
+#undef SFGPI_SCAN
+                                }
+                            }
+                        } else
 #pragma unroll 1
                         for (int c0 = c_first; c0 < n_cols_it; c0 += c_step) {
                             uint32_t v[8];
@@ -665,8 +746,9 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
     const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
     const float *P = params + (size_t)(policy_lo + pl) * net.row_stride;
     float acc = 0.0f, bacc = 0.0f;
-    if (row < nw * A_) {
-        const int wi = row / A_, act = row - wi * A_;
+    int wi, act;
+    gpi_row_to_wa(row, nw, A_, wi, act);
+    if (row < gpi_ncols(nw, A_) && wi < nw) {
         const float *wv = w + (size_t)(w_diag ? pl : wi) * D;
         const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH;
         const float *bo = P + net.b_off[L - 1] + act * D;
@@ -765,8 +847,9 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
         const int nw = a.w_diag ? 1 : a.n_w;
         const float *P = a.fold_params + (size_t)(a.fold_lo + pl) * net.row_stride;
         float acc = 0.0f, bacc = 0.0f;
-        if (row < nw * A_) {
-            const int wi = row / A_, act = row - wi * A_;
+        int wi, act;
+        gpi_row_to_wa(row, nw, A_, wi, act);
+        if (row < gpi_ncols(nw, A_) && wi < nw) {
             const float *wv = a.w + (size_t)(a.w_diag ? pl : wi) * D;
             const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH;
             const float *bo = P + net.b_off[L - 1] + act * D;
@@ -854,7 +937,7 @@ extern "C" int sfgpi_bf16_rows_per_policy(const sfgpi_net_desc *net) {
     return (net->n_layers - 1) * kH + ((AD + 15) & ~15);
 }
 
-extern "C" int sfgpi_gpi_fold_rows(const sfgpi_net_desc *net, int32_t n_w) { return (n_w * net->n_actions + 15) & ~15; }
+extern "C" int sfgpi_gpi_fold_rows(const sfgpi_net_desc *net, int32_t n_w) { return (gpi_ncols(n_w, net->n_actions) + 15) & ~15; }
 
 extern "C" int sfgpi_pack_bf16(const sfgpi_net_desc *net, const float *params, int32_t policy_lo, int32_t n_pol, void *out_bf16,
                                void *stream) {

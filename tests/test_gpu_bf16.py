@@ -265,3 +265,51 @@ def test_staged_keys_equal_atomic_keys(monkeypatch):
         out = torch.empty(n, dtype=torch.int64, device='cuda')
         _lib.call('sfgpi_keys_reduce', st.data_ptr(), n_pol, n, out.data_ptr(), _stream())
         assert torch.equal(out, st.max(dim=0).values)
+
+
+@pytest.mark.parametrize('S,A,D,N,B,nws', [(4, 9, 12, 3, 1000, (4, 5, 8, 13, 40)), (11, 27, 50, 2, 333, (6, 10)), (4, 2, 20, 2, 200, (4, 9, 70))])
+def test_multi_vector_gpi_keys_equal_single_vector_runs(S, A, D, N, B, nws):
+    """
+    The folded GPI output layer interleaves reward vectors in blocks of 8 (4) columns (csrc/mlp_forward_tc.cu: gpi_wblock).
+    Every output element is an independent dot product, so scoring n_w vectors in one launch must give, for every vector,
+    exactly the keys of a single-vector launch -- across block padding, 256-column chunk boundaries and ragged row tiles.
+    """
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    from deep_successor_features_for_transfer_b200.library import _stream
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=47)
+    sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+    lib = sf._library
+    x = synthetic_transitions(B, S, A, D, gen)[0].cuda()
+    lib._pack('online', 0, N)
+
+    def run(w):
+        nw = w.shape[0]
+        ka = torch.empty(nw, B, dtype=torch.int64, device='cuda')
+        kt = torch.empty(nw, B, dtype=torch.int64, device='cuda')
+        _lib.call('sfgpi_keys_fill', ka.data_ptr(), ka.numel(), _stream())
+        _lib.call('sfgpi_keys_fill', kt.data_ptr(), kt.numel(), _stream())
+        a = lib._fwd_args(lib.online, 0, N, x)
+        a.w, a.n_w, a.w_diag, a.task_base = w.data_ptr(), nw, 0, 7
+        a.key_action, a.key_task = ka.data_ptr(), kt.data_ptr()
+        q = torch.zeros(B, N, A, device='cuda')
+        a.q_out = q.data_ptr()
+        wq = torch.empty(N * _lib.lib().sfgpi_gpi_fold_rows(C.byref(lib.spec.desc()), nw) * 256, dtype=torch.bfloat16, device='cuda')
+        bq = torch.empty(wq.numel() // 256, device='cuda')
+        _lib.call('sfgpi_fold_gpi', C.byref(lib.spec.desc()), lib.online.data_ptr(), 0, N, w.data_ptr(), nw, 0, wq.data_ptr(), bq.data_ptr(), _stream())
+        _lib.call('sfgpi_mlp_forward_tc', C.byref(a), lib._shadow_for('online').data_ptr(), lib.cap, wq.data_ptr(), bq.data_ptr(), _stream())
+        torch.cuda.synchronize()
+        return ka, kt, q
+
+    for nw in nws:
+        w = (torch.rand(nw, D, generator=gen) * 0.02 - 0.01).cuda().contiguous()
+        ka, kt, q = run(w)
+        for wi in sorted({0, 1, nw // 2, nw - 2, nw - 1}):
+            ka1, kt1, q1 = run(w[wi:wi + 1].contiguous())
+            assert torch.equal(ka[wi], ka1[0]) and torch.equal(kt[wi], kt1[0]), f'n_w={nw}, vector {wi}'
+            if wi == 0:
+                assert torch.equal(q, q1)                     # q_out carries reward vector 0
+        # and the keys are the argmax of that q (vector 0), first-index ties
+        assert torch.equal(lib.decode_keys(ka[0]), torch.argmax(q.max(dim=1).values, dim=-1))
+        assert torch.equal(lib.decode_keys(kt[0]) - 7, torch.argmax(q.max(dim=2).values, dim=1))
