@@ -222,8 +222,11 @@ int sfgpi_bf16_rows_per_policy(const sfgpi_net_desc *net);
 int sfgpi_pack_bf16(const sfgpi_net_desc *net, const float *params, int32_t policy_lo, int32_t n_pol, void *out_bf16, void *stream);
 /*
  * GPI form of the tensor-core forward: q = psi . w is folded into the output layer,
- *   Wq[p][wi*A + a][:] = sum_d w[wi][d] * W_out[p][a*D + d][:],  bq likewise from b_out   (fp32 accumulate, bf16 Wq),
- * so the last GEMM has n_w*A columns instead of A*D and psi[B,N,A,D] is never formed (GPI_w, sfdqn.py:215-240).
+ *   Wq[p][row(wi, a)][:] = sum_d w[wi][d] * W_out[p][a*D + d][:],  bq likewise from b_out   (fp32 accumulate, bf16 Wq),
+ * so the last GEMM has ~n_w*A columns instead of A*D and psi[B,N,A,D] is never formed (GPI_w, sfdqn.py:215-240).
+ * Row order (an internal contract between sfgpi_fold_gpi / sfgpi_step_prep and sfgpi_mlp_forward_tc; treat wq / bq as opaque):
+ * reward vectors are interleaved in blocks of WB = 8 (4 when 4 <= n_w < 8, 1 below): row = (block*A + a)*WB + (wi mod WB), vectors
+ * padded to a multiple of WB with zero rows, so that the epilogue's per-state scan runs WB independent max/argmax chains.
  * wq_out: bf16 [n_pol][sfgpi_gpi_fold_rows()][256]; bq_out: fp32 [n_pol][sfgpi_gpi_fold_rows()].
  */
 int sfgpi_gpi_fold_rows(const sfgpi_net_desc *net, int32_t n_w);

@@ -1,6 +1,6 @@
 """Prints per-layer relative Frobenius errors of PackedSFLibrary.psi_gradients (both precision modes) vs torch autograd."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from tests.synthetic import synthetic_transitions
 from tests import gpu_util as gu

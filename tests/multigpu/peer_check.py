@@ -5,13 +5,13 @@ two policy-sharded TSF agents are built from the same weights on every rank, one
 are summed in rank order either way), so after K train steps -- with deliberate rank skew to shake the flag protocol -- the
 two agents must be BIT-identical.  Then both are timed with CUDA events.
 
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/peer_check.py [fp32|bf16] [steps]
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu/peer_check.py [fp32|bf16] [steps]
 """
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 

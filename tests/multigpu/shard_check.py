@@ -3,12 +3,12 @@ Multi-GPU check (torchrun, NCCL): a policy-sharded library must reproduce the si
 Every rank builds (a) the FULL N-policy TSF agent and (b) its own shard (policies [lo, hi)), runs K all-task train steps with
 GPI on identical batches, and compares losses / weights / GPI keys of its shard against the same policies of the full run.
 
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/shard_check.py [fp32|bf16]
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu/shard_check.py [fp32|bf16]
 """
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 
