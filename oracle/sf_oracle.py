@@ -406,6 +406,97 @@ def oracle_phi_pre_train(phi, head_ws, train_tasks, n_samples_pre_train, n_cycle
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# G4: joint psi / phi step -- features/deep_phi.py:95-224 (DeepSF_PHI.update_successor) with the shared phi model and the
+# per-task loss coefficient of agents/sfdqn_phi.py:144-165.  ORACLE ONLY so far (second half): the product does
+# not implement this step yet; the restatement is pinned to the reference so that the kernel path can be built against it.
+# ----------------------------------------------------------------------------------------------------------------
+class OracleG4:
+    """
+    State: N psi nets + targets (as OracleSF), reward maps fit_w[i] = Linear(D, 1) WITH bias (features/deep_phi.py:268),
+    one shared phi MLP over cat[s, a, s'] (main_sfdqn_phi_torch.py:52-73), one loss coefficient per task (init 1).
+    Every call builds a FRESH torch.optim.Adam (features/deep_phi.py:170), so each update is a first Adam step
+    (step = 1, zero moments: p -= lr * g / (|g| + eps) up to rounding); the coefficient's group has maximize=True.
+    """
+
+    LR = 1e-3
+
+    def __init__(self, A, D, psi_acts, phi_layers, phi_acts, target_update_ev=1000):
+        self.A, self.D = A, D
+        self.psi_acts, self.phi_acts = list(psi_acts), list(phi_acts)
+        self.phi = [(W.clone().float(), b.clone().float()) for W, b in phi_layers]
+        self.psi, self.tgt, self.w, self.coef = [], [], [], []
+        self.target_update_ev = target_update_ev
+        self.updates_since_target_updated = []
+
+    def add_policy(self, layers, w):
+        self.psi.append([(W.clone().float(), b.clone().float()) for W, b in layers])
+        self.tgt.append([(W.clone(), b.clone()) for W, b in self.psi[-1]])
+        self.w.append((w[0].clone().float(), w[1].clone().float()))          # (weight [1,D], bias [1])
+        self.coef.append(torch.ones(1))
+        self.updates_since_target_updated.append(0)
+
+    def get_successor(self, x, i, layers=None):
+        return mlp_forward(self.psi[i] if layers is None else layers, self.psi_acts, x).reshape(-1, self.A, self.D)
+
+    def GPI(self, x, i):                                                      # features/deep_phi.py:226-251: q = w(psi)[..., 0]
+        psi = torch.stack([self.get_successor(x, j) for j in range(len(self.psi))], dim=1)
+        q = torch.nn.functional.linear(psi, *self.w[i])[:, :, :, 0]
+        return q, torch.squeeze(torch.argmax(torch.max(q, dim=2).values, dim=1))
+
+    def update_successor(self, transitions, i, use_gpi=True):
+        if transitions is None:
+            return None
+        states, actions, rs, _, next_states, gammas = transitions
+        B = len(gammas)
+        idx = torch.arange(B)
+        gammas = gammas.reshape(-1, 1)
+        lin = torch.nn.functional.linear
+        flat_phi = [t for Wb in self.phi for t in Wb]
+        flat_psi = [t for Wb in self.psi[i] for t in Wb]
+        leaves_phi = [t.detach().requires_grad_(True) for t in flat_phi]
+        leaves_psi = [t.detach().requires_grad_(True) for t in flat_psi]
+        w_leaf = [t.detach().requires_grad_(True) for t in self.w[i]]
+        c_leaf = self.coef[i].detach().requires_grad_(True)
+        phi_layers = [(leaves_phi[2 * l], leaves_phi[2 * l + 1]) for l in range(len(self.phi))]
+        psi_layers = [(leaves_psi[2 * l], leaves_psi[2 * l + 1]) for l in range(len(self.psi[i]))]
+        x_phi = torch.cat([states, actions.reshape(B, 1), next_states], dim=1)               # :110
+        phis = mlp_forward(phi_layers, self.phi_acts, x_phi)                                  # :111 (carries grad)
+        with torch.no_grad():                                                                 # next actions: indices only
+            if use_gpi:
+                q1, _ = self.GPI(next_states, i)                                              # :114-116
+                next_actions = torch.argmax(torch.max(q1, dim=1).values, dim=-1)
+            else:
+                q1 = lin(self.get_successor(next_states, i), *self.w[i])                      # :118-123
+                next_actions = torch.squeeze(torch.argmax(q1, dim=1), dim=1)
+            next_psi = mlp_forward(self.tgt[i], self.psi_acts, next_states).reshape(B, self.A, self.D)[idx, next_actions, :]
+        cur = self.get_successor(states, i, psi_layers)
+        targets = phis + gammas * next_psi                                                    # :136 (phi's grad flows in)
+        merge = cur.clone()
+        merge[idx, actions, :] = targets                                                      # :142-143
+        r_fit = lin(phis, *w_leaf)                                                            # :147
+        phi_loss = torch.nn.functional.mse_loss(r_fit, rs).unsqueeze(0)                       # :175
+        psi_loss = torch.nn.functional.mse_loss(cur, merge).unsqueeze(0)                      # :180
+        loss = phi_loss + c_leaf * psi_loss                                                   # :185
+        params = leaves_psi + leaves_phi + w_leaf + [c_leaf]
+        grads = torch.autograd.grad(loss, params)
+        with torch.no_grad():
+            targets_flat = flat_psi + flat_phi + list(self.w[i]) + [self.coef[i]]
+            for k, (p, g) in enumerate(zip(targets_flat, grads)):
+                g = g.clamp(-1e10, 1e10)                                                      # :205-208
+                if k == len(targets_flat) - 1:
+                    g = -g                                                                    # maximize=True (:169)
+                OracleSF._adam_tensor(p, g, torch.zeros_like(p), torch.zeros_like(p), 1, self.LR, 0.0)
+            self.coef[i].clamp_(1e-2, 1e6)                                                    # :212-215
+            self.updates_since_target_updated[i] += 1
+            if self.updates_since_target_updated[i] >= self.target_update_ev:                 # :219-224
+                for (Wt, bt), (W, b) in zip(self.tgt[i], self.psi[i]):
+                    Wt.copy_(W)
+                    bt.copy_(b)
+                self.updates_since_target_updated[i] = 0
+        return loss.detach(), psi_loss.detach(), phi_loss.detach(), self.coef[i].clone()
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Synthetic replay batches (SURVEY.md section 8d "Synthetic inputs")
 # ----------------------------------------------------------------------------------------------------------------
 def synthetic_transitions(B, S, A, D, gen, hopper=False, five_tuple=False):
