@@ -59,6 +59,37 @@ def init_linear(out_f, in_f, gen):
     return W, b
 
 
+def g_apply(x, g):
+    """
+    The TSF g-function of policy i applied to states x.  g = (W, b): Linear(S, G) (tsfdqn.py:537-539).  g = [flow_0, ..., (W, b)]
+    with flow_k = (weight [1,S], bias [1], scale [1,S]): the normalising-flow form of tsfdqn_nf.py:331-358 -- planar flows
+    z <- z + scale * tanh(z . weight + bias) followed by the Linear(S, G).
+    """
+    if isinstance(g, tuple):
+        return torch.nn.functional.linear(x, *g)
+    z = x
+    for weight, bias, scale in g[:-1]:
+        z = z + scale * torch.tanh(torch.nn.functional.linear(z, weight, bias))
+    return torch.nn.functional.linear(z, *g[-1])
+
+
+def g_flat(g):
+    """Parameters of a g-function in `module.parameters()` order (flow: weight, bias, scale; then the Linear's W, b)."""
+    if isinstance(g, tuple):
+        return list(g)
+    return [t for part in g for t in part]
+
+
+def g_unflat(g, flat):
+    if isinstance(g, tuple):
+        return tuple(flat)
+    out, k = [], 0
+    for part in g:
+        out.append(tuple(flat[k:k + len(part)]))
+        k += len(part)
+    return out
+
+
 class OracleSF:
     """
     State of the SF library: N online/target psi nets, N reward maps w, per-policy Adam state (sfdqn.py:94-371),
@@ -91,7 +122,7 @@ class OracleSF:
         self.tgt.append([(W.clone(), b.clone()) for W, b in layers])       # update_models_weights(model, target_model)
         self.w.append(w.clone().float().reshape(1, self.D))
         if self.tsf_dim is not None:
-            self.g.append((g[0].clone().float(), g[1].clone().float()))
+            self.g.append(g_unflat(g, [t.clone().float() for t in g_flat(g)]))
             if self.h is None:
                 self.h = (h[0].clone().float(), h[1].clone().float())
         self.adam.append({'step': 0, 'm': None, 'v': None})
@@ -230,11 +261,12 @@ class OracleSF:
         leaves = [t.detach().requires_grad_(True) for t in flat]
         layers = [(leaves[2 * l], leaves[2 * l + 1]) for l in range(len(self.psi[i]))]
         w_leaf = self.w[i].detach().requires_grad_(True)
-        g_leaf = [t.detach().requires_grad_(True) for t in self.g[i]]
+        g_leaf = [t.detach().requires_grad_(True) for t in g_flat(self.g[i])]
         h_leaf = [t.detach().requires_grad_(True) for t in self.h]
         lin = torch.nn.functional.linear
         cur = mlp_forward(layers, self.acts, states).reshape(B, self.A, self.D)
-        ts, ts1 = lin(states, *g_leaf), lin(next_states, *g_leaf)           # :621-622
+        g_fn = g_unflat(self.g[i], g_leaf)                                  # Linear (tsfdqn.py) or flow chain (tsfdqn_nf.py:653-654)
+        ts, ts1 = g_apply(states, g_fn), g_apply(next_states, g_fn)         # :621-622
         aff = lin(ts, *h_leaf) + lin(ts1, *h_leaf)                          # :623
         tphis = aff * phis                                                  # :624
         targets = tphis + gammas * next_psis                                # :629 (carries grad to g_i, h)
@@ -247,8 +279,8 @@ class OracleSF:
         n = len(leaves)
         groups = [('sf', flat, list(grads[:n]), self.lr['sf'], self.wd['sf']),
                   ('w', [self.w[i]], [grads[n]], self.lr['w'], self.wd['w']),
-                  ('g', list(self.g[i]), list(grads[n + 1:n + 3]), self.lr['g'], self.wd['g']),
-                  ('h', list(self.h), list(grads[n + 3:n + 5]), self.lr['h'], self.wd['h'])]
+                  ('g', g_flat(self.g[i]), list(grads[n + 1:n + 1 + len(g_leaf)]), self.lr['g'], self.wd['g']),
+                  ('h', list(self.h), list(grads[n + 1 + len(g_leaf):]), self.lr['h'], self.wd['h'])]
         self.last_grads = {k: [g.clone() for g in gr] for k, _, gr, _, _ in groups}
         with torch.no_grad():
             self._adam_step(i, groups)
@@ -274,8 +306,8 @@ class OracleSF:
         w_leaf, om_leaf = tt['w'].detach().requires_grad_(True), tt['omegas'].detach().requires_grad_(True)
         norm = om_leaf / torch.sum(om_leaf, dim=1, keepdim=True)                               # :929
         with torch.no_grad():
-            ts = torch.vstack([lin(s, *g) for g in self.g]).unsqueeze(1)                      # :931-940
-            ts1 = torch.vstack([lin(s1, *g) for g in self.g]).unsqueeze(1)
+            ts = torch.vstack([g_apply(s, g) for g in self.g]).unsqueeze(1)                   # :931-940
+            ts1 = torch.vstack([g_apply(s1, g) for g in self.g]).unsqueeze(1)
             psi, next_psi = self.get_successors(s), self.get_next_successors(s1)               # :948-950
         aff = lin(torch.sum(ts * norm, dim=1), *self.h) + lin(torch.sum(ts1 * norm, dim=1), *self.h)     # :942-944
         tphi = phi * aff.squeeze(0)                                                          # :945
