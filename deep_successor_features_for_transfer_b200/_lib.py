@@ -129,7 +129,7 @@ class AdamArgs(C.Structure):
     _fields_ = [('n_seg', C.c_int32), ('n_pol', C.c_int32), ('seg', AdamSegment * MAX_SEGMENTS), ('step', C.c_void_p),
                 ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
                 ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
-                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p)]
+                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p), ('consts_next', C.c_void_p)]
 
 
 # every symbol include/sfgpi.h declares: name -> (restype, argtypes)
@@ -144,6 +144,7 @@ SYMBOLS = {
     'sfgpi_td_step': (C.c_int, [C.POINTER(TdArgs), C.c_void_p]),
     'sfgpi_mlp_backward': (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     'sfgpi_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
+    'sfgpi_adam_refresh': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
     'sfgpi_bf16_rows_per_policy': (C.c_int, [C.POINTER(NetDesc)]),
     'sfgpi_pack_bf16': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'sfgpi_gpi_fold_rows': (C.c_int, [C.POINTER(NetDesc), C.c_int32]),

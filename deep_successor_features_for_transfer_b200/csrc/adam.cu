@@ -174,6 +174,28 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             }
         }
     }
+    // fused finish (consts_next given): optimizer p's first CTA advances the step counter and derives the NEXT step's bias
+    // corrections into the other buffer.  Nothing in this launch reads `step` or `consts_next`, so there is no ordering to
+    // enforce -- unlike a last-CTA tail, this adds no serial work after the update itself.
+    if (a.consts_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int s_new = a.step[p] + 1;
+        a.step[p] = s_new;
+        const double t = (double)(s_new + 1);
+        a.consts_next[2 * p] = 1.0 - pow(a.beta1, t);
+        a.consts_next[2 * p + 1] = sqrt(1.0 - pow(a.beta2, t));
+    }
+}
+
+__global__ void adam_refresh_kernel(const int32_t *step, double *ca, double *cb, int n, double beta1, double beta2) {
+    pdl_launch_dependents();
+    pdl_wait();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double t = (double)(step[i] + 1);
+        const double c0 = 1.0 - pow(beta1, t), c1 = sqrt(1.0 - pow(beta2, t));
+        ca[2 * i] = c0; ca[2 * i + 1] = c1;
+        cb[2 * i] = c0; cb[2 * i + 1] = c1;
+    }
 }
 
 __global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double beta1, double beta2) {
@@ -193,6 +215,10 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
         set_error("sfgpi_adam_step: invalid arguments");
         return SFGPI_E_INVALID;
     }
+    if (a.consts_next != nullptr && (a.consts == nullptr || a.consts_next == a.consts)) {
+        set_error("sfgpi_adam_step: consts_next needs a distinct consts buffer to read from");
+        return SFGPI_E_INVALID;
+    }
     int max_len = 0;
     for (int s = 0; s < a.n_seg; ++s) {
         if (a.seg[s].len < 0 || a.seg[s].n_part < 1) { set_error("sfgpi_adam_step: bad segment %d", s); return SFGPI_E_INVALID; }
@@ -206,7 +232,14 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     launch_pdl(adam_kernel, grid, dim3(kAdamThreads), 0, st, a, blocks);
     int rc = check_launch("sfgpi_adam_step");
-    if (rc) return rc;
+    if (rc || a.consts_next != nullptr) return rc;
     launch_pdl(adam_finish_kernel, dim3((a.n_pol + 127) / 128), dim3(128), 0, st, a.step, a.consts, a.n_pol, a.beta1, a.beta2);
     return check_launch("sfgpi_adam_step(finish)");
+}
+
+extern "C" int sfgpi_adam_refresh(const int32_t *step, double *consts_a, double *consts_b, int32_t n, double beta1, double beta2, void *stream) {
+    if (n < 0 || !step || !consts_a || !consts_b) { set_error("sfgpi_adam_refresh: invalid arguments"); return SFGPI_E_INVALID; }
+    if (n == 0) return SFGPI_OK;
+    launch_pdl(adam_refresh_kernel, dim3((n + 127) / 128), dim3(128), 0, (cudaStream_t)stream, step, consts_a, consts_b, (int)n, beta1, beta2);
+    return check_launch("sfgpi_adam_refresh");
 }

@@ -236,7 +236,11 @@ class PackedSFLibrary:
                    step=torch.zeros(cap, dtype=torch.int32, device=dev),
                    # Adam bias corrections of every optimizer's NEXT step (t = step + 1), double like torch's host math
                    adam_consts=torch.tensor([[1.0 - 0.9 ** 1, math.sqrt(1.0 - 0.999 ** 1)]], dtype=torch.float64,
-                                            device=dev).repeat(cap, 1).contiguous())
+                                            device=dev).repeat(cap, 1).contiguous(),
+                   # ... and its twin: the train step's Adam launch reads one buffer and writes the next step's corrections
+                   # into the other (sfgpi_adam_args.consts_next); _adam_par[i] says which buffer is current for policy i
+                   adam_consts2=torch.tensor([[1.0 - 0.9 ** 1, math.sqrt(1.0 - 0.999 ** 1)]], dtype=torch.float64,
+                                             device=dev).repeat(cap, 1).contiguous())
         if self.G is not None:
             gl = self.G * sp.dims[0] + self.G
             hl = sp.n_features * self.G + sp.n_features
@@ -247,6 +251,7 @@ class PackedSFLibrary:
                 t[:self.n].copy_(old[:self.n])
             setattr(self, k, t)
         self.cap = cap
+        self._adam_par = (getattr(self, '_adam_par', None) or []) + [0] * (cap - len(getattr(self, '_adam_par', None) or []))
         self._ws = {}
         self.invalidate_exchange()
         for i, mods in enumerate(self._views):
@@ -305,7 +310,8 @@ class PackedSFLibrary:
 
     def reset(self):
         self.spec, self.n, self.cap, self._views, self._ws, self.h = None, 0, 0, [], {}, None
-        for k in ('online', 'target', 'm', 'v', 'w', 'w_m', 'w_v', 'step', 'adam_consts', 'g', 'g_m', 'g_v', 'h_m', 'h_v'):
+        self._adam_par = []
+        for k in ('online', 'target', 'm', 'v', 'w', 'w_m', 'w_v', 'step', 'adam_consts', 'adam_consts2', 'g', 'g_m', 'g_v', 'h_m', 'h_v'):
             if hasattr(self, k):
                 delattr(self, k)
 
@@ -534,7 +540,7 @@ class PackedSFLibrary:
         # (6) Adam over (psi | w | g | h) for all stepped optimizers, + loss reduction    sfdqn.py:362, tsfdqn.py:700
         ad = _lib.AdamArgs()
         ad.n_pol, ad.step = n_pol, C.c_void_p(self.step[lo:].data_ptr())
-        ad.consts = C.c_void_p(self.adam_consts[lo:].data_ptr())
+        ad.consts = C.c_void_p(self.adam_consts[lo:].data_ptr())          # (consts / consts_next: patched per step, see train_step)
         ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
         rs_, nblk, al = sp.row_stride, ws['nblk'], ws['aux_len']
         npa = 1 if variant == 2 else nblk          # variant 2: the TD step leaves ONE reduced aux-gradient row per policy
@@ -564,7 +570,7 @@ class PackedSFLibrary:
         ad.l1_scale, ad.l2_scale = 1.0 / (B * A * D), 1.0 / B
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
-        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, tc=tc, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
+        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, lo=lo, tc=tc, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
                     peer=peer, variant=variant, stage=stage,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
@@ -639,6 +645,17 @@ class PackedSFLibrary:
         plan['ring'] = (plan['ring'] + 1) % 64
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
+        # Adam bias corrections are double-buffered: this launch reads the current buffer of its optimizers and writes the next
+        # step's corrections into the other one (no finishing launch).  Optimizers stepped together must be in phase.
+        lo_, n_ = plan['lo'], plan['n_pol']
+        par = self._adam_par[lo_:lo_ + n_]
+        if len(set(par)) > 1:                                 # out of phase (single-policy and all-policy steps were mixed)
+            _lib.call('sfgpi_adam_refresh', self.step[lo_:].data_ptr(), self.adam_consts[lo_:].data_ptr(),
+                      self.adam_consts2[lo_:].data_ptr(), n_, 0.9, 0.999, _stream())
+            par = [0] * n_
+        cur, nxt = (self.adam_consts, self.adam_consts2) if par[0] == 0 else (self.adam_consts2, self.adam_consts)
+        ad.consts, ad.consts_next = cur[lo_:].data_ptr(), nxt[lo_:].data_ptr()
+        self._adam_par[lo_:lo_ + n_] = [par[0] ^ 1] * n_
         peer = plan.get('peer')
         if peer is not None:
             # peer-memory exchange: epoch numbers (identical on every rank) pick the arena halves this step writes / pulls
@@ -845,7 +862,7 @@ class PackedSFLibrary:
                     arr[k].p[q] = v
                 for q, v in enumerate(i):
                     arr[k].i[q] = int(v)
-                launches += _lib.OP_LAUNCHES[arr[k].op] - (1 if op == 'BACKWARD_TC' and b.xo_ready else 0) \
+                launches += _lib.OP_LAUNCHES[arr[k].op] - (1 if op == 'BACKWARD_TC' and b.xo_ready else 0) - (1 if op == 'ADAM' else 0) \
                     + (1 if op == 'TD' and t.variant == 2 and not t.defer_expand else 0)
             if plan['h2d'] is None:
                 plan['h2d'] = [arr[k] for k in range(6)]

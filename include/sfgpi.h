@@ -207,9 +207,16 @@ typedef struct {
     int32_t sequential_shared;      /* 1: segments with param_stride 0 are stepped by optimizer 0..n_pol-1 in order */
     double *consts;                 /* optional [n_pol][2]: {1 - beta1^t, sqrt(1 - beta2^t)} for t = step + 1; must be consistent
                                        with `step` on entry, refreshed on device after the step.  NULL: computed in-kernel */
+    double *consts_next;            /* optional second [n_pol][2] buffer (needs consts): the update kernel itself advances `step`
+                                       and writes the NEXT step's corrections here (nothing reads this buffer or `step` during the
+                                       launch), so the one-block finishing launch drops off the step's dependent chain; the caller
+                                       swaps the two buffers for the next call */
 } sfgpi_adam_args;
 
 int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
+/* consts_a[i] = consts_b[i] = {1 - beta1^(step[i]+1), sqrt(1 - beta2^(step[i]+1))}, i < n: re-derives both correction buffers
+ * from the step counters (used when optimizers whose buffers are out of phase are stepped together) */
+int sfgpi_adam_refresh(const int32_t *step, double *consts_a, double *consts_b, int32_t n, double beta1, double beta2, void *stream);
 
 /*
  * Tensor-core mode (mode 1): bf16 operands on tcgen05 with fp32 accumulation in TMEM, weights streamed by TMA.  Same
