@@ -316,14 +316,20 @@ def main():
 
     # ---------------- e2e: public API from pinned host batches, losses read back every step ----------------
     e2e_steps = args.steps
+    losses_host = torch.zeros(n_local, 3).pin_memory()              # the step's command list ends with the D2H copy into it
+    stream = torch.cuda.current_stream()
     for k in range(3):
-        ag.update_successor_all(pinned[k % 8], use_gpi=True).cpu()
+        ag.update_successor_all(pinned[k % 8], use_gpi=True, host_losses=losses_host)
+        stream.synchronize()
     barrier()
+    check = 0.0
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        losses = ag.update_successor_all(pinned[k % 8], use_gpi=True)
-        losses_host = losses.cpu()                                  # D2H read of the step's result (syncs)
+        ag.update_successor_all(pinned[k % 8], use_gpi=True, host_losses=losses_host)
+        stream.synchronize()                                        # the step's result is on the host from here on
+        check += float(losses_host[0, 0])                           # (read it: D2H of the losses every step)
     barrier()
+    assert check == check and check > 0.0, 'e2e losses did not reach the host'
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

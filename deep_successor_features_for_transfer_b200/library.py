@@ -574,7 +574,7 @@ class PackedSFLibrary:
                     peer=peer, variant=variant, stage=stage,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
-    def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0):
+    def train_step(self, transitions, policy, use_gpi=True, variant=1, beta=1.0, host_losses=None):
         """
         One fused SF TD update.  policy = int -> sequential semantics (sfdqn.py:303-371 / tsfdqn.py:588-709): only that
         policy's (psi, w, g, h) are stepped, next actions by GPI over all policies (use_gpi) or its own psi.
@@ -582,6 +582,8 @@ class PackedSFLibrary:
         the same pre-step library; with use_gpi every policy i gets a* = argmax_a max_j psi_j(s',a).w_i.
         variant: 0 = G1 (l1 only, 5-tuple), 1 = G2, 2 = G3 (TSF).  Returns losses [n_pol][3] = (loss, l1, l2) on device
         (no host sync; the buffer is one slot of a 64-deep ring, valid for the next 63 steps).
+        host_losses: optional CPU float32 tensor with >= n_pol * 3 elements (pinned for a truly asynchronous copy): the step's
+        command list then ends with a device-to-host copy of the losses into it -- synchronise the stream before reading.
         """
         if variant == 0:
             states, actions, phis, next_states, gammas = transitions
@@ -645,6 +647,14 @@ class PackedSFLibrary:
         plan['ring'] = (plan['ring'] + 1) % 64
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
+        d2h = plan['d2h_cmd']
+        if host_losses is None:
+            d2h.op = 0
+        else:
+            if host_losses.is_cuda or host_losses.dtype != torch.float32 or not host_losses.is_contiguous() \
+                    or host_losses.numel() < plan['n_pol'] * 3:
+                raise ValueError('host_losses must be a contiguous CPU float32 tensor with at least n_pol * 3 elements')
+            d2h.op, d2h.p[0], d2h.p[1], d2h.i[0] = _lib.OP['D2H'], host_losses.data_ptr(), losses.data_ptr(), plan['n_pol'] * 12
         # Adam bias corrections are double-buffered: this launch reads the current buffer of its optimizers and writes the next
         # step's corrections into the other one (no finishing launch).  Optimizers stepped together must be in phase.
         lo_, n_ = plan['lo'], plan['n_pol']
@@ -830,6 +840,7 @@ class PackedSFLibrary:
         cmd(seg2, 'TD', (C.addressof(t),))
         cmd(seg2, 'BACKWARD_TC' if plan['tc'] else 'BACKWARD', (C.addressof(b),))
         cmd(seg2, 'ADAM', (C.addressof(ad),))
+        cmd(seg2, 'NOP', (0, 0), (0, 0, 0, 777))              # slot of the optional D2H read-back of the losses (host_losses)
         if peer is not None:
             # peer mode: the exchanges are kernels of the chain -> the sharded step is ONE command list again
             pa, xc = self._peer, self._xchg
@@ -867,6 +878,9 @@ class PackedSFLibrary:
             if plan['h2d'] is None:
                 plan['h2d'] = [arr[k] for k in range(6)]
             plan['probe'] += [arr[k] for k, (op, p, i) in enumerate(seg) if op == 'NOP' and not p]
+            for k, (op, p, i) in enumerate(seg):
+                if op == 'NOP' and len(i) == 4 and i[3] == 777:
+                    plan['d2h_cmd'] = arr[k]
             plan['segments'].append((arr, len(seg), launches))
         if peer is not None:
             arr = plan['segments'][0][0]

@@ -130,12 +130,16 @@ class TSFDQN(SFDQN):
         self.sf._after_update(policy_index)
         return losses[0, 0], losses[0, 1], losses[0, 2]
 
-    def update_successor_all(self, transitions, use_gpi=True):
-        """Ensemble extension (BASELINE config 4-ii): all policies stepped on one batch, frozen-snapshot semantics."""
+    def update_successor_all(self, transitions, use_gpi=True, host_losses=None):
+        """
+        Ensemble extension (BASELINE config 4-ii): all policies stepped on one batch, frozen-snapshot semantics.  Returns the
+        losses [n_tasks][3] on the device; with host_losses (a pinned CPU float32 tensor of that shape) the step also copies
+        them there asynchronously -- synchronise the current stream before reading it.
+        """
         if transitions is None:
             return
         beta = self.hyperparameters['beta_loss_coefficient']
-        losses = self.sf._library.train_step(transitions, 'all', use_gpi=use_gpi, variant=2, beta=beta)
+        losses = self.sf._library.train_step(transitions, 'all', use_gpi=use_gpi, variant=2, beta=beta, host_losses=host_losses)
         for i in range(self.sf.n_tasks):
             self.sf._after_update(i)
         return losses

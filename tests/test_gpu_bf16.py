@@ -235,6 +235,14 @@ def test_train_step_from_host_batches_equals_device_batches(kind):
     n = N
     assert torch.equal(sf_d._library.online[:n], sf_h._library.online[:n])
     assert torch.equal(sf_d._library.g[:n], sf_h._library.g[:n]) and torch.equal(sf_d._library.h, sf_h._library.h)
+    # asynchronous read-back of the losses as the last command of the step
+    hl = torch.zeros(N, 3).pin_memory() if kind == 'pinned' else torch.zeros(N, 3)
+    ld = ag_d.update_successor_all(tuple(t.cuda() for t in batches[0]), use_gpi=True, host_losses=hl)
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(hl, ld.cpu()) and float(hl.abs().sum()) > 0
+    ld2 = ag_d.update_successor_all(tuple(t.cuda() for t in batches[1]), use_gpi=True)      # and the slot switches off again
+    torch.cuda.synchronize()
+    assert not torch.equal(hl, ld2.cpu())
 
 
 def test_staged_keys_equal_atomic_keys(monkeypatch):
