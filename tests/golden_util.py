@@ -5,8 +5,6 @@ import os
 import numpy as np
 import torch
 
-from oracle.sf_oracle import OracleSF
-
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
@@ -29,6 +27,7 @@ def net_layers(z, prefix, meta):
 
 
 def oracle_from_golden(meta, z, **kw):
+    from oracle.sf_oracle import OracleSF          # (lazy: bench.py's measured arm imports this module for FakeTask & co only)
     tsf = meta['kind'] in ('g3', 'g3_target')
     o = OracleSF(meta['S'], meta['A'], meta['D'], meta['hidden'], meta['acts'],
                  tsf_dim=meta.get('gdim') if tsf else None, beta=meta.get('beta', 1),
