@@ -161,3 +161,62 @@ def test_sharded_gpi_equals_unsharded_gloo_world2(n_total):
     assert torch.equal(keys[0], ka) and torch.equal(keys[1], kt)
     _, task = sdist.unpack_keys(keys[1])
     assert torch.equal(task, torch.argmax(q.max(dim=2).values, dim=-1))
+
+
+# ---- host logic that needs no GPU ---------------------------------------------------------------------------------------
+def test_no_cpu_fallback_constructors_raise_without_cuda():
+    """The product has no CPU path: on a box without CUDA every public constructor fails loudly."""
+    if torch.cuda.is_available():
+        pytest.skip('needs a CUDA-less host')
+    from deep_successor_features_for_transfer_b200.library import PackedSFLibrary
+    from deep_successor_features_for_transfer_b200.sfdqn import DeepSF
+    from deep_successor_features_for_transfer_b200.sfdqn_phi import PhiFunction
+    from tests.gpu_util import FakeTask, model_lambda, HYPER
+    with pytest.raises(RuntimeError, match='CUDA'):
+        PackedSFLibrary()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        sf = DeepSF(pytorch_model_handle=model_lambda([256, 256], ['relu', 'relu']), hyperparameters=dict(HYPER))
+        sf.reset()
+        sf.add_training_task(FakeTask(4, 9, 12, 0))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        PhiFunction(4, 1, 20)
+
+
+def test_missing_native_library_fails_loudly(tmp_path, monkeypatch):
+    """No libsfgpi.so and no way to build it -> RuntimeError / OSError from _lib.lib(), never a silent fallback."""
+    import importlib
+    import deep_successor_features_for_transfer_b200._lib as L
+    monkeypatch.setattr(L, '_lib', None)
+    monkeypatch.setattr(L, 'LIB_PATH', str(tmp_path / 'libsfgpi_absent.so'))
+    monkeypatch.setattr(L, 'CSRC', str(tmp_path))                     # no sources either: the build must fail
+    (tmp_path / 'dummy.cuh').write_text('')
+    with pytest.raises((RuntimeError, OSError)):
+        L.lib()
+    monkeypatch.undo()
+    importlib.reload(L)
+    assert L.lib().sfgpi_version() >= 100
+
+
+def test_netspec_adopts_reference_shaped_models_and_rejects_the_rest():
+    """utils/torch.py:19-22 shapes (Linear / ReLU / Tanh / Unflatten) are introspected; anything else is rejected."""
+    from collections import OrderedDict
+    from deep_successor_features_for_transfer_b200.library import NetSpec
+    from tests.gpu_util import model_lambda
+    model, _, _ = model_lambda([256, 256], ['relu', 'tanh'])(4, 9 * 12, (9, 12), 1)
+    spec, linears = NetSpec.from_module(model, 9, 12)
+    assert spec.dims == [4, 256, 256, 256, 108] and spec.acts == ['none', 'relu', 'tanh', 'none'] and len(linears) == 4
+    assert spec.n_params == sum(p.numel() for p in model.parameters()) == 160620      # SURVEY 8: P(Reacher) = 160 620
+    assert all(o % 4 == 0 for o in spec.w_off + spec.b_off) and spec.row_stride % 32 == 0 and spec.row_stride >= spec.n_params
+    d = spec.desc()
+    assert d.n_layers == 4 and list(d.dims)[:5] == spec.dims and d.n_actions == 9 and d.n_features == 12
+    views = spec.views(torch.arange(spec.row_stride, dtype=torch.float32))
+    assert [tuple(W.shape) for W, _ in views] == [(256, 4), (256, 256), (256, 256), (108, 256)]
+    bad = torch.nn.Sequential(OrderedDict(a=torch.nn.Linear(4, 8), b=torch.nn.Sigmoid(), c=torch.nn.Linear(8, 108)))
+    with pytest.raises(TypeError, match='unsupported layer'):
+        NetSpec.from_module(bad, 9, 12)
+    with pytest.raises(ValueError, match='n_actions \\* n_features'):
+        NetSpec.from_module(model, 9, 13)
+    with pytest.raises(ValueError, match='linear'):
+        NetSpec.from_module(torch.nn.Sequential(torch.nn.Linear(4, 108), torch.nn.ReLU()), 9, 12)
+    with pytest.raises(ValueError, match='bias'):
+        NetSpec.from_module(torch.nn.Sequential(torch.nn.Linear(4, 108, bias=False)), 9, 12)
