@@ -184,7 +184,6 @@ def test_no_cpu_fallback_constructors_raise_without_cuda():
 
 def test_missing_native_library_fails_loudly(tmp_path, monkeypatch):
     """No libsfgpi.so and no way to build it -> RuntimeError / OSError from _lib.lib(), never a silent fallback."""
-    import importlib
     import deep_successor_features_for_transfer_b200._lib as L
     monkeypatch.setattr(L, '_lib', None)
     monkeypatch.setattr(L, 'LIB_PATH', str(tmp_path / 'libsfgpi_absent.so'))
@@ -192,8 +191,7 @@ def test_missing_native_library_fails_loudly(tmp_path, monkeypatch):
     (tmp_path / 'dummy.cuh').write_text('')
     with pytest.raises((RuntimeError, OSError)):
         L.lib()
-    monkeypatch.undo()
-    importlib.reload(L)
+    monkeypatch.undo()                                                # (restores the loaded handle and the real paths)
     assert L.lib().sfgpi_version() >= 100
 
 
