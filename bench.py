@@ -232,6 +232,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='tsfdqn_reacher_b4096')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpi-eval', action='store_true', help='skip the secondary M2 measurement (quick A/B runs)')
     ap.add_argument('--l2', default='flush', choices=['flush', 'inputs'],
                     help='flush: 256 MiB write between timed steps (everything cold, weights included); inputs: cycle through '
                          'more distinct resident batches than fit in L2 (inputs cold, weights stay L2-resident)')
@@ -369,7 +370,7 @@ def main():
     # policies, packed (value, index) keys MAX-all-reduced across ranks (NCCL).  CUDA events, max over ranks.
     gpi_eval = None
     try:
-        gpi_eval = time_gpi_eval(world, rank, dev, args.precision, barrier)
+        gpi_eval = {'skipped': '--no-gpi-eval'} if args.no_gpi_eval else time_gpi_eval(world, rank, dev, args.precision, barrier)
     except Exception as e:                                          # the headline line must not depend on the secondary metric
         gpi_eval = {'error': f'{type(e).__name__}: {e}'}
 

@@ -344,7 +344,8 @@ class PackedSFLibrary:
                 ws['dzo16'], ws['xo16'] = bf(n_pol, B, adp), bf(B, 64)
                 ws['masks'] = torch.zeros(L - 1, n_pol, B, 8, dtype=torch.int32, device=self.device)   # ReLU sign bits
                 items = (sp.dims[-1] + 127) // 128 + 2 * (L - 1)
-                n_split = _lib.lib().sfgpi_bwd_tc_splits(B, max(1, 148 // (items * n_pol)))      # one wave of CTAs
+                want = int(os.environ.get('SFGPI_WGRAD_SPLIT', '0')) or max(1, 148 // (items * n_pol))       # (env: experiment knob)
+                n_split = _lib.lib().sfgpi_bwd_tc_splits(B, want)                                # one wave of CTAs
             ws['n_split'] = n_split
             ws['grad_part'] = torch.zeros(n_pol, n_split, sp.row_stride, dtype=torch.float32, device=self.device)
             if self.G is not None:
