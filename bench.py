@@ -153,8 +153,6 @@ def workload_config(name, cfg, n_total, world, precision='fp32', l2='flush', exc
                         f'{cfg["n_local"]} policies/GPU ({n_total} total), all-task fused TD update with GPI next actions',
             'batch': cfg['B'], 'policies_total': n_total, 'policies_per_gpu': cfg['n_local'],
             'parallelism': f'policy-sharded x{world}' if world > 1 else 'single GPU',
-            'warmup_note': 'at least 1000 untimed steps are run before the timed region whatever --warmup says (clocks under load, '
-                           'identical count on every rank)',
             'l2': ('flushed between timed steps (256 MiB write), flush excluded from the per-step CUDA-event time' if l2 == 'flush'
                    else 'inputs larger than L2: >160 MB of distinct resident batches cycled, weights / optimizer state stay '
                         'L2-resident as in a real training loop'),
@@ -387,6 +385,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_t) / e2e_steps * 1e3},
+            'warmup_steps_run': n_warm,                     # >= --warmup: a fixed count on every rank, clocks settled under load
             'gpu_launches': launches,
             'roofline': roofline,
             'step_tflops_per_gpu': step_tflops,
