@@ -218,3 +218,38 @@ def test_netspec_adopts_reference_shaped_models_and_rejects_the_rest():
         NetSpec.from_module(torch.nn.Sequential(torch.nn.Linear(4, 108), torch.nn.ReLU()), 9, 12)
     with pytest.raises(ValueError, match='bias'):
         NetSpec.from_module(torch.nn.Sequential(torch.nn.Linear(4, 108, bias=False)), 9, 12)
+
+
+def test_host_side_size_helpers_of_the_abi():
+    """The pure-host helpers callers size their buffers with (no CUDA call inside): values for the reference's shapes."""
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200.library import NetSpec
+    L = _lib.lib()
+
+    def desc(S, A, D):
+        dims = [S, 256, 256, 256, A * D]
+        return NetSpec(dims, ['none', 'relu', 'relu', 'none'], A, D).desc()
+
+    reacher, hopper, cartpole = desc(4, 9, 12), desc(11, 27, 50), desc(4, 2, 20)
+    # bf16 shadow rows per policy: 3 x 256 (input + 2 hidden) + A*D padded to 16
+    assert L.sfgpi_bf16_rows_per_policy(C.byref(reacher)) == 768 + 112
+    assert L.sfgpi_bf16_rows_per_policy(C.byref(hopper)) == 768 + 1360
+    assert L.sfgpi_bf16_rows_per_policy(C.byref(cartpole)) == 768 + 48
+    # folded GPI rows: reward vectors in blocks of WB = 8 (4 for 4..7, 1 below), n_w padded to WB, x A, padded to 16
+    fold = lambda d, nw: L.sfgpi_gpi_fold_rows(C.byref(d), nw)
+    assert fold(reacher, 1) == 16 and fold(reacher, 3) == 32                  # plain order: n_w * 9 -> 16
+    assert fold(reacher, 4) == 48 and fold(reacher, 5) == 80                  # WB = 4: 36 -> 48; 5 -> 8 vectors: 72 -> 80
+    assert fold(reacher, 8) == 80 and fold(reacher, 32) == 288 and fold(reacher, 256) == 2304
+    assert fold(hopper, 1) == 32 and fold(hopper, 10) == 432                 # 27 -> 32; 10 -> 16 vectors x 27
+    for nw in range(1, 70):                                                   # never fewer rows than real (vector, action) pairs
+        assert fold(reacher, nw) >= nw * 9 and fold(reacher, nw) % 16 == 0
+    # TD partials: one per 8-CTA cluster of 32-row CTAs; phi-head partials: one per 256 rows
+    assert [L.sfgpi_td_partials(b) for b in (0, 1, 256, 257, 4096)] == [1, 1, 1, 2, 16]
+    assert [L.sfgpi_phi_head_partials(b) for b in (1, 256, 257)] == [1, 1, 2]
+    # wgrad split-K: splits of whole 64-row groups, none empty
+    for B in (32, 1000, 4096, 4219, 65536):
+        for want in (1, 3, 5, 8, 64):
+            n = L.sfgpi_bwd_tc_splits(B, want)
+            bs = (((B + want - 1) // want) + 63) // 64 * 64
+            assert 1 <= n <= want and (n - 1) * bs < B <= n * bs and L.sfgpi_bwd_tc_splits(B, n) == n
+    assert L.sfgpi_bwd_tc_out_pad(C.byref(reacher)) >= 108 and L.sfgpi_bwd_tc_out_pad(C.byref(reacher)) % 64 == 0
