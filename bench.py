@@ -394,7 +394,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             cval, cper = time_cpu(cfg, n_total, 10 if n_total <= 8 else 1, 2 if n_total <= 8 else 0, cores)
-            out['cpu_baseline'] = {'value': cval, 'unit': 'updates/s', 'cores': cores, 'kind': 'port',
+            try:                                                    # "also a 1-thread number" (3 steps)
+                c1, _ = time_cpu(cfg, n_total, 3 if n_total <= 8 else 1, 1 if n_total <= 8 else 0, 1)
+            except Exception:
+                c1 = None
+            out['cpu_baseline'] = {'value': cval, 'unit': 'updates/s', 'cores': cores, 'kind': 'port', 'value_1_thread': c1,
                                    'sample': f'10 all-task steps ({n_total} update_successor calls each), B={B}, '
                                              f'{cper * 1e3:.1f} ms/step, oracle port on torch CPU fp32'}
         print(json.dumps(out))
