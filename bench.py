@@ -395,7 +395,7 @@ def main():
             cores = os.cpu_count() or 1
             cval, cper = time_cpu(cfg, n_total, 10 if n_total <= 8 else 1, 2 if n_total <= 8 else 0, cores)
             try:                                                    # "also a 1-thread number" (3 steps)
-                c1, _ = time_cpu(cfg, n_total, 3 if n_total <= 8 else 1, 1 if n_total <= 8 else 0, 1)
+                c1 = time_cpu(cfg, n_total, 3, 1, 1)[0] if n_total <= 8 else None      # (large ensembles: minutes at one thread)
             except Exception:
                 c1 = None
             out['cpu_baseline'] = {'value': cval, 'unit': 'updates/s', 'cores': cores, 'kind': 'port', 'value_1_thread': c1,
