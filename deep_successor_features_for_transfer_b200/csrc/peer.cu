@@ -24,7 +24,13 @@ __global__ void __launch_bounds__(256) peer_reduce_keys_kernel(const __grid_cons
     const int64_t n = (int64_t)a.n_rows * a.B, off = (int64_t)a.row_lo * a.B;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i >= n) return;
-    if (i + 1 < n && ((off + i) & 1) == 0) {
+    // 128-bit pulls need every rank's element address 16-byte aligned: the element parity AND the arena base (an odd
+    // n_total * B leaves the odd-epoch half of an unpadded arena only 8-byte aligned)
+    bool vec = i + 1 < n;
+#pragma unroll
+    for (int r = 0; r < SFGPI_MAX_PEERS; ++r)
+        if (r < a.ctx.world) vec = vec && ((reinterpret_cast<uintptr_t>(reinterpret_cast<const long long *>(a.keys_all[r]) + off + i) & 15) == 0);
+    if (vec) {
         longlong2 v[SFGPI_MAX_PEERS];
 #pragma unroll
         for (int r = 0; r < SFGPI_MAX_PEERS; ++r)

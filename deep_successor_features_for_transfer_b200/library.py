@@ -141,9 +141,11 @@ class PackedSFLibrary:
 
     def set_precision(self, precision):
         """
-        'fp32': CUDA-core kernels, 1e-5 parity with the reference.  'bf16': the ensemble MLP forwards (GPI, online, target)
-        run on the tcgen05 tensor cores with bf16 operands / fp32 accumulation (stated tolerance 2e-2 on psi / q); the
-        backward pass, TD and Adam stay fp32 on fp32 master weights.
+        'fp32': CUDA-core FFMA kernels, 1e-5 parity with the reference.
+        'bf16': every psi GEMM of the step -- the three forwards (online, GPI, target) AND the backward pass (dgrad chain,
+        split-K wgrad) -- runs on the tcgen05 tensor cores with bf16 operands (states, weights, stored activations, dZ) and
+        fp32 accumulation in TMEM; master weights, TD target / losses, g / h gradients and Adam stay fp32.  Stated tolerance:
+        2e-2 scale-relative on psi / q, losses 3e-2, K-step weight / moment bounds in tests/test_gpu_bf16.py.
         """
         if precision not in ('fp32', 'bf16'):
             raise ValueError("precision must be 'fp32' or 'bf16'")
@@ -199,8 +201,13 @@ class PackedSFLibrary:
         """Declare this library one policy shard of a multi-GPU ensemble (call on every rank after the tasks were added)."""
         from .dist import ShardContext
         self.shard = ShardContext(self.n, group)
-        self._ws = {k: v for k, v in self._ws.items() if not (isinstance(k, tuple) and k and k[0] == 'plan')}
+        self._drop_plans()
         self._xchg = None
+        if getattr(self, '_peer', None) is not None:         # re-sharding: no peer may still be pulling from the old arenas
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)
+        self._close_peer()
         if self.shard.world > 1:
             D, sh = self.spec.n_features, self.shard
             nh = self.h.numel() if self.h is not None else 0
@@ -209,7 +216,6 @@ class PackedSFLibrary:
                 x.update(local=self._f(self.n * D + nh), all=self._f(sh.world, self.n * D + nh),
                          h_prev=self.h.clone() if nh else None)
             self._xchg = x
-            self._peer = None
             import torch.distributed as dist
             from . import peer as _peer
             if sh.uniform and sh.world <= _lib.MAX_PEERS and dist.get_backend(group) == 'nccl' and _peer_mode_ok(_peer):
@@ -305,10 +311,30 @@ class PackedSFLibrary:
         self._views.append(mods)
         self._point_views(i, mods)
         self.n += 1
+        # cached train-step plans hard-code the policy count (GPI range, pack range, 'all' = n policies): drop them
+        self._drop_plans()
         self.invalidate_exchange()
         return i
 
+    def _drop_plans(self):
+        self._ws = {k: v for k, v in self._ws.items() if not (isinstance(k, tuple) and k and k[0] == 'plan')}
+
+    def _close_peer(self):
+        """Unmap / free the peer arenas (collective-free: every rank just releases its own mappings and allocation)."""
+        pa, self._peer = getattr(self, '_peer', None), None
+        if pa is not None:
+            torch.cuda.synchronize(self.device)              # no kernel of this rank may still touch a mapping
+            for arena in [pa['base']] + list(pa['keys'].values()):
+                arena.close()
+
+    def __del__(self):
+        try:
+            self._close_peer()
+        except Exception:
+            pass
+
     def reset(self):
+        self._close_peer()
         self.spec, self.n, self.cap, self._views, self._ws, self.h = None, 0, 0, [], {}, None
         self._adam_par = []
         for k in ('online', 'target', 'm', 'v', 'w', 'w_m', 'w_v', 'step', 'adam_consts', 'adam_consts2', 'g', 'g_m', 'g_v', 'h_m', 'h_v'):
@@ -413,6 +439,28 @@ class PackedSFLibrary:
             allreduce_max_keys(keys, self.shard.group)          # packed (value,index) MAX over NVLink: global GPI
         return q, keys[0], keys[1]
 
+    def gpi_select(self, x, w_vec, lo=0, n_pol=None):
+        """
+        Caller-side selection of the agents (sfdqn.py:585-594, tsfdqn.py:529-535) straight from the packed keys the fused GPI
+        kernel produces: returns an int64 device tensor [2][B], row 0 = argmax_a max_j q (the greedy action), row 1 =
+        argmax_j max_a q (the policy active in GPI, global index) -- no q[B,N,A] tensor, no eager indexing / argmax launches.
+        With (lo, n_pol) = (i, 1) row 0 is argmax_a q_i: the `use_gpi=False` selection, at the cost of ONE net instead of N.
+        Tie clause: the reference takes the first maximal task and then the first maximal action of THAT task's row; the key
+        takes the smallest action among all cells holding the maximum -- they differ only under exact fp32 ties across policies.
+        The result lives in a per-batch-size workspace and is valid until the next gpi_select call of the same size.
+        """
+        x = self._check_x(x)
+        n_pol = self.n - lo if n_pol is None else n_pol
+        B = x.shape[0]
+        ws = self._ws.get(('select', B))
+        if ws is None:
+            ws = self._ws[('select', B)] = (torch.empty(2, B, dtype=torch.int64, device=self.device),
+                                            torch.empty(2, B, dtype=torch.int64, device=self.device))
+        keys, idx = ws
+        self.gpi(x, w_vec, lo, n_pol, want_q=False, keys_out=keys)
+        _lib.call('sfgpi_keys_decode', ptr(keys), 2 * B, ptr(idx), None, _stream())
+        return idx
+
     def decode_keys(self, keys, want_value=False):
         idx = torch.empty(keys.shape, dtype=torch.int64, device=self.device)
         val = self._f(*keys.shape) if want_value else None
@@ -472,7 +520,7 @@ class PackedSFLibrary:
                     # peer mode: this rank's keys [nt][B] live in a mapped arena (double-buffered on epoch parity); the
                     # exchange kernel leaves the MAX over ranks of this rank's own rows in keys_own
                     from .peer import PeerArena
-                    kb = nt * B * 8
+                    kb = (nt * B * 8 + 15) // 16 * 16      # halves stay 16-byte aligned (128-bit peer loads)
                     karena = self._peer['keys'].get(B)
                     if karena is None:
                         karena = self._peer['keys'][B] = PeerArena(2 * kb, self.shard.group)

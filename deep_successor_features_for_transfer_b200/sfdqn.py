@@ -84,20 +84,45 @@ class DeviceReplayBuffer:
         f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
         self._out = (f32(B, S), torch.empty(B, dtype=torch.int64, device=dev), f32(B, 1), f32(B, D), f32(B, S), f32(B))
         self._picks = torch.empty(B, dtype=torch.int64, device=dev)
-        self._picks_host = torch.empty(B, dtype=torch.int64).pin_memory()
+        # pinned staging of the picks: a small ring, each slot guarded by the event of the copy that last read it, so a host
+        # that runs ahead of the stream (replay -> train_step loops never synchronise) cannot rewrite picks still in flight
+        self._picks_host = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(4)]
+        self._picks_done = [None] * 4
+        self._picks_slot = 0
+        self._row_host = [torch.empty(self.row, dtype=torch.float32).pin_memory() for _ in range(16)]
+        self._row_done = [None] * 16
+        self._row_slot = 0
         a = self._args = _lib.ReplayArgs()
         a.ring, a.row_stride, a.S, a.D, a.B, a.picks = self.ring.data_ptr(), self.row, S, D, B, self._picks.data_ptr()
         a.states, a.actions, a.rewards, a.phis, a.next_states, a.gammas = (t.data_ptr() for t in self._out)
 
     def append(self, state, action, reward, phi, next_state, gamma):
-        dev = _device()
-        flat = lambda v: torch.as_tensor(v, dtype=torch.float32).reshape(-1).to(dev, non_blocking=True)
-        s, s1, p = flat(state), flat(next_state), flat(phi)
-        if self.ring is None:
-            self._alloc(s.numel(), p.numel())
-        if int(torch.as_tensor(action).reshape(-1)[0]) >= (1 << 24):
-            raise ValueError('action index too large for the packed fp32 row')
-        self.ring[self.index].copy_(torch.cat([s, s1, p, flat(reward), flat(gamma), flat(action)]))
+        """
+        One transition -> one packed fp32 row of the ring.  Host-resident fields (what the environments hand over) are
+        assembled into a pinned staging row and leave with ONE asynchronous copy: no device sync, no per-field launches
+        (the reference stores python tuples, sfdqn.py:86-89).  Device-resident fields fall back to a device-side concatenation.
+        """
+        parts = (state, next_state, phi, reward, gamma, action)
+        if any(torch.is_tensor(v) and v.is_cuda for v in parts):
+            dev = _device()
+            flat = lambda v: torch.as_tensor(v).detach().to(dev, non_blocking=True).to(torch.float32).reshape(-1)
+            row = torch.cat([flat(v) for v in parts])
+            if self.ring is None:
+                self._alloc(flat(state).numel(), flat(phi).numel())
+            self.ring[self.index].copy_(row)
+        else:
+            host = [np.asarray(v.detach() if torch.is_tensor(v) else v, dtype=np.float32).reshape(-1) for v in parts]
+            if host[5][0] >= (1 << 24):
+                raise ValueError('action index too large for the packed fp32 row')
+            if self.ring is None:
+                self._alloc(host[0].size, host[2].size)
+            k = self._row_slot = (self._row_slot + 1) % len(self._row_host)
+            if self._row_done[k] is not None:
+                self._row_done[k].synchronize()              # (waits only when the host is a whole staging ring ahead)
+            np.concatenate(host, out=self._row_host[k].numpy())
+            self.ring[self.index].copy_(self._row_host[k], non_blocking=True)
+            ev = self._row_done[k] = self._row_done[k] or torch.cuda.Event()
+            ev.record()
         self.size = min(self.size + 1, self.n_samples)
         self.index = (self.index + 1) % self.n_samples
 
@@ -107,8 +132,13 @@ class DeviceReplayBuffer:
             return None
         import ctypes as C
         from . import _lib
-        self._picks_host.copy_(torch.from_numpy(np.random.randint(low=0, high=self.size, size=(self.n_batch,))))
-        self._picks.copy_(self._picks_host, non_blocking=True)
+        k = self._picks_slot = (self._picks_slot + 1) % len(self._picks_host)
+        if self._picks_done[k] is not None:
+            self._picks_done[k].synchronize()                # (only ever waits when the host is > 3 replays ahead)
+        self._picks_host[k].copy_(torch.from_numpy(np.random.randint(low=0, high=self.size, size=(self.n_batch,))))
+        self._picks.copy_(self._picks_host[k], non_blocking=True)
+        ev = self._picks_done[k] = self._picks_done[k] or torch.cuda.Event()
+        ev.record()
         _lib.call('sfgpi_replay_gather', C.byref(self._args), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return self._out
 
@@ -258,6 +288,31 @@ class DeepSF:
             self.gpi_counters[task_index][task.cpu().numpy()] += 1
         return q, task
 
+    def greedy_action(self, state, task_index, use_gpi=True, agent=None):
+        """
+        The action-selection call of next_sample (sfdqn.py:585-594 / tsfdqn.py:529-535, 420-433) in one fused pass: GPI under
+        fit_w[task_index], c = argmax_j max_a q (counted in gpi_counters when use_gpi, as GPI(update_counters=True) does),
+        a = argmax_a q[0, c, :].  use_gpi=False: c = task_index and only that policy's net runs.  One device->host read of
+        (a, c) -- the same single sync the reference pays at `int(action)` (tasks/reacher.py:46).  Returns a 0-dim int64 tensor.
+        """
+        lib = self._library
+        w = self.fit_w[task_index]
+        w_vec = w.weight if isinstance(w, torch.nn.Module) else w
+        if use_gpi:
+            idx = lib.gpi_select(state, w_vec)
+        else:
+            idx = lib.gpi_select(state, w_vec, task_index, 1)
+        if idx.shape[1] != 1:
+            raise ValueError('greedy_action selects for ONE state (the agents act at batch 1)')
+        a, c = (int(v) for v in idx[:, 0].tolist())
+        if not use_gpi:
+            c = task_index
+        else:
+            self.gpi_counters[task_index][c] += 1
+        if agent is not None:
+            agent.c = c
+        return torch.tensor(a)
+
     # ---- train step ---------------------------------------------------------------------------------------------------
     def _after_update(self, policy_index):
         self.updates_since_target_updated[policy_index] += 1
@@ -346,14 +401,17 @@ class SFDQN:
             self.logger.log_losses(total_loss.item(), psi_loss.item(), phi_loss.item(), [1], self.total_training_steps)
 
     def _greedy_action(self):
-        with torch.no_grad():
-            q, c = self.sf.GPI(self.s_enc, self.task_index, update_counters=self.use_gpi)
-            if not self.use_gpi:
-                c = self.task_index
-            self.c = c
-            q = q[:, c, :].flatten()
-            assert q.size()[0] == self.n_actions
-            return torch.argmax(q)
+        """sfdqn.py:585-594: a = argmax_a q[0, c, :], c = the GPI task (use_gpi) or the active task -- read off the packed keys."""
+        return self.sf.greedy_action(self.s_enc, self.task_index, self.use_gpi, agent=self)
+
+    def _choose_action(self):
+        """epsilon-greedy of sfdqn.py:578-597: the GPI forward runs (and the GPI counters move) only on greedy steps."""
+        if random.random() <= self.epsilon:
+            a = torch.tensor(random.randrange(self.n_actions))
+        else:
+            a = self._greedy_action()
+        self.epsilon = max(self.epsilon * self.epsilon_decay, self.epsilon_min)
+        return a
 
     def next_sample(self, viewer=None, n_view_ev=None):
         if self.new_episode:
@@ -366,11 +424,7 @@ class SFDQN:
             self.reward_since_last_episode = 0.
             if self.episode > 1:
                 self.episode_reward_hist.append(self.episode_reward)
-        if random.random() <= self.epsilon:
-            a = torch.tensor(random.randrange(self.n_actions)).to(self.device)
-        else:
-            a = self._greedy_action()
-        self.epsilon = max(self.epsilon * self.epsilon_decay, self.epsilon_min)
+        a = self._choose_action()
         s1, r, terminal = self.active_task.transition(a)
         s1_enc = self.encoding(s1)
         gamma = 0. if terminal else self.gamma

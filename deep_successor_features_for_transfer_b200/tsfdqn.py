@@ -104,10 +104,19 @@ class TSFDQN(SFDQN):
             self.c = c
             return q[:, c, :]
 
-    def _greedy_action(self):
-        q = self.get_Q_values(self.s, self.s_enc).flatten()
-        assert q.size()[0] == self.n_actions
-        return torch.argmax(q)
+
+    def _choose_action(self):
+        """
+        tsfdqn.py:453-457 + 416-432: unlike SFDQN.next_sample the TSF agent evaluates GPI on EVERY step (so gpi_counters move on
+        exploratory steps too) and only then draws the epsilon-greedy coin.
+        """
+        greedy = self._greedy_action()
+        if random.random() <= self.epsilon:
+            a = torch.tensor(random.randrange(self.n_actions))
+        else:
+            a = greedy
+        self.epsilon = max(self.epsilon * self.epsilon_decay, self.epsilon_min)
+        return a
 
     # ---- the TSF train step -------------------------------------------------------------------------------------------
     def train_agent(self, s, s_enc, a, r, s1, s1_enc, gamma):

@@ -46,6 +46,62 @@ def mlp_forward(layers, acts, x):
     return h
 
 
+# ---- reduced-precision emulation of the tensor-core modes (checker for the bf16 / tf32 kernels, not a reference function) ----
+# The tcgen05 kernels round every GEMM OPERAND (states, weights, stored activations, dZ) to bf16 (or tf32) and accumulate in
+# fp32.  mlp_forward_emul restates exactly that on the CPU so that the tensor-core modes can be checked at a tight bound
+# against an oracle with the SAME rounding points (what remains is summation order and rounding-boundary flips), in addition to
+# the stated mode tolerance against the fp32 oracle.
+def _round_bf16(t):
+    return t.bfloat16().float()
+
+
+def _round_tf32(t):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) onto 10 explicit mantissa bits."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+ROUNDERS = {'bf16': _round_bf16, 'tf32': _round_tf32}
+
+
+class _RoundOperand(torch.autograd.Function):
+    """forward: the value the tensor core consumes; backward: identity (the fp32 master copy receives the gradient)."""
+
+    @staticmethod
+    def forward(ctx, t, mode):
+        return ROUNDERS[mode](t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class _RoundGrad(torch.autograd.Function):
+    """forward: identity; backward: rounds the gradient (dZ is an MMA operand of both the dgrad chain and wgrad)."""
+
+    @staticmethod
+    def forward(ctx, t, mode):
+        ctx.mode = mode
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ROUNDERS[ctx.mode](g), None
+
+
+def mlp_forward_emul(layers, acts, x, mode, upto=None):
+    """mlp_forward with the tensor-core kernels' rounding points; upto = L-1 stops before the output layer (returns its input)."""
+    h = _RoundOperand.apply(x, mode)
+    for l, ((W, b), a) in enumerate(zip(layers, acts)):
+        if upto is not None and l == upto:
+            return h
+        z = _RoundGrad.apply(torch.addmm(b, h, _RoundOperand.apply(W, mode).t()), mode)
+        h = act_fn(a)(z)
+        if l + 1 < len(layers):
+            h = _RoundOperand.apply(h, mode)
+    return h
+
+
 def make_acts(n_hidden_layers, activations):
     """Activation pattern produced by sf_model_lambda: none after layer_input, act_k after layer_k, none after output."""
     return ['none'] + list(activations)[:n_hidden_layers] + ['none']
@@ -97,8 +153,9 @@ class OracleSF:
     """
 
     def __init__(self, S, A, D, hidden=(256, 256), activations=('relu', 'relu'), lr=None, wd=None, tsf_dim=None, beta=1,
-                 target_update_ev=1000):
+                 target_update_ev=1000, emulate=None):
         self.S, self.A, self.D = S, A, D
+        self.emulate = emulate          # None: the reference's fp32 arithmetic; 'bf16' / 'tf32': tensor-core rounding points
         self.hidden, self.activations = tuple(hidden), tuple(activations)
         self.acts = make_acts(len(hidden), activations)
         self.dims = [S, hidden[0]] + list(hidden) + [A * D]      # layer l maps dims[l] -> dims[l+1]
@@ -128,6 +185,21 @@ class OracleSF:
         self.adam.append({'step': 0, 'm': None, 'v': None})
         self.updates_since_target_updated.append(0)
 
+    def to(self, device):
+        """Moves every tensor of the library to `device` (bench.py's eager-GPU comparator runs this same op sequence on cuda:0)."""
+        mv = lambda t: t.to(device)
+        self.psi = [[(mv(W), mv(b)) for W, b in layers] for layers in self.psi]
+        self.tgt = [[(mv(W), mv(b)) for W, b in layers] for layers in self.tgt]
+        self.w = [mv(w) for w in self.w]
+        self.g = [g_unflat(g, [mv(t) for t in g_flat(g)]) for g in self.g]
+        if self.h is not None:
+            self.h = tuple(mv(t) for t in self.h)
+        for st in self.adam:
+            for k in ('m', 'v'):
+                if st[k] is not None:
+                    st[k] = {key: [mv(t) for t in ts] for key, ts in st[k].items()}
+        return self
+
     def add_random_policy(self, gen):
         layers = [init_linear(self.dims[l + 1], self.dims[l], gen) for l in range(len(self.dims) - 1)]
         w = (torch.rand(1, self.D, generator=gen) * 0.02 - 0.01)           # U(-0.01, 0.01), sfdqn.py:197
@@ -138,23 +210,47 @@ class OracleSF:
                 h = init_linear(self.D, self.tsf_dim, gen)                # tsfdqn.py:548-560
         self.add_policy(layers, w, g, h)
 
+    def _mlp(self, layers, x):
+        if self.emulate is None:
+            return mlp_forward(layers, self.acts, x)
+        return mlp_forward_emul(layers, self.acts, x, self.emulate)
+
     # ---------------- A2 / A3: forwards ----------------
     def get_successor(self, x, i):                                        # sfdqn.py:290-293
-        return mlp_forward(self.psi[i], self.acts, x).reshape(-1, self.A, self.D)
+        return self._mlp(self.psi[i], x).reshape(-1, self.A, self.D)
 
     def get_successors(self, x):                                          # sfdqn.py:295-301
         return torch.stack([self.get_successor(x, i) for i in range(self.n_tasks)], dim=1)
 
     def get_next_successor(self, x, i):                                   # tsfdqn.py:296-299 (target nets)
-        return mlp_forward(self.tgt[i], self.acts, x).reshape(-1, self.A, self.D)
+        return self._mlp(self.tgt[i], x).reshape(-1, self.A, self.D)
 
     def get_next_successors(self, x):                                     # tsfdqn.py:301-307
         return torch.stack([self.get_next_successor(x, i) for i in range(self.n_tasks)], dim=1)
 
     # ---------------- A4 / A5: GPI ----------------
     def GPI_w(self, x, w):                                                # sfdqn.py:215-240
+        if self.emulate is not None:
+            return self._gpi_w_folded(x, w)
         psi = self.get_successors(x)                                      # [B,N,A,D]
         q = torch.nn.functional.linear(psi, w.reshape(1, self.D))[:, :, :, 0]
+        task = torch.squeeze(torch.argmax(torch.max(q, dim=2).values, dim=1))
+        return q, task
+
+    def _gpi_w_folded(self, x, w, policies=None):
+        """
+        Emulation of the kernels' GPI form: w is folded into the output layer in fp32, Wq[a,:] = sum_d w[d] W_out[a*D+d,:]
+        (bq likewise), Wq is rounded to the operand type and q = round(h_last) . Wq + bq -- psi is never formed.
+        """
+        qs = []
+        L = len(self.acts)
+        for layers in (self.psi if policies is None else [self.psi[j] for j in policies]):
+            h = mlp_forward_emul(layers, self.acts, x, self.emulate, upto=L - 1)
+            Wo, bo = layers[-1]
+            Wq = torch.einsum('d,adk->ak', w.reshape(-1), Wo.reshape(self.A, self.D, -1))
+            bq = bo.reshape(self.A, self.D) @ w.reshape(-1)
+            qs.append(torch.addmm(bq, h, ROUNDERS[self.emulate](Wq).t()))
+        q = torch.stack(qs, dim=1)
         task = torch.squeeze(torch.argmax(torch.max(q, dim=2).values, dim=1))
         return q, task
 
@@ -165,6 +261,8 @@ class OracleSF:
         if use_gpi:
             q1, _ = self.GPI(next_states, i)
             return torch.argmax(torch.max(q1, dim=1).values, dim=-1)
+        if self.emulate is not None:                                      # the kernels' folded form, own policy only
+            return torch.argmax(self._gpi_w_folded(next_states, self.w[i], [i])[0][:, 0, :], dim=-1)
         sf = self.get_successor(next_states, i)
         q1 = torch.nn.functional.linear(sf, self.w[i])                    # [B,A,1]
         return torch.squeeze(torch.argmax(q1, dim=1), dim=1)
@@ -223,7 +321,7 @@ class OracleSF:
         leaves = [t.detach().requires_grad_(True) for t in flat]
         layers = [(leaves[2 * l], leaves[2 * l + 1]) for l in range(len(self.psi[i]))]
         w_leaf = self.w[i].detach().requires_grad_(True)
-        cur = mlp_forward(layers, self.acts, states).reshape(B, self.A, self.D)
+        cur = self._mlp(layers, states).reshape(B, self.A, self.D)
         merge = cur.clone()
         merge[idx, actions, :] = targets
         l1 = torch.nn.functional.mse_loss(cur, merge)
@@ -264,7 +362,7 @@ class OracleSF:
         g_leaf = [t.detach().requires_grad_(True) for t in g_flat(self.g[i])]
         h_leaf = [t.detach().requires_grad_(True) for t in self.h]
         lin = torch.nn.functional.linear
-        cur = mlp_forward(layers, self.acts, states).reshape(B, self.A, self.D)
+        cur = self._mlp(layers, states).reshape(B, self.A, self.D)
         g_fn = g_unflat(self.g[i], g_leaf)                                  # Linear (tsfdqn.py) or flow chain (tsfdqn_nf.py:653-654)
         ts, ts1 = g_apply(states, g_fn), g_apply(next_states, g_fn)         # :621-622
         aff = lin(ts, *h_leaf) + lin(ts1, *h_leaf)                          # :623

@@ -5,51 +5,9 @@ import torch
 
 from tests.golden_util import n_layers, t
 
-ACTS = {'relu': torch.nn.ReLU, 'tanh': torch.nn.Tanh}
-
-HYPER = {"learning_rate_sf": 1e-3, "learning_rate_w": 1e-3, "learning_rate_g": 1e-3, "learning_rate_h": 1e-3,
-         "weight_decay_sf": 0, "weight_decay_w": 0, "weight_decay_g": 0, "weight_decay_h": 0,
-         "g_h_function_dims": 100, "beta_loss_coefficient": 1}
-
-
-class FakeTask:
-    """Task protocol consumed by the SF library (tasks/task.py): shapes only."""
-
-    def __init__(self, S, A, D, index=0):
-        self.S, self.A, self.D, self.index = S, A, D, index
-
-    def action_count(self):
-        return self.A
-
-    def feature_dim(self):
-        return self.D
-
-    def encode_dim(self):
-        return self.S
-
-    def get_w(self):
-        w = torch.zeros(self.D, 1)
-        w[self.index % self.D, 0] = 1.0
-        return w
-
-    def features(self, s, a, s1):
-        return torch.zeros(self.D)
-
-
-def model_lambda(hidden, acts):
-    """Same shape contract as the mains' sf_model_lambda (main_tsfdqn_sequential_torch.py:44-75)."""
-
-    def handle(num_inputs, output_dim, reshape_dim, reshape_axis=1):
-        layers = OrderedDict()
-        layers['layer_input'] = torch.nn.Linear(num_inputs, hidden[0])
-        for k, (n, a) in enumerate(zip(hidden, acts)):
-            layers[f'layer_{k}'] = torch.nn.Linear(n, n)
-            layers[f'activation_layer_{k}'] = ACTS[a]()
-        layers['layer_output'] = torch.nn.Linear(hidden[-1], output_dim)
-        layers['layer_unflatten'] = torch.nn.Unflatten(reshape_axis, reshape_dim)
-        return torch.nn.Sequential(layers), torch.nn.MSELoss(), None
-
-    return handle
+from deep_successor_features_for_transfer_b200.workloads import ACTS, HYPER, ShapeTask as FakeTask, model_lambda  # noqa: F401,E402
+# (the shapes-only task, the mains' MLP factory and the cfg hyper-parameters live in the package: bench.py's measured arm uses
+# them too and must not import test helpers)
 
 
 def linears(m):

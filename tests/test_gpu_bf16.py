@@ -321,3 +321,204 @@ def test_multi_vector_gpi_keys_equal_single_vector_runs(S, A, D, N, B, nws):
         # and the keys are the argmax of that q (vector 0), first-index ties
         assert torch.equal(lib.decode_keys(ka[0]), torch.argmax(q.max(dim=1).values, dim=-1))
         assert torch.equal(lib.decode_keys(kt[0]) - 7, torch.argmax(q.max(dim=2).values, dim=1))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# K-step parity of the tensor-core TRAIN STEP (the path every BENCH / SCALE number comes from): post-step weights, Adam
+# moments and losses of the all-task step after K = 1 and K = 10 steps, against
+#   (a) the oracle with the kernels' own rounding points (oracle/sf_oracle.py: emulate='bf16' -- operands of every GEMM,
+#       forward and backward, rounded to bf16, fp32 accumulation).  What is left is summation order plus the occasional value
+#       that lands on the other side of a bf16 rounding boundary: bound EMUL_*;
+#   (b) the reference's fp32 arithmetic: the mode's stated tolerance, bound FP32_*.
+# Metrics: relative Frobenius error of the Adam first moment m (after one step m = 0.1 g: the gradient itself), of sqrt(v), and
+# of the weight UPDATE W_K - W_0 (Adam's first steps move every weight by ~lr * sign(g), so a flipped sign of a noise-level
+# gradient element is a full 2*lr error in that element: the update error is ~2 sqrt(fraction of flipped signs) and is the
+# loosest of the three by construction).  The bounds are ~3x the values measured on B200 (profiles/r02_bf16_drift.md).
+# ------------------------------------------------------------------------------------------------------------------------
+EMUL_M, EMUL_V, EMUL_DW, EMUL_LOSS = 5e-3, 5e-3, 8e-2, 2e-3
+FP32_M, FP32_V, FP32_DW, FP32_LOSS = 8e-2, 8e-2, 3e-1, 3e-2
+
+
+def _adam_views(lib, i):
+    sp = lib.spec
+    return sp.views(lib.m[i].cpu()), sp.views(lib.v[i].cpu())
+
+
+def kstep_metrics(variant, N, K, B=4096, seed=51, precision='bf16'):
+    """Runs K all-task steps on the CUDA path and on both oracles from identical weights / batches; returns worst-case metrics."""
+    S, A, D = 4, 9, 12
+    tsf = variant == 'g3'
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True)
+    o32, gen = make(S, A, D, N, seed=seed, tsf_dim=100 if tsf else None)
+    oem, _ = make(S, A, D, N, seed=seed, tsf_dim=100 if tsf else None)
+    oem.emulate = 'bf16' if precision == 'bf16' else ('tf32' if precision == 'tf32' else None)
+    if tsf:
+        sf, ag = gu.build_g3(meta, oracle=o32)
+        sf._library.set_precision(precision)
+    else:
+        sf = ag = gu.build_g2(meta, oracle=o32, hyper=dict(gu.HYPER, precision=precision))
+    lib = sf._library
+    W0 = [[W.clone() for W, _ in o32.psi[i]] for i in range(N)]
+    out = dict(emul=dict(m=0.0, v=0.0, dw=0.0, loss=0.0, w=0.0, g=0.0, h=0.0), fp32=dict(m=0.0, v=0.0, dw=0.0, loss=0.0, w=0.0, g=0.0, h=0.0))
+    for k in range(K):
+        tr = synthetic_transitions(B, S, A, D, gen)
+        got = ag.update_successor_all(gu.cuda_tr(tr), use_gpi=True).cpu()
+        for name, o in (('emul', oem), ('fp32', o32)):
+            ref = o.ensemble_update_frozen(tr, tsf=tsf, use_gpi=True)
+            for i in range(N):
+                r = torch.stack([torch.as_tensor(float(x)) for x in ref[i]])
+                out[name]['loss'] = max(out[name]['loss'], float(((got[i] - r).abs() / r.abs().clamp_min(1e-12)).max()))
+    for name, o in (('emul', oem), ('fp32', o32)):
+        for i in range(N):
+            ms, vs = _adam_views(lib, i)
+            params = gu.psi_params(sf, i)
+            for l in range(len(params)):
+                m_ref, v_ref = o.adam[i]['m']['sf'][2 * l], o.adam[i]['v']['sf'][2 * l]
+                out[name]['m'] = max(out[name]['m'], fro_err(ms[l][0], m_ref))
+                out[name]['v'] = max(out[name]['v'], fro_err(vs[l][0].sqrt(), v_ref.sqrt()))
+                out[name]['dw'] = max(out[name]['dw'], fro_err(params[l][0] - W0[i][l], o.psi[i][l][0] - W0[i][l]))
+            fw = sf.fit_w[i].weight.data.cpu()
+            out[name]['w'] = max(out[name]['w'], rel_err(fw, o.w[i]))
+            if tsf:
+                out[name]['g'] = max(out[name]['g'], rel_err(ag.g_functions[i].weight.data.cpu(), o.g[i][0]))
+        if tsf:
+            out[name]['h'] = rel_err(ag.h_function.weight.data.cpu(), o.h[0])
+        assert [int(s) for s in lib.step[:N].cpu()] == [o.adam[i]['step'] for i in range(N)]
+    return out
+
+
+@pytest.mark.parametrize('variant,N,K', [('g2', 4, 1), ('g3', 4, 1), ('g3', 4, 10), ('g2', 3, 10)])
+def test_bf16_k_steps_weights_moments_losses(variant, N, K):
+    mt = kstep_metrics(variant, N, K)
+    e, f = mt['emul'], mt['fp32']
+    msg = f'{variant} N={N} K={K}: {mt}'
+    assert e['m'] < EMUL_M and e['v'] < EMUL_V and e['dw'] < EMUL_DW and e['loss'] < EMUL_LOSS, msg
+    assert f['m'] < FP32_M and f['v'] < FP32_V and f['dw'] < FP32_DW and f['loss'] < FP32_LOSS, msg
+    # the fp32 side-paths (reward head w, TSF g / h) see bf16 only through psi: tight against both oracles
+    assert max(e['w'], e['g'], e['h']) < 2e-3 and max(f['w'], f['g'], f['h']) < 2e-2, msg
+
+
+def test_bf16_1001_steps_cross_a_target_sync():
+    """
+    SURVEY 8c: K = 1001 single-policy TSF steps crossing the target sync at update 1000 (target_update_ev = 1000), bf16 mode
+    against the fp32 oracle on the same 16 recycled batches (B = 256, 2 policies).  Stated drift bound: every one of the 1001
+    (loss, l1, l2) triples within LOSS_DRIFT of the fp32 trajectory; after the run the target net is the online net of update
+    1000 (one further update applied to online only), the sync counter restarted.
+    """
+    LOSS_DRIFT = 5e-2
+    S, A, D, N, B, K = 4, 9, 12, 2, 256, 1001
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True, target_update_ev=1000)
+    o, gen = make(S, A, D, N, seed=61, tsf_dim=100)
+    o.target_update_ev = 1000
+    sf, ag = gu.build_g3(meta, oracle=o)
+    sf._library.set_precision('bf16')
+    batches = [synthetic_transitions(B, S, A, D, gen) for _ in range(16)]
+    dev_b = [gu.cuda_tr(b) for b in batches]
+    got, ref = [], []
+    tgt_before = gu.psi_params(sf, 1, target=True)[1][0].clone()
+    for k in range(K):
+        got.append(torch.stack(list(ag.update_successor(dev_b[k % 16], 1, True))))
+        ref.append([float(x) for x in o.tsf_update_successor(batches[k % 16], 1, True)])
+        if k == 999:
+            online_at_sync = [W.clone() for W, _ in gu.psi_params(sf, 1)]
+    got = torch.stack(got).cpu().double().numpy()
+    ref = np.array(ref)
+    drift = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-9)
+    assert drift.max() < LOSS_DRIFT, f'worst loss drift {drift.max():.3e} at step {int(drift.max(axis=1).argmax())}'
+    assert sf.updates_since_target_updated[1] == 1 and o.updates_since_target_updated[1] == 1
+    tgt = [W for W, _ in gu.psi_params(sf, 1, target=True)]
+    assert all(torch.equal(a, b) for a, b in zip(tgt, online_at_sync))          # target == online of update 1000, bit for bit
+    assert not torch.equal(tgt[1], tgt_before)
+    assert not torch.equal(tgt[1], gu.psi_params(sf, 1)[1][0])                    # ... and online has moved on since
+    assert fro_err(tgt[1], o.tgt[1][1][0]) < 0.25                                 # same place as the fp32 oracle's target (update-level bound)
+
+
+def test_bf16_gpi_256_reward_vectors_vs_oracle():
+    """
+    BASELINE config 4's GPI epilogue (n_w = 256 reward vectors, 2304 folded output columns = 9 chunks of 256, blocked column
+    order) against the ORACLE, not against itself: for every one of the 256 vectors the action key must be the oracle's
+    argmax_a max_j q (ties inside the bf16 tolerance may flip) and the key's value within BF16_TOL of the oracle's max.
+    """
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    from deep_successor_features_for_transfer_b200.library import _stream
+    S, A, D, N, B, NW = 4, 9, 12, 6, 700, 256
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=71)
+    sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+    lib = sf._library
+    x = synthetic_transitions(B, S, A, D, gen)[0]
+    w = (torch.rand(NW, D, generator=gen) * 0.02 - 0.01).contiguous()
+    lib._pack('online', 0, N)
+    ka = torch.empty(NW, B, dtype=torch.int64, device='cuda')
+    kt = torch.empty(NW, B, dtype=torch.int64, device='cuda')
+    _lib.call('sfgpi_keys_fill', ka.data_ptr(), ka.numel(), _stream())
+    _lib.call('sfgpi_keys_fill', kt.data_ptr(), kt.numel(), _stream())
+    xd, wd = x.cuda(), w.cuda()
+    a = lib._fwd_args(lib.online, 0, N, xd)
+    a.w, a.n_w, a.w_diag, a.task_base = wd.data_ptr(), NW, 0, 0
+    a.key_action, a.key_task = ka.data_ptr(), kt.data_ptr()
+    wq, bq = lib._fold(a, 'online')
+    _lib.call('sfgpi_mlp_forward_tc', C.byref(a), lib._shadow_for('online').data_ptr(), lib.cap, wq.data_ptr(), bq.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    act, val = lib.decode_keys(ka, want_value=True)
+    task = lib.decode_keys(kt)
+    psi = o.get_successors(x)                                                     # [B,N,A,D] fp32 oracle
+    q_all = torch.einsum('bnad,wd->wbna', psi, w)                                 # [NW,B,N,A]
+    scale = float(q_all.abs().max())
+    n_flip = 0
+    for wi in range(NW):
+        q = q_all[wi]
+        assert float((val[wi].cpu() - q.reshape(B, -1).max(dim=1).values).abs().max()) < BF16_TOL * scale
+        a_ref = torch.argmax(q.max(dim=1).values, dim=-1)
+        t_ref = torch.argmax(q.max(dim=2).values, dim=1)
+        ok, nb = gu.argmax_mismatch_ok(q, a_ref, act[wi].cpu(), 'action', BF16_TOL)
+        assert ok, f'vector {wi}: {nb} action mismatches outside tolerance'
+        ok2, nb2 = gu.argmax_mismatch_ok(q, t_ref, task[wi].cpu(), 'task', BF16_TOL)
+        assert ok2, f'vector {wi}: {nb2} task mismatches outside tolerance'
+        n_flip += nb
+    assert n_flip < 0.03 * NW * B                                                 # flips are confined to near-ties (SURVEY 7: ~0.5 %)
+
+
+def test_bf16_ensemble_step_32_policies_vs_frozen_oracle():
+    """The multi-vector train step at n_w = N = 32 (the 8-GPU shard's GPI width) against the frozen-snapshot oracle, B = 256."""
+    S, A, D, N, B = 4, 9, 12, 32, 256
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=30, use_gpi=True)
+    o, gen = make(S, A, D, N, seed=73, tsf_dim=100, beta=30)
+    sf, ag = gu.build_g3(meta, oracle=o)
+    sf._library.set_precision('bf16')
+    tr = synthetic_transitions(B, S, A, D, gen)
+    ref = o.ensemble_update_frozen(tr, tsf=True, use_gpi=True)
+    got = ag.update_successor_all(gu.cuda_tr(tr), use_gpi=True).cpu()
+    for i in range(N):
+        assert np.allclose(got[i].numpy(), [float(v) for v in ref[i]], rtol=3e-2, atol=1e-6), (i, got[i], ref[i])
+    assert rel_err(ag.h_function.weight.data.cpu(), o.h[0]) < 2e-2
+
+
+def test_bf16_hopper_64_policies_65536_states_spot_check_vs_oracle():
+    """
+    BASELINE config 3 at FULL size (Hopper S11/A27/D50, 64 policies, 65 536 states, bf16 mode): the fused GPI keys of 512 spot
+    states against the fp32 oracle's GPI over all 64 policies -- value within BF16_TOL, action / task equal except ties inside
+    the tolerance -- plus size-independent properties over all 65 536 states (indices in range, key value == max of q_out rows).
+    """
+    S, A, D, N, B = 11, 27, 50, 64, 65536
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=79)
+    sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+    lib = sf._library
+    x = torch.sigmoid(torch.randn(B, S, generator=gen))
+    w = sf.fit_w[5].weight.data.cpu().reshape(-1)
+    q_dev, ka, kt = lib.gpi(x.cuda(), w, want_q=True)
+    act, val = lib.decode_keys(ka, want_value=True)
+    task = lib.decode_keys(kt)
+    assert int(act.min()) >= 0 and int(act.max()) < A and int(task.min()) >= 0 and int(task.max()) < N
+    assert torch.equal(val, q_dev.reshape(B, -1).max(dim=1).values)
+    spot = torch.arange(0, B, B // 512)[:512]
+    q_ref, task_ref = o.GPI_w(x[spot], w)
+    scale = float(q_ref.abs().max())
+    assert float((val[spot.cuda()].cpu() - q_ref.reshape(512, -1).max(dim=1).values).abs().max()) < BF16_TOL * scale
+    a_ref = torch.argmax(q_ref.max(dim=1).values, dim=-1)
+    ok, nb = gu.argmax_mismatch_ok(q_ref, a_ref, act[spot.cuda()].cpu(), 'action', BF16_TOL)
+    assert ok, f'{nb} action mismatches outside tolerance'
+    ok, nb = gu.argmax_mismatch_ok(q_ref, task_ref, task[spot.cuda()].cpu(), 'task', BF16_TOL)
+    assert ok, f'{nb} task mismatches outside tolerance'
