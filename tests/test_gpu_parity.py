@@ -413,3 +413,50 @@ def test_phi_pre_train_vs_golden():
     assert np.allclose(losses, ref, rtol=2e-2, atol=1e-4)           # 149 chained Adam updates: fp32 summation-order drift
     out = model(torch.from_numpy(z['probe.s']), torch.from_numpy(z['probe.a']), torch.from_numpy(z['probe.s1']))
     assert rel_err(out.cpu(), torch.from_numpy(z['probe.phi'])) < 2e-2
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_add_policy_without_growth_drops_cached_plans(precision):
+    """
+    The reference's G1 flow adds a task, trains, adds the next (agents/agent.py train_on_task; agents/sfdqn.py:59 steps every
+    index each batch).  A library of capacity 4 grows 2 -> 3 policies WITHOUT reallocating: the cached train-step plans (GPI
+    range, pack range, 'all' = n policies) must not survive add_policy.  After the third policy arrives, the single-policy
+    step's GPI must see all 3 nets and the all-task step must train all 3 -- checked against the oracle.
+    """
+    S, A, D, hidden, B = 4, 9, 12, (256, 256), 384
+    tol_l, tol_w = (3e-5, STEP_TOL) if precision == 'fp32' else (3e-2, None)
+    meta = dict(S=S, A=A, D=D, hidden=list(hidden), acts=['relu', 'relu'], N=2)
+    o, gen = make_oracle(S, A, D, hidden, meta['acts'], 3, seed=13)
+    third = (o.psi.pop(), o.tgt.pop(), o.w.pop(), o.adam.pop(), o.updates_since_target_updated.pop())
+    sf = gu.build_g2(meta, oracle=o, hyper=dict(gu.HYPER, precision=precision))
+    assert sf._library.cap == 4
+    tr = [synthetic_transitions(B, S, A, D, gen) for _ in range(4)]
+    # plans built at n = 2
+    for k, fn in ((0, lambda b: sf.update_successor(b, 0, True)), (1, lambda b: sf.update_successor_all(b, use_gpi=True))):
+        ref = o.update_successor(tr[k], 0, True) if k == 0 else o.ensemble_update_frozen(tr[k], use_gpi=True)
+        got = fn(gu.cuda_tr(tr[k]))
+        got = [float(v) for v in got] if k == 0 else got.cpu().tolist()[0]
+        assert np.allclose(got, [float(v) for v in (ref if k == 0 else ref[0])], rtol=tol_l, atol=1e-8)
+    # third policy: no capacity growth
+    sf.add_training_task(gu.FakeTask(S, A, D, 2))
+    assert sf._library.cap == 4 and sf._library.n == 3
+    gu.load_policy(sf, 2, third[0], third[2])
+    o.psi.append(third[0]); o.tgt.append(third[1]); o.w.append(third[2]); o.adam.append(third[3]); o.updates_since_target_updated.append(third[4])
+    # make the newcomer dominate GPI so that a stale 2-policy plan would give different next actions
+    with torch.no_grad():
+        big = o.psi[2][-1][1] + 5.0 * torch.sign(o.w[0].reshape(-1)).repeat(A)
+        o.psi[2][-1] = (o.psi[2][-1][0], big)
+        gu.linears(sf.psi[2][0][0].net)[-1].bias.data.copy_(big)
+    ref = o.update_successor(tr[2], 0, True)
+    got = sf.update_successor(gu.cuda_tr(tr[2]), 0, True)
+    assert np.allclose([float(v) for v in got], [float(v) for v in ref], rtol=tol_l, atol=1e-8)
+    ref = o.ensemble_update_frozen(tr[3], use_gpi=True)
+    got = sf.update_successor_all(gu.cuda_tr(tr[3]), use_gpi=True).cpu()
+    assert got.shape[0] == 3
+    for i in range(3):
+        assert np.allclose(got[i].numpy(), [float(v) for v in ref[i]], rtol=tol_l, atol=1e-8)
+    if tol_w is not None:
+        for i in range(3):
+            for l, (W, b) in enumerate(gu.psi_params(sf, i)):
+                assert rel_err(W, o.psi[i][l][0]) < tol_w
+    assert int(sf._library.step[2]) == 1                      # the newcomer was stepped exactly once (the 'all' plan saw it)
