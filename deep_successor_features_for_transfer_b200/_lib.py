@@ -10,10 +10,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('SFGPI_LIB_PATH') or os.path.join(HERE, 'libsfgpi.so')      # (override: A/B runs of two builds)
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
+PREC = {'fp32': 0, 'bf16': 1, 'tf32': 2, 'tf32x3': 3}
 
 
 def build(force=False, verbose=False):
@@ -78,6 +79,13 @@ class BackwardTcArgs(C.Structure):
                 ('grad_part', C.c_void_p), ('n_split', C.c_int32), ('xo_ready', C.c_int32), ('expand_td', C.c_void_p)]
 
 
+class BackwardStreamArgs(C.Structure):
+    _fields_ = [('net', NetDesc), ('precision', C.c_int32), ('shadow_t', C.c_void_p), ('wout_t', C.c_void_p),
+                ('n_policies_total', C.c_int32), ('policy_lo', C.c_int32), ('n_pol', C.c_int32), ('x', C.c_void_p), ('B', C.c_int32),
+                ('acts', C.c_void_p), ('relu_masks', C.c_void_p), ('actions', C.c_void_p), ('d_out', C.c_void_p), ('dz', C.c_void_p),
+                ('dzo', C.c_void_p), ('xo', C.c_void_p), ('grad_part', C.c_void_p), ('n_split', C.c_int32)]
+
+
 class StepPrepArgs(C.Structure):
     _fields_ = [('net', NetDesc), ('pack_params', C.c_void_p * 2), ('pack_out', C.c_void_p * 2), ('pack_lo', C.c_int32 * 2),
                 ('pack_n', C.c_int32 * 2), ('keys', C.c_void_p), ('n_keys', C.c_int64), ('fold_params', C.c_void_p),
@@ -97,8 +105,10 @@ class Cmd(C.Structure):
 
 
 OP = dict(H2D=1, D2H=2, D2D=3, KEYS_FILL=4, PACK_BF16=5, FOLD_GPI=6, FORWARD=7, FORWARD_TC_JOBS=8, TD=9, BACKWARD=10,
-          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16, STEP_PREP=17, KEYS_REDUCE=18)
-OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1, 17: 1, 18: 1}
+          BACKWARD_TC=11, ADAM=12, EVENT=13, PEER_KEYS=14, SHARD_PACK=15, PEER_UNPACK=16, STEP_PREP=17, KEYS_REDUCE=18,
+          PACK_F32=19, FOLD_GPI_F32=20, FORWARD_STREAM=21, BACKWARD_STREAM=22, KEYS_DECODE=23)
+OP_LAUNCHES = {13: 0, 0: 0, 1: 0, 2: 0, 3: 0, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 2, 11: 3, 12: 2, 14: 1, 15: 1, 16: 1, 17: 1, 18: 1,
+               19: 1, 20: 1, 21: 1, 22: 3, 23: 1}
 MAX_PEERS = 16
 PEER_CHANNELS = 4
 IPC_HANDLE_BYTES = 64
@@ -155,6 +165,13 @@ SYMBOLS = {
     'sfgpi_bwd_tc_splits': (C.c_int, [C.c_int32, C.c_int32]),
     'sfgpi_mlp_backward_tc': (C.c_int, [C.POINTER(BackwardTcArgs), C.c_void_p]),
     'sfgpi_mlp_forward_tc_jobs': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    'sfgpi_f32_out_pad': (C.c_int, [C.POINTER(NetDesc)]),
+    'sfgpi_pack_f32': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    'sfgpi_fold_gpi_f32': (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_mlp_forward_stream': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    'sfgpi_mlp_backward_stream': (C.c_int, [C.POINTER(BackwardStreamArgs), C.c_void_p]),
     'sfgpi_replay_gather': (C.c_int, [C.POINTER(ReplayArgs), C.c_void_p]),
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -177,7 +194,7 @@ _lib = None
 launch_count = 0          # kernels launched through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES_PER_CALL = {'sfgpi_pack_bf16': 1, 'sfgpi_fold_gpi': 1, 'sfgpi_mlp_forward_tc': 1, 'sfgpi_mlp_forward': 1, 'sfgpi_keys_fill': 1, 'sfgpi_keys_decode': 1, 'sfgpi_gpi_from_psi': 1,
                      'sfgpi_td_step': 2, 'sfgpi_mlp_backward': 2, 'sfgpi_mlp_backward_tc': 3, 'sfgpi_adam_step': 2,
-                     'sfgpi_step_prep': 1,
+                     'sfgpi_step_prep': 1, 'sfgpi_mlp_backward_stream': 3,
     'sfgpi_peer_alloc': 0, 'sfgpi_peer_open': 0, 'sfgpi_peer_close': 0, 'sfgpi_peer_free': 0}
 
 

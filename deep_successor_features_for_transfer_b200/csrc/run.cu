@@ -61,6 +61,27 @@ extern "C" int sfgpi_run(const sfgpi_cmd *cmds, int32_t n, void *stream) {
             case SFGPI_OP_KEYS_REDUCE:
                 rc = sfgpi_keys_reduce(reinterpret_cast<const int64_t *>(c.p[0]), (int32_t)c.i[0], c.i[1], reinterpret_cast<int64_t *>(c.p[1]), stream);
                 break;
+            case SFGPI_OP_PACK_F32:
+                rc = sfgpi_pack_f32(reinterpret_cast<const sfgpi_net_desc *>(c.p[0]), reinterpret_cast<const float *>(c.p[1]), (int32_t)c.i[0],
+                                    (int32_t)c.i[1], (int32_t)c.i[2], (int32_t)c.i[3], reinterpret_cast<float *>(c.p[2]),
+                                    reinterpret_cast<float *>(c.p[3]), reinterpret_cast<float *>(c.p[4]), stream);
+                break;
+            case SFGPI_OP_FOLD_GPI_F32:
+                rc = sfgpi_fold_gpi_f32(reinterpret_cast<const sfgpi_net_desc *>(c.p[0]), reinterpret_cast<const float *>(c.p[1]), (int32_t)c.i[0],
+                                        (int32_t)c.i[1], reinterpret_cast<const float *>(c.p[2]), (int32_t)(c.i[2] & 0x7fffffff),
+                                        (int32_t)((c.i[2] >> 31) & 1), (int32_t)c.i[3], reinterpret_cast<float *>(c.p[3]),
+                                        reinterpret_cast<float *>(c.p[4]), stream);
+                break;
+            case SFGPI_OP_FORWARD_STREAM:
+                rc = sfgpi_mlp_forward_stream(reinterpret_cast<const sfgpi_forward_tc_job *>(c.p[0]), (int32_t)c.i[0], (int32_t)c.i[1], stream);
+                break;
+            case SFGPI_OP_BACKWARD_STREAM:
+                rc = sfgpi_mlp_backward_stream(reinterpret_cast<const sfgpi_backward_stream_args *>(c.p[0]), stream);
+                break;
+            case SFGPI_OP_KEYS_DECODE:
+                rc = sfgpi_keys_decode(reinterpret_cast<const int64_t *>(c.p[0]), c.i[0], reinterpret_cast<int64_t *>(c.p[1]),
+                                       reinterpret_cast<float *>(c.p[2]), stream);
+                break;
             case SFGPI_OP_PEER_KEYS:
                 rc = sfgpi_peer_reduce_keys(reinterpret_cast<const sfgpi_peer_keys_args *>(c.p[0]), stream);
                 break;

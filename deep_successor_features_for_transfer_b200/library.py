@@ -146,27 +146,55 @@ class PackedSFLibrary:
         split-K wgrad) -- runs on the tcgen05 tensor cores with bf16 operands (states, weights, stored activations, dZ) and
         fp32 accumulation in TMEM; master weights, TD target / losses, g / h gradients and Adam stay fp32.  Stated tolerance:
         2e-2 scale-relative on psi / q, losses 3e-2, K-step weight / moment bounds in tests/test_gpu_bf16.py.
+        'tf32x3': the same GEMMs on the tensor cores at the REFERENCE's precision -- tcgen05 kind::tf32 on fp32 operands split
+        into hi + lo, three passes a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, fp32 accumulation (csrc/mlp_stream_tc.cu): passes the
+        fp32 mode's 1e-5 parity suite.  'tf32': one pass (operands rounded to tf32), stated tolerance 2e-3.
         """
-        if precision not in ('fp32', 'bf16'):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ('fp32', 'bf16', 'tf32', 'tf32x3'):
+            raise ValueError("precision must be 'fp32', 'bf16', 'tf32' or 'tf32x3'")
         self.precision = precision
+        self._prec = _lib.PREC[precision]
+        self._stream = precision in ('tf32', 'tf32x3')       # kind::tf32 streaming kernels on fp32 hi (/ lo) operand shadows
+        self._parts = 2 if precision == 'tf32x3' else 1
         self._ws = {}
         self._shadow = {}
 
     def _shadow_for(self, which):
-        """bf16 shadow [cap][rows_per_policy][256] of the online / target rows, (re)allocated with the storage."""
+        """Operand shadow of the online / target rows, (re)allocated with the storage: bf16 [cap][rows][256], or for the tf32
+        modes fp32 [parts][cap][rows][256] (hi, lo)."""
         buf = self._shadow.get(which)
         if buf is None or buf[1] != self.cap:
             desc = self.spec.desc()
             rpp = _lib.lib().sfgpi_bf16_rows_per_policy(C.byref(desc))
-            buf = (torch.zeros(self.cap * rpp * 256, dtype=torch.bfloat16, device=self.device), self.cap)
+            if self._stream:
+                buf = (torch.zeros(self._parts * self.cap * rpp * 256, dtype=torch.float32, device=self.device), self.cap)
+            else:
+                buf = (torch.zeros(self.cap * rpp * 256, dtype=torch.bfloat16, device=self.device), self.cap)
             self._shadow[which] = buf
         return buf[0]
 
-    def _pack(self, which, lo, n_pol):
+    def _shadow_t(self):
+        """tf32 modes: transposed operand shadows of the ONLINE rows for the dgrad chain: (W_l^T [parts][cap][L-2][256][256],
+        W_out^T [parts][cap][256][ADp])."""
+        buf = self._shadow.get('online_t')
+        if buf is None or buf[2] != self.cap:
+            desc = self.spec.desc()
+            adp = _lib.lib().sfgpi_f32_out_pad(C.byref(desc))
+            Lh = len(self.spec.acts) - 2
+            buf = (torch.zeros(self._parts * self.cap * Lh * 256 * 256, dtype=torch.float32, device=self.device),
+                   torch.zeros(self._parts * self.cap * 256 * adp, dtype=torch.float32, device=self.device), self.cap)
+            self._shadow['online_t'] = buf
+        return buf[0], buf[1]
+
+    def _pack(self, which, lo, n_pol, transposed=False):
         desc = self.spec.desc()
-        _lib.call('sfgpi_pack_bf16', C.byref(desc), ptr(self.target if which == 'target' else self.online), lo, n_pol,
-                  ptr(self._shadow_for(which)), _stream())
+        src = self.target if which == 'target' else self.online
+        if self._stream:
+            st, wt = self._shadow_t() if transposed else (None, None)
+            _lib.call('sfgpi_pack_f32', C.byref(desc), ptr(src), lo, n_pol, self.cap, self._prec, ptr(self._shadow_for(which)),
+                      ptr(st), ptr(wt), _stream())
+        else:
+            _lib.call('sfgpi_pack_bf16', C.byref(desc), ptr(src), lo, n_pol, ptr(self._shadow_for(which)), _stream())
 
     def _fold(self, a, which):
         """GPI form of the tensor-core forward: fold the reward vectors of `a` into the output layer -> (wq, bq)."""
@@ -176,21 +204,32 @@ class PackedSFLibrary:
         key = ('fold', a.n_pol, nq)
         buf = self._ws.get(key)
         if buf is None:
-            buf = self._ws[key] = (torch.empty(a.n_pol * nq * 256, dtype=torch.bfloat16, device=self.device),
-                                   self._f(a.n_pol * nq))
+            wq = torch.empty(self._parts * a.n_pol * nq * 256, dtype=torch.float32, device=self.device) if self._stream else \
+                torch.empty(a.n_pol * nq * 256, dtype=torch.bfloat16, device=self.device)
+            buf = self._ws[key] = (wq, self._f(a.n_pol * nq))
         wq, bq = buf
-        _lib.call('sfgpi_fold_gpi', C.byref(desc), ptr(self.target if which == 'target' else self.online), a.policy_lo,
-                  a.n_pol, a.w, a.n_w, a.w_diag, ptr(wq), ptr(bq), _stream())
+        src = self.target if which == 'target' else self.online
+        if self._stream:
+            _lib.call('sfgpi_fold_gpi_f32', C.byref(desc), ptr(src), a.policy_lo, a.n_pol, a.w, a.n_w, a.w_diag, self._prec, ptr(wq),
+                      ptr(bq), _stream())
+        else:
+            _lib.call('sfgpi_fold_gpi', C.byref(desc), ptr(src), a.policy_lo, a.n_pol, a.w, a.n_w, a.w_diag, ptr(wq), ptr(bq), _stream())
         return wq, bq
 
     def _forward(self, a, which, fresh=False):
-        """Dispatch one fused forward: fp32 CUDA-core kernel or the tcgen05 kernel on the bf16 shadow (packed on demand)."""
+        """Dispatch one fused forward: fp32 CUDA-core kernel, or a tensor-core kernel on the operand shadow (packed on demand)."""
         if self.precision == 'fp32':
             _lib.call('sfgpi_mlp_forward', C.byref(a), _stream())
+            return
+        if not fresh:
+            self._pack(which, a.policy_lo, a.n_pol)
+        wq, bq = self._fold(a, which) if a.w else (None, None)     # GPI form
+        if self._stream:
+            job = _lib.ForwardTcJob()
+            job.args, job.params_bf16, job.n_policies_total = a, self._shadow_for(which).data_ptr(), self.cap
+            job.wq, job.bq = (wq.data_ptr(), bq.data_ptr()) if wq is not None else (None, None)
+            _lib.call('sfgpi_mlp_forward_stream', C.byref(job), 1, self._prec, _stream())
         else:
-            if not fresh:
-                self._pack(which, a.policy_lo, a.n_pol)
-            wq, bq = self._fold(a, which) if a.w else (None, None)     # GPI form
             _lib.call('sfgpi_mlp_forward_tc', C.byref(a), ptr(self._shadow_for(which)), self.cap, ptr(wq), ptr(bq), _stream())
 
     def _forward_jobs(self, jobs, n):
@@ -356,7 +395,18 @@ class PackedSFLibrary:
             nblk = _lib.lib().sfgpi_td_partials(B)        # one TD partial per 8-CTA cluster (256 transitions)
             ws['nblk'] = nblk
             ws['loss_part'] = self._f(n_pol, nblk, 2)
-            if self.precision == 'fp32':
+            if self._stream:
+                # tf32 modes: fp32 hi (/ lo) activations and dZ, row-major, written by TMA and read back MN-major by wgrad
+                desc = sp.desc()
+                z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
+                adp = _lib.lib().sfgpi_f32_out_pad(C.byref(desc))
+                P_ = self._parts
+                ws['acts32'], ws['dz32'] = z(P_, L - 1, n_pol, B, 256), z(P_, L - 1, n_pol, B, 256)
+                ws['dzo32'], ws['xo32'] = z(P_, n_pol, B, adp), z(P_, B, 32)
+                ws['masks'] = torch.zeros(L - 1, n_pol, B, 8, dtype=torch.int32, device=self.device)
+                items = (sp.dims[-1] + 127) // 128 + 2 * (L - 1)
+                n_split = _lib.lib().sfgpi_bwd_tc_splits(B, max(1, 148 // (items * n_pol)))
+            elif self.precision == 'fp32':
                 ws['acts'] = [self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)]
                 ws['dz'] = [self._f(n_pol, B, sp.dims[l + 1]) for l in range(L - 1)]
                 tiles = sum(((sp.dims[l + 1] + 63) // 64) * ((sp.dims[l] + 255) // 256) for l in range(L))
@@ -494,7 +544,10 @@ class PackedSFLibrary:
         # (1) online forward on s: saves hidden outputs, gathers psi(s)[a_b]            sfdqn.py:328
         a1 = self._fwd_args(self.online, lo, n_pol, None, B)
         tc = self.precision != 'fp32'
-        if tc:
+        st_mode = self._stream
+        if st_mode:
+            a1.acts_bf16_out, a1.relu_mask_out = ws['acts32'].data_ptr(), ws['masks'].data_ptr()
+        elif tc:
             a1.acts_bf16_out, a1.relu_mask_out = ws['acts16'].data_ptr(), ws['masks'].data_ptr()
         else:
             for l in range(L - 1):
@@ -516,7 +569,7 @@ class PackedSFLibrary:
                 nt = self.shard.n_total
                 w_all = self._xchg['w_all']
                 a2.w, a2.n_w, a2.w_diag, key_row0 = ptr(w_all), nt, 0, self.shard.lo
-                if getattr(self, '_peer', None) is not None:
+                if getattr(self, '_peer', None) is not None and not st_mode:
                     # peer mode: this rank's keys [nt][B] live in a mapped arena (double-buffered on epoch parity); the
                     # exchange kernel leaves the MAX over ranks of this rank's own rows in keys_own
                     from .peer import PeerArena
@@ -542,7 +595,7 @@ class PackedSFLibrary:
         # 32 policies x 256 reward vectors (33 M atomics per step: 5.48 ms forward with atomics, 5.55 ms staged), and the extra
         # launch costs ~4 us on the small configurations, so the default keeps the atomics.
         stage = None
-        if tc and use_gpi and not a2.w_diag and a2.n_w * a2.n_pol >= int(os.environ.get('SFGPI_STAGE_MIN', str(1 << 62))):
+        if tc and not st_mode and use_gpi and not a2.w_diag and a2.n_w * a2.n_pol >= int(os.environ.get('SFGPI_STAGE_MIN', str(1 << 62))):
             stage = ws.setdefault(('key_stage', a2.n_w), torch.empty(a2.n_pol, a2.n_w, B, dtype=torch.int64, device=self.device))
             a2.key_stage = stage.data_ptr()
         # (3) target forward on s', gather psi^-(s')[a*]                                sfdqn.py:330-331
@@ -570,7 +623,14 @@ class PackedSFLibrary:
         if variant == 2:
             t.tsf_part = ptr(ws['tsf_part'])
         # (5) backward through psi: dgrad chain + split-K wgrad
-        if tc:
+        if st_mode:
+            b = _lib.BackwardStreamArgs()
+            sh_t, wo_t = self._shadow_t()
+            b.net, b.precision, b.shadow_t, b.wout_t, b.n_policies_total = sp.desc(), self._prec, ptr(sh_t), ptr(wo_t), self.cap
+            b.policy_lo, b.n_pol, b.B, b.d_out = lo, n_pol, B, ptr(ws['d_out'])
+            b.acts, b.dz, b.dzo, b.xo = (ptr(ws[k]) for k in ('acts32', 'dz32', 'dzo32', 'xo32'))
+            b.relu_masks = ptr(ws['masks'])
+        elif tc:
             b = _lib.BackwardTcArgs()
             b.net, b.params_bf16, b.n_policies_total = sp.desc(), ptr(self._shadow_for('online')), self.cap
             b.policy_lo, b.n_pol, b.B, b.d_out = lo, n_pol, B, ptr(ws['d_out'])
@@ -619,7 +679,7 @@ class PackedSFLibrary:
         ad.l1_scale, ad.l2_scale = 1.0 / (B * A * D), 1.0 / B
         ad.beta_loss = (float(beta) if variant == 2 else 1.0) if variant >= 1 else 0.0
         ad.sequential_shared = 1
-        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, lo=lo, tc=tc, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
+        return dict(ws=ws, a1=a1, a2=a2, a3=a3, t=t, b=b, ad=ad, n_pol=n_pol, lo=lo, tc=tc, st=st_mode, B=B, ring=0, keys=keys, w_all=w_all, sharded=sharded,
                     peer=peer, variant=variant, stage=stage,
                     losses=torch.zeros(64, n_pol, 3, dtype=torch.float32, device=self.device))
 
@@ -835,7 +895,8 @@ class PackedSFLibrary:
         keys_ptr = keys.data_ptr() if peer is None else peer['karena'].local      # peer: patched per step (epoch parity)
         # one-launch prologue (sfgpi_step_prep) whenever nothing has to happen between the packs and the fold, i.e. always
         # except on the NCCL-collective sharded path, whose first steps gather w between them
-        merged = plan['tc'] and not (plan['sharded'] and peer is None)
+        st_mode = plan['st']
+        merged = plan['tc'] and not st_mode and not (plan['sharded'] and peer is None)
         plan['prep'] = None
         stage = plan.get('stage')
         if stage is not None:
@@ -844,7 +905,8 @@ class PackedSFLibrary:
             dref = C.addressof(plan['desc'])
             nw = 1 if a2.w_diag else a2.n_w
             nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(plan['desc']), nw)
-            plan['wq'] = torch.empty(a2.n_pol * nq * 256, dtype=torch.bfloat16, device=dev)
+            plan['wq'] = torch.empty(self._parts * a2.n_pol * nq * 256, dtype=torch.float32, device=dev) if st_mode else \
+                torch.empty(a2.n_pol * nq * 256, dtype=torch.bfloat16, device=dev)
             plan['bq'] = self._f(a2.n_pol * nq)
         if merged:
             pr = plan['prep'] = _lib.StepPrepArgs()
@@ -861,12 +923,25 @@ class PackedSFLibrary:
             b.xo_ready = 1
             cmd(seg0, 'STEP_PREP', (C.addressof(pr),))
         else:
-            if plan['tc']:
+            if st_mode:
+                sh_t, wo_t = self._shadow_t()
+                on_sh, tg_sh = self._shadow_for('online').data_ptr(), self._shadow_for('target').data_ptr()
+                if a1.n_pol == self.n:      # every policy is stepped: one pack writes the forward AND the transposed (dgrad) operands
+                    cmd(seg0, 'PACK_F32', (dref, self.online.data_ptr(), on_sh, sh_t.data_ptr(), wo_t.data_ptr()), (0, self.n, self.cap, self._prec))
+                else:                       # GPI reads all policies' forward operands, the dgrad chain only the stepped one's
+                    cmd(seg0, 'PACK_F32', (dref, self.online.data_ptr(), on_sh, 0, 0), (0, self.n, self.cap, self._prec))
+                    cmd(seg0, 'PACK_F32', (dref, self.online.data_ptr(), on_sh, sh_t.data_ptr(), wo_t.data_ptr()),
+                        (a1.policy_lo, a1.n_pol, self.cap, self._prec))
+                cmd(seg0, 'PACK_F32', (dref, self.target.data_ptr(), tg_sh, 0, 0), (a3.policy_lo, a3.n_pol, self.cap, self._prec))
+            elif plan['tc']:
                 cmd(seg0, 'PACK_BF16', (dref, self.online.data_ptr(), self._shadow_for('online').data_ptr()), (0, self.n))
                 cmd(seg0, 'PACK_BF16', (dref, self.target.data_ptr(), self._shadow_for('target').data_ptr()), (a3.policy_lo, a3.n_pol))
             if stage is None:
                 cmd(seg0, 'KEYS_FILL', (keys_ptr,), (n_keys,))
-            if plan['tc']:
+            if st_mode:
+                cmd(seg1, 'FOLD_GPI_F32', (dref, self.online.data_ptr(), a2.w, plan['wq'].data_ptr(), plan['bq'].data_ptr()),
+                    (a2.policy_lo, a2.n_pol, a2.n_w | (a2.w_diag << 31), self._prec))
+            elif plan['tc']:
                 cmd(seg1, 'FOLD_GPI', (dref, self.online.data_ptr(), a2.w, plan['wq'].data_ptr(), plan['bq'].data_ptr()),
                     (a2.policy_lo, a2.n_pol, a2.n_w, a2.w_diag))
         if plan['tc']:
@@ -875,7 +950,10 @@ class PackedSFLibrary:
                 jobs[j].params_bf16, jobs[j].n_policies_total = self._shadow_for(which).data_ptr(), self.cap
             jobs[1].wq, jobs[1].bq = plan['wq'].data_ptr(), plan['bq'].data_ptr()
             cmd(seg1, 'NOP')                                  # probe slot (set_probe): event before the dominant kernel
-            cmd(seg1, 'FORWARD_TC_JOBS', (C.addressof(jobs),), (3,))
+            if st_mode:
+                cmd(seg1, 'FORWARD_STREAM', (C.addressof(jobs),), (3, self._prec))
+            else:
+                cmd(seg1, 'FORWARD_TC_JOBS', (C.addressof(jobs),), (3,))
             cmd(seg1, 'NOP')                                  # probe slot: event after it
             if stage is not None:
                 cmd(seg1, 'KEYS_REDUCE', (stage.data_ptr(), keys_ptr), (a2.n_pol, a2.n_w * B))
@@ -887,7 +965,7 @@ class PackedSFLibrary:
             cmd(seg1, 'NOP')
             cmd(seg2, 'FORWARD', (C.addressof(a3),))
         cmd(seg2, 'TD', (C.addressof(t),))
-        cmd(seg2, 'BACKWARD_TC' if plan['tc'] else 'BACKWARD', (C.addressof(b),))
+        cmd(seg2, 'BACKWARD_STREAM' if st_mode else ('BACKWARD_TC' if plan['tc'] else 'BACKWARD'), (C.addressof(b),))
         cmd(seg2, 'ADAM', (C.addressof(ad),))
         cmd(seg2, 'NOP', (0, 0), (0, 0, 0, 777))              # slot of the optional D2H read-back of the losses (host_losses)
         if peer is not None:
@@ -968,7 +1046,17 @@ class PackedSFLibrary:
         st = _stream()
         a1 = self._fwd_args(self.online, lo, n_pol, x)
         a1.sel_actions, a1.sel_out = actions.data_ptr(), ptr(ws['cur_sel'])
-        if self.precision != 'fp32':
+        if self._stream:
+            self._pack('online', lo, n_pol, transposed=True)
+            a1.acts_bf16_out, a1.relu_mask_out = ws['acts32'].data_ptr(), ws['masks'].data_ptr()
+            self._forward(a1, 'online', fresh=True)
+            b = _lib.BackwardStreamArgs()
+            sh_t, wo_t = self._shadow_t()
+            b.net, b.precision, b.shadow_t, b.wout_t, b.n_policies_total = sp.desc(), self._prec, ptr(sh_t), ptr(wo_t), self.cap
+            b.acts, b.dz, b.dzo, b.xo = (ptr(ws[k]) for k in ('acts32', 'dz32', 'dzo32', 'xo32'))
+            b.relu_masks = ptr(ws['masks'])
+            name = 'sfgpi_mlp_backward_stream'
+        elif self.precision != 'fp32':
             self._pack('online', lo, n_pol)
             a1.acts_bf16_out, a1.relu_mask_out = ws['acts16'].data_ptr(), ws['masks'].data_ptr()
             self._forward(a1, 'online', fresh=True)

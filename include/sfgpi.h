@@ -289,6 +289,51 @@ int sfgpi_bwd_tc_splits(int32_t B, int32_t want);
 int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream);
 
 /*
+ * Tensor-core modes at the REFERENCE's precision: tcgen05.mma kind::tf32 on fp32 operands (csrc/mlp_stream_tc.cu).
+ *   SFGPI_PREC_TF32    one pass, operands rounded to nearest tf32 (stated tolerance 2e-3 on psi / q)
+ *   SFGPI_PREC_TF32X3  3-pass split a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, fp32 accumulation in TMEM: meets the fp32 mode's 1e-5
+ * Both read hi (/ lo) fp32 operand shadows of the library rows produced by sfgpi_pack_f32 (parts = 1 for TF32, 2 for TF32X3):
+ *   shadow   [parts][n_policies_total][sfgpi_bf16_rows_per_policy()][256]   W_0 | hidden W_l | W_out padded: the forward's operands
+ *   shadow_t [parts][n_policies_total][L-2][256][256]  W_l^T, l = 1..L-2   (optional: the dgrad chain's operands)
+ *   wout_t   [parts][n_policies_total][256][sfgpi_f32_out_pad()]  W_{L-1}^T (optional)
+ * (buffers must be zero-initialised once by the caller: padding columns are never written).  Shapes: hidden widths == 256, S <= 31.
+ * sfgpi_mlp_forward_stream takes the same jobs as sfgpi_mlp_forward_tc_jobs with params_bf16 -> shadow, wq / bq -> the output of
+ * sfgpi_fold_gpi_f32 (wq fp32 [parts][n_pol][sfgpi_gpi_fold_rows()][256]), args.acts_bf16_out -> fp32 [parts][L-1][n_pol][B][256].
+ */
+#define SFGPI_PREC_FP32 0
+#define SFGPI_PREC_BF16 1
+#define SFGPI_PREC_TF32 2
+#define SFGPI_PREC_TF32X3 3
+int sfgpi_f32_out_pad(const sfgpi_net_desc *net);
+int sfgpi_pack_f32(const sfgpi_net_desc *net, const float *params, int32_t policy_lo, int32_t n_pol, int32_t n_policies_total,
+                   int32_t precision, float *shadow, float *shadow_t, float *wout_t, void *stream);
+int sfgpi_fold_gpi_f32(const sfgpi_net_desc *net, const float *params, int32_t policy_lo, int32_t n_pol, const float *w, int32_t n_w,
+                       int32_t w_diag, int32_t precision, float *wq_out, float *bq_out, void *stream);
+int sfgpi_mlp_forward_stream(const sfgpi_forward_tc_job *jobs, int32_t n_jobs, int32_t precision, void *stream);
+/*
+ * Backward of the psi MLP in the tf32 modes (the twin of sfgpi_mlp_backward_tc): streaming dgrad chain on the transposed operand
+ * shadows + split-K wgrad with MN-major fp32 operands (csrc/mlp_stream_tc.cu, csrc/mlp_wgrad_tf32.cu).  Scratch (caller-allocated
+ * fp32, parts = 1 / 2): dz [parts][L-1][n_pol][B][256], dzo [parts][n_pol][B][sfgpi_f32_out_pad()], xo [parts][B][32].
+ */
+typedef struct {
+    sfgpi_net_desc net;
+    int32_t precision;              /* SFGPI_PREC_TF32 / SFGPI_PREC_TF32X3 */
+    const float *shadow_t;          /* sfgpi_pack_f32 outputs for the ONLINE rows */
+    const float *wout_t;
+    int32_t n_policies_total, policy_lo, n_pol;
+    const float *x;                 /* [B][S] */
+    int32_t B;
+    const float *acts;              /* [parts][L-1][n_pol][B][256] from sfgpi_mlp_forward_stream (acts_bf16_out) */
+    const void *relu_masks;         /* [L-1][n_pol][B][8] uint32 from the forward (required for ReLU layers) */
+    const int64_t *actions;         /* [B] */
+    const float *d_out;             /* [n_pol][B][D] */
+    float *dz, *dzo, *xo;
+    float *grad_part;               /* [n_pol][n_split][row_stride] */
+    int32_t n_split;                /* == sfgpi_bwd_tc_splits(B, wanted) */
+} sfgpi_backward_stream_args;
+int sfgpi_mlp_backward_stream(const sfgpi_backward_stream_args *args, void *stream);
+
+/*
  * Learned features (phi), SURVEY 8f N3: the reward-regression head of SFDQN.pre_train (sfdqn_phi.py:850-862).
  *   phi [B][D] = output of the PhiFunction MLP (sfdqn_phi.py:90-123; run it with sfgpi_mlp_forward, n_actions = 1),
  *   e_b = w . phi_b - r_b ;  loss = mean_b e_b^2 (= mse_loss(reward_batch, fit_w(phis)))
@@ -377,6 +422,11 @@ int sfgpi_replay_gather(const sfgpi_replay_args *args, void *stream);
 #define SFGPI_OP_PEER_UNPACK 16     /* p0 = sfgpi_peer_unpack_args */
 #define SFGPI_OP_STEP_PREP 17       /* p0 = sfgpi_step_prep_args */
 #define SFGPI_OP_KEYS_REDUCE 18     /* p0 = stage, p1 = keys_out, i0 = n_pol, i1 = n */
+#define SFGPI_OP_PACK_F32 19        /* p0 = net desc, p1 = params, p2 = shadow, p3 = shadow_t, p4 = wout_t, i0 = policy_lo, i1 = n_pol, i2 = n_policies_total, i3 = precision */
+#define SFGPI_OP_FOLD_GPI_F32 20    /* p0 = net desc, p1 = params, p2 = w, p3 = wq, p4 = bq, i0 = policy_lo, i1 = n_pol, i2 = n_w | w_diag << 31, i3 = precision */
+#define SFGPI_OP_FORWARD_STREAM 21  /* p0 = sfgpi_forward_tc_job[], i0 = n_jobs, i1 = precision */
+#define SFGPI_OP_BACKWARD_STREAM 22 /* p0 = sfgpi_backward_stream_args */
+#define SFGPI_OP_KEYS_DECODE 23     /* p0 = keys, p1 = index_out, p2 = value_out, i0 = n */
 typedef struct {
     int32_t op;
     void *p[5];
