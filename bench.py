@@ -44,7 +44,7 @@ WORKLOADS = {
 }
 SEED = 1024
 REF_SOURCE = '/root/reference/source'          # present in the build container only; the GPU box times the port
-PARITY_MODE = 'fp32'                           # the mode that meets the reference's 1e-5 (set to 'tf32x3' once built)
+PARITY_MODE = 'tf32x3'                         # the tensor-core mode that meets the reference's 1e-5 on psi / q / losses
 
 
 def flops_per_net_pass(S, hidden, AD):

@@ -124,7 +124,7 @@ __device__ __forceinline__ uint32_t s_write_a16(const float (&h)[16], uint32_t s
             const float x = h[4 * q + i];
             bits |= (x > 0.f ? 1u : 0u) << (4 * q + i);
             hi[i] = tf32_rna(x);
-            lo[i] = x - hi[i];
+            lo[i] = tf32_rna(x - hi[i]);          // exactly representable: the tensor core's truncation of lo is then a no-op
         }
         const uint32_t off = a32_chunk_off(r, cb + 4 * q);
         sts128(stage + off, __float_as_uint(hi[0]), __float_as_uint(hi[1]), __float_as_uint(hi[2]), __float_as_uint(hi[3]));
@@ -284,7 +284,7 @@ mlp_forward_stream_kernel(const __grid_constant__ SMulti m, const __grid_constan
                         for (int i = 0; i < 4; ++i) {
                             const float x = (row_ok && c + i < S) ? xr[c + i] : 0.0f;
                             hi[i] = tf32_rna(x);
-                            lo[i] = x - hi[i];
+                            lo[i] = tf32_rna(x - hi[i]);          // exactly representable: the tensor core's truncation of lo is then a no-op
                         }
                         const uint32_t off = a32_chunk_off(r, c);
                         sts128(stage + off, __float_as_uint(hi[0]), __float_as_uint(hi[1]), __float_as_uint(hi[2]), __float_as_uint(hi[3]));
@@ -695,7 +695,7 @@ __global__ void build_xo_f32_kernel(const float *__restrict__ x, int B, int S, i
     const float v = c < S ? x[(size_t)b * S + c] : (c == S ? 1.0f : 0.0f);
     const float hi = tf32_rna(v);
     xo[i] = hi;
-    if (parts == 2) xo[(size_t)B * 32 + i] = v - hi;
+    if (parts == 2) xo[(size_t)B * 32 + i] = tf32_rna(v - hi);
 }
 
 // ---- fp32 library rows -> hi / lo operand shadows ---------------------------------------------------------------------------
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(256) pack_f32_kernel(sfgpi_net_desc net, const
         if (rr < rows_here) {
             float *dst = shadow + ((size_t)pl * rpp + row_base + rr) * kH + cc;
             dst[0] = hi;
-            if (parts == 2) dst[part_stride] = v - hi;
+            if (parts == 2) dst[part_stride] = tf32_rna(v - hi);
         }
     }
     if (mat == 0 || (shadow_t == nullptr && wout_t == nullptr)) return;
@@ -748,12 +748,12 @@ __global__ void __launch_bounds__(256) pack_f32_kernel(sfgpi_net_desc net, const
             if (shadow_t != nullptr) {
                 float *dst = shadow_t + (((size_t)pl * Lh + (mat - 1)) * kH + kk) * kH + nn;
                 dst[0] = hi;
-                if (parts == 2) dst[(size_t)n_total * Lh * kH * kH] = v - hi;
+                if (parts == 2) dst[(size_t)n_total * Lh * kH * kH] = tf32_rna(v - hi);
             }
         } else if (wout_t != nullptr && nn < ADp) {
             float *dst = wout_t + ((size_t)pl * kH + kk) * ADp + nn;
             dst[0] = hi;
-            if (parts == 2) dst[(size_t)n_total * kH * ADp] = v - hi;
+            if (parts == 2) dst[(size_t)n_total * kH * ADp] = tf32_rna(v - hi);
         }
     }
 }
@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(256) fold_gpi_f32_kernel(sfgpi_net_desc net, c
     const float hi = tf32_rna(acc);
     const size_t o = ((size_t)pl * nqpad + row) * kH + k;
     wq[o] = hi;
-    if (parts == 2) wq[o + (size_t)n_pol * nqpad * kH] = acc - hi;
+    if (parts == 2) wq[o + (size_t)n_pol * nqpad * kH] = tf32_rna(acc - hi);
     if (k == 0) bq[(size_t)pl * nqpad + row] = bacc;
 }
 

@@ -3,7 +3,8 @@
 // Precision modes on 32-bit operands (measured on B200, scripts/tf32_probe.cu):
 //   TF32   one pass.  The tensor core TRUNCATES the low 13 mantissa bits of an fp32 operand (error vs truncated inputs 1.6e-7,
 //          vs round-to-nearest inputs 8e-4), so operands are stored already rounded to nearest (cvt.rna): ~2e-4 per product.
-//   TF32X3 three passes  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  with hi = rna_tf32(x), lo = x - hi (exact in fp32), fp32 accumulation
+//   TF32X3 three passes  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  with hi = rna_tf32(x), lo = rna_tf32(x - hi) (so that the core's truncation
+//          of lo is a no-op and the split error is an unbiased 2^-22 instead of a one-sided 2^-21), fp32 accumulation
 //          in TMEM: 4e-7 relative error of a K = 32 product against fp64 -- the reference's fp32 arithmetic on the tensor cores.
 //   One M128 N256 K8 instruction executes in 128 cycles (half the bf16 rate): a 128 x 256 x 256 tile-layer is 4096 cycles per pass.
 // Operand layouts: K-major SWIZZLE_128B exactly as for bf16 (a 128-byte span holds 32 fp32 = four K = 8 steps, 32 bytes apart);
