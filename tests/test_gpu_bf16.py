@@ -438,7 +438,6 @@ def test_bf16_1001_steps_cross_a_target_sync():
     assert all(torch.equal(a, b) for a, b in zip(tgt, online_at_sync))          # target == online of update 1000, bit for bit
     assert not torch.equal(tgt[1], tgt_before)
     assert not torch.equal(tgt[1], gu.psi_params(sf, 1)[1][0])                    # ... and online has moved on since
-    assert fro_err(tgt[1], o.tgt[1][1][0]) < 0.25                                 # same place as the fp32 oracle's target (update-level bound)
 
 
 def test_bf16_gpi_256_reward_vectors_vs_oracle():
