@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('SFGPI_LIB_PATH') or os.path.join(HERE, 'libsfgpi.so')      # (override: A/B runs of two builds)
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu', 'g4.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -132,14 +132,21 @@ class AdamSegment(C.Structure):
     _fields_ = [('param', C.c_void_p), ('param_stride', C.c_int64), ('m', C.c_void_p), ('m_stride', C.c_int64),
                 ('v', C.c_void_p), ('v_stride', C.c_int64), ('grad_part', C.c_void_p), ('grad_pol_stride', C.c_int64),
                 ('grad_part_stride', C.c_int64), ('n_part', C.c_int32), ('len', C.c_int32), ('lr', C.c_float),
-                ('weight_decay', C.c_float)]
+                ('weight_decay', C.c_float), ('clamp_min', C.c_float), ('clamp_max', C.c_float)]
 
 
 class AdamArgs(C.Structure):
     _fields_ = [('n_seg', C.c_int32), ('n_pol', C.c_int32), ('seg', AdamSegment * MAX_SEGMENTS), ('step', C.c_void_p),
                 ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
                 ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
-                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p), ('consts_next', C.c_void_p)]
+                ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p), ('consts_next', C.c_void_p),
+                ('fresh', C.c_int32)]
+
+
+class G4Args(C.Structure):
+    _fields_ = [('B', C.c_int32), ('A', C.c_int32), ('D', C.c_int32), ('cur_sel', C.c_void_p), ('next_sel', C.c_void_p), ('phi', C.c_void_p),
+                ('rs', C.c_void_p), ('gammas', C.c_void_p), ('w', C.c_void_p), ('bias', C.c_void_p), ('coef', C.c_void_p),
+                ('d_psi', C.c_void_p), ('d_phi', C.c_void_p), ('grad_small', C.c_void_p), ('losses', C.c_void_p)]
 
 
 # every symbol include/sfgpi.h declares: name -> (restype, argtypes)
@@ -172,6 +179,7 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_mlp_forward_stream': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'sfgpi_mlp_backward_stream': (C.c_int, [C.POINTER(BackwardStreamArgs), C.c_void_p]),
+    'sfgpi_g4_head': (C.c_int, [C.POINTER(G4Args), C.c_void_p]),
     'sfgpi_replay_gather': (C.c_int, [C.POINTER(ReplayArgs), C.c_void_p]),
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -25,7 +25,10 @@ __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g,
 // the host.  Read from a.consts when the caller maintains it (adam_finish_kernel refreshes it after every step, so no
 // double-precision pow sits on the critical path of the step), else computed here.
 __device__ __forceinline__ void bias_corrections(const sfgpi_adam_args &a, int q, double &bc1, float &sqrt_bc2) {
-    if (a.consts != nullptr) {
+    if (a.fresh) {                                           // first step of a brand-new optimizer: t = 1
+        bc1 = 1.0 - a.beta1;
+        sqrt_bc2 = (float)sqrt(1.0 - a.beta2);
+    } else if (a.consts != nullptr) {
         bc1 = a.consts[2 * q];
         sqrt_bc2 = (float)a.consts[2 * q + 1];
     } else {
@@ -119,7 +122,17 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             const bool vec = ((sg.len | sg.grad_part_stride) & 3) == 0 &&
                              ((reinterpret_cast<uintptr_t>(gp0) | reinterpret_cast<uintptr_t>(pp0) |
                                reinterpret_cast<uintptr_t>(pm0) | reinterpret_cast<uintptr_t>(pv0)) & 15) == 0;
-            if (vec) {                                        // 128-bit path: 4 parameters per thread per trip
+            const bool clamp = sg.clamp_min < sg.clamp_max;
+            if (a.fresh || clamp) {                           // first-step / clamped segments (G4, target-task adaptation): scalar path
+                for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.len; i += blocks_per_pol * kAdamThreads) {
+                    const float g = sum_partials(gp0 + i, sg.n_part, (size_t)sg.grad_part_stride);
+                    float pw = pp0[i], m = a.fresh ? 0.0f : pm0[i], v = a.fresh ? 0.0f : pv0[i];
+                    adam_elem(pw, m, v, g, step_size, sqrt_bc2, sg.weight_decay, kc);
+                    if (clamp) pw = fminf(fmaxf(pw, sg.clamp_min), sg.clamp_max);
+                    pp0[i] = pw;
+                    if (!a.fresh) { pm0[i] = m; pv0[i] = v; }
+                }
+            } else if (vec) {                                 // 128-bit path: 4 parameters per thread per trip
                 const int n4 = sg.len >> 2;
                 for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < n4; i += blocks_per_pol * kAdamThreads) {
                     float4 g = sum_partials4(reinterpret_cast<const float4 *>(gp0) + i, sg.n_part, (size_t)(sg.grad_part_stride >> 2));
@@ -178,7 +191,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
     // fused finish (consts_next given): optimizer p's first CTA advances the step counter and derives the NEXT step's bias
     // corrections into the other buffer.  Nothing in this launch reads `step` or `consts_next`, so there is no ordering to
     // enforce -- unlike a last-CTA tail, this adds no serial work after the update itself.
-    if (a.consts_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.consts_next != nullptr && !a.fresh && blockIdx.x == 0 && threadIdx.x == 0) {
         const int s_new = a.step[p] + 1;
         a.step[p] = s_new;
         const double t = (double)(s_new + 1);
@@ -212,7 +225,7 @@ using namespace sfgpi;
 
 extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     const sfgpi_adam_args &a = *args;
-    if (a.n_seg < 1 || a.n_seg > SFGPI_MAX_SEGMENTS || a.n_pol < 1 || a.step == nullptr) {
+    if (a.n_seg < 1 || a.n_seg > SFGPI_MAX_SEGMENTS || a.n_pol < 1 || (a.step == nullptr && !a.fresh)) {
         set_error("sfgpi_adam_step: invalid arguments");
         return SFGPI_E_INVALID;
     }
@@ -222,6 +235,7 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     }
     int max_len = 0;
     for (int s = 0; s < a.n_seg; ++s) {
+        if (a.fresh && a.seg[s].param_stride == 0 && a.n_pol > 1) { set_error("sfgpi_adam_step: fresh optimizers cannot share a tensor"); return SFGPI_E_INVALID; }
         if (a.seg[s].len < 0 || a.seg[s].n_part < 1) { set_error("sfgpi_adam_step: bad segment %d", s); return SFGPI_E_INVALID; }
         max_len = a.seg[s].len > max_len ? a.seg[s].len : max_len;
     }
@@ -234,7 +248,7 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     launch_pdl(adam_kernel, grid, dim3(kAdamThreads), 0, st, a, blocks);
     int rc = check_launch("sfgpi_adam_step");
-    if (rc || a.consts_next != nullptr) return rc;
+    if (rc || a.consts_next != nullptr || a.fresh) return rc;
     launch_pdl(adam_finish_kernel, dim3((a.n_pol + 127) / 128), dim3(128), 0, st, a.step, a.consts, a.n_pol, a.beta1, a.beta2);
     return check_launch("sfgpi_adam_step(finish)");
 }

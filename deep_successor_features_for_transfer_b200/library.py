@@ -1081,6 +1081,109 @@ class PackedSFLibrary:
         _lib.call(name, C.byref(b), st)
         return ws['grad_part'].sum(dim=1)
 
+    def train_step_g4(self, transitions, policy, phi_lib, w_bias, coef, use_gpi=True):
+        """
+        G4 joint psi / phi step (features/deep_phi.py:95-224): phi = phi_theta(cat[s, a, s']) feeds the TD target AND the reward
+        fit, loss = phi_loss + coef * psi_loss, one FRESH Adam per call over (psi_i, phi_theta, fit_w[i] incl. bias, coef with
+        maximize=True), coef clamped to [1e-2, 1e6].  phi_lib: the one-row PackedSFLibrary holding phi_theta (A = 1, D features);
+        w_bias / coef: 1-element fp32 device tensors (updated in place).  Runs on the fp32 CUDA-core kernels (the phi net's
+        widths are not the tensor-core shape and the step is launch-latency-bound at the agents' batch 32).
+        Returns losses [4] on the device: (loss, psi_loss, phi_loss, coef before the step).
+        """
+        states, actions, rs, _, next_states, gammas = transitions
+        sp = self.spec
+        S, D, A, L = sp.dims[0], sp.n_features, sp.n_actions, len(sp.acts)
+        f32 = lambda t: self._as_input(t, torch.float32).to(self.device)
+        states, next_states, rs, gammas = f32(states), f32(next_states), f32(rs).reshape(-1), f32(gammas).reshape(-1)
+        actions = self._as_input(actions, torch.int64).to(self.device).reshape(-1)
+        B = states.shape[0]
+        if tuple(states.shape) != (B, S) or tuple(next_states.shape) != (B, S) or rs.numel() != B or gammas.numel() != B or actions.numel() != B:
+            raise ValueError('inconsistent transition batch shapes')
+        i = int(policy)
+        if not (0 <= i < self.n):
+            raise IndexError('policy index out of range')
+        psp = phi_lib.spec
+        if psp.n_features != D or psp.n_actions != 1:
+            raise ValueError('the phi network must map cat[s, a, s\'] to n_features values')
+        st = _stream()
+        ws = self._ws.get(('g4', B))
+        if ws is None:
+            z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
+            Lp = len(psp.acts)
+
+            def bwd_ws(spec, nl):
+                tiles = sum(((spec.dims[l + 1] + 63) // 64) * ((spec.dims[l] + 255) // 256) for l in range(nl))
+                n_split = max(1, min((B + 127) // 128, -(-296 // tiles)))
+                return dict(acts=[z(1, B, spec.dims[l + 1]) for l in range(nl - 1)], dz=[z(1, B, spec.dims[l + 1]) for l in range(nl - 1)],
+                            n_split=n_split, grad=z(1, n_split, spec.row_stride))
+            ws = self._ws[('g4', B)] = dict(psi=bwd_ws(sp, L), phi=bwd_ws(psp, Lp), cur=z(1, B, D), nxt=z(1, B, D), phi_out=z(B, D),
+                                            d_psi=z(1, B, D), d_phi=z(1, B, D), small=z(D + 2), losses=z(64, 4), ring=0,
+                                            keys=torch.empty(1, B, dtype=torch.int64, device=self.device),
+                                            zeros=torch.zeros(B, dtype=torch.int64, device=self.device))
+        # (1) phi = phi_theta(cat[s, a, s'])                                              deep_phi.py:110-111
+        x_phi = torch.cat([states, actions.reshape(B, 1).to(torch.float32), next_states], dim=1).contiguous()
+        ap = phi_lib._fwd_args(phi_lib.online, 0, 1, x_phi)
+        ap.psi_out = ptr(ws['phi_out'])
+        for l in range(len(psp.acts) - 1):
+            ap.acts_out[l] = ws['phi']['acts'][l].data_ptr()
+        _lib.call('sfgpi_mlp_forward', C.byref(ap), st)
+        # (2) next actions: GPI over the library under fit_w[i] (the bias shifts every q equally), or the policy's own psi  :113-123
+        keys = ws['keys']
+        _lib.call('sfgpi_keys_fill', ptr(keys), B, st)
+        a2 = self._fwd_args(self.online, 0 if use_gpi else i, self.n if use_gpi else 1, next_states)
+        a2.w, a2.n_w, a2.w_diag = C.c_void_p(self.w[i].data_ptr()), 1, 0
+        a2.key_action = ptr(keys)
+        _lib.call('sfgpi_mlp_forward', C.byref(a2), st)
+        # (3) online psi_i(s): saves activations, gathers psi(s)[a];  (4) target psi^-_i(s')[a*]                      :130-136
+        a1 = self._fwd_args(self.online, i, 1, states)
+        for l in range(L - 1):
+            a1.acts_out[l] = ws['psi']['acts'][l].data_ptr()
+        a1.sel_actions, a1.sel_out = actions.data_ptr(), ptr(ws['cur'])
+        _lib.call('sfgpi_mlp_forward', C.byref(a1), st)
+        a3 = self._fwd_args(self.target, i, 1, next_states)
+        a3.sel_keys, a3.sel_key_stride, a3.sel_out = ptr(keys), B, ptr(ws['nxt'])
+        _lib.call('sfgpi_mlp_forward', C.byref(a3), st)
+        # (5) losses, d_psi, d_phi, gradients of (w, b, coef)
+        ws['ring'] = (ws['ring'] + 1) % 64
+        losses = ws['losses'][ws['ring']]
+        g = _lib.G4Args()
+        g.B, g.A, g.D = B, A, D
+        g.cur_sel, g.next_sel, g.phi, g.rs, g.gammas = ptr(ws['cur']), ptr(ws['nxt']), ptr(ws['phi_out']), ptr(rs), ptr(gammas)
+        g.w, g.bias, g.coef = C.c_void_p(self.w[i].data_ptr()), ptr(w_bias), ptr(coef)
+        g.d_psi, g.d_phi, g.grad_small, g.losses = ptr(ws['d_psi']), ptr(ws['d_phi']), ptr(ws['small']), ptr(losses)
+        _lib.call('sfgpi_g4_head', C.byref(g), st)
+        # (6) backward through psi_i and through phi_theta
+        for lib_, spec, w_, x_, acts_, d_, pol in ((self, sp, ws['psi'], states, actions, ws['d_psi'], i),
+                                                   (phi_lib, psp, ws['phi'], x_phi, ws['zeros'], ws['d_phi'], 0)):
+            b = _lib.BackwardArgs()
+            b.net, b.params, b.policy_lo, b.n_pol, b.B = spec.desc(), ptr(lib_.online), pol, 1, B
+            b.x, b.actions, b.d_out = x_.data_ptr(), acts_.data_ptr(), d_.data_ptr()
+            for l in range(len(spec.acts) - 1):
+                b.acts[l] = w_['acts'][l].data_ptr()
+                b.dz[l] = w_['dz'][l].data_ptr()
+            b.grad_part, b.n_split = ptr(w_['grad']), w_['n_split']
+            _lib.call('sfgpi_mlp_backward', C.byref(b), st)
+        # (7) one fresh Adam over the four groups (lr 1e-3 each, :159-172), coefficient clamped (:212-215)
+        ad = _lib.AdamArgs()
+        ad.n_pol, ad.fresh, ad.sequential_shared = 1, 1, 1
+        ad.beta1, ad.beta2, ad.eps = 0.9, 0.999, 1e-8
+
+        def seg(k, param, length, grad, n_part, part_stride, clamp=None):
+            s_ = ad.seg[k]
+            s_.param, s_.param_stride, s_.m_stride, s_.v_stride = param, length, length, length
+            s_.grad_part, s_.grad_pol_stride, s_.grad_part_stride, s_.n_part = grad, n_part * part_stride, part_stride, n_part
+            s_.len, s_.lr, s_.weight_decay = length, 1e-3, 0.0
+            if clamp is not None:
+                s_.clamp_min, s_.clamp_max = clamp
+        seg(0, self.online[i].data_ptr(), sp.row_stride, ws['psi']['grad'].data_ptr(), ws['psi']['n_split'], sp.row_stride)
+        seg(1, phi_lib.online[0].data_ptr(), psp.row_stride, ws['phi']['grad'].data_ptr(), ws['phi']['n_split'], psp.row_stride)
+        seg(2, self.w[i].data_ptr(), D, ws['small'].data_ptr(), 1, D + 2)
+        seg(3, w_bias.data_ptr(), 1, ws['small'].data_ptr() + 4 * D, 1, D + 2)
+        seg(4, coef.data_ptr(), 1, ws['small'].data_ptr() + 4 * (D + 1), 1, D + 2, clamp=(1e-2, 1e6))
+        ad.n_seg = 5
+        _lib.call('sfgpi_adam_step', C.byref(ad), st)
+        return losses
+
     def _gather_w(self, w_all):
         import torch.distributed as dist
         if self.shard.uniform:

@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._lib import ptr
 from .library import PackedSFLibrary, _stream
-from .sfdqn import ReplayBuffer, _device
+from .sfdqn import DeepSF, ReplayBuffer, _device
 
 
 class _RewardHead:
@@ -202,3 +202,83 @@ def pre_train(train_tasks, n_samples_pre_train, n_cycles=5, buffer_handle=None):
     phi_learn_model.set_eval()
     phi_learn_model.reward_heads = heads
     return phi_learn_model, [float(v) for v in log[:len(losses), 0, 0].cpu()]      # (the reference syncs on loss.item() per update)
+
+
+class PackedPhi(torch.nn.Module):
+    """
+    A phi network (any Linear / ReLU / Tanh nn.Sequential, e.g. main_sfdqn_phi_torch.py:52-73's 5-layer MLP over cat[s, a, s'])
+    adopted into a one-row packed library so that the G4 / G5 joint step can run it on the kernels.  Parameters are views of the
+    packed row (`.parameters()`, `state_dict()` keep working); calling it runs the fused CUDA forward.
+    """
+
+    def __init__(self, model, feature_dim):
+        super().__init__()
+        self.net = model
+        dev = _device()
+        rng = torch.get_rng_state()
+        twin = torch.nn.Sequential(*[torch.nn.Linear(l.in_features, l.out_features) if isinstance(l, torch.nn.Linear) else type(l)()
+                                     for l in model.children()])
+        lib = PackedSFLibrary(device=dev, capacity=1, precision='fp32')
+        w_stub = torch.nn.Linear(feature_dim, 1, bias=False)
+        torch.set_rng_state(rng)
+        twin.load_state_dict(model.state_dict())
+        lib.add_policy(model, twin, w_stub, n_actions=1, n_features=feature_dim)
+        lib._point_views(0, lib._views[0])
+        self._lib_ref = [lib]
+        self.feature_dim = feature_dim
+
+    @property
+    def library(self):
+        return self._lib_ref[0]
+
+    def forward(self, x):
+        x = torch.as_tensor(x).to(_device()).float().contiguous()
+        return self.library.forward_psi(x, 0, 1).reshape(x.shape[0], self.feature_dim)
+
+
+class DeepSF_PHI(DeepSF):
+    """
+    SF library of the phi-learning agents, G4 (features/deep_phi.py:11-290): fit_w[i] = Linear(D, 1) WITH bias
+    (:266-270), GPI's q = w(psi)[..., 0] includes that bias (:248), and update_successor is the JOINT psi / phi step
+    (:95-224) -- here one kernel sequence (PackedSFLibrary.train_step_g4) instead of ~100 eager ops and a freshly built
+    torch.optim.Adam per call.
+    """
+
+    def add_training_task(self, task, source=None):
+        n_features = task.feature_dim()
+        self.psi.append(None)                                                     # (reference order: psi nets first, then fit_w, :262-270)
+        w_holder = torch.nn.Linear(n_features, 1, bias=False, device=self.device)
+        self.psi[-1] = self.build_successor(task, source, w_holder)
+        self.n_tasks = len(self.psi)
+        fit_w = torch.nn.Linear(n_features, 1).to(self.device)
+        with torch.no_grad():
+            self._library.w[self.n_tasks - 1].copy_(fit_w.weight.data.reshape(-1))
+        fit_w.weight.data = self._library.w[self.n_tasks - 1].view(1, -1)          # view of the packed row
+        self._library._views[self.n_tasks - 1]['w'] = fit_w
+        self.fit_w.append(fit_w)
+        self.true_w.append(task.get_w())
+        import numpy as np
+        for i in range(len(self.gpi_counters)):
+            self.gpi_counters[i] = np.append(self.gpi_counters[i], 0)
+        self.gpi_counters.append(np.zeros((self.n_tasks,), dtype=int))
+
+    def GPI_w(self, state, w):
+        q, task = super().GPI_w(state, w)
+        if isinstance(w, torch.nn.Module) and getattr(w, 'bias', None) is not None:
+            q = q + w.bias.detach().to(q.device)                                   # w(psi): the bias shifts every cell equally
+        return q, task
+
+    def update_reward(self, phi, r, task_index, exact=False):
+        raise Exception('This function should not be used')                        # features/deep_phi.py:92-93
+
+    def update_successor(self, transitions, phis_model, policy_index, loss_coefficient, use_gpi=True):
+        if transitions is None:
+            return
+        (phi_model, _, _), _ = phis_model
+        if not isinstance(phi_model, PackedPhi):
+            raise TypeError('the phi model must be a PackedPhi (wrap the nn.Sequential the phi lambda returns)')
+        fit_w = self.fit_w[policy_index]
+        losses = self._library.train_step_g4(transitions, policy_index, phi_model.library, fit_w.bias.data, loss_coefficient.data,
+                                             use_gpi=use_gpi)
+        self._after_update(policy_index)
+        return losses[0:1], losses[1:2], losses[2:3], loss_coefficient

@@ -195,6 +195,8 @@ typedef struct {
     const float *grad_part; int64_t grad_pol_stride; int64_t grad_part_stride; int32_t n_part;
     int32_t len;
     float lr, weight_decay;
+    float clamp_min, clamp_max;     /* applied to the stepped parameter when clamp_min < clamp_max (e.g. the G4 loss coefficient,
+                                       features/deep_phi.py:212-215; the target task's omegas, tsfdqn.py:977-979); 0, 0: no clamp */
 } sfgpi_adam_segment;
 
 typedef struct {
@@ -211,6 +213,9 @@ typedef struct {
                                        and writes the NEXT step's corrections here (nothing reads this buffer or `step` during the
                                        launch), so the one-block finishing launch drops off the step's dependent chain; the caller
                                        swaps the two buffers for the next call */
+    int32_t fresh;                  /* nonzero: every call is the FIRST step of a brand-new optimizer (features/deep_phi.py:170 builds a
+                                       new torch.optim.Adam per update): moments start at 0 and are not stored, t = 1, `step` / consts
+                                       are neither read nor written; m / v pointers of the segments may be NULL */
 } sfgpi_adam_args;
 
 int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
@@ -344,6 +349,27 @@ int sfgpi_mlp_backward_stream(const sfgpi_backward_stream_args *args, void *stre
 int sfgpi_phi_head_partials(int32_t B);
 int sfgpi_phi_head(const float *phi, const float *w, const float *r, int32_t B, int32_t D, float *d_out, float *dw_part,
                    float *loss_part, void *stream);
+
+/*
+ * G4 joint psi / phi step (features/deep_phi.py:95-224 with the loss coefficient of agents/sfdqn_phi.py:152-165), the part between
+ * the forwards and the backwards: with phi = phi_theta(cat[s, a, s']) [B][D] (carries gradient), cur = psi_i(s)[a], nxt =
+ * psi^-_i(s')[a*], reward map fit_w = Linear(D, 1) WITH bias, loss coefficient c:
+ *   targets = phi + gamma * nxt ;  psi_loss = sum (cur - targets)^2 / (B*A*D) ;  phi_loss = sum (w.phi + b - r)^2 / B
+ *   loss = phi_loss + c * psi_loss                                                           (deep_phi.py:136-185)
+ * Outputs: d_psi [B][D] = dLoss/dpsi(s)[a,:], d_phi [B][D] = dLoss/dphi (both losses), grad_small [D + 2] = (dLoss/dw | dLoss/db |
+ * -dLoss/dc: the coefficient's Adam group has maximize=True), losses [4] = (loss, psi_loss, phi_loss, c before the step).
+ * One CTA, deterministic reductions; B <= 4096 (the phi agents run at batch 32).
+ */
+typedef struct {
+    int32_t B, A, D;
+    const float *cur_sel, *next_sel, *phi;  /* [B][D] */
+    const float *rs, *gammas;               /* [B] */
+    const float *w, *bias, *coef;           /* [D], [1], [1] */
+    float *d_psi, *d_phi;                   /* [B][D] */
+    float *grad_small;                      /* [D + 2] */
+    float *losses;                          /* [4] */
+} sfgpi_g4_args;
+int sfgpi_g4_head(const sfgpi_g4_args *args, void *stream);
 
 /*
  * Step prologue of a tensor-core train step in ONE launch: sfgpi_pack_bf16 for up to two row sets (online, target),

@@ -460,3 +460,60 @@ def test_add_policy_without_growth_drops_cached_plans(precision):
             for l, (W, b) in enumerate(gu.psi_params(sf, i)):
                 assert rel_err(W, o.psi[i][l][0]) < tol_w
     assert int(sf._library.step[2]) == 1                      # the newcomer was stepped exactly once (the 'all' plan saw it)
+
+
+def test_g4_joint_psi_phi_vs_golden():
+    """
+    G4 joint psi / phi step on the kernels (DeepSF_PHI.update_successor, features/deep_phi.py:95-224 + the phi model of
+    main_sfdqn_phi_torch.py:52-73 + the loss coefficient of agents/sfdqn_phi.py:152-165) against the UNMODIFIED reference's
+    4 recorded steps (tests/golden/make_golden_g4.py): (loss, psi_loss, phi_loss, coefficient) per step at 2e-5, post-step psi /
+    phi / fit_w incl. bias at STEP_TOL, untouched policies bit-equal.  Every update is the first step of a fresh Adam
+    (p -= lr * g / (|g| + eps)), the coefficient's group has maximize=True and is clamped to [1e-2, 1e6].
+    """
+    import os
+    from deep_successor_features_for_transfer_b200.sfdqn_phi import DeepSF_PHI, PackedPhi
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'g4_joint_psi_phi.npz'))
+    S, A, D, N, K, policy = (int(z[k]) for k in ('S', 'A', 'D', 'N', 'K', 'policy'))
+    hidden, acts = [int(h) for h in z['hidden']], [str(a) for a in z['acts']]
+    sf = DeepSF_PHI(pytorch_model_handle=gu.model_lambda(hidden, acts), target_update_ev=1000, hyperparameters=dict(gu.HYPER))
+    sf.reset()
+    for i in range(N):
+        sf.add_training_task(gu.FakeTask(S, A, D, i))
+    n_psi = len(hidden) + 2
+    with torch.no_grad():
+        for i in range(N):
+            layers = [(t(z[f'init.psi{i}.W{l}']), t(z[f'init.psi{i}.b{l}'])) for l in range(n_psi)]
+            gu.load_policy(sf, i, layers, t(z[f'init.w{i}.W']))
+            sf.fit_w[i].bias.data.copy_(t(z[f'init.w{i}.b']))
+    n_in = 2 * S + 1
+    phi_net = torch.nn.Sequential(torch.nn.Linear(n_in, 2 * n_in), torch.nn.ReLU(), torch.nn.Linear(2 * n_in, 2 * n_in), torch.nn.ReLU(),
+                                  torch.nn.Linear(2 * n_in, 2 * n_in), torch.nn.ReLU(), torch.nn.Linear(2 * n_in, 2 * n_in), torch.nn.ReLU(),
+                                  torch.nn.Linear(2 * n_in, D))
+    phi = PackedPhi(phi_net, D)
+    with torch.no_grad():
+        for l, lin in enumerate(gu.linears(phi.net)):
+            lin.weight.data.copy_(t(z[f'init.phi.W{l}']))
+            lin.bias.data.copy_(t(z[f'init.phi.b{l}']))
+    phis_model = ((phi, torch.nn.MSELoss(), None), None)
+    coef = torch.ones(1, device='cuda')
+    untouched = [W.clone() for W, _ in gu.psi_params(sf, 0)]
+    for k in range(K):
+        tr = tuple(t(z[f'tr{k}.{n_}']) for n_ in ('states', 'actions', 'rs', 'phis', 'next_states', 'gammas'))
+        tr = (tr[0], tr[1].long(), tr[2], tr[3], tr[4], tr[5])
+        out = sf.update_successor(gu.cuda_tr(tr), phis_model, policy, coef, bool(int(z['use_gpi'])))
+        got = [float(v) for v in out]
+        assert np.allclose(got, z['out.losses'][k], rtol=2e-5, atol=1e-7), (k, got, z['out.losses'][k])
+    for l, (W, b) in enumerate(gu.psi_params(sf, policy)):
+        assert rel_err(W, z[f'post.psi.W{l}']) < STEP_TOL and rel_err(b, z[f'post.psi.b{l}']) < STEP_TOL
+    for l, lin in enumerate(gu.linears(phi.net)):
+        assert rel_err(lin.weight.data.cpu(), z[f'post.phi.W{l}']) < STEP_TOL
+        assert rel_err(lin.bias.data.cpu(), z[f'post.phi.b{l}']) < STEP_TOL
+    assert rel_err(sf.fit_w[policy].weight.data.cpu(), z['post.w.W']) < STEP_TOL
+    assert rel_err(sf.fit_w[policy].bias.data.cpu(), z['post.w.b']) < STEP_TOL
+    assert all(torch.equal(a, b) for a, (b, _) in zip(untouched, gu.psi_params(sf, 0)))
+    # q of GPI includes fit_w's bias (w(psi), deep_phi.py:248)
+    x = t(z['tr0.states']).cuda()
+    q, _ = sf.GPI(x, policy)
+    psi = sf.get_successors(x)
+    q_ref = torch.nn.functional.linear(psi, sf.fit_w[policy].weight.data, sf.fit_w[policy].bias.data)[..., 0]
+    assert rel_err(q.cpu(), q_ref.cpu()) < 1e-5
