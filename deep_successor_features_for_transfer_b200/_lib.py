@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('SFGPI_LIB_PATH') or os.path.join(HERE, 'libsfgpi.so')      # (override: A/B runs of two builds)
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu', 'g4.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu', 'g4.cu', 'target.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -143,6 +143,15 @@ class AdamArgs(C.Structure):
                 ('fresh', C.c_int32)]
 
 
+class TargetArgs(C.Structure):
+    _fields_ = [('N', C.c_int32), ('A', C.c_int32), ('D', C.c_int32), ('G', C.c_int32), ('S', C.c_int32), ('psi', C.c_void_p),
+                ('next_psi', C.c_void_p), ('g', C.c_void_p), ('g_stride', C.c_int32), ('h', C.c_void_p), ('s', C.c_void_p), ('s1', C.c_void_p),
+                ('phi', C.c_void_p), ('r', C.c_float), ('gamma', C.c_float), ('a', C.c_int32), ('a1', C.c_int32), ('beta', C.c_float),
+                ('l1_coef', C.c_float), ('lr_w', C.c_float), ('wd_w', C.c_float), ('lr_omega', C.c_float), ('wd_omega', C.c_float),
+                ('lr_omega_decay', C.c_float), ('w', C.c_void_p), ('omegas', C.c_void_p), ('w_m', C.c_void_p), ('w_v', C.c_void_p),
+                ('o_m', C.c_void_p), ('o_v', C.c_void_p), ('step', C.c_void_p), ('epoch', C.c_void_p), ('losses', C.c_void_p)]
+
+
 class G4Args(C.Structure):
     _fields_ = [('B', C.c_int32), ('A', C.c_int32), ('D', C.c_int32), ('cur_sel', C.c_void_p), ('next_sel', C.c_void_p), ('phi', C.c_void_p),
                 ('rs', C.c_void_p), ('gammas', C.c_void_p), ('w', C.c_void_p), ('bias', C.c_void_p), ('coef', C.c_void_p),
@@ -180,6 +189,9 @@ SYMBOLS = {
     'sfgpi_mlp_forward_stream': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'sfgpi_mlp_backward_stream': (C.c_int, [C.POINTER(BackwardStreamArgs), C.c_void_p]),
     'sfgpi_g4_head': (C.c_int, [C.POINTER(G4Args), C.c_void_p]),
+    'sfgpi_target_q': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sfgpi_target_adapt': (C.c_int, [C.POINTER(TargetArgs), C.c_void_p]),
+    'sfgpi_lms_update': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p]),
     'sfgpi_replay_gather': (C.c_int, [C.POINTER(ReplayArgs), C.c_void_p]),
     'sfgpi_run': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -53,12 +53,18 @@ class DeepSF(_DeepSF):
         self._w_holders = []
 
     def update_reward(self, phi, r, task_index, exact=False):
-        """LMS rule w += alpha_w (r - phi.w) phi, in place on the packed row (features/successor.py:146-167)."""
+        """LMS rule w += alpha_w (r - phi.w) phi, in place on the packed row (features/successor.py:146-167): one tiny kernel
+        (sfgpi_lms_update) -- this is the per-environment-step op of main_sfdqn_torch.py."""
+        import ctypes as C
+        from . import _lib
+        from .library import _stream
         w = self.fit_w[task_index]
-        phi = torch.as_tensor(phi).float().to(self.device).reshape(w.shape)
-        r = torch.as_tensor(r).float().to(self.device)
-        w.add_(self.alpha_w * (r - torch.sum(phi * w)) * phi)
-        if exact and not torch.allclose(r, torch.sum(phi * self.true_w[task_index].reshape(w.shape))):
+        phi = torch.as_tensor(phi).float().to(self.device).reshape(-1).contiguous()
+        r = torch.as_tensor(r).float().to(self.device).reshape(-1).contiguous()
+        if phi.numel() != w.numel():
+            raise ValueError('phi must have n_features elements')
+        _lib.call('sfgpi_lms_update', w.data_ptr(), phi.data_ptr(), r.data_ptr(), w.numel(), float(self.alpha_w), _stream())
+        if exact and not torch.allclose(r, torch.sum(phi.reshape(w.shape) * self.true_w[task_index].reshape(w.shape))):
             raise Exception('sampled reward {} != linear reward - please check task {}!'.format(r, task_index))
 
     def GPE_w(self, state, policy_index, w):

@@ -9,7 +9,75 @@ import random
 import numpy as np
 import torch
 
+import ctypes as C
+
+from . import _lib
+from .library import _stream
 from .sfdqn import DeepSF, DeviceReplayBuffer, ReplayBuffer, SFDQN, _device  # noqa: F401  (re-exported like the reference file)
+
+
+class PackedTargetOptim:
+    """
+    Adam over {w_target, omega} + the LambdaLR on omega's rate of one target task (tsfdqn.py:803-832) with all state on the
+    device: moments, the step counter and the scheduler's epoch.  `step_fused` = update_test_reward_mapper + scheduler.step() as
+    ONE kernel after the two ensemble forwards (csrc/target.cu: sfgpi_target_adapt).  `param_groups` / `scheduler` mimic what the
+    agent's logging reads (tsfdqn.py:902-903).
+    """
+
+    class _Scheduler:
+        def step(self):
+            pass                                               # the epoch advances inside the fused kernel (tsfdqn.py:895)
+
+    def __init__(self, w_approx, omegas, hp):
+        dev = omegas.device
+        self.hp = hp
+        self.w_flat = w_approx.weight.data.reshape(-1).contiguous()
+        w_approx.weight.data = self.w_flat.view(1, -1)
+        z = lambda t: torch.zeros(t.numel(), dtype=torch.float32, device=dev)
+        self.w_m, self.w_v, self.o_m, self.o_v = z(self.w_flat), z(self.w_flat), z(omegas), z(omegas)
+        self.counters = torch.zeros(2, dtype=torch.int32, device=dev)              # [step, epoch]
+        self.losses = torch.zeros(64, 3, dtype=torch.float32, device=dev)
+        self.ring = 0
+        self.scheduler = self._Scheduler()
+        self._stage = torch.zeros(64, dtype=torch.float32, device=dev)
+
+    @property
+    def param_groups(self):
+        epoch = int(self.counters[1])
+        return [dict(lr=self.hp['learning_rate_w'], weight_decay=self.hp['weight_decay_w']),
+                dict(lr=self.hp['learning_rate_omega'] * (1 - self.hp['learning_rate_omega_decay']) ** epoch,
+                     weight_decay=self.hp['weight_decay_omega'])]
+
+    def step_fused(self, agent, w_approx, omegas, phi, r, s, a, s1, a1):
+        lib = agent.sf._library
+        sp = lib.spec
+        hp = self.hp
+        if w_approx.weight.data.data_ptr() != self.w_flat.data_ptr() or not omegas.is_contiguous():
+            raise ValueError('w_approx / omegas are not the tensors this optimizer was built for')
+        with torch.no_grad():
+            psi = lib.forward_psi(s, 0, lib.n)                                     # [1, N, A, D] online nets   (tsfdqn.py:948)
+            next_psi = lib.forward_psi(s1, 0, lib.n, target=True)                  # target nets                (tsfdqn.py:950)
+        if psi.shape[0] != 1:
+            raise ValueError('the target-task step is a batch-1 update')
+        t = _lib.TargetArgs()
+        t.N, t.A, t.D, t.G, t.S = lib.n, sp.n_actions, sp.n_features, lib.G, sp.dims[0]
+        t.psi, t.next_psi = psi.data_ptr(), next_psi.data_ptr()
+        t.g, t.g_stride, t.h = lib.g.data_ptr(), lib.g.shape[1], lib.h.data_ptr()
+        sv, s1v = s.reshape(-1).contiguous(), s1.reshape(-1).contiguous()
+        phiv = phi.reshape(-1).contiguous()
+        t.s, t.s1, t.phi = sv.data_ptr(), s1v.data_ptr(), phiv.data_ptr()
+        t.r, t.gamma, t.a, t.a1 = float(r), float(agent.gamma), int(a), int(a1)
+        t.beta, t.l1_coef = float(hp['beta_loss_coefficient']), float(hp['omegas_l1_coefficient'])
+        t.lr_w, t.wd_w = float(hp['learning_rate_w']), float(hp['weight_decay_w'])
+        t.lr_omega, t.wd_omega, t.lr_omega_decay = float(hp['learning_rate_omega']), float(hp['weight_decay_omega']), float(hp['learning_rate_omega_decay'])
+        t.w, t.omegas = self.w_flat.data_ptr(), omegas.data_ptr()
+        t.w_m, t.w_v, t.o_m, t.o_v = self.w_m.data_ptr(), self.w_v.data_ptr(), self.o_m.data_ptr(), self.o_v.data_ptr()
+        t.step, t.epoch = self.counters.data_ptr(), self.counters.data_ptr() + 4
+        self.ring = (self.ring + 1) % 64
+        losses = self.losses[self.ring]
+        t.losses = losses.data_ptr()
+        _lib.call('sfgpi_target_adapt', C.byref(t), _stream())
+        return losses[0], losses[1], losses[2]
 
 
 class DeepTSF(DeepSF):
@@ -166,9 +234,21 @@ class TSFDQN(SFDQN):
         self.epsilon = max(self.epsilon * self.epsilon_decay, self.epsilon_min)
         return a
 
-    def _new_target_task(self, feature_dim, omegas_init):
-        """(w_approx, Adam over {w, omega}, LambdaLR decaying only omega's lr) for one target task (tsfdqn.py:803-832)."""
+    def _new_target_task(self, feature_dim, omegas_init, fused=True):
+        """
+        (w_approx, Adam over {w, omega}, LambdaLR decaying only omega's lr, omegas) for one target task (tsfdqn.py:803-832).
+        fused (default): the optimizer / scheduler are views of a PackedTargetOptim -- moments, step and the scheduler's epoch live
+        on the device and update_test_reward_mapper runs as ONE kernel (csrc/target.cu); fused=False builds the reference's own
+        torch.optim.Adam + LambdaLR (the eager path, kept for callers that hand in their own optimizer).
+        """
         hp = self.hyperparameters
+        if fused:
+            omegas = omegas_init.clone().detach().to(self.device).float().contiguous()
+            w_approx = torch.nn.Linear(feature_dim, 1, bias=False, device=self.device)
+            with torch.no_grad():
+                w_approx.weight.uniform_(-0.01, 0.01)
+            optim = PackedTargetOptim(w_approx, omegas, hp)
+            return w_approx, optim, optim.scheduler, omegas
         omegas = omegas_init.clone().detach().requires_grad_(True)
         w_approx = torch.nn.Linear(feature_dim, 1, bias=False, device=self.device)
         with torch.no_grad():
@@ -222,8 +302,19 @@ class TSFDQN(SFDQN):
         with torch.no_grad():
             if random.random() <= self.test_epsilon:
                 return torch.tensor(random.randrange(self.n_actions)).to(self.device)
-            tsf = torch.sum(self.sf.get_successors(s_enc) * self._normalized(omegas), axis=1)      # [1, A, D]
-            return torch.argmax(w(tsf))                       # the target task acts by Q-learning on the mixed psi
+            lib = self.sf._library
+            psi = self.sf.get_successors(s_enc)                                   # [1, N, A, D]  (ensemble kernel)
+            if psi.shape[0] != 1:
+                tsf = torch.sum(psi * self._normalized(omegas), axis=1)
+                return torch.argmax(w(tsf))
+            # fused: q = w(sum_j omega^_j psi_j(s)) and its argmax in one kernel (csrc/target.cu)
+            act = lib._ws.get('target_action')
+            if act is None:
+                act = lib._ws['target_action'] = torch.empty(1, dtype=torch.int64, device=self.device)
+            wv = w.weight if isinstance(w, torch.nn.Module) else w
+            _lib.call('sfgpi_target_q', psi.data_ptr(), psi.shape[1], psi.shape[2], psi.shape[3],
+                      omegas.detach().contiguous().data_ptr(), wv.detach().contiguous().data_ptr(), None, act.data_ptr(), _stream())
+            return act[0].clone()                             # the target task acts by Q-learning on the mixed psi
 
     def test_agent(self, task, test_index):
         R = 0.0
@@ -258,6 +349,8 @@ class TSFDQN(SFDQN):
         hp = self.hyperparameters
         s, s1 = torch.as_tensor(s).float().to(self.device), torch.as_tensor(s1).float().to(self.device)
         phi = torch.as_tensor(task.features(s, a, s1)).float().to(self.device)
+        if isinstance(optim, PackedTargetOptim):
+            return optim.step_fused(self, w_approx, omegas, phi, r, s, a, s1, a1)
         norm = self._normalized(omegas)
         with torch.no_grad():
             ts = torch.vstack([g(s) for g in self.g_functions]).unsqueeze(1)          # [N, 1, G] -> broadcasts with [1, N, 1, 1]

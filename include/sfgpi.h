@@ -372,6 +372,42 @@ typedef struct {
 int sfgpi_g4_head(const sfgpi_g4_args *args, void *stream);
 
 /*
+ * Target-task adaptation of the TSF agent, batch 1 (tsfdqn.py:859-997).  psi / next_psi: [N][A][D] = get_successors(s)
+ * / get_next_successors(s') of sfgpi_mlp_forward* for ONE state.
+ *   sfgpi_target_q     q[a] = w . sum_j (omega_j / sum omega) psi_j[a,:]  (get_test_action's greedy branch, :864-871), q_out [A]
+ *                      and / or action_out [1] = argmax (first maximal index); A <= 256
+ *   sfgpi_target_adapt update_test_reward_mapper (:917-997) + scheduler.step() (:895) in one kernel: loss = MSE(tsf(s,a),
+ *                      phi~ + gamma tsf^-(s',a')) + beta (w.phi~ - r)^2 + l1_coef |omega|_1 with phi~ = phi * (h(sum_j omega^_j g_j(s))
+ *                      + h(sum_j omega^_j g_j(s'))); Adam (betas 0.9 / 0.999, eps 1e-8, torch op order) on w (lr_w, wd_w) and omega
+ *                      (lr_omega * (1 - lr_omega_decay)^epoch, wd_omega); omega clamped to >= 1e-7; step and epoch advance on the
+ *                      device.  losses [3] = (loss, reward loss, psi loss) as the reference returns them.
+ */
+typedef struct {
+    int32_t N, A, D, G, S;
+    const float *psi, *next_psi;            /* [N][A][D] */
+    const float *g; int32_t g_stride;       /* [N][g_stride]: W[G][S] | b[G] */
+    const float *h;                         /* W[D][G] | b[D] */
+    const float *s, *s1;                    /* [S] */
+    const float *phi;                       /* [D] */
+    float r, gamma;
+    int32_t a, a1;
+    float beta, l1_coef, lr_w, wd_w, lr_omega, wd_omega, lr_omega_decay;
+    float *w, *omegas;                      /* [D], [N]: updated in place */
+    float *w_m, *w_v, *o_m, *o_v;           /* Adam moments */
+    int32_t *step, *epoch;                  /* [1] each, device */
+    float *losses;                          /* [3] */
+} sfgpi_target_args;
+int sfgpi_target_q(const float *psi, int32_t N, int32_t A, int32_t D, const float *omegas, const float *w, float *q_out,
+                   int64_t *action_out, void *stream);
+int sfgpi_target_adapt(const sfgpi_target_args *args, void *stream);
+
+/*
+ * G1's per-environment-step LMS rule on the raw reward vector (features/successor.py:146-167): w += alpha (r - phi . w) phi,
+ * one tiny kernel instead of 4 - 5 eager launches; phi [D], r [1] device pointers.
+ */
+int sfgpi_lms_update(float *w, const float *phi, const float *r, int32_t D, float alpha, void *stream);
+
+/*
  * Step prologue of a tensor-core train step in ONE launch: sfgpi_pack_bf16 for up to two row sets (online, target),
  * sfgpi_keys_fill, sfgpi_fold_gpi and the backward pass's xo = [x | 1 | 0] operand (bf16 [B][64]) -- five independent
  * elementwise passes that would otherwise be five launches on the step's dependent chain -- plus, optionally, the staging of the

@@ -305,8 +305,12 @@ def test_device_replay_buffer_matches_host_ring():
             assert torch.equal(x.cpu(), y.cpu()), name
 
 
-def test_g3_target_task_adaptation_vs_golden():
-    """TSFDQN.get_test_action / update_test_reward_mapper on the kernel-backed library == the reference."""
+@pytest.mark.parametrize('fused', [True, False])
+def test_g3_target_task_adaptation_vs_golden(fused):
+    """TSFDQN.get_test_action / update_test_reward_mapper on the kernel-backed library == the reference: 5 adaptation
+    steps of the unmodified reference (actions chosen, the three losses, w and omega after every step).  fused: the whole update
+    incl. Adam(w, omega), the LambdaLR decay and the clamp is ONE kernel (csrc/target.cu) after the two ensemble forwards;
+    fused=False: the eager op sequence with torch.optim (kept for callers that bring their own optimizer)."""
     meta, z = load('g3_reacher_target_adapt')
     dsf, ag = gu.build_g3(dict(meta, use_gpi=True), z=z)
     ag.hyperparameters.update({k: meta[k] for k in ('learning_rate_omega', 'weight_decay_omega', 'learning_rate_omega_decay',
@@ -322,7 +326,8 @@ def test_g3_target_task_adaptation_vs_golden():
             return t(z[f'step{self.k}.phi'])
 
     task = Task()
-    w_approx, optim, sched, omegas = ag._new_target_task(meta['D'], t(z['init.omegas']).cuda())
+    w_approx, optim, sched, omegas = ag._new_target_task(meta['D'], t(z['init.omegas']).cuda(), fused=fused)
+    assert type(optim).__name__ == ('PackedTargetOptim' if fused else 'Adam')
     with torch.no_grad():
         w_approx.weight.copy_(t(z['init.w_target']))
     for k in range(meta['K']):
@@ -517,3 +522,20 @@ def test_g4_joint_psi_phi_vs_golden():
     psi = sf.get_successors(x)
     q_ref = torch.nn.functional.linear(psi, sf.fit_w[policy].weight.data, sf.fit_w[policy].bias.data)[..., 0]
     assert rel_err(q.cpu(), q_ref.cpu()) < 1e-5
+
+
+def test_g1_lms_update_reward_kernel():
+    """G1's per-step LMS rule (features/successor.py:146-167) as one kernel == the torch formula, on the packed reward row."""
+    from deep_successor_features_for_transfer_b200.ensemble import DeepSF as DeepSF_G1
+    sf = DeepSF_G1(pytorch_model_handle=gu.model_lambda([64, 64], ['relu', 'relu']), hyperparameters={'learning_rate_w': 0.5})
+    sf.reset()
+    for i in range(3):
+        sf.add_training_task(gu.FakeTask(4, 9, 12, i))
+    gen = torch.Generator().manual_seed(3)
+    w_ref = sf.fit_w[1].clone().cpu()
+    for _ in range(20):
+        phi, r = torch.rand(12, generator=gen) * 2.5 - 1.5, torch.randn((), generator=gen)
+        w_ref = w_ref + 0.5 * (r - torch.sum(phi.reshape(-1, 1) * w_ref)) * phi.reshape(-1, 1)
+        sf.update_reward(phi, r, 1)
+    assert rel_err(sf.fit_w[1].cpu(), w_ref) < 1e-5
+    assert torch.equal(sf.fit_w[1], sf._library.w[1].view(-1, 1))          # in place on the packed row
