@@ -48,7 +48,12 @@ def weights_close(W, W_ref, mean_tol=STEP_MEAN_TOL, outliers=STEP_OUTLIERS):
     return True
 
 
-XX
+def check_moments(stats, n_layers, hidden_tol=5e-3, out_tol=MOMENT_TOL):
+    """stats: (layer, Frobenius error of Adam's m) per (policy, layer).  Layers below a ReLU gate: hidden_tol (one flipped gate);
+    the output layer (no gate between it and the loss): out_tol for EVERY policy."""
+    for l, err in stats:
+        bound = out_tol if l == n_layers - 1 else hidden_tol
+        assert err < bound, f'layer {l}: Adam m error {err:.2e} (bound {bound})'
 
 
 def mean_err(a, b):
