@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('SFGPI_LIB_PATH') or os.path.join(HERE, 'libsfgpi.so')      # (override: A/B runs of two builds)
-SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu', 'g4.cu', 'target.cu']
+SOURCES = ['mlp_forward.cu', 'gpi.cu', 'td.cu', 'mlp_backward.cu', 'adam.cu', 'mlp_forward_tc.cu', 'mlp_chain_tc.cu', 'mlp_backward_tc.cu', 'run.cu', 'replay.cu', 'peer.cu', 'phi.cu', 'mlp_stream_tc.cu', 'mlp_wgrad_tf32.cu', 'g4.cu', 'target.cu']
 MAX_LAYERS = 8
 MAX_SEGMENTS = 8
 ACT = {'none': 0, 'relu': 1, 'tanh': 2}
@@ -206,6 +206,7 @@ SYMBOLS = {
     'sfgpi_peer_reduce_keys': (C.c_int, [C.POINTER(PeerKeysArgs), C.c_void_p]),
     'sfgpi_peer_unpack': (C.c_int, [C.POINTER(PeerUnpackArgs), C.c_void_p]),
     'sfgpi_set_option': (C.c_int, [C.c_char_p, C.c_int32]),
+    'sfgpi_trace_dump': (None, []),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
 }

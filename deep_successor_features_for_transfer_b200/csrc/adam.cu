@@ -83,8 +83,8 @@ __device__ __forceinline__ void adam_finish_one(int32_t *step, double *consts, i
 
 __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constant__ sfgpi_adam_args a, int blocks_per_pol) {
     __shared__ float sqrt_bc2_s, step_size_s[SFGPI_MAX_SEGMENTS];
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_launch_dependents(SFGPI_TR_ADAM);
+    pdl_wait(SFGPI_TR_ADAM);
     const int p = blockIdx.y;                               // optimizer (policy slot)
     // ---- losses (block 0 of each optimizer): fixed-order sum of the TD kernel's per-CTA partials ----
     if (blockIdx.x == 0 && a.loss_part != nullptr && threadIdx.x < 32) {
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
         a.consts_next[2 * p] = 1.0 - pow(a.beta1, t);
         a.consts_next[2 * p + 1] = sqrt(1.0 - pow(a.beta2, t));
     }
+    trace_exit(SFGPI_TR_ADAM);
 }
 
 __global__ void adam_refresh_kernel(const int32_t *step, double *ca, double *cb, int n, double beta1, double beta2) {
@@ -224,6 +225,7 @@ __global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double 
 using namespace sfgpi;
 
 extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
+    trace_bind();
     const sfgpi_adam_args &a = *args;
     if (a.n_seg < 1 || a.n_seg > SFGPI_MAX_SEGMENTS || a.n_pol < 1 || (a.step == nullptr && !a.fresh)) {
         set_error("sfgpi_adam_step: invalid arguments");

@@ -22,8 +22,36 @@ int check_launch(const char *what);
 // ---- programmatic dependent launch (PDL): the kernels of one train step are a dependent chain of a dozen small launches, so
 // launch latency and per-kernel set-up are a large share of the step.  Every kernel lets its successor be scheduled at once
 // (launch_dependents) and itself waits for its predecessor's memory (wait) only after its own data-independent set-up.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Developer aid (env SFGPI_TRACE=1, sfgpi_trace_dump): %globaltimer window of every step kernel -- first CTA entry, first CTA
+// past its dependency wait, last CTA exit -- so that the gaps BETWEEN the kernels of a step can be read, not only their own
+// durations.  The buffer pointer is a per-translation-unit device global bound lazily by trace_bind() in the launching host code.
+enum { SFGPI_TR_PREP = 0, SFGPI_TR_FWD = 1, SFGPI_TR_TD = 2, SFGPI_TR_DGRAD = 3, SFGPI_TR_WGRAD = 4, SFGPI_TR_ADAM = 5, SFGPI_TR_SLOTS = 8 };
+unsigned long long *trace_buffer();          // gpi.cu: device buffer [SFGPI_TR_SLOTS][3], or NULL when tracing is off
+static __device__ unsigned long long *g_trace = nullptr;
+static inline void trace_bind() {
+    static bool bound = false;
+    if (bound) return;
+    unsigned long long *p = trace_buffer();
+    if (p != nullptr) cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+    bound = true;
+}
+__device__ __forceinline__ void trace_mark(int slot, int what) {
+    if (slot >= 0 && threadIdx.x == 0 && g_trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (what == 2) atomicMax(g_trace + 3 * slot + 2, t);
+        else atomicMin(g_trace + 3 * slot + what, t);
+    }
+}
+__device__ __forceinline__ void pdl_launch_dependents(int trace_slot = -1) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    trace_mark(trace_slot, 0);
+}
+__device__ __forceinline__ void pdl_wait(int trace_slot = -1) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    trace_mark(trace_slot, 1);
+}
+__device__ __forceinline__ void trace_exit(int trace_slot) { trace_mark(trace_slot, 2); }
 
 bool pdl_enabled();
 

@@ -1,0 +1,151 @@
+// Definitions shared by the tensor-core forward kernels (mlp_forward_tc.cu: ping-pong pairs / 2-CTA pairs;
+// mlp_chain_tc.cu: the single-tile layer-pipelined chain): job / launch parameter blocks, the item (layer) table, the hidden-layer epilogue.
+#pragma once
+#include "tc_common.cuh"
+#include "gpi_scan.cuh"
+
+namespace sfgpi {
+namespace tc {
+
+constexpr int kNB = 128;                 // weight rows (output columns) per stage
+constexpr int kStageBytes = kNB * kKB * 2;          // 16 KB
+constexpr int kNStage = 4;
+constexpr int kABytes = kTM * kH * 2;               // 64 KB per tile slot
+constexpr int kThreadsTc = 416;                      // 4 producer warps + 1 MMA warp + 2 x 4 epilogue warps
+constexpr int kMmaWarp = 4, kEpiWarp0 = 5;
+constexpr int kBiasFloatsMax = 6144;                // all layers' biases of one policy, fp32 (24 KB)
+
+struct TcParams {
+    sfgpi_forward_args a;
+    int rows_per_policy;     // rows of the bf16 shadow per policy = (1 + Lh)*256 + n3pad
+    int n_final;             // output columns actually computed (padded to 16): n3pad (psi form) or nqpad (GPI form)
+    int Lh;                  // number of 256x256 MMA layers (n_layers - 2)
+    int n_items;             // 1 + Lh + ceil(n_final / 256)
+    int ks0;                 // K=16 steps of the input layer = ceil(S / 16)
+    int gpi;                 // 1: GPI form (folded weights, tmap_q / bq)
+    int nw;                  // reward vectors scored per policy in GPI form
+    int tiles_per_policy, pairs_per_policy, total_pairs, paired;
+    const float *bq;         // folded bias [n_pol][n_final] (GPI form)
+};
+
+struct ItemInfo { int row_base, n_cols, col0, kind, n_kb, n_k16; };   // kind: 0 input layer, 1 hidden, 2 final
+
+__device__ __forceinline__ ItemInfo item_info(const TcParams &p, int it) {
+    ItemInfo r;
+    if (it == 0) { r.row_base = 0; r.n_cols = kH; r.col0 = 0; r.kind = 0; r.n_kb = 1; r.n_k16 = p.ks0; }
+    else if (it <= p.Lh) { r.row_base = it * kH; r.n_cols = kH; r.col0 = 0; r.kind = 1; r.n_kb = kH / kKB; r.n_k16 = kKB / 16; }
+    else {
+        const int c = it - 1 - p.Lh;
+        r.col0 = c * 256;
+        r.n_cols = min(256, p.n_final - r.col0);
+        r.row_base = (p.gpi ? 0 : (1 + p.Lh) * kH) + r.col0;
+        r.kind = 2; r.n_kb = kH / kKB; r.n_k16 = kKB / 16;
+    }
+    return r;
+}
+
+// (lo, hi) + (blo, bhi) as one packed fp32 instruction (sm_100: add.f32x2; each lane rounds exactly like add.rn.f32)
+__device__ __forceinline__ void add_f32x2(float lo, float hi, float blo, float bhi, float &rlo, float &rhi) {
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(rlo), "=f"(rhi) : "f"(lo), "f"(hi), "f"(blo), "f"(bhi));
+}
+// bf16x2(max(lo, 0), max(hi, 0)), round to nearest even: the ReLU rides in the conversion
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+__device__ __forceinline__ float act_apply_fast(float v, int act) {
+    return act == SFGPI_ACT_RELU ? fmaxf(v, 0.0f) : (act == SFGPI_ACT_TANH ? tanhf(v) : v);
+}
+
+// One hidden-type epilogue for one row: 256 accumulator columns -> bias + activation -> bf16 -> next layer's A operand.
+// The TMEM load of the next 32 columns is in flight while the current 32 are processed.
+// NCH = 32-column chunks handled by this thread (8: the whole row; 4: one half, when both epilogue groups share a tile),
+// starting at column cbase.
+template <int ACT, int NCH, bool MASK>
+__device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save,
+                                                uint32_t *mask_out, int cbase) {
+    uint32_t v[2][32];
+    uint32_t mbits[NCH];                               // bit i of word cb: activation (cbase + 32 cb + i) > 0
+    tmem_ld32(t_lane + cbase, v[0]);
+#pragma unroll
+    for (int cb = 0; cb < NCH; ++cb) {
+        const int c0 = cbase + cb * 32;
+        tmem_wait_ld();
+        if (cb + 1 < NCH) tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
+        const uint32_t(&u)[32] = v[cb & 1];
+        uint32_t pk[16];
+        uint32_t mb = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 bv = lds128(bias + 4u * (c0 + 4 * g));
+            // packed fp32 adds (add.f32x2) and, for ReLU, the clamp fused into the bf16 conversion (cvt.rn.relu.bf16x2.f32):
+            // 4 instructions per 4 columns instead of 10 -- the epilogue is issue / latency bound (2 warps per scheduler)
+            float h0, h1, h2, h3;
+            add_f32x2(__uint_as_float(u[4 * g]), __uint_as_float(u[4 * g + 1]), bv.x, bv.y, h0, h1);
+            add_f32x2(__uint_as_float(u[4 * g + 2]), __uint_as_float(u[4 * g + 3]), bv.z, bv.w, h2, h3);
+            if (ACT == SFGPI_ACT_RELU) {
+                if (MASK)
+                    mb |= (h0 > 0.f ? 1u : 0u) << (4 * g) | (h1 > 0.f ? 2u : 0u) << (4 * g) | (h2 > 0.f ? 4u : 0u) << (4 * g) |
+                          (h3 > 0.f ? 8u : 0u) << (4 * g);
+                pk[2 * g] = pack_bf16x2_relu(h0, h1);
+                pk[2 * g + 1] = pack_bf16x2_relu(h2, h3);
+            } else {
+                if (ACT == SFGPI_ACT_TANH) { h0 = tanhf(h0); h1 = tanhf(h1); h2 = tanhf(h2); h3 = tanhf(h3); }
+                pk[2 * g] = pack_bf16x2(h0, h1);
+                pk[2 * g + 1] = pack_bf16x2(h2, h3);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            sts128(Arow + a_chunk_off(r, c0 + 8 * g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        mbits[cb] = mb;
+        if (save) {                                    // the bf16-rounded values the next layer really consumed
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4 *>(save + c0 + 4 * g) =
+                    make_float4(__uint_as_float(pk[2 * g] << 16), __uint_as_float(pk[2 * g] & 0xFFFF0000u),
+                                __uint_as_float(pk[2 * g + 1] << 16), __uint_as_float(pk[2 * g + 1] & 0xFFFF0000u));
+        }
+    }
+    if (MASK && ACT == SFGPI_ACT_RELU && mask_out != nullptr) {    // 1 bit per activation: all the backward pass needs of a ReLU layer
+        static_assert(NCH == 4 || NCH == 2, "mask row layout: 8 words per row; a call covers 4 (column half) or 2 (quarter) of them");
+        if (NCH == 4) *reinterpret_cast<uint4 *>(mask_out + (cbase >> 5)) = make_uint4(mbits[0], mbits[1], mbits[NCH - 2], mbits[NCH - 1]);
+        else *reinterpret_cast<uint2 *>(mask_out + (cbase >> 5)) = make_uint2(mbits[0], mbits[1]);
+    }
+}
+
+// Up to kMaxJobs independent forwards (e.g. online psi(s), GPI on s', target psi(s') of one train step) share ONE launch: the
+// persistent tile loop runs over the concatenated pair lists, so the small per-step forwards fill the machine together
+// instead of queueing as three single-wave kernels.
+constexpr int kMaxJobs = 3;
+struct TcMulti {
+    long long *timeline;             // developer aid (env SFGPI_TIMELINE=1): clock64() stamps of CTA 0's roles, else NULL
+    int n_jobs, total_pairs;
+    int sched;                       // 1: work units come from the UnitTable (see below)
+    int paired;                      // 1: two tiles ping-pong per CTA; 0: one tile per CTA (small launches), see kernel header
+    int pair_start[kMaxJobs + 1];
+    TcParams job[kMaxJobs];
+};
+struct TmapSet { CUtensorMap w[kMaxJobs]; CUtensorMap q[kMaxJobs]; CUtensorMap acts[kMaxJobs]; };
+
+// Balanced schedule for mid-size launches (m.sched = 1): the host lists the work units explicitly -- ping-pong PAIRS of row
+// tiles for the full rounds, then SINGLE tiles for the remainder -- so that no CTA is left with a whole extra pair while
+// others idle (384 tiles on 148 SMs: pair + single everywhere instead of 2 pairs on 44 CTAs and 1 on 104).
+// entry = job << 30 | has_y << 29 | policy << 16 | first tile.
+constexpr int kMaxUnits = 1024;
+struct UnitTable { uint32_t u[kMaxUnits]; };
+struct Unit { int jb, pl, pip, tile0, tstep; bool has_y; };
+
+
+// role 0 = epilogue X (thread 0), 1 = MMA issuer, 2 = producer warp 0, 3 = epilogue Y (thread 0); 64 slots each
+#define TL_STAMP(role, cnt) do { if (m.timeline != nullptr && blockIdx.x == 0 && (cnt) < 64) m.timeline[(role) * 64 + (cnt)++] = clock64(); } while (0)
+
+// mlp_chain_tc.cu: the layer-pipelined single-tile kernel (the default for cta_group::1 launches)
+bool forward_chain_supported(const TcMulti &m);
+int launch_forward_chain(TcMulti &m, const TmapSet &maps, int total_tiles, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace sfgpi

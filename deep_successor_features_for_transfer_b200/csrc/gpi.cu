@@ -20,6 +20,20 @@ bool pdl_enabled() {
     return on;
 }
 
+unsigned long long *trace_buffer() {
+    static unsigned long long *buf = nullptr;
+    static bool init = false;
+    if (!init) {
+        init = true;
+        if (getenv("SFGPI_TRACE") != nullptr && cudaMalloc(&buf, SFGPI_TR_SLOTS * 3 * sizeof(unsigned long long)) == cudaSuccess) {
+            unsigned long long h[SFGPI_TR_SLOTS * 3];
+            for (int i = 0; i < SFGPI_TR_SLOTS; ++i) { h[3 * i] = h[3 * i + 1] = ~0ull; h[3 * i + 2] = 0; }
+            cudaMemcpy(buf, h, sizeof(h), cudaMemcpyHostToDevice);
+        } else buf = nullptr;
+    }
+    return buf;
+}
+
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -28,6 +42,27 @@ int check_launch(const char *what) {
     }
     return SFGPI_OK;
 }
+
+}  // namespace sfgpi
+
+// Prints (stderr) and resets the kernel windows collected since the last call; synchronises the device.  No-op unless SFGPI_TRACE=1.
+extern "C" void sfgpi_trace_dump(void) {
+    unsigned long long *buf = sfgpi::trace_buffer();
+    if (buf == nullptr) return;
+    cudaDeviceSynchronize();
+    unsigned long long h[sfgpi::SFGPI_TR_SLOTS * 3], t0 = ~0ull;
+    cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char *name[sfgpi::SFGPI_TR_SLOTS] = {"prep", "forward", "td", "dgrad", "wgrad", "adam", "-", "-"};
+    for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i) if (h[3 * i] < t0) t0 = h[3 * i];
+    fprintf(stderr, "[sfgpi trace] ns since the first kernel entry: entry / past dependency wait / last exit\n");
+    for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i)
+        if (h[3 * i + 2] != 0)
+            fprintf(stderr, "  %-8s %8lld %8lld %8lld\n", name[i], (long long)(h[3 * i] - t0), (long long)(h[3 * i + 1] - t0), (long long)(h[3 * i + 2] - t0));
+    for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i) { h[3 * i] = h[3 * i + 1] = ~0ull; h[3 * i + 2] = 0; }
+    cudaMemcpy(buf, h, sizeof(h), cudaMemcpyHostToDevice);
+}
+
+namespace sfgpi {
 
 __global__ void keys_fill_kernel(long long *keys, long long n) {
     pdl_launch_dependents();

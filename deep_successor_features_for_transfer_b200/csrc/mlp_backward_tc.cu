@@ -136,7 +136,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_dzo,
                     const __grid_constant__ sfgpi_td_args ex, int ex_nclu) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    pdl_launch_dependents();
+    pdl_launch_dependents(SFGPI_TR_DGRAD);
     if ((int)blockIdx.x >= p.n_main) {
         // Rider CTAs: the TSF expand of the TD step (one policy each).  It depends only on the TD kernel -- this launch's
         // predecessor -- and only the Adam kernel consumes it, so instead of a launch of its own on the step's dependent chain
@@ -174,7 +174,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
-    pdl_wait();
+    pdl_wait(SFGPI_TR_DGRAD);
 
     const int B = p.B, D = net.n_features;
 
@@ -371,6 +371,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    trace_exit(SFGPI_TR_DGRAD);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -396,7 +397,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
                     const __grid_constant__ CUtensorMap tmap_dzo, const __grid_constant__ CUtensorMap tmap_acts,
                     const __grid_constant__ CUtensorMap tmap_xo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    pdl_launch_dependents();
+    pdl_launch_dependents(SFGPI_TR_WGRAD);
     const sfgpi_net_desc &net = p.net;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem_raw);
@@ -429,7 +430,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
-    pdl_wait();
+    pdl_wait(SFGPI_TR_WGRAD);
 
     if (warp < kWgStages) {
         {
@@ -529,6 +530,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    trace_exit(SFGPI_TR_WGRAD);
 }
 
 // xo[b][c] = x[b][c] for c < S, 1 for c == S, 0 otherwise  (bf16 [B][64])
@@ -576,6 +578,7 @@ extern "C" int sfgpi_bwd_tc_splits(int32_t B, int32_t want) {
 }
 
 extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *stream) {
+    trace_bind();
     const sfgpi_backward_tc_args &a = *args;
     const sfgpi_net_desc &net = a.net;
     const int L = net.n_layers;

@@ -17,8 +17,7 @@
 //   GPI form  : q = psi . w is folded into the weights beforehand (sfgpi_fold_gpi: Wq[w,a,:] = sum_d w[d] W_out[a*D+d,:]),
 //               so the layer has only n_w * A columns and the epilogue is a running (max, argmax) per reward vector --
 //               psi[B,N,A,D] is never formed, not even on chip.  (GPI_w, sfdqn.py:215-240.)
-#include "tc_common.cuh"
-#include "gpi_scan.cuh"
+#include "forward_tc.cuh"
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,122 +25,6 @@
 namespace sfgpi {
 namespace tc {
 
-constexpr int kNB = 128;                 // weight rows (output columns) per stage
-constexpr int kStageBytes = kNB * kKB * 2;          // 16 KB
-constexpr int kNStage = 4;
-constexpr int kABytes = kTM * kH * 2;               // 64 KB per tile slot
-constexpr int kThreadsTc = 416;                      // 4 producer warps + 1 MMA warp + 2 x 4 epilogue warps
-constexpr int kMmaWarp = 4, kEpiWarp0 = 5;
-constexpr int kBiasFloatsMax = 6144;                // all layers' biases of one policy, fp32 (24 KB)
-
-struct TcParams {
-    sfgpi_forward_args a;
-    int rows_per_policy;     // rows of the bf16 shadow per policy = (1 + Lh)*256 + n3pad
-    int n_final;             // output columns actually computed (padded to 16): n3pad (psi form) or nqpad (GPI form)
-    int Lh;                  // number of 256x256 MMA layers (n_layers - 2)
-    int n_items;             // 1 + Lh + ceil(n_final / 256)
-    int ks0;                 // K=16 steps of the input layer = ceil(S / 16)
-    int gpi;                 // 1: GPI form (folded weights, tmap_q / bq)
-    int nw;                  // reward vectors scored per policy in GPI form
-    int tiles_per_policy, pairs_per_policy, total_pairs, paired;
-    const float *bq;         // folded bias [n_pol][n_final] (GPI form)
-};
-
-struct ItemInfo { int row_base, n_cols, col0, kind, n_kb, n_k16; };   // kind: 0 input layer, 1 hidden, 2 final
-
-__device__ __forceinline__ ItemInfo item_info(const TcParams &p, int it) {
-    ItemInfo r;
-    if (it == 0) { r.row_base = 0; r.n_cols = kH; r.col0 = 0; r.kind = 0; r.n_kb = 1; r.n_k16 = p.ks0; }
-    else if (it <= p.Lh) { r.row_base = it * kH; r.n_cols = kH; r.col0 = 0; r.kind = 1; r.n_kb = kH / kKB; r.n_k16 = kKB / 16; }
-    else {
-        const int c = it - 1 - p.Lh;
-        r.col0 = c * 256;
-        r.n_cols = min(256, p.n_final - r.col0);
-        r.row_base = (p.gpi ? 0 : (1 + p.Lh) * kH) + r.col0;
-        r.kind = 2; r.n_kb = kH / kKB; r.n_k16 = kKB / 16;
-    }
-    return r;
-}
-
-__device__ __forceinline__ float act_apply_fast(float v, int act) {
-    return act == SFGPI_ACT_RELU ? fmaxf(v, 0.0f) : (act == SFGPI_ACT_TANH ? tanhf(v) : v);
-}
-
-// One hidden-type epilogue for one row: 256 accumulator columns -> bias + activation -> bf16 -> next layer's A operand.
-// The TMEM load of the next 32 columns is in flight while the current 32 are processed.
-// NCH = 32-column chunks handled by this thread (8: the whole row; 4: one half, when both epilogue groups share a tile),
-// starting at column cbase.
-template <int ACT, int NCH, bool MASK>
-__device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, uint32_t Arow, int r, float *save,
-                                                uint32_t *mask_out, int cbase) {
-    uint32_t v[2][32];
-    uint32_t mbits[NCH];                               // bit i of word cb: activation (cbase + 32 cb + i) > 0
-    tmem_ld32(t_lane + cbase, v[0]);
-#pragma unroll
-    for (int cb = 0; cb < NCH; ++cb) {
-        const int c0 = cbase + cb * 32;
-        tmem_wait_ld();
-        if (cb + 1 < NCH) tmem_ld32(t_lane + c0 + 32, v[(cb + 1) & 1]);
-        const uint32_t(&u)[32] = v[cb & 1];
-        uint32_t pk[16];
-        uint32_t mb = 0;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const float4 bv = lds128(bias + 4u * (c0 + 4 * g));
-            float h0 = __uint_as_float(u[4 * g]) + bv.x, h1 = __uint_as_float(u[4 * g + 1]) + bv.y;
-            float h2 = __uint_as_float(u[4 * g + 2]) + bv.z, h3 = __uint_as_float(u[4 * g + 3]) + bv.w;
-            if (ACT == SFGPI_ACT_RELU) {
-                if (MASK)
-                    mb |= (h0 > 0.f ? 1u : 0u) << (4 * g) | (h1 > 0.f ? 2u : 0u) << (4 * g) | (h2 > 0.f ? 4u : 0u) << (4 * g) |
-                          (h3 > 0.f ? 8u : 0u) << (4 * g);
-                h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f);
-            }
-            if (ACT == SFGPI_ACT_TANH) { h0 = tanhf(h0); h1 = tanhf(h1); h2 = tanhf(h2); h3 = tanhf(h3); }
-            pk[2 * g] = pack_bf16x2(h0, h1);
-            pk[2 * g + 1] = pack_bf16x2(h2, h3);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-            sts128(Arow + a_chunk_off(r, c0 + 8 * g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        mbits[cb] = mb;
-        if (save) {                                    // the bf16-rounded values the next layer really consumed
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<float4 *>(save + c0 + 4 * g) =
-                    make_float4(__uint_as_float(pk[2 * g] << 16), __uint_as_float(pk[2 * g] & 0xFFFF0000u),
-                                __uint_as_float(pk[2 * g + 1] << 16), __uint_as_float(pk[2 * g + 1] & 0xFFFF0000u));
-        }
-    }
-    if (MASK && ACT == SFGPI_ACT_RELU && mask_out != nullptr) {    // 1 bit per activation: all the backward pass needs of a ReLU layer
-        static_assert(NCH == 4, "mask row layout: 8 words per row, 4 per column half");
-        *reinterpret_cast<uint4 *>(mask_out + (cbase >> 5)) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-    }
-}
-
-// Up to kMaxJobs independent forwards (e.g. online psi(s), GPI on s', target psi(s') of one train step) share ONE launch: the
-// persistent tile loop runs over the concatenated pair lists, so the small per-step forwards fill the machine together
-// instead of queueing as three single-wave kernels.
-constexpr int kMaxJobs = 3;
-struct TcMulti {
-    long long *timeline;             // developer aid (env SFGPI_TIMELINE=1): clock64() stamps of CTA 0's roles, else NULL
-    int n_jobs, total_pairs;
-    int sched;                       // 1: work units come from the UnitTable (see below)
-    int paired;                      // 1: two tiles ping-pong per CTA; 0: one tile per CTA (small launches), see kernel header
-    int pair_start[kMaxJobs + 1];
-    TcParams job[kMaxJobs];
-};
-struct TmapSet { CUtensorMap w[kMaxJobs]; CUtensorMap q[kMaxJobs]; CUtensorMap acts[kMaxJobs]; };
-
-// Balanced schedule for mid-size launches (m.sched = 1): the host lists the work units explicitly -- ping-pong PAIRS of row
-// tiles for the full rounds, then SINGLE tiles for the remainder -- so that no CTA is left with a whole extra pair while
-// others idle (384 tiles on 148 SMs: pair + single everywhere instead of 2 pairs on 44 CTAs and 1 on 104).
-// entry = job << 30 | has_y << 29 | policy << 16 | first tile.
-constexpr int kMaxUnits = 1024;
-struct UnitTable { uint32_t u[kMaxUnits]; };
-struct Unit { int jb, pl, pip, tile0, tstep; bool has_y; };
-
-// role 0 = epilogue X (thread 0), 1 = MMA issuer, 2 = producer warp 0, 3 = epilogue Y (thread 0); 64 slots each
-#define TL_STAMP(role, cnt) do { if (m.timeline != nullptr && blockIdx.x == 0 && (cnt) < 64) m.timeline[(role) * 64 + (cnt)++] = clock64(); } while (0)
 
 __device__ __forceinline__ int job_of_pair(const TcMulti &m, int pair) {
     int j = 0;
@@ -178,8 +61,10 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
         else { u.tile0 = p.paired ? 2 * u.pip : u.pip; u.tstep = 1; u.has_y = p.paired && (2 * u.pip + 1 < p.tiles_per_policy); }
         return u;
     };
-    pdl_launch_dependents();
+    pdl_launch_dependents(SFGPI_TR_FWD);
     if (m.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) m.timeline[255] = clock64();      // kernel entry
+    const long long cta_t0 = clock64();
+    if (m.timeline != nullptr && threadIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); m.timeline[768 + blockIdx.x] = (long long)gt; }
 
     // ---- carve-up: [A slot X 64K][A slot Y 64K][weight ring 4 x 16K][biases 24K][barriers] ----
     const uint32_t sbase = smem_u32(smem_raw);
@@ -213,7 +98,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder_addr));
-    pdl_wait();                                              // set-up above overlapped the predecessor's tail
+    pdl_wait(SFGPI_TR_FWD);                                  // set-up above overlapped the predecessor's tail
 
 
     if (warp < kNStage) {
@@ -649,6 +534,10 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
     }
 
     // ---- teardown ----
+    if (m.timeline != nullptr && threadIdx.x == 0) {
+        m.timeline[512 + blockIdx.x] = clock64() - cta_t0;   // per-CTA busy cycles
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); m.timeline[1024 + blockIdx.x] = (long long)gt;
+    }
     tc_fence_before();
     if (TWO) cluster_sync_all(); else __syncthreads();       // (pair: nobody retires while the peer may still touch it)
     if (warp == kMmaWarp) {
@@ -656,6 +545,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
         tc_fence_after();
         if (TWO) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
+    trace_exit(SFGPI_TR_FWD);
 }
 
 // fp32 library rows -> bf16 shadow [n_pol][rows_per_policy][256]:
@@ -758,8 +648,8 @@ __device__ __forceinline__ void prep_pack8(const sfgpi_net_desc &net, const floa
 }
 
 __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ PrepParams pp) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_launch_dependents(SFGPI_TR_PREP);
+    pdl_wait(SFGPI_TR_PREP);
     const sfgpi_step_prep_args &a = pp.a;
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -774,6 +664,7 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
             *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(src + off);
         else
             for (long long q = off; q < min(off + 16, n); ++q) dst[q] = src[q];
+        trace_exit(SFGPI_TR_PREP);
         return;
     }
     bid -= pp.copy_end[SFGPI_PREP_COPIES - 1];
@@ -823,6 +714,7 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
     }
+    trace_exit(SFGPI_TR_PREP);
 }
 
 static int make_tmap(CUtensorMap *tm, const void *base, uint64_t rows) {
@@ -855,6 +747,30 @@ static int make_tmap_acts(CUtensorMap *tm, const void *base, uint64_t slabs, uin
 }
 
 static int g_two_cta_min = getenv("SFGPI_2CTA_MIN") ? atoi(getenv("SFGPI_2CTA_MIN")) : 0x7fffffff;
+static int g_forward_chain = getenv("SFGPI_CHAIN") ? atoi(getenv("SFGPI_CHAIN")) : 1;
+
+// developer aid (SFGPI_TIMELINE=1): dump CTA 0's role timelines (cycles since the first stamp)
+static void dump_timeline(long long *tl_buf, cudaStream_t st, int n_jobs, int units, int grid, const char *mode) {
+    long long h[1280];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, tl_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = 0;
+    for (int i = 0; i < 512; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+    if (h[256]) { fprintf(stderr, "  detail:"); for (int i = 256; i < 512 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - t0); fprintf(stderr, "\n"); }
+    { long long g0 = 0, g1 = 0, gs = 0; for (int i = 0; i < grid && i < 256; ++i) { if (!g0 || h[768 + i] < g0) g0 = h[768 + i]; if (h[768 + i] > gs) gs = h[768 + i]; if (h[1024 + i] > g1) g1 = h[1024 + i]; }
+      fprintf(stderr, "  globaltimer: first CTA start -> last CTA start %lld ns, -> last CTA end %lld ns; CTA 0: %lld cycles in %lld ns = %.0f MHz\n", gs - g0, g1 - g0,
+              h[512], h[1024] - h[768], 1000.0 * (double)h[512] / (double)(h[1024] - h[768])); }
+    fprintf(stderr, "  per-CTA busy cycles (k):");
+    for (int i = 0; i < grid && i < 256; ++i) fprintf(stderr, " %lld", h[512 + i] / 1000);
+    fprintf(stderr, "\n");
+    static const char *role[4] = {"epiX", "mma", "tma0", "epiY"};
+    fprintf(stderr, "[sfgpi timeline] jobs=%d units=%d grid=%d %s\n", n_jobs, units, grid, mode);
+    for (int r = 0; r < 4; ++r) {
+        fprintf(stderr, "  %-4s:", role[r]);
+        for (int i = 0; i < 64 && h[r * 64 + i]; ++i) fprintf(stderr, " %lld", h[r * 64 + i] - t0);
+        fprintf(stderr, "\n");
+    }
+}
 
 static bool tc_shape_ok(const sfgpi_net_desc &net, const char **why) {
     if (net.n_layers < 3) { *why = "needs >= 3 Linear layers"; return false; }
@@ -877,6 +793,11 @@ extern "C" int sfgpi_set_option(const char *name, int32_t value) {
     if (name != nullptr && strcmp(name, "2cta_min_tiles") == 0) {
         const int old = g_two_cta_min;
         g_two_cta_min = value;
+        return old;
+    }
+    if (name != nullptr && strcmp(name, "forward_chain") == 0) {      // 0: never, 1 (default): launches of <= 148 tiles, 2: always
+        const int old = g_forward_chain;
+        g_forward_chain = value;
         return old;
     }
     set_error("sfgpi_set_option: unknown option");
@@ -922,6 +843,7 @@ extern "C" int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, in
 }
 
 extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
+    trace_bind();
     if (!args) { set_error("sfgpi_step_prep: null args"); return SFGPI_E_INVALID; }
     PrepParams pp;
     pp.a = *args;
@@ -978,6 +900,7 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
 // the same (policy_lo, n_pol, w).
 extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32_t n_jobs, void *stream) {
     if (n_jobs < 1 || n_jobs > kMaxJobs) { set_error("sfgpi_mlp_forward_tc_jobs: 1..%d jobs per launch", kMaxJobs); return SFGPI_E_INVALID; }
+    trace_bind();
     TcMulti m;
     TmapSet maps;
     m.n_jobs = 0;
@@ -1031,8 +954,8 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     if (m.n_jobs == 0) return SFGPI_OK;
     static long long *tl_buf = nullptr;
     static const bool tl_on = getenv("SFGPI_TIMELINE") != nullptr;
-    if (tl_on && !tl_buf) cudaMalloc(&tl_buf, 256 * sizeof(long long));
-    if (tl_on) cudaMemsetAsync(tl_buf, 0, 256 * sizeof(long long), (cudaStream_t)stream);
+    if (tl_on && !tl_buf) cudaMalloc(&tl_buf, 1280 * sizeof(long long));
+    if (tl_on) cudaMemsetAsync(tl_buf, 0, 1280 * sizeof(long long), (cudaStream_t)stream);
     m.timeline = tl_on ? tl_buf : nullptr;
     static const int pair_min = getenv("SFGPI_PAIR_MIN") ? atoi(getenv("SFGPI_PAIR_MIN")) : 148;
     // 2-CTA pairs are opt-in (sfgpi_set_option("2cta_min_tiles", n) or env SFGPI_2CTA_MIN): measured on B200 they remove the
@@ -1041,6 +964,17 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     const int two_min = g_two_cta_min;
     const int paired = total_tiles > pair_min ? 1 : 0;           // small launches: one tile per CTA, no ping-pong partner
     const bool two = paired && total_tiles > two_min;            // >= 2 row tiles per SM: 2-CTA pairs (4 tiles per work unit)
+    // Launches that fit in ONE wave (<= 148 row tiles: every CTA has a single tile, nothing to ping-pong with) take the layer-
+    // pipelined single-tile kernel (mlp_chain_tc.cu): measured 84 vs 90 us per B = 32 step.  Larger launches keep the ping-pong
+    // pairs: with the MMA phase shared-memory-bound at ~3 k cycles per tile-layer, overlapping it with ANOTHER tile's epilogue
+    // (3.1 k per tile-layer) beats overlapping it with its own tile's previous epilogue (~5 k), 50 vs 52 us at 384 tiles.
+    // sfgpi_set_option("forward_chain", 0 / 1 / 2) = never / one-wave launches (default) / always.
+    if (g_forward_chain && (g_forward_chain > 1 || total_tiles <= 148) && !two && forward_chain_supported(m)) {
+        for (int j = m.n_jobs; j < kMaxJobs; ++j) { m.job[j] = m.job[0]; maps.w[j] = maps.w[0]; maps.q[j] = maps.q[0]; maps.acts[j] = maps.acts[0]; }
+        const int grid = launch_forward_chain(m, maps, total_tiles, (cudaStream_t)stream);
+        if (tl_on) dump_timeline(tl_buf, (cudaStream_t)stream, m.n_jobs, m.total_pairs, grid, "chain (one tile, layer-pipelined)");
+        return check_launch("sfgpi_mlp_forward_tc(chain)");
+    }
     m.total_pairs = 0;
     m.paired = paired;
     for (int j = 0; j < m.n_jobs; ++j) {
@@ -1119,20 +1053,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     const int grid = two ? (m.total_pairs < 74 ? 2 * m.total_pairs : 148) : (m.total_pairs < 148 ? m.total_pairs : 148);
     if (two) launch_pdl_cluster(mlp_forward_tc_kernel<true>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, 2, m, maps, ut);
     else launch_pdl(mlp_forward_tc_kernel<false>, dim3(grid), dim3(kThreadsTc), smem_bytes, (cudaStream_t)stream, m, maps, ut);
-    if (tl_on) {                                                 // developer aid: dump CTA 0's role timelines (cycles since t0)
-        long long h[256];
-        cudaStreamSynchronize((cudaStream_t)stream);
-        cudaMemcpy(h, tl_buf, sizeof(h), cudaMemcpyDeviceToHost);
-        long long t0 = 0;
-        for (int i = 0; i < 256; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
-        static const char *role[4] = {"epiX", "mma", "tma0", "epiY"};
-        fprintf(stderr, "[sfgpi timeline] jobs=%d units=%d grid=%d %s\n", m.n_jobs, m.total_pairs, grid, two ? "2-CTA pairs" : (m.sched ? "pairs + singles (unit table)" : (paired ? "paired" : "one-tile")));
-        for (int r = 0; r < 4; ++r) {
-            fprintf(stderr, "  %-4s:", role[r]);
-            for (int i = 0; i < 64 && h[r * 64 + i]; ++i) fprintf(stderr, " %lld", h[r * 64 + i] - t0);
-            fprintf(stderr, "\n");
-        }
-    }
+    if (tl_on) dump_timeline(tl_buf, (cudaStream_t)stream, m.n_jobs, m.total_pairs, grid, two ? "2-CTA pairs" : (m.sched ? "pairs + singles (unit table)" : (paired ? "paired" : "one-tile")));
     return check_launch("sfgpi_mlp_forward_tc");
 }
 

@@ -29,8 +29,8 @@ __global__ void __cluster_dims__(kTdCluster, 1, 1) __launch_bounds__(kTdThreads)
 td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi_peer_keys_args pk) {
     extern __shared__ __align__(16) float sm[];
     __shared__ int astar_s[kTdRows];                        // a*_b of this CTA's rows, decoded from the GPI keys
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_launch_dependents(SFGPI_TR_TD);
+    pdl_wait(SFGPI_TR_TD);
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const int B = a.B, S = a.S, D = a.D, G = a.G;
@@ -222,7 +222,7 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
         }
     }
     cluster.sync();                                          // nobody leaves while its shared memory is still being read
-
+    trace_exit(SFGPI_TR_TD);
 }
 
 __global__ void __launch_bounds__(256) tsf_expand_kernel(const __grid_constant__ sfgpi_td_args a, int nclu) {
@@ -240,6 +240,7 @@ extern "C" int sfgpi_td_partials(int32_t B) { return B <= 0 ? 1 : (B + kTdRows *
 
 extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     const sfgpi_td_args &a = *args;
+    trace_bind();
     if (a.variant < 0 || a.variant > 2 || a.B < 0 || a.n_pol < 0 || a.D < 1) { set_error("sfgpi_td_step: invalid arguments"); return SFGPI_E_INVALID; }
     if (a.B == 0 || a.n_pol == 0) return SFGPI_OK;
     const bool tsf = a.variant == 2;

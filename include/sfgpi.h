@@ -550,9 +550,17 @@ int sfgpi_peer_free(void *dptr);
 int sfgpi_peer_reduce_keys(const sfgpi_peer_keys_args *args, void *stream);
 int sfgpi_peer_unpack(const sfgpi_peer_unpack_args *args, void *stream);
 
-/* Runtime options: "2cta_min_tiles" = tensor-core forward launches with more 128-row tiles than this run as 2-CTA pairs
- * (tcgen05 cta_group::2, each CTA holds half of every weight block); default: never.  Returns the previous value or -1. */
+/* Runtime options.  Returns the previous value or -1 (unknown option).
+ *   "2cta_min_tiles"  tensor-core forward launches with more 128-row tiles than this run as 2-CTA pairs (tcgen05
+ *                     cta_group::2, each CTA holds half of every weight block); default: never.
+ *   "forward_chain"   which bf16 forward kernel runs: 0 = ping-pong tile pairs always (csrc/mlp_forward_tc.cu), 1 (default) =
+ *                     the layer-pipelined single-tile kernel (csrc/mlp_chain_tc.cu) for launches of <= 148 tiles, 2 = always. */
 int sfgpi_set_option(const char *name, int32_t value);
+
+/* Developer aid: with SFGPI_TRACE=1 in the environment every step kernel records the %globaltimer of its first CTA entry, of
+ * the first CTA past its dependency wait and of its last CTA exit; this call synchronises the device, prints the windows
+ * collected since the previous call to stderr and resets them.  No-op otherwise. */
+void sfgpi_trace_dump(void);
 
 const char *sfgpi_last_error(void);
 int sfgpi_version(void);

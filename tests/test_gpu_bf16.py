@@ -47,6 +47,50 @@ def test_bf16_forward_gpi_vs_oracle(S, A, D, N, B, hopper):
         _lib.lib().sfgpi_set_option(b'2cta_min_tiles', old)
 
 
+@pytest.mark.parametrize('S,A,D,N,B,hopper', [
+    (4, 9, 12, 6, 33 * 128 - 5, False),  # 198 tiles on 148 CTAs: two tiles on some CTAs (prefetch + early staging of the next tile)
+    (4, 9, 12, 10, 33 * 128 - 5, False), # 330 tiles: up to three tiles per CTA
+    (11, 27, 50, 5, 2048, True),         # Hopper: 6 output chunks alternate the two accumulators, S = 11 (two staged k-chunks)
+])
+def test_bf16_forward_chain_kernel_multi_tile(S, A, D, N, B, hopper):
+    """The layer-pipelined single-tile kernel (csrc/mlp_chain_tc.cu) forced onto launches of more than one wave -- by default it
+    only takes launches of <= 148 tiles, which the cases of test_bf16_forward_gpi_vs_oracle with few tiles already cover."""
+    from deep_successor_features_for_transfer_b200 import _lib
+    old = _lib.lib().sfgpi_set_option(b'forward_chain', 2)
+    try:
+        _bf16_forward_gpi_vs_oracle(S, A, D, N, B, hopper)
+    finally:
+        _lib.lib().sfgpi_set_option(b'forward_chain', old)
+
+
+@pytest.mark.parametrize('variant', ['g2', 'g3'])
+def test_bf16_chain_and_pair_kernels_agree_bit_for_bit(variant):
+    """Both forward kernels issue the same MMAs in the same k order on the same bf16 operands and share the epilogue arithmetic:
+    an all-task train step (online forward with saved activations / ReLU masks, fused GPI with 4 reward vectors, target
+    forward) must leave bit-identical losses, weights and Adam moments whichever kernel ran the forward."""
+    from deep_successor_features_for_transfer_b200 import _lib
+    S, A, D, N, B = 4, 9, 12, 4, 1000
+    tsf = variant == 'g3'
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True)
+    outs = []
+    for mode in (0, 2):
+        old = _lib.lib().sfgpi_set_option(b'forward_chain', mode)
+        try:
+            o, gen = make(S, A, D, N, seed=5, tsf_dim=100 if tsf else None)
+            if tsf:
+                sf, ag = gu.build_g3(meta, oracle=o)
+                sf._library.set_precision('bf16')
+            else:
+                sf = ag = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+            losses = [ag.update_successor_all(gu.cuda_tr(synthetic_transitions(B, S, A, D, gen)), use_gpi=True).clone() for _ in range(3)]
+            lib = sf._library
+            outs.append((torch.stack(losses).cpu(), lib.online[:N].clone().cpu(), lib.m[:N].clone().cpu(), lib.w[:N].clone().cpu()))
+        finally:
+            _lib.lib().sfgpi_set_option(b'forward_chain', old)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def _bf16_forward_gpi_vs_oracle(S, A, D, N, B, hopper):
     meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
     o, gen = make(S, A, D, N, seed=21)
