@@ -220,6 +220,105 @@ __global__ void adam_finish_kernel(int32_t *step, double *consts, int n, double 
     if (i < n) adam_finish_one(step, consts, i, beta1, beta2);
 }
 
+// ---- flattened fast path -----------------------------------------------------------------------------------------------------
+// adam_kernel above walks the segments one after the other and starts with a one-thread prologue (bias corrections in double,
+// __syncthreads): with ~1 trip per thread that is a chain of 5-6 dependent memory round trips (prologue, psi, w, g, shared h)
+// on a kernel that moves 31 MB -- 16.5 us for 4.8 us of HBM time (profiles/r01_step_kernels_full_v2.md).  Here every segment
+// has its own block range of ONE grid, every thread owns exactly one 128-bit item and issues all of its loads (bias
+// corrections, partials, p, m, v) before the first use, and the step size (lr / (1 - beta1^t), a double division as on the
+// host) is computed by each thread while those loads are in flight.  Same arithmetic and summation order per element as
+// adam_kernel: bit-identical results.  Taken when every per-optimizer segment is 128-bit aligned and neither fresh nor clamped.
+struct AdamFlat {
+    int blk_end[SFGPI_MAX_SEGMENTS];   // exclusive prefix ends of the per-optimizer segments' block ranges (shared segments: empty)
+    int n_own;                         // blocks of per-optimizer segments
+    int n_shared;                      // blocks (per grid row) that step the shared segments, warp per element
+};
+
+__global__ void __launch_bounds__(kAdamThreads) adam_flat_kernel(const __grid_constant__ sfgpi_adam_args a, const __grid_constant__ AdamFlat f) {
+    pdl_launch_dependents(SFGPI_TR_ADAM);
+    pdl_wait(SFGPI_TR_ADAM);
+    const int p = blockIdx.y;                               // optimizer (policy slot)
+    const int bid = blockIdx.x;
+    const AdamConsts kc = {(float)a.beta2, (float)(1.0 - a.beta1), (float)(1.0 - a.beta2), (float)a.eps};
+    if (bid < f.n_own) {
+        int s = 0;
+        while (bid >= f.blk_end[s]) ++s;
+        const sfgpi_adam_segment &sg = a.seg[s];
+        const int i = (bid - (s ? f.blk_end[s - 1] : 0)) * kAdamThreads + threadIdx.x;
+        if (i < (sg.len >> 2)) {
+            const double bc1 = a.consts[2 * p];
+            const float sqrt_bc2 = (float)a.consts[2 * p + 1];
+            const float4 *gp = reinterpret_cast<const float4 *>(sg.grad_part + (size_t)p * sg.grad_pol_stride) + i;
+            float4 *pp = reinterpret_cast<float4 *>(sg.param + (size_t)p * sg.param_stride) + i;
+            float4 *pm = reinterpret_cast<float4 *>(sg.m + (size_t)p * sg.m_stride) + i;
+            float4 *pv = reinterpret_cast<float4 *>(sg.v + (size_t)p * sg.v_stride) + i;
+            float4 pw = *pp, m = *pm, v = *pv;
+            const float4 g = sum_partials4(gp, sg.n_part, (size_t)(sg.grad_part_stride >> 2));
+            const float step_size = (float)((double)sg.lr / bc1);
+            adam_elem(pw.x, m.x, v.x, g.x, step_size, sqrt_bc2, sg.weight_decay, kc);
+            adam_elem(pw.y, m.y, v.y, g.y, step_size, sqrt_bc2, sg.weight_decay, kc);
+            adam_elem(pw.z, m.z, v.z, g.z, step_size, sqrt_bc2, sg.weight_decay, kc);
+            adam_elem(pw.w, m.w, v.w, g.w, step_size, sqrt_bc2, sg.weight_decay, kc);
+            *pp = pw; *pm = m; *pv = v;
+        }
+    } else if (bid < f.n_own + f.n_shared) {
+        // shared tensors (TSF's h): every optimizer steps them from the SAME pre-step value, each with its own moments; one warp
+        // per element, lane = optimizer, deltas summed by a fixed butterfly (as in adam_kernel)
+        const int lane = threadIdx.x & 31;
+        const int warps_total = f.n_shared * gridDim.y * (kAdamThreads / 32);
+        const int wg = (blockIdx.y * f.n_shared + (bid - f.n_own)) * (kAdamThreads / 32) + (threadIdx.x >> 5);
+        for (int s = 0; s < a.n_seg; ++s) {
+            const sfgpi_adam_segment &sg = a.seg[s];
+            if (!(sg.param_stride == 0 && a.n_pol > 1)) continue;
+            for (int i = wg; i < sg.len; i += warps_total) {
+                const float p0 = sg.param[i];
+                float dsum = 0.0f;
+                for (int q0 = 0; q0 < a.n_pol; q0 += 32) {
+                    const int q = q0 + lane;
+                    float delta = 0.0f;
+                    if (q < a.n_pol) {
+                        const double qbc1 = a.consts[2 * q];
+                        const float qsb2 = (float)a.consts[2 * q + 1];
+                        float *pm = sg.m + (size_t)q * sg.m_stride + i;
+                        float *pv = sg.v + (size_t)q * sg.v_stride + i;
+                        float pw = p0, m = *pm, v = *pv;
+                        const float g = sum_partials(sg.grad_part + (size_t)q * sg.grad_pol_stride + i, sg.n_part, (size_t)sg.grad_part_stride);
+                        adam_elem(pw, m, v, g, (float)((double)sg.lr / qbc1), qsb2, sg.weight_decay, kc);
+                        *pm = m; *pv = v;
+                        delta = pw - p0;
+                    }
+                    dsum += warp_sum(delta);
+                }
+                __syncwarp();
+                if (lane == 0) sg.param[i] = p0 + dsum;
+            }
+        }
+    } else {
+        // the last block of every grid row: the losses (fixed-order sum of the TD kernel's per-CTA partials) and the step
+        // counter / next step's bias corrections (consts_next: nothing in this launch reads it or `step`)
+        if (a.loss_part != nullptr && threadIdx.x < 32) {
+            float s1 = 0.0f, s2 = 0.0f;
+            const float *lp = a.loss_part + (size_t)p * a.n_loss_part * 2;
+            for (int i = threadIdx.x; i < a.n_loss_part; i += 32) { s1 += lp[2 * i]; s2 += lp[2 * i + 1]; }
+            s1 = warp_sum(s1); s2 = warp_sum(s2);
+            if (threadIdx.x == 0) {
+                const float l1 = s1 * a.l1_scale, l2 = s2 * a.l2_scale;
+                a.losses[p * 3 + 0] = l1 + a.beta_loss * l2;
+                a.losses[p * 3 + 1] = l1;
+                a.losses[p * 3 + 2] = l2;
+            }
+        }
+        if (threadIdx.x == 32) {
+            const int s_new = a.step[p] + 1;
+            a.step[p] = s_new;
+            const double t = (double)(s_new + 1);
+            a.consts_next[2 * p] = 1.0 - pow(a.beta1, t);
+            a.consts_next[2 * p + 1] = sqrt(1.0 - pow(a.beta2, t));
+        }
+    }
+    trace_exit(SFGPI_TR_ADAM);
+}
+
 }  // namespace sfgpi
 
 using namespace sfgpi;
@@ -241,13 +340,43 @@ extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
         if (a.seg[s].len < 0 || a.seg[s].n_part < 1) { set_error("sfgpi_adam_step: bad segment %d", s); return SFGPI_E_INVALID; }
         max_len = a.seg[s].len > max_len ? a.seg[s].len : max_len;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    // flattened fast path (see adam_flat_kernel): the train steps' shape -- double-buffered corrections, 128-bit aligned segments
+    static const bool flat_off = getenv("SFGPI_ADAM_FLAT") != nullptr && atoi(getenv("SFGPI_ADAM_FLAT")) == 0;
+    if (!flat_off && !a.fresh && a.consts != nullptr && a.consts_next != nullptr) {
+        AdamFlat f;
+        bool ok = true;
+        int nb = 0, shared_len = 0;
+        for (int s = 0; s < SFGPI_MAX_SEGMENTS; ++s) {
+            if (s < a.n_seg) {
+                const sfgpi_adam_segment &sg = a.seg[s];
+                const bool shared = sg.param_stride == 0 && a.n_pol > 1;
+                if (shared) shared_len = sg.len > shared_len ? sg.len : shared_len;
+                else {
+                    const bool vec = ((sg.len | sg.grad_part_stride | sg.grad_pol_stride | sg.param_stride | sg.m_stride | sg.v_stride) & 3) == 0 &&
+                                     ((reinterpret_cast<uintptr_t>(sg.grad_part) | reinterpret_cast<uintptr_t>(sg.param) |
+                                       reinterpret_cast<uintptr_t>(sg.m) | reinterpret_cast<uintptr_t>(sg.v)) & 15) == 0;
+                    if (!vec || sg.clamp_min < sg.clamp_max) { ok = false; break; }
+                    nb += ((sg.len >> 2) + kAdamThreads - 1) / kAdamThreads;
+                }
+            }
+            f.blk_end[s] = nb;
+        }
+        if (ok) {
+            f.n_own = nb;
+            const int warps = (shared_len + a.n_pol - 1) / a.n_pol;                  // warps per grid row: one element each
+            f.n_shared = shared_len > 0 ? (warps + kAdamThreads / 32 - 1) / (kAdamThreads / 32) : 0;
+            if (f.n_shared > 296) f.n_shared = 296;
+            launch_pdl(adam_flat_kernel, dim3(f.n_own + f.n_shared + 1, a.n_pol), dim3(kAdamThreads), 0, st, a, f);
+            return check_launch("sfgpi_adam_step(flat)");
+        }
+    }
     int blocks = (max_len + kAdamThreads - 1) / kAdamThreads;
     if (blocks < 1) blocks = 1;
     static const int ctas_per_sm = getenv("SFGPI_ADAM_CTAS") ? atoi(getenv("SFGPI_ADAM_CTAS")) : 8;       // (experiment knob)
     const int cap = (148 * ctas_per_sm + a.n_pol - 1) / a.n_pol;       // ~8 CTAs per SM over the whole launch
     if (blocks > cap) blocks = cap < 1 ? 1 : cap;
     dim3 grid(blocks, a.n_pol);
-    cudaStream_t st = (cudaStream_t)stream;
     launch_pdl(adam_kernel, grid, dim3(kAdamThreads), 0, st, a, blocks);
     int rc = check_launch("sfgpi_adam_step");
     if (rc || a.consts_next != nullptr || a.fresh) return rc;
