@@ -58,7 +58,8 @@ class TdArgs(C.Structure):
                 ('next_states', C.c_void_p), ('w', C.c_void_p), ('g', C.c_void_p), ('h', C.c_void_p),
                 ('w_stride', C.c_int32), ('g_stride', C.c_int32), ('d_out', C.c_void_p), ('loss_part', C.c_void_p),
                 ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32), ('next_psi', C.c_void_p), ('next_keys', C.c_void_p),
-                ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p), ('peer_keys', C.c_void_p), ('defer_expand', C.c_int32)]
+                ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p), ('peer_keys', C.c_void_p), ('defer_expand', C.c_int32),
+                ('tsf_mc', C.c_void_p)]
 
 
 class ForwardTcJob(C.Structure):
@@ -91,7 +92,9 @@ class StepPrepArgs(C.Structure):
                 ('pack_n', C.c_int32 * 2), ('keys', C.c_void_p), ('n_keys', C.c_int64), ('fold_params', C.c_void_p),
                 ('fold_lo', C.c_int32), ('fold_n', C.c_int32), ('w', C.c_void_p), ('n_w', C.c_int32), ('w_diag', C.c_int32),
                 ('wq', C.c_void_p), ('bq', C.c_void_p), ('x', C.c_void_p), ('B', C.c_int32), ('xo_bf16', C.c_void_p),
-                ('copy_src', C.c_void_p * 6), ('copy_dst', C.c_void_p * 6), ('copy_bytes', C.c_int64 * 6)]
+                ('copy_src', C.c_void_p * 6), ('copy_dst', C.c_void_p * 6), ('copy_bytes', C.c_int64 * 6),
+                ('tsf_g', C.c_void_p), ('tsf_h', C.c_void_p), ('tsf_mc', C.c_void_p), ('tsf_g_stride', C.c_int32), ('tsf_G', C.c_int32),
+                ('tsf_lo', C.c_int32), ('tsf_n', C.c_int32)]
 
 
 class ReplayArgs(C.Structure):

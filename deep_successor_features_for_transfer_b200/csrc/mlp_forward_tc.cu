@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
 struct PrepParams {
     sfgpi_step_prep_args a;
     int rows_per_policy, Lh, nqpad;
-    int blk_end[5];                  // exclusive prefix ends of the block ranges: pack 0, pack 1, keys, fold, xo
+    int blk_end[6];                  // exclusive prefix ends of the block ranges: pack 0, pack 1, keys, fold, xo, TSF M / c
     int copy_end[SFGPI_PREP_COPIES]; // ... preceded by the staging copies' ranges (blocks [0, copy_end[5]))
     const void *copy_src_dev[SFGPI_PREP_COPIES];      // device-visible addresses of the (pinned host) sources
 };
@@ -653,6 +653,37 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
     const sfgpi_step_prep_args &a = pp.a;
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
+    if (bid < a.tsf_n) {                                      // ---- TSF: M = Wh Wg, c = 2 (Wh bg + bh) of one policy (csrc/td.cu) ----
+        // first in the grid (the longest chain of the launch: staging, then D*(S+1) dot products of length G)
+        extern __shared__ __align__(16) float tsf_sm[];
+        const int pl = bid, S = a.net.dims[0], D = a.net.n_features, G = a.tsf_G;
+        float *Wg_s = tsf_sm, *bg_s = Wg_s + G * S, *Wh_s = bg_s + G, *bh_s = Wh_s + D * G;
+        const float *gp = a.tsf_g + (size_t)(a.tsf_lo + pl) * a.tsf_g_stride;
+        const uint32_t d0 = smem_u32(tsf_sm);
+        for (int e = tid; e < G * S + G; e += 256)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * e), "l"(gp + e) : "memory");
+        for (int e = tid; e < D * G + D; e += 256)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * (G * S + G + e)), "l"(a.tsf_h + e) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        float *mc = a.tsf_mc + (size_t)pl * (D * S + D);
+        for (int o = tid; o < D * (S + 1); o += 256) {               // same dot products, same order as the TD kernel's own derivation
+            const int d = o / (S + 1), sx = o - d * (S + 1);
+            const float *wh = Wh_s + d * G;
+            float acc = 0.0f;
+            if (sx < S) {
+                for (int g = 0; g < G; ++g) acc = fmaf(wh[g], Wg_s[g * S + sx], acc);
+                mc[d * S + sx] = acc;
+            } else {
+                for (int g = 0; g < G; ++g) acc = fmaf(wh[g], bg_s[g], acc);
+                mc[D * S + d] = 2.0f * (acc + bh_s[d]);
+            }
+        }
+        trace_exit(SFGPI_TR_PREP);
+        return;
+    }
+    bid -= a.tsf_n;
     if (bid < pp.copy_end[SFGPI_PREP_COPIES - 1]) {           // ---- staging copies (pinned host -> HBM over PCIe), first in the grid ----
         int j = 0;
         while (bid >= pp.copy_end[j]) ++j;
@@ -888,10 +919,19 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     pp.blk_end[3] = (int)n;
     if (a.x != nullptr && a.B > 0) n += ((long long)a.B * 8 + 255) / 256;
     pp.blk_end[4] = (int)n;
+    size_t tsf_bytes = 0;
+    if (a.tsf_n < 0) { set_error("sfgpi_step_prep: tsf_n < 0"); return SFGPI_E_INVALID; }
+    if (a.tsf_n > 0) {
+        if (!a.tsf_g || !a.tsf_h || !a.tsf_mc || a.tsf_G < 1) { set_error("sfgpi_step_prep: incomplete TSF M / c arguments"); return SFGPI_E_INVALID; }
+        tsf_bytes = ((size_t)a.tsf_G * a.net.dims[0] + a.tsf_G + (size_t)a.net.n_features * a.tsf_G + a.net.n_features) * sizeof(float);
+        if (tsf_bytes > 48 * 1024) { set_error("sfgpi_step_prep: g / h too large for the M / c blocks (%zu B)", tsf_bytes); return SFGPI_E_SMEM; }
+        n += a.tsf_n;
+    }
+    pp.blk_end[5] = (int)n;
     n += nc;
     if (n == 0) return SFGPI_OK;
     if (n > 0x7fffffffLL) { set_error("sfgpi_step_prep: too many blocks"); return SFGPI_E_INVALID; }
-    launch_pdl(step_prep_kernel, dim3((unsigned)n), dim3(256), 0, (cudaStream_t)stream, pp);
+    launch_pdl(step_prep_kernel, dim3((unsigned)n), dim3(256), tsf_bytes, (cudaStream_t)stream, pp);
     return check_launch("sfgpi_step_prep");
 }
 

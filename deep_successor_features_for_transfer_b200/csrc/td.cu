@@ -50,18 +50,58 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
     float *e_s = diff_s + kTdRows * D;            // [32]
     float *red_s = e_s + kTdRows;                 // [8] block-reduction scratch
     float *gacc_s = red_s + 8;                    // [n_acc] this CTA's partials, summed across the cluster
-    float *M_s = gacc_s + n_acc;                  // [D][S]   (tsf only from here)
+    float *cur_s = gacc_s + n_acc;                // [32][D]  psi(s)[a]
+    float *gam_s = cur_s + kTdRows * D;           // [32] gammas | [32] rewards
+    float *rs_s = gam_s + kTdRows;
+    float *M_s = rs_s + kTdRows;                  // [D][S]   (tsf only from here)
     float *c_s = M_s + D * S;                     // [D]
-    float *ss_s = c_s + D;                        // [32][S]  s + s'
-    float *Wg_s = ss_s + kTdRows * S;             // [G][S] | bg [G] | Wh [D][G] | bh [D]   staging for M, c
+    float *ss_s = c_s + D;                        // [32][S]  s, then s + s'
+    float *sn_s = ss_s + kTdRows * S;             // [32][S]  s'
+    float *Wg_s = sn_s + kTdRows * S;             // [G][S] | bg [G] | Wh [D][G] | bh [D]   staging for M, c (only without a.tsf_mc)
     float *bg_s = Wg_s + G * S, *Wh_s = bg_s + G, *bh_s = Wh_s + D * G;
+    const bool own_mc = tsf && a.tsf_mc == nullptr;
 
     for (int e = tid; e < n_acc; e += kTdThreads) gacc_s[e] = 0.0f;
+
+    // Everything this CTA reads that does not depend on a*, in ONE memory round trip: the GPI key of each row into a register,
+    // all the rest straight into shared memory with cp.async (fire and forget), one wait at the end.  As plain load -> store
+    // loops these were 6-7 dependent round trips (each loop's first store waits for its loads) of a kernel that is nothing but
+    // latency: 512 CTAs in one wave, 4 MB of data.
+    long long key_r = 0;
+    const bool sharded = a.next_psi != nullptr && pk.ctx.world > 0;
+    if (a.next_psi != nullptr && !sharded && tid < rows) key_r = a.next_keys[(size_t)pl * a.next_key_stride + row0 + tid];
+
+    const float *cur = a.cur_sel + (size_t)pl * B * D;
+    const float *nxt = a.next_sel + (size_t)pl * B * D;
+    float *dout = a.d_out + (size_t)pl * B * D;
+    auto stage = [&](float *dst, const float *src, int n_valid, int n_total) {       // dst[e] = e < n_valid ? src[e] : 0
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+        for (int e = tid; e < n_total; e += kTdThreads) {
+            const uint32_t nb = e < n_valid ? 4u : 0u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * e), "l"(src + (e < n_valid ? e : 0)), "r"(nb) : "memory");
+        }
+    };
+    if (reward) stage(w_s, a.w + (size_t)pl * a.w_stride, D, D);
+    stage(phi_s, a.phis + (size_t)row0 * D, rows * D, kTdRows * D);
+    stage(cur_s, cur + (size_t)row0 * D, rows * D, kTdRows * D);
+    stage(gam_s, a.gammas + row0, rows, kTdRows);
+    if (reward) stage(rs_s, a.rs + row0, rows, kTdRows);
+    if (tsf) {
+        stage(ss_s, a.states + (size_t)row0 * S, rows * S, kTdRows * S);
+        stage(sn_s, a.next_states + (size_t)row0 * S, rows * S, kTdRows * S);
+        if (own_mc) {
+            stage(Wg_s, a.g + (size_t)pl * a.g_stride, G * S + G, G * S + G);            // Wg | bg (contiguous in the row)
+            stage(Wh_s, a.h, D * G + D, D * G + D);                                      // Wh | bh
+        } else {
+            stage(M_s, a.tsf_mc + (size_t)pl * (D * S + D), D * S + D, D * S + D);       // M | c (contiguous, like M_s | c_s)
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     if (a.next_psi != nullptr) {
         // next actions: one key per row.  Sharded over peer memory, the key is the MAX over ranks of the rows this rank owns,
         // pulled here from the peers' arenas (csrc/peer.cu) once every rank has signalled that its forward pass is complete.
-        if (pk.ctx.world > 0) {
+        if (sharded) {
             peer_signal_and_wait(pk.ctx, SFGPI_PEER_CH_KEYS, (unsigned long long)pk.epoch, blockIdx.x == 0 && blockIdx.y == 0);
             if (tid < rows) {
                 const size_t off = (size_t)(pk.row_lo + pl) * B + row0 + tid;
@@ -77,37 +117,27 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
                 if (pk.keys_out != nullptr) pk.keys_out[(size_t)pl * B + row0 + tid] = k;
             }
         } else if (tid < rows) {
-            astar_s[tid] = (int)key_index(a.next_keys[(size_t)pl * a.next_key_stride + row0 + tid]);
+            astar_s[tid] = (int)key_index(key_r);
         }
     }
-
-    const float *cur = a.cur_sel + (size_t)pl * B * D;
-    const float *nxt = a.next_sel + (size_t)pl * B * D;
-    float *dout = a.d_out + (size_t)pl * B * D;
-
-    if (reward) for (int d = tid; d < D; d += kTdThreads) w_s[d] = a.w[(size_t)pl * a.w_stride + d];
-    for (int e = tid; e < kTdRows * D; e += kTdThreads) phi_s[e] = e < rows * D ? a.phis[(size_t)row0 * D + e] : 0.0f;
-    if (tsf) {
-        const float *gp = a.g + (size_t)pl * a.g_stride;
-        for (int e = tid; e < G * S + G; e += kTdThreads) Wg_s[e] = gp[e];                 // Wg | bg (contiguous in the row)
-        for (int e = tid; e < D * G + D; e += kTdThreads) Wh_s[e] = a.h[e];                // Wh | bh
-        for (int e = tid; e < kTdRows * S; e += kTdThreads)
-            ss_s[e] = e < rows * S ? a.states[(size_t)row0 * S + e] + a.next_states[(size_t)row0 * S + e] : 0.0f;
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     if (tsf) {
-        // M = Wh Wg, c = 2 (Wh bg + bh): D*(S+1) dot products of length G
-        for (int o = tid; o < D * (S + 1); o += kTdThreads) {
-            const int d = o / (S + 1), s = o - d * (S + 1);
-            const float *wh = Wh_s + d * G;
-            float acc = 0.0f;
-            if (s < S) {
-                for (int g = 0; g < G; ++g) acc = fmaf(wh[g], Wg_s[g * S + s], acc);
-                M_s[d * S + s] = acc;
-            } else {
-                for (int g = 0; g < G; ++g) acc = fmaf(wh[g], bg_s[g], acc);
-                c_s[d] = 2.0f * (acc + bh_s[d]);
+        for (int e = tid; e < kTdRows * S; e += kTdThreads) ss_s[e] += sn_s[e];           // s + s'
+        if (own_mc) {
+            // M = Wh Wg, c = 2 (Wh bg + bh): D*(S+1) dot products of length G
+            for (int o = tid; o < D * (S + 1); o += kTdThreads) {
+                const int d = o / (S + 1), s = o - d * (S + 1);
+                const float *wh = Wh_s + d * G;
+                float acc = 0.0f;
+                if (s < S) {
+                    for (int g = 0; g < G; ++g) acc = fmaf(wh[g], Wg_s[g * S + s], acc);
+                    M_s[d * S + s] = acc;
+                } else {
+                    for (int g = 0; g < G; ++g) acc = fmaf(wh[g], bg_s[g], acc);
+                    c_s[d] = 2.0f * (acc + bh_s[d]);
+                }
             }
         }
         __syncthreads();
@@ -133,8 +163,8 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
             } else {
                 nv = nxt[gi];
             }
-            const float target = fmaf(a.gammas[row0 + r], nv, tphi);
-            df = cur[gi] - target;
+            const float target = fmaf(gam_s[r], nv, tphi);
+            df = cur_s[e] - target;
             dout[gi] = c1 * df;
             l1_acc = fmaf(df, df, l1_acc);
         }
@@ -150,7 +180,7 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
             float ev = 0.0f;
             if (tid < rows) {
                 for (int d = 0; d < D; ++d) ev = fmaf(w_s[d], tphi_s[tid * D + d], ev);
-                ev -= a.rs[row0 + tid];
+                ev -= rs_s[tid];
                 l2_acc = ev * ev;
             }
             e_s[tid] = ev;
@@ -248,8 +278,8 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     if (a.aux_len < want_aux) { set_error("sfgpi_td_step: aux_len %d < %d", a.aux_len, want_aux); return SFGPI_E_INVALID; }
     if (tsf && a.tsf_part == nullptr) { set_error("sfgpi_td_step: variant 2 needs the tsf_part scratch buffer"); return SFGPI_E_INVALID; }
     const int n_red = tsf ? tsf_red_len(a.D, a.S) : a.D;
-    size_t fl = a.D + 3 * (size_t)kTdRows * a.D + kTdRows + 8 + (size_t)n_red + 2;
-    if (tsf) fl += (size_t)a.D * a.S + a.D + (size_t)kTdRows * a.S + (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D;
+    size_t fl = a.D + 4 * (size_t)kTdRows * a.D + 3 * kTdRows + 8 + (size_t)n_red + 2;
+    if (tsf) fl += (size_t)a.D * a.S + a.D + 2 * (size_t)kTdRows * a.S + (a.tsf_mc ? 0 : (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D);
     const size_t bytes = fl * sizeof(float);
     if (bytes > (size_t)kMaxSmem) { set_error("sfgpi_td_step: D/G too large for shared memory (%zu B)", bytes); return SFGPI_E_SMEM; }
     if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);

@@ -921,6 +921,12 @@ class PackedSFLibrary:
             pr.wq, pr.bq = plan['wq'].data_ptr(), plan['bq'].data_ptr()
             pr.B, pr.xo_bf16 = B, ws['xo16'].data_ptr()       # pr.x = this step's states, patched per step
             b.xo_ready = 1
+            if t.variant == 2:                                # M = Wh Wg, c once per policy here, not once per CTA of the TD kernel
+                if ws.get('tsf_mc') is None:
+                    ws['tsf_mc'] = self._f(n_pol, D * S + D)
+                pr.tsf_g, pr.tsf_g_stride, pr.tsf_h, pr.tsf_G = self.g.data_ptr(), self.g.shape[1], self.h.data_ptr(), self.G
+                pr.tsf_lo, pr.tsf_n, pr.tsf_mc = plan['lo'], n_pol, ws['tsf_mc'].data_ptr()
+                t.tsf_mc = ws['tsf_mc'].data_ptr()
             cmd(seg0, 'STEP_PREP', (C.addressof(pr),))
         else:
             if st_mode:

@@ -153,6 +153,8 @@ typedef struct {
                                        the MAX reduce-scatter of the GPI keys fused into the TD step */
     int32_t defer_expand;           /* variant 2, nonzero: skip the expand launch here; the caller hands this struct to
                                        sfgpi_mlp_backward_tc (expand_td), whose dgrad launch runs it on otherwise idle SMs */
+    const float *tsf_mc;            /* variant 2, optional [n_pol][D*S + D]: M = Wh Wg (row-major [D][S]) then c = 2 (Wh bg + bh) of
+                                       every policy, e.g. from sfgpi_step_prep (tsf_* fields); NULL: every CTA derives them itself */
 } sfgpi_td_args;
 
 int sfgpi_td_partials(int32_t B);
@@ -437,6 +439,13 @@ typedef struct {
     const void *copy_src[SFGPI_PREP_COPIES];
     void *copy_dst[SFGPI_PREP_COPIES];
     int64_t copy_bytes[SFGPI_PREP_COPIES];
+    /* optional (TSF): M = Wh Wg, c = 2 (Wh bg + bh) of tsf_n policies from tsf_lo on, once per step instead of once per CTA of the
+       TD kernel (h(g(s)) + h(g(s')) = M (s + s') + c, tsfdqn.py:621-623): tsf_g [.][tsf_g_stride] = W[G][S] | b[G] per policy,
+       tsf_h = W[D][G] | b[D] (shared), tsf_mc out [tsf_n][D*S + D].  tsf_n = 0: skipped */
+    const float *tsf_g;
+    const float *tsf_h;
+    float *tsf_mc;
+    int32_t tsf_g_stride, tsf_G, tsf_lo, tsf_n;
 } sfgpi_step_prep_args;
 int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream);
 
