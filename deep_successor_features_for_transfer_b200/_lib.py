@@ -59,7 +59,7 @@ class TdArgs(C.Structure):
                 ('w_stride', C.c_int32), ('g_stride', C.c_int32), ('d_out', C.c_void_p), ('loss_part', C.c_void_p),
                 ('aux_grad_part', C.c_void_p), ('aux_len', C.c_int32), ('next_psi', C.c_void_p), ('next_keys', C.c_void_p),
                 ('next_key_stride', C.c_int32), ('tsf_part', C.c_void_p), ('peer_keys', C.c_void_p), ('defer_expand', C.c_int32),
-                ('tsf_mc', C.c_void_p)]
+                ('tsf_mc', C.c_void_p), ('n_flows', C.c_int32)]
 
 
 class ForwardTcJob(C.Structure):

@@ -236,15 +236,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---- TSF expand (csrc/td.cu explains the mathematics) ---------------------------------------------------------------------
-__host__ __device__ inline int tsf_red_len(int D, int S) { return D + D * S + D; }      // [dw | T | t]
+__host__ __device__ inline int tsf_flow_len(int S, int K) { return K * (2 * S + 1); }      // K x (weight[S] | bias | scale[S])
+__host__ __device__ inline int tsf_red_len(int D, int S, int K = 0) { return D + D * S + D + tsf_flow_len(S, K); }      // [dw | T | t | flow gradients]
 
 // TSF: (dw, T, t) partials [n_pol][nclu][2D + D*S] -> the full reduced gradient row [dw | dWg | dbg | dWh | dbh] of each
 // policy (written to partial slot 0 of aux_grad_part; the Adam kernel reads it with n_part = 1).  red: [n_red] shared scratch,
 // Wg_s: [G][S] | bg [G], Wh_s: [D][G] already staged in shared memory; nt threads of one CTA take part.
 __device__ __forceinline__ void tsf_expand_policy(const sfgpi_td_args &a, int pl, int nclu, float *red, const float *Wg_s,
                                                   const float *Wh_s, int tid, int nt) {
-    const int S = a.S, D = a.D, G = a.G;
-    const int n_red = tsf_red_len(D, S);
+    const int S = a.S, D = a.D, G = a.G, nfl = tsf_flow_len(a.S, a.n_flows);
+    const int n_red = tsf_red_len(D, S, a.n_flows);
     const float *part = a.tsf_part + (size_t)pl * nclu * n_red;
     for (int e = tid; e < n_red; e += nt) {                  // fixed order k = 0, 1, ...; 8 loads in flight at a time
         float acc = 0.0f;
@@ -262,8 +263,9 @@ __device__ __forceinline__ void tsf_expand_policy(const sfgpi_td_args &a, int pl
     __syncthreads();
     const float *T = red + D, *tv = T + D * S, *bg_s = Wg_s + G * S;
     float *out = a.aux_grad_part + (size_t)pl * nclu * a.aux_len;        // slot 0 of this policy
-    float *gW = out + D, *gb = gW + G * S, *hW = gb + G, *hb = hW + D * G;
+    float *gW = out + D, *gb = gW + G * S, *gf = gb + G, *hW = gf + nfl, *hb = hW + D * G;
     for (int d = tid; d < D; d += nt) { out[d] = red[d]; hb[d] = 2.0f * tv[d]; }
+    for (int e = tid; e < nfl; e += nt) gf[e] = tv[D + e];    // the flows' gradients are complete sums already
     for (int e = tid; e < G * S; e += nt) {                  // dWg[g][s] = sum_d Wh[d][g] T[d][s]
         const int g = e / S, s = e - g * S;
         float acc = 0.0f;
@@ -284,11 +286,11 @@ __device__ __forceinline__ void tsf_expand_policy(const sfgpi_td_args &a, int pl
 }
 
 // whole expand of policy pl by one CTA of nt threads; sm: dynamic shared memory of >= tsf_expand_smem_floats() floats
-__host__ __device__ inline int tsf_expand_smem_floats(int D, int S, int G) { return tsf_red_len(D, S) + G * S + G + D * G; }
+__host__ __device__ inline int tsf_expand_smem_floats(int D, int S, int G, int K = 0) { return tsf_red_len(D, S, K) + G * S + G + D * G; }
 __device__ __forceinline__ void tsf_expand_cta(const sfgpi_td_args &a, int pl, int nclu, float *sm, int tid, int nt) {
     const int S = a.S, D = a.D, G = a.G;
     float *red = sm;                              // [dw | T | t]
-    float *Wg_s = red + tsf_red_len(D, S);        // [G][S] | bg [G]
+    float *Wg_s = red + tsf_red_len(D, S, a.n_flows);   // [G][S] | bg [G]
     float *Wh_s = Wg_s + G * S + G;               // [D][G]
     const float *gp = a.g + (size_t)pl * a.g_stride;
     for (int e = tid; e < G * S + G; e += nt) Wg_s[e] = gp[e];

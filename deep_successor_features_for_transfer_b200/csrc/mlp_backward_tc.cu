@@ -649,7 +649,7 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
     if (a.expand_td != nullptr) {                                    // deferred TSF expand (sfgpi_td_args.defer_expand)
         ex = *reinterpret_cast<const sfgpi_td_args *>(a.expand_td);
         if (ex.variant != 2 || ex.n_pol < 1 || !ex.tsf_part || !ex.aux_grad_part || !ex.g || !ex.h ||
-            (size_t)tsf_expand_smem_floats(ex.D, ex.S, ex.G) * sizeof(float) > (size_t)dg_smem) {
+            (size_t)tsf_expand_smem_floats(ex.D, ex.S, ex.G, ex.n_flows) * sizeof(float) > (size_t)dg_smem) {
             set_error("sfgpi_mlp_backward_tc: expand_td is not a variant-2 TD step that fits the dgrad launch");
             return SFGPI_E_INVALID;
         }

@@ -39,7 +39,8 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
     const int row0 = blk * kTdRows;
     const int rows = max(0, min(kTdRows, B - row0));         // the grid is padded to whole clusters: trailing CTAs add zeros
     const bool tsf = a.variant == 2, reward = a.variant >= 1;
-    const int n_red = tsf ? tsf_red_len(D, S) : (reward ? D : 0);      // gradient partials of this variant
+    const int K = tsf ? a.n_flows : 0, nfl = tsf_flow_len(S, K);      // normalising-flow g: K planar flows ahead of the Linear
+    const int n_red = tsf ? tsf_red_len(D, S, K) : (reward ? D : 0);      // gradient partials of this variant
     const int n_acc = n_red + 2;                             // [partials | sum diff^2 | sum e^2]
 
     // carve-up
@@ -60,6 +61,10 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
     float *Wg_s = sn_s + kTdRows * S;             // [G][S] | bg [G] | Wh [D][G] | bh [D]   staging for M, c (only without a.tsf_mc)
     float *bg_s = Wg_s + G * S, *Wh_s = bg_s + G, *bh_s = Wh_s + D * G;
     const bool own_mc = tsf && a.tsf_mc == nullptr;
+    float *fl_s = own_mc ? bh_s + D : Wg_s;       // (flows only) [K][weight S | bias | scale S]
+    float *zh_s = fl_s + nfl;                     // [64][K + 1][S]  z_0 .. z_K of (branch, row): branch 0 = s, 1 = s'
+    float *th_s = zh_s + 2 * kTdRows * (K + 1) * S;          // [64][K]  tanh of every flow's activation
+    float *fw_s = th_s + 2 * kTdRows * K;         // [2][nfl] the two warps' sums of the flows' gradients
 
     for (int e = tid; e < n_acc; e += kTdThreads) gacc_s[e] = 0.0f;
 
@@ -95,6 +100,7 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
         } else {
             stage(M_s, a.tsf_mc + (size_t)pl * (D * S + D), D * S + D, D * S + D);       // M | c (contiguous, like M_s | c_s)
         }
+        if (K > 0) stage(fl_s, a.g + (size_t)pl * a.g_stride + G * S + G, nfl, nfl);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 
@@ -123,6 +129,31 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
+    if (K > 0) {
+        // normalising-flow g (tsfdqn_nf.py:347-349): both state rows of every transition run through the K planar flows,
+        // z <- z + scale_k * tanh(z . weight_k + bias_k); thread t < 64 owns (branch t / 32, row t % 32) and keeps z_0 .. z_K and
+        // the tanh values for the backward sweep below.  h(g(.)) stays affine in the FLOWED states: aff = M (z + z') + c.
+        if (tid < 2 * kTdRows) {
+            const float *src = (tid < kTdRows ? ss_s : sn_s) + (tid & (kTdRows - 1)) * S;
+            float *z = zh_s + (size_t)tid * (K + 1) * S;
+            for (int s_ = 0; s_ < S; ++s_) z[s_] = src[s_];
+            for (int k = 0; k < K; ++k) {
+                const float *fw = fl_s + k * (2 * S + 1), *fsc = fw + S + 1;
+                float act = fw[S];
+                for (int s_ = 0; s_ < S; ++s_) act = fmaf(z[s_], fw[s_], act);
+                const float th = tanhf(act);
+                th_s[tid * K + k] = th;
+                for (int s_ = 0; s_ < S; ++s_) z[S + s_] = fmaf(fsc[s_], th, z[s_]);
+                z += S;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < 2 * kTdRows * S; e += kTdThreads) {                        // ss_s <- z_K(s), sn_s <- z_K(s')
+            const int t = e / S, s_ = e - t * S;
+            (t < kTdRows ? ss_s : sn_s)[(t & (kTdRows - 1)) * S + s_] = zh_s[((size_t)t * (K + 1) + K) * S + s_];
+        }
+        __syncthreads();
+    }
     if (tsf) {
         for (int e = tid; e < kTdRows * S; e += kTdThreads) ss_s[e] += sn_s[e];           // s + s'
         if (own_mc) {
@@ -229,6 +260,44 @@ td_kernel(const __grid_constant__ sfgpi_td_args a, const __grid_constant__ sfgpi
                 tv[d] = acc;
             }
         }
+        if (K > 0) {
+            // backward sweep through the flows: dL/dz_K = M^T daff for both branches, then per flow (t = tanh, a = its argument)
+            //   dscale = dz * t,  da = (dz . scale) (1 - t^2),  dweight = da * z_in,  dbias = da,  dz_in = dz + da * weight.
+            // Every contribution is summed over the 32 rows of a branch by a fixed butterfly, the two branches are added in order.
+            float *fgrad = tv + D;                       // [nfl] behind [dw | T | t]
+            if (tid < 2 * kTdRows) {
+                const int r = tid & (kTdRows - 1), wp = tid >> 5, ln = tid & 31;
+                float *zrow = zh_s + (size_t)tid * (K + 1) * S;
+                float *dz = zrow + K * S;                 // z_K is not needed any more: its slot holds dz
+                for (int s_ = 0; s_ < S; ++s_) {
+                    float acc = 0.0f;
+                    for (int d = 0; d < D; ++d) acc = fmaf(M_s[d * S + s_], daff_s[r * D + d], acc);
+                    dz[s_] = acc;
+                }
+                for (int k = K - 1; k >= 0; --k) {
+                    const float *fw = fl_s + k * (2 * S + 1), *fsc = fw + S + 1;
+                    const float *zin = zrow + k * S;
+                    float *out = fw_s + wp * nfl + k * (2 * S + 1);
+                    const float th = th_s[tid * K + k];
+                    float dt = 0.0f;
+                    for (int s_ = 0; s_ < S; ++s_) {
+                        const float v = warp_sum(dz[s_] * th);
+                        if (ln == 0) out[S + 1 + s_] = v;
+                        dt = fmaf(dz[s_], fsc[s_], dt);
+                    }
+                    const float da = dt * (1.0f - th * th);
+                    for (int s_ = 0; s_ < S; ++s_) {
+                        const float v = warp_sum(da * zin[s_]);
+                        if (ln == 0) out[s_] = v;
+                        dz[s_] = fmaf(da, fw[s_], dz[s_]);
+                    }
+                    const float vb = warp_sum(da);
+                    if (ln == 0) out[S] = vb;
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < nfl; e += kTdThreads) fgrad[e] = fw_s[e] + fw_s[nfl + e];
+        }
     }
 
     // ---- cluster reduction through distributed shared memory: rank r sums slice r of the 8 CTAs' partials, rank order ----
@@ -274,12 +343,15 @@ extern "C" int sfgpi_td_step(const sfgpi_td_args *args, void *stream) {
     if (a.variant < 0 || a.variant > 2 || a.B < 0 || a.n_pol < 0 || a.D < 1) { set_error("sfgpi_td_step: invalid arguments"); return SFGPI_E_INVALID; }
     if (a.B == 0 || a.n_pol == 0) return SFGPI_OK;
     const bool tsf = a.variant == 2;
-    const int want_aux = a.variant == 0 ? 0 : (tsf ? a.D + a.G * a.S + a.G + a.D * a.G + a.D : a.D);
+    const int want_aux = a.variant == 0 ? 0 : (tsf ? a.D + a.G * a.S + a.G + tsf_flow_len(a.S, a.n_flows) + a.D * a.G + a.D : a.D);
     if (a.aux_len < want_aux) { set_error("sfgpi_td_step: aux_len %d < %d", a.aux_len, want_aux); return SFGPI_E_INVALID; }
     if (tsf && a.tsf_part == nullptr) { set_error("sfgpi_td_step: variant 2 needs the tsf_part scratch buffer"); return SFGPI_E_INVALID; }
-    const int n_red = tsf ? tsf_red_len(a.D, a.S) : a.D;
+    const int K = tsf ? a.n_flows : 0;
+    if (K < 0) { set_error("sfgpi_td_step: n_flows < 0"); return SFGPI_E_INVALID; }
+    const int n_red = tsf ? tsf_red_len(a.D, a.S, K) : a.D;
     size_t fl = a.D + 4 * (size_t)kTdRows * a.D + 3 * kTdRows + 8 + (size_t)n_red + 2;
     if (tsf) fl += (size_t)a.D * a.S + a.D + 2 * (size_t)kTdRows * a.S + (a.tsf_mc ? 0 : (size_t)a.G * a.S + a.G + (size_t)a.D * a.G + a.D);
+    if (K > 0) fl += 3 * (size_t)tsf_flow_len(a.S, K) + 2 * (size_t)kTdRows * ((size_t)(K + 1) * a.S + K);
     const size_t bytes = fl * sizeof(float);
     if (bytes > (size_t)kMaxSmem) { set_error("sfgpi_td_step: D/G too large for shared memory (%zu B)", bytes); return SFGPI_E_SMEM; }
     if (bytes > 48 * 1024) cudaFuncSetAttribute(td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);

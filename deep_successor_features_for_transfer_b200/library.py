@@ -127,6 +127,7 @@ class PackedSFLibrary:
         self.lr = dict(sf=1e-3, w=1e-3, g=1e-3, h=1e-3) if lr is None else dict(lr)
         self.wd = dict(sf=0.0, w=0.0, g=0.0, h=0.0) if wd is None else dict(wd)
         self.G = tsf_dim
+        self.n_flows = 0            # planar flows ahead of g's Linear (normalising-flow g, tsfdqn_nf.py); set by the first add_policy
         self.spec = None
         self.n = 0
         self.cap = 0
@@ -287,7 +288,7 @@ class PackedSFLibrary:
                    adam_consts2=torch.tensor([[1.0 - 0.9 ** 1, math.sqrt(1.0 - 0.999 ** 1)]], dtype=torch.float64,
                                              device=dev).repeat(cap, 1).contiguous())
         if self.G is not None:
-            gl = self.G * sp.dims[0] + self.G
+            gl = self.G * sp.dims[0] + self.G + self.n_flows * (2 * sp.dims[0] + 1)      # W | b | K x (weight | bias | scale)
             hl = sp.n_features * self.G + sp.n_features
             new.update(g=z(cap, gl), g_m=z(cap, gl), g_v=z(cap, gl), h_m=z(cap, hl), h_v=z(cap, hl))
         for k, t in new.items():
@@ -310,8 +311,20 @@ class PackedSFLibrary:
         mods['w'].weight.data = self.w[i].view(1, -1)
         if mods.get('g') is not None:
             S = self.spec.dims[0]
-            mods['g'].weight.data = self.g[i, :self.G * S].view(self.G, S)
-            mods['g'].bias.data = self.g[i, self.G * S:]
+            flows, lin = self._split_g(mods['g'])
+            lin.weight.data = self.g[i, :self.G * S].view(self.G, S)
+            lin.bias.data = self.g[i, self.G * S:self.G * S + self.G]
+            for k, f in enumerate(flows):
+                o = self.G * S + self.G + k * (2 * S + 1)
+                f.weight.data, f.bias.data, f.scale.data = self.g[i, o:o + S].view(1, S), self.g[i, o + S:o + S + 1], self.g[i, o + S + 1:o + 2 * S + 1].view(1, S)
+
+    @staticmethod
+    def _split_g(g):
+        """g-function module -> (planar flows, final Linear): nn.Linear (tsfdqn.py:537-539) or Sequential(flows..., Linear) (tsfdqn_nf.py:352-358)."""
+        if isinstance(g, torch.nn.Linear):
+            return [], g
+        mods = list(g)
+        return mods[:-1], mods[-1]
 
     def add_policy(self, model, target_model, w_linear, g_linear=None, h_linear=None, n_actions=None, n_features=None):
         """Adopts freshly built reference-style modules into packed storage (sfdqn.py:180-288)."""
@@ -323,6 +336,12 @@ class PackedSFLibrary:
             raise ValueError('all psi networks of a library must share one architecture')
         if (g_linear is None) != (self.G is None):
             raise ValueError('g/h functions must be given iff the library was built with tsf_dim')
+        if g_linear is not None:
+            flows, g_lin = self._split_g(g_linear)
+            if self.n == 0 and self.n_flows != len(flows):
+                self.n_flows, self.cap = len(flows), 0           # (re-allocated below with the g row's real length)
+            if len(flows) != self.n_flows:
+                raise ValueError('every g function of a library must have the same number of flows')
         if self.n == self.cap:
             self._alloc(max(self._cap0, 2 * self.cap))
         i = self.n
@@ -337,10 +356,13 @@ class PackedSFLibrary:
             mods = dict(online=lin_on, target=lin_tg, w=w_linear, g=g_linear)
             if g_linear is not None:
                 S = self.spec.dims[0]
-                if g_linear.out_features != self.G or g_linear.in_features != S:
+                if g_lin.out_features != self.G or g_lin.in_features != S:
                     raise ValueError('g function shape mismatch')
-                self.g[i, :self.G * S].copy_(g_linear.weight.data.reshape(-1))
-                self.g[i, self.G * S:].copy_(g_linear.bias.data)
+                self.g[i, :self.G * S].copy_(g_lin.weight.data.reshape(-1))
+                self.g[i, self.G * S:self.G * S + self.G].copy_(g_lin.bias.data)
+                for k, f in enumerate(flows):
+                    o = self.G * S + self.G + k * (2 * S + 1)
+                    self.g[i, o:o + 2 * S + 1].copy_(torch.cat([f.weight.data.reshape(-1), f.bias.data.reshape(-1), f.scale.data.reshape(-1)]))
                 if self.h is None:
                     D = self.spec.n_features
                     self.h = torch.cat([h_linear.weight.data.reshape(-1), h_linear.bias.data.reshape(-1)]).float().to(self.device).contiguous()
@@ -426,12 +448,12 @@ class PackedSFLibrary:
             ws['grad_part'] = torch.zeros(n_pol, n_split, sp.row_stride, dtype=torch.float32, device=self.device)
             if self.G is not None:
                 S = sp.dims[0]
-                ws['aux_len'] = D + self.G * S + self.G + D * self.G + D
+                ws['aux_len'] = D + self.g.shape[1] + D * self.G + D
             else:
                 ws['aux_len'] = D
             ws['aux_part'] = self._f(n_pol, nblk, ws['aux_len'])
             if self.G is not None:
-                ws['tsf_part'] = self._f(n_pol, nblk, 2 * D + D * sp.dims[0])
+                ws['tsf_part'] = self._f(n_pol, nblk, 2 * D + D * sp.dims[0] + self.n_flows * (2 * sp.dims[0] + 1))
             self._ws[key] = ws
         return ws
 
@@ -618,7 +640,7 @@ class PackedSFLibrary:
             t.next_psi, t.next_keys, t.next_key_stride = ptr(ws['next_psi']), C.c_void_p(keys[key_row0:].data_ptr()), B
         t.w, t.w_stride = P(self.w), D
         if variant == 2:
-            t.g, t.g_stride, t.h = P(self.g), self.g.shape[1], ptr(self.h)
+            t.g, t.g_stride, t.h, t.n_flows = P(self.g), self.g.shape[1], ptr(self.h), self.n_flows
         t.d_out, t.loss_part, t.aux_grad_part, t.aux_len = ptr(ws['d_out']), ptr(ws['loss_part']), ptr(ws['aux_part']), ws['aux_len']
         if variant == 2:
             t.tsf_part = ptr(ws['tsf_part'])

@@ -12,7 +12,7 @@ import torch
 import ctypes as C
 
 from . import _lib
-from .library import _stream
+from .library import PackedSFLibrary, _stream
 from .sfdqn import DeepSF, DeviceReplayBuffer, ReplayBuffer, SFDQN, _device  # noqa: F401  (re-exported like the reference file)
 
 
@@ -91,7 +91,7 @@ class DeepTSF(DeepSF):
         if g_function_model is None or h_function_model is None:
             raise Exception('DeepTSF.add_training_task needs the g and h functions (tsfdqn.py:137)')
         if self._tsf_dim is None:
-            self._tsf_dim = g_function_model.out_features
+            self._tsf_dim = PackedSFLibrary._split_g(g_function_model)[1].out_features
             self._library = self._new_library()
         true_w = task.get_w()
         n_features = task.feature_dim()
@@ -242,6 +242,8 @@ class TSFDQN(SFDQN):
         torch.optim.Adam + LambdaLR (the eager path, kept for callers that hand in their own optimizer).
         """
         hp = self.hyperparameters
+        if fused and self.sf._library.n_flows > 0:
+            fused = False                                     # the fused target kernel evaluates a LINEAR g (csrc/target.cu)
         if fused:
             omegas = omegas_init.clone().detach().to(self.device).float().contiguous()
             w_approx = torch.nn.Linear(feature_dim, 1, bias=False, device=self.device)

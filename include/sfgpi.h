@@ -155,6 +155,11 @@ typedef struct {
                                        sfgpi_mlp_backward_tc (expand_td), whose dgrad launch runs it on otherwise idle SMs */
     const float *tsf_mc;            /* variant 2, optional [n_pol][D*S + D]: M = Wh Wg (row-major [D][S]) then c = 2 (Wh bg + bh) of
                                        every policy, e.g. from sfgpi_step_prep (tsf_* fields); NULL: every CTA derives them itself */
+    int32_t n_flows;                /* variant 2: K planar flows z <- z + scale_k * tanh(z . weight_k + bias_k) applied to s and s' ahead
+                                       of g's Linear (normalising-flow g, tsfdqn_nf.py:331-358, 569-571).  The flows' parameters follow
+                                       the Linear in every g row: W[G][S] | b[G] | K x (weight[S] | bias | scale[S]); g_stride, aux_len and
+                                       the gradient row [w | dW | db | K x (dweight | dbias | dscale) | dWh | dbh] grow by K*(2S+1), and
+                                       tsf_part by the same per block.  0: g is the plain Linear of tsfdqn.py:537-539 */
 } sfgpi_td_args;
 
 int sfgpi_td_partials(int32_t B);

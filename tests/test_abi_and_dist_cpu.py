@@ -253,3 +253,20 @@ def test_host_side_size_helpers_of_the_abi():
             bs = (((B + want - 1) // want) + 63) // 64 * 64
             assert 1 <= n <= want and (n - 1) * bs < B <= n * bs and L.sfgpi_bwd_tc_splits(B, n) == n
     assert L.sfgpi_bwd_tc_out_pad(C.byref(reacher)) >= 108 and L.sfgpi_bwd_tc_out_pad(C.byref(reacher)) % 64 == 0
+
+
+def test_planar_flow_module_matches_the_oracle_on_cpu():
+    """tsfdqn_nf's host surface (PlanarFlow, build_planar_flow; tsfdqn_nf.py:331-358): registered parameters in the reference's
+    order, same forward as the oracle's g_apply."""
+    import torch
+    from deep_successor_features_for_transfer_b200 import tsfdqn_nf
+    from oracle.sf_oracle import g_apply
+    torch.manual_seed(3)
+    g = tsfdqn_nf.PlanarFlow.build_planar_flow(4, 100, 5)
+    assert [n for n, _ in g.named_parameters()][:3] == ['0.weight', '0.bias', '0.scale'] and len(list(g.parameters())) == 17
+    assert all(float(p.abs().max()) <= 0.01 for f in list(g)[:-1] for p in f.parameters())
+    x = torch.randn(7, 4)
+    spec = [(f.weight.data, f.bias.data, f.scale.data) for f in list(g)[:-1]] + [(g[-1].weight.data, g[-1].bias.data)]
+    assert torch.allclose(g(x), g_apply(x, spec), atol=1e-6)
+    assert issubclass(tsfdqn_nf.TSFDQN, __import__('deep_successor_features_for_transfer_b200.tsfdqn', fromlist=['TSFDQN']).TSFDQN)
+    assert tsfdqn_nf.DeepTSF is not None and tsfdqn_nf.ReplayBuffer is not None

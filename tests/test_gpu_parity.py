@@ -7,6 +7,8 @@ seeded inputs.  Tolerances (fp32 mode, BASELINE north_star: 1e-5 relative):
                  difference on near-zero gradients into a visible fraction of lr; the mean error stays < 1e-6)
   GPI argmax: bit-exact except where the reference's top-1/top-2 gap is below FWD_TOL * max|q| (ties inside tolerance).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -539,3 +541,95 @@ def test_g1_lms_update_reward_kernel():
         sf.update_reward(phi, r, 1)
     assert rel_err(sf.fit_w[1].cpu(), w_ref) < 1e-5
     assert torch.equal(sf.fit_w[1], sf._library.w[1].view(-1, 1))          # in place on the packed row
+
+
+def _build_nf(meta, g_of, h, psi_of, w_of, precision='fp32'):
+    """TSF agent with planar-flow g functions (deep_successor_features_for_transfer_b200.tsfdqn_nf) loaded with given CPU tensors."""
+    from deep_successor_features_for_transfer_b200.tsfdqn_nf import DeepTSF, TSFDQN, ReplayBuffer
+    hyper = dict(gu.HYPER, g_h_function_dims=meta['gdim'], beta_loss_coefficient=meta['beta'], n_coupling_layers=meta['n_flows'],
+                 precision=precision)
+    dsf = DeepTSF(pytorch_model_handle=gu.model_lambda(meta['hidden'], meta['acts']), use_true_reward=False, target_update_ev=1000,
+                  hyperparameters=hyper)
+    ag = TSFDQN(deep_sf=dsf, buffer_handle=lambda: ReplayBuffer(), gamma=0.9, T=500, encoding=None, use_gpi=True, hyperparameters=hyper)
+    ag.reset()
+    for i in range(meta['N']):
+        ag.add_training_task(gu.FakeTask(meta['S'], meta['A'], meta['D'], i))
+    with torch.no_grad():
+        for i in range(meta['N']):
+            gu.load_policy(dsf, i, psi_of(i), w_of(i))
+            mods = list(ag.g_functions[i])
+            assert len(mods) == meta['n_flows'] + 1 and sum(1 for _ in ag.g_functions[i].parameters()) == 3 * meta['n_flows'] + 2
+            for f, (fw, fb, fs) in zip(mods[:-1], g_of(i)[:-1]):
+                f.weight.data.copy_(fw); f.bias.data.copy_(fb); f.scale.data.copy_(fs)
+            mods[-1].weight.data.copy_(g_of(i)[-1][0]); mods[-1].bias.data.copy_(g_of(i)[-1][1])
+        ag.h_function.weight.data.copy_(h[0]); ag.h_function.bias.data.copy_(h[1])
+    return dsf, ag
+
+
+def test_g3_normalising_flow_g_vs_golden():
+    """tsfdqn_nf.py (PlanarFlow :331-358, update :620-720) on the kernels: the unmodified reference's 4 steps with 5 planar flows
+    per g -- losses, post-step psi / w / h and every flow parameter."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'g3_nf_reacher.npz'))
+    meta = dict(S=int(z['S']), A=int(z['A']), D=int(z['D']), N=int(z['N']), gdim=int(z['gdim']), beta=int(z['beta']),
+                n_flows=int(z['n_flows']), hidden=[int(v) for v in z['hidden']], acts=[str(a) for a in z['acts']])
+    K, policy, nf = int(z['K']), int(z['policy']), meta['n_flows']
+    n_psi = len(meta['hidden']) + 2
+    g_of = lambda i: [(t(z[f'init.g{i}.f{k}.weight']), t(z[f'init.g{i}.f{k}.bias']), t(z[f'init.g{i}.f{k}.scale'])) for k in range(nf)] + \
+        [(t(z[f'init.g{i}.W']), t(z[f'init.g{i}.b']))]
+    dsf, ag = _build_nf(meta, g_of, (t(z['init.h.W']), t(z['init.h.b'])),
+                        lambda i: [(t(z[f'init.psi{i}.W{l}']), t(z[f'init.psi{i}.b{l}'])) for l in range(n_psi)], lambda i: t(z[f'init.w{i}']))
+    for k in range(K):
+        tr = tuple(t(z[f'tr{k}.{n}']) for n in ('states', 'actions', 'rs', 'phis', 'next_states', 'gammas'))
+        out = ag.update_successor(gu.cuda_tr(tr), policy, True)
+        assert np.allclose([float(v) for v in out], z['out.losses'][k], rtol=2e-5, atol=1e-7), (k, out, z['out.losses'][k])
+    for l, (W, b) in enumerate(gu.psi_params(dsf, policy)):
+        assert np.allclose(W.numpy(), z[f'post.psi.W{l}'], rtol=1e-4, atol=2e-6)
+    mods = list(ag.g_functions[policy])
+    for k, f in enumerate(mods[:-1]):
+        for name in ('weight', 'bias', 'scale'):
+            assert np.allclose(getattr(f, name).data.cpu().numpy(), z[f'post.g.f{k}.{name}'], rtol=1e-4, atol=2e-6), (k, name)
+    assert np.allclose(mods[-1].weight.data.cpu().numpy(), z['post.g.W'], rtol=1e-4, atol=2e-6)
+    assert np.allclose(mods[-1].bias.data.cpu().numpy(), z['post.g.b'], rtol=1e-4, atol=2e-6)
+    assert np.allclose(ag.h_function.weight.data.cpu().numpy(), z['post.h.W'], rtol=1e-4, atol=2e-6)
+    assert np.allclose(dsf.fit_w[policy].weight.data.cpu().numpy(), z['post.w'], rtol=1e-4, atol=2e-6)
+    for i in range(meta['N']):                                   # the other policies' flows are untouched
+        if i != policy:
+            assert torch.equal(list(ag.g_functions[i])[0].weight.data.cpu(), g_of(i)[0][0])
+
+
+@pytest.mark.parametrize('precision,n_flows', [('fp32', 3), ('bf16', 3), ('fp32', 10)])
+def test_g3_normalising_flow_steps_vs_oracle(precision, n_flows):
+    """Planar-flow g at the bench's shape (256-wide psi nets, B = 1000: several thread-block clusters, a ragged last tile) against
+    the oracle: single-policy steps and the all-task ensemble step; flows, Linear and h within the fp32 path's 1e-4 (the flows'
+    arithmetic is fp32 in every precision mode; bf16 mode: psi-dependent quantities at that mode's bounds)."""
+    from oracle.sf_oracle import init_linear
+    S, A, D, N, B, G = 4, 9, 12, 3, 1000, 100
+    meta = dict(S=S, A=A, D=D, N=N, gdim=G, beta=30, n_flows=n_flows, hidden=[256, 256], acts=['relu', 'relu'])
+    gen = torch.Generator().manual_seed(17)
+    o = OracleSF(S, A, D, (256, 256), ('relu', 'relu'), tsf_dim=G, beta=30)
+    h = init_linear(D, G, gen)
+    for i in range(N):
+        psi = [init_linear(256, S, gen), init_linear(256, 256, gen), init_linear(256, 256, gen), init_linear(A * D, 256, gen)]
+        flows = [((torch.rand(1, S, generator=gen) - 0.5) * 0.6, (torch.rand(1, generator=gen) - 0.5) * 0.6,
+                  (torch.rand(1, S, generator=gen) - 0.5) * 0.6) for _ in range(n_flows)]       # (larger than the init range: tanh is exercised)
+        o.add_policy(psi, (torch.rand(1, D, generator=gen) * 0.02 - 0.01), flows + [init_linear(G, S, gen)], h)
+    dsf, ag = _build_nf(meta, lambda i: o.g[i], o.h, lambda i: o.psi[i], lambda i: o.w[i], precision)
+    ltol = 2e-5 if precision == 'fp32' else 3e-2
+    for pol in (1, 2, 1):
+        tr = synthetic_transitions(B, S, A, D, gen)
+        ref = o.tsf_update_successor(tr, pol, True)
+        out = ag.update_successor(gu.cuda_tr(tr), pol, True)
+        assert np.allclose([float(v) for v in out], [float(v) for v in ref], rtol=ltol, atol=1e-7), (pol, out, ref)
+    if precision == 'fp32':
+        for pol in (1, 2):
+            mods = list(ag.g_functions[pol])
+            for k, f in enumerate(mods[:-1]):
+                for j, name in enumerate(('weight', 'bias', 'scale')):
+                    assert rel_err(getattr(f, name).data.cpu(), o.g[pol][k][j]) < 1e-4, (pol, k, name)
+            assert rel_err(mods[-1].weight.data.cpu(), o.g[pol][-1][0]) < 1e-4
+        assert rel_err(ag.h_function.weight.data.cpu(), o.h[0]) < 1e-4
+    tr = synthetic_transitions(B, S, A, D, gen)
+    ref = o.ensemble_update_frozen(tr, tsf=True, use_gpi=True)
+    losses = ag.update_successor_all(gu.cuda_tr(tr), use_gpi=True).cpu()
+    for i in range(N):
+        assert np.allclose(losses[i].numpy(), [float(v) for v in ref[i]], rtol=ltol, atol=1e-7), (i, losses[i], ref[i])
