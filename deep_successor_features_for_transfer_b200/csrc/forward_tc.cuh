@@ -117,6 +117,56 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
     }
 }
 
+// ---- folded-GPI scan of the columns [c_begin, c_end) of one accumulator chunk by one thread (= one state), 8 columns per trip
+// of a rolled loop.  Column = (block * A + act) * WB + w_in_block (gpi_scan.cuh), WB | 8.  The range need not start or end at a
+// block boundary: a partially seen block is emitted as it is -- every emission is an atomicMax on the (reward vector, state)
+// key, so the rest of the block (the other epilogue group's half, or the next chunk) merges.
+template <int WB>
+__device__ __noinline__ void gpi_scan_rolled(uint32_t t_acc, uint32_t bias0, int col0_it, int c_begin, int c_end, int A_, int nw,
+                                            long long *ka, long long *kt, uint32_t kstep, bool row_ok, uint32_t task_id, float *q_row) {
+    const int per_blk = A_ * WB;
+    int blk = c_begin / per_blk;
+    int act_i = (c_begin - blk * per_blk) / WB;
+    float bb[WB];
+    int ba[WB];
+#pragma unroll
+    for (int i = 0; i < WB; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(t_acc + (uint32_t)(c0 - col0_it), v);
+        const float4 b0 = lds128(bias0 + 4u * (uint32_t)c0), b1 = lds128(bias0 + 4u * (uint32_t)(c0 + 4));
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8 / WB; ++j) {
+            const int col = c0 + j * WB;
+            if (col < c_end) {                                   // (a range may end inside a trip: c_end is a multiple of WB, not of 8)
+#pragma unroll
+                for (int ws = 0; ws < WB; ++ws) {
+                    const float q = __uint_as_float(v[j * WB + ws]) + bv[j * WB + ws];
+                    if (q > bb[ws]) { bb[ws] = q; ba[ws] = act_i; }
+                }
+                if (q_row != nullptr && blk == 0) q_row[act_i] = __uint_as_float(v[j * WB]) + bv[j * WB];      // reward vector 0
+                ++act_i;
+                if (act_i == A_ || col + WB >= c_end) {          // block complete, or the range ends inside it
+#pragma unroll
+                    for (int ws = 0; ws < WB; ++ws) {
+                        const int wi = blk * WB + ws;
+                        if (row_ok && wi < nw) {
+                            if (ka != nullptr) atomicMax(ka + (size_t)wi * kstep, pack_key(bb[ws], (uint32_t)ba[ws]));
+                            if (kt != nullptr) atomicMax(kt + (size_t)wi * kstep, pack_key(bb[ws], task_id));
+                        }
+                        bb[ws] = -INFINITY;
+                        ba[ws] = 0;
+                    }
+                    if (act_i == A_) { act_i = 0; ++blk; }
+                }
+            }
+        }
+    }
+}
+
 // Up to kMaxJobs independent forwards (e.g. online psi(s), GPI on s', target psi(s') of one train step) share ONE launch: the
 // persistent tile loop runs over the concatenated pair lists, so the small per-step forwards fill the machine together
 // instead of queueing as three single-wave kernels.

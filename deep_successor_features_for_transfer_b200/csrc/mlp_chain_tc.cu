@@ -173,56 +173,6 @@ __device__ __forceinline__ void chain_hidden_epilogue(uint32_t t_acc, uint32_t b
     }
 }
 
-// ---- folded-GPI scan of the columns [c_begin, c_end) of one accumulator chunk by one thread (= one state), 8 columns per trip
-// of a rolled loop.  Column = (block * A + act) * WB + w_in_block (gpi_scan.cuh), WB | 8.  The range need not start or end at a
-// block boundary: a partially seen block is emitted as it is -- every emission is an atomicMax on the (reward vector, state)
-// key, so the rest of the block (the other epilogue group's half, or the next chunk) merges.
-template <int WB>
-__device__ __noinline__ void chain_gpi_scan(uint32_t t_acc, uint32_t bias0, int col0_it, int c_begin, int c_end, int A_, int nw,
-                                            long long *ka, long long *kt, uint32_t kstep, bool row_ok, uint32_t task_id, float *q_row) {
-    const int per_blk = A_ * WB;
-    int blk = c_begin / per_blk;
-    int act_i = (c_begin - blk * per_blk) / WB;
-    float bb[WB];
-    int ba[WB];
-#pragma unroll
-    for (int i = 0; i < WB; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
-#pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 8) {
-        uint32_t v[8];
-        tmem_ld8(t_acc + (uint32_t)(c0 - col0_it), v);
-        const float4 b0 = lds128(bias0 + 4u * (uint32_t)c0), b1 = lds128(bias0 + 4u * (uint32_t)(c0 + 4));
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 8 / WB; ++j) {
-            const int col = c0 + j * WB;
-            if (col < c_end) {                                   // (a range may end inside a trip: c_end is a multiple of WB, not of 8)
-#pragma unroll
-                for (int ws = 0; ws < WB; ++ws) {
-                    const float q = __uint_as_float(v[j * WB + ws]) + bv[j * WB + ws];
-                    if (q > bb[ws]) { bb[ws] = q; ba[ws] = act_i; }
-                }
-                if (q_row != nullptr && blk == 0) q_row[act_i] = __uint_as_float(v[j * WB]) + bv[j * WB];      // reward vector 0
-                ++act_i;
-                if (act_i == A_ || col + WB >= c_end) {          // block complete, or the range ends inside it
-#pragma unroll
-                    for (int ws = 0; ws < WB; ++ws) {
-                        const int wi = blk * WB + ws;
-                        if (row_ok && wi < nw) {
-                            if (ka != nullptr) atomicMax(ka + (size_t)wi * kstep, pack_key(bb[ws], (uint32_t)ba[ws]));
-                            if (kt != nullptr) atomicMax(kt + (size_t)wi * kstep, pack_key(bb[ws], task_id));
-                        }
-                        bb[ws] = -INFINITY;
-                        ba[ws] = 0;
-                    }
-                    if (act_i == A_) { act_i = 0; ++blk; }
-                }
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kThreadsTc, 1)
 mlp_chain_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ TmapSet maps, const int bias_dbl) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -443,9 +393,9 @@ mlp_chain_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__ T
                         const int cb = wblk > 1 ? col0_it + group * 128 : (group == 0 ? col0_it : c_hi);
                         const int ce = wblk > 1 ? min(cb + 128, c_hi) : c_hi;
                         if (cb < ce) {
-                            if (wblk == 8) chain_gpi_scan<8>(t_acc, bias, col0_it, cb, ce, A_, nw, ka, kt, kstep, row_ok, tid_, q_row);
-                            else if (wblk == 4) chain_gpi_scan<4>(t_acc, bias, col0_it, cb, ce, A_, nw, ka, kt, kstep, row_ok, tid_, q_row);
-                            else chain_gpi_scan<1>(t_acc, bias, col0_it, cb, ce, A_, nw, ka, kt, kstep, row_ok, tid_, q_row);
+                            if (wblk == 8) gpi_scan_rolled<8>(t_acc, bias, col0_it, cb, ce, A_, nw, ka, kt, kstep, row_ok, tid_, q_row);
+                            else if (wblk == 4) gpi_scan_rolled<4>(t_acc, bias, col0_it, cb, ce, A_, nw, ka, kt, kstep, row_ok, tid_, q_row);
+                            else gpi_scan_rolled<1>(t_acc, bias, col0_it, cb, ce, A_, nw, ka, kt, kstep, row_ok, tid_, q_row);
                         }
                     } else {
                         float *const psi_out = a.psi_out, *const sel_out = a.sel_out;

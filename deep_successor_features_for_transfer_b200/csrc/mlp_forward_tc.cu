@@ -432,8 +432,24 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                         }
                         const int nw_job = p.nw;
                         float *const q_row = (q_out != nullptr && row_ok) ? q_out + ((size_t)b * n_pol_job + pl) * A_ : nullptr;
-                        if (gpi_form && wblk > 1) {
-                            // blocked GPI scan: 32 columns per TMEM load, then four 8-column sub-trips out of registers.  (Double-
+                        if (gpi_form && !k_staged) {
+                            // Rolled 8-column scan (gpi_scan_rolled, forward_tc.cuh): this code runs once per tile, so it is
+                            // instruction-FETCH bound -- the unrolled 32-column windows below cost 9-13 k cycles per tile for 36
+                            // columns (profiles/r02_forward_chain.md), the rolled loop ~2.5 k.  Every emission is an atomicMax,
+                            // so a chunk needs no state from the previous one and each group takes one 128-column half.
+                            long long *ka = a.key_action ? reinterpret_cast<long long *>(a.key_action) + (a.w_diag ? (size_t)pl * B : 0) + b : nullptr;
+                            long long *kt = a.key_task ? reinterpret_cast<long long *>(a.key_task) + (a.w_diag ? (size_t)pl * B : 0) + b : nullptr;
+                            const int c_hi = min(col0_it + n_cols_it, ncol);
+                            const int cb = wblk > 1 ? col0_it + group * 128 : (group == slot ? col0_it : c_hi);
+                            const int ce = wblk > 1 ? min(cb + 128, c_hi) : c_hi;
+                            const uint32_t tid_ = (uint32_t)(task_base + pl);
+                            if (cb < ce) {
+                                if (wblk == 8) gpi_scan_rolled<8>(t_lane, bias - 4u * col0_it, col0_it, cb, ce, A_, nw_job, ka, kt, kstep, row_ok, tid_, q_row);
+                                else if (wblk == 4) gpi_scan_rolled<4>(t_lane, bias - 4u * col0_it, col0_it, cb, ce, A_, nw_job, ka, kt, kstep, row_ok, tid_, q_row);
+                                else gpi_scan_rolled<1>(t_lane, bias - 4u * col0_it, col0_it, cb, ce, A_, nw_job, ka, kt, kstep, row_ok, tid_, q_row);
+                            }
+                        } else if (gpi_form && wblk > 1) {
+                            // (staged keys only) blocked GPI scan: 32 columns per TMEM load, then four 8-column sub-trips out of registers.  (Double-
                             // buffering the loads was tried: no gain at 256 reward vectors and the extra 32 live registers cost the
                             // hidden-layer epilogues ~5 us per launch in spills.)
                             if (group == slot) {
