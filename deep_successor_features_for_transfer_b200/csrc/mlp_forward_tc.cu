@@ -295,6 +295,24 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             };
             if (store_pending[0] || store_pending[1]) { a_slot_guard(true); store_pending[0] = store_pending[1] = false; }
 
+            // Biases of a new (job, policy): the global loads are ISSUED here, ahead of the state staging, and land in shared memory
+            // after it -- one memory round trip for both instead of two back to back (~2 k cycles per work unit).
+            const bool new_bias = jb * 65536 + pl != cur_policy;
+            const bool bias_pre = new_bias && n_bias <= 4 * 256;
+            float bias_v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            auto bias_load = [&](int e) {
+                float v = 0.0f;
+                if (e < (1 + p.Lh) * kH) v = P[net.b_off[e >> 8] + (e & 255)];
+                else if (e < n_bias) {
+                    const int c = e - (1 + p.Lh) * kH;
+                    v = p.gpi ? p.bq[(size_t)pl * p.n_final + c] : (c < AD ? P[net.b_off[L - 1] + c] : 0.0f);
+                }
+                return v;
+            };
+            if (bias_pre) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bias_v[u] = bias_load(et + u * 256);
+            }
             int bs[2], sel_base[2];
             // ---------------- stage the state tiles as the input layer's A operands (bf16, K padded to 16*ks0) ----------------
 #pragma unroll
@@ -326,23 +344,21 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             TL_EPI();                                         // state tiles staged
 
             // Biases AFTER the state tiles were handed to the MMA warp: their global-load latency hides behind the input layer.
-            if (jb * 65536 + pl != cur_policy) {             // per-(job, policy) biases -> smem (all 256 epilogue threads)
+            if (new_bias) {                                  // per-(job, policy) biases -> smem (all 256 epilogue threads)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int e0 = et; e0 < n_bias; e0 += 4 * 256) {       // 4 independent loads in flight per thread
-                    float v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int e = e0 + u * 256;
-                        v[u] = 0.0f;
-                        if (e < (1 + p.Lh) * kH) v[u] = P[net.b_off[e >> 8] + (e & 255)];
-                        else if (e < n_bias) {
-                            const int c = e - (1 + p.Lh) * kH;
-                            v[u] = p.gpi ? p.bq[(size_t)pl * p.n_final + c] : (c < AD ? P[net.b_off[L - 1] + c] : 0.0f);
-                        }
-                    }
+                if (bias_pre) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (e0 + u * 256 < n_bias) sts32(bias_addr + 4u * (e0 + u * 256), v[u]);
+                        if (et + u * 256 < n_bias) sts32(bias_addr + 4u * (et + u * 256), bias_v[u]);
+                } else {
+                    for (int e0 = et; e0 < n_bias; e0 += 4 * 256) {       // 4 independent loads in flight per thread
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = bias_load(e0 + u * 256);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (e0 + u * 256 < n_bias) sts32(bias_addr + 4u * (e0 + u * 256), v[u]);
+                    }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_policy = jb * 65536 + pl;
