@@ -282,7 +282,7 @@ def workload_config(name, cfg, n_total, world, l2='flush', exchange=None):
             'parallelism': f'policy-sharded x{world}' if world > 1 else 'single GPU',
             'l2': ('flushed between timed steps (256 MiB write), flush excluded from the per-step CUDA-event time' if l2 == 'flush'
                    else 'inputs larger than L2: >160 MB of distinct resident batches cycled, weights / optimizer state stay '
-                        'L2-resident as in a real training loop')}
+                        'L2-resident as in a real training loop (--l2 flush: 256 MiB write between per-step brackets)')}
 
 
 PRECISION_TEXT = {
@@ -471,6 +471,88 @@ def gpu_eager_baseline(cfg, n_total, dev, steps=3):
             'sample': f'{steps} all-task steps ({n_total} update_successor calls each), wall clock with synchronize'}
 
 
+TRACE_SLOTS = ('prep', 'forward', 'td', 'dgrad', 'wgrad', 'adam')
+
+
+def trace_steps(step_fn, n=9):
+    """
+    Kernel windows of n ISOLATED steps from the in-kernel %globaltimer trace (csrc/common.cuh, sfgpi_trace_*): per kernel the
+    median of [first CTA past its dependency wait -> last CTA exit] and of the hand-over gap to it (predecessor's last exit ->
+    this kernel past its wait), in microseconds.  Unlike a CUDA-event bracket the trace does not sit between two kernels of the
+    chain, so their programmatic-dependent-launch overlap stays as it is in the timed steps.
+    """
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    L = _lib.lib()
+    L.sfgpi_trace_enable(1)
+    buf = (C.c_uint64 * (3 * 8))()
+    rows = []
+    try:
+        for k in range(n + 2):
+            step_fn(k)
+            if L.sfgpi_trace_read(buf, 8) == 0:
+                return None
+            if k >= 2:
+                rows.append([int(v) for v in buf])
+    finally:
+        L.sfgpi_trace_enable(0)
+    out, none = {}, (1 << 64) - 1
+    for i, name in enumerate(TRACE_SLOTS):
+        busy = [(r[3 * i + 2] - r[3 * i + 1]) / 1e3 for r in rows if r[3 * i] != none]
+        if not busy:
+            continue
+        out[name] = {'busy_us': statistics.median(busy)}
+        if i > 0:
+            gaps = [(r[3 * i + 1] - r[3 * (i - 1) + 2]) / 1e3 for r in rows if r[3 * i] != none and r[3 * (i - 1)] != none]
+            if gaps:
+                out[name]['handover_us'] = statistics.median(gaps)
+    spans = [(max(r[3 * i + 2] for i in range(6)) - min(r[3 * i] for i in range(6) if r[3 * i] != none)) / 1e3 for r in rows]
+    out['step_span_us'] = statistics.median(spans)
+    out['what'] = ('isolated steps (device synchronised between them: clocks ramp down a little, so these are upper bounds of the '
+                   'in-stream times); busy = first CTA past its dependency wait -> last CTA exit; handover = predecessor\'s last '
+                   'exit -> this kernel past its wait')
+    return out
+
+
+def config4_strong(world, rank, dev, precision, barrier, steps=20, warm=5):
+    """
+    BASELINE config 4 (ii) on ALL ranks of this run (strong scaling): 256 TSFDQN policies (beta = 30) split over the GPUs, every
+    policy stepped on every batch with GPI over all 256 reward vectors.  Secondary line of the multi-GPU runs: the driver's
+    scaling sweep launches the default (weak-scaling) workload; this adds the multi-GPU train configuration BASELINE names.
+    """
+    import torch.distributed as dist
+    from deep_successor_features_for_transfer_b200.workloads import synthetic_transitions
+    cfg = dict(WORKLOADS['tsfdqn_dissimilar_n256'])
+    if cfg['n_total'] % world:
+        return {'skipped': f'{cfg["n_total"]} policies do not split over {world} ranks'}
+    n_local = cfg['n_total'] // world
+    shp = env_shapes(cfg)
+    dsf, ag = build_agent(cfg, n_local, precision, first_policy=rank * n_local)
+    lib = dsf._library
+    if world > 1:
+        lib.enable_sharding()
+    gen = torch.Generator().manual_seed(SEED)
+    res = [tuple(t.to(dev) for t in synthetic_transitions(cfg['B'], shp['S'], shp['A'], shp['D'], gen)) for _ in range(4)]
+    for k in range(warm):
+        ag.update_successor_all(res[k % 4], use_gpi=True)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        ev[k][0].record()
+        ag.update_successor_all(res[k % 4], use_gpi=True)
+        ev[k][1].record()
+    barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        lib._close_peer()
+    ms = float(ms)
+    del dsf, ag
+    return {'workload': 'tsfdqn_dissimilar_n256 (BASELINE config 4 ii)', 'ms_per_step': ms, 'value': cfg['B'] * cfg['n_total'] / (ms * 1e-3),
+            'unit': 'updates/s', 'scaling': 'strong', 'policies_per_gpu': n_local, 'steps_timed': steps, 'precision': precision,
+            'l2': 'not flushed between steps (one step streams > 1 GB)'}
+
+
 def shard_check(cfg, n_local, precision, rank, world, dev, K=3):
     """
     Driver-side evidence that the policy-sharded step (the path every N > 1 number comes from) computes what one GPU computes:
@@ -532,7 +614,7 @@ def main():
     ap.add_argument('--no-gpi-eval', action='store_true', help='skip the secondary M2 measurement (quick A/B runs)')
     ap.add_argument('--no-secondary', action='store_true', help='skip configs 1 / 4 / 5, parity mode, eager-GPU comparator')
     ap.add_argument('--no-config4', action='store_true', help='skip the 256-policy secondary line (builds 256 policies)')
-    ap.add_argument('--l2', default='flush', choices=['flush', 'inputs'],
+    ap.add_argument('--l2', default='inputs', choices=['flush', 'inputs'],
                     help='flush: 256 MiB write between timed steps (everything cold, weights included); inputs: cycle through '
                          'more distinct resident batches than fit in L2 (inputs cold, weights stay L2-resident)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32', 'tf32', 'tf32x3'])
@@ -587,14 +669,32 @@ def main():
     for k in range(n_warm):
         ag.update_successor_all(resident[k % n_res], use_gpi=True)
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    # probes around the dominant kernel (the one-launch fused forward: online psi(s) + GPI(s') + target psi(s')), recorded by
-    # the command list itself inside every timed step
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     plan_key = lib.last_plan_key
+    launches = None
+    stream_ms = None
+    if args.l2 == 'inputs':
+        # The K timed steps as ONE stream of work between two events (inputs larger than L2: n_res distinct resident batches are
+        # cycled, > 160 MB): what a training loop sees -- the kernels of consecutive steps chain through programmatic dependent
+        # launch, no event sits between them.
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            ag.update_successor_all(resident[(n_warm + k) % n_res], use_gpi=True)
+        e1.record()
+        barrier()
+        launches = _lib.launch_count - l0
+        stream_ms = e0.elapsed_time(e1)
+    # per-step brackets: an event pair around every step and probes around the dominant kernel (the one-launch fused forward:
+    # online psi(s) + GPI(s') + target psi(s')), recorded by the command list itself inside the step.  'flush' mode: these ARE
+    # the timed steps (256 MiB write between them, outside the brackets).
+    n_probe = args.steps if args.l2 == 'flush' else min(args.steps, 100)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
     l0 = _lib.launch_count
     barrier()
-    for k in range(args.steps):
+    for k in range(n_probe):
         if args.l2 == 'flush':
             flush.fill_(k & 0xFF)
         lib.set_probe(plan_key, *kev[k])
@@ -603,14 +703,16 @@ def main():
         ev[k][1].record()
     barrier()
     lib.set_probe(plan_key, None, None)
-    launches = _lib.launch_count - l0
+    if launches is None:
+        launches = _lib.launch_count - l0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    tmax = torch.tensor([total_ms, statistics.median(step_ms)], dtype=torch.float64, device=dev)
+    bracket_ms = sum(step_ms) / n_probe
+    total_ms = sum(step_ms) if stream_ms is None else stream_ms
+    k_ms = sum(a.elapsed_time(b) for a, b in kev) / n_probe
+    tmax = torch.tensor([total_ms, statistics.median(step_ms), bracket_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms, median_ms = float(tmax[0]), float(tmax[1])
+    total_ms, median_ms, bracket_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
     updates_per_step = B * n_total
     value = updates_per_step * args.steps / (total_ms * 1e-3)
 
@@ -638,6 +740,14 @@ def main():
     e2e_val = updates_per_step * e2e_steps / float(e2e_t)
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
     d2h = losses_host.numel() * 4
+
+    # ---------------- in-kernel trace: where the step's time goes without an event between the kernels ----------------
+    trace = None
+    try:
+        if world == 1:
+            trace = trace_steps(lambda k: ag.update_successor_all(resident[k % n_res], use_gpi=True))
+    except Exception as e:
+        trace = {'error': f'{type(e).__name__}: {e}'}
 
     # ---------------- roofline of the dominant kernel ----------------
     # tensor-core modes: mlp_forward_tc_kernel, ONE launch per step carrying 3 of the step's 5 net passes per (transition,
@@ -669,7 +779,12 @@ def main():
                 'traffic_source': traffic['source'] if traffic else 'no ncu --set full capture of this workload / precision committed',
                 'peak_source': f'{peaks["src"]} bf16 cuBLAS burst',
                 'kernel_ms': k_ms, 'flops_per_launch': k_flops, 'executed_flops_per_launch': k_exec,
-                'timing': 'CUDA events recorded by the command list around the kernel inside every timed step (mean)',
+                'in_kernel_window_ms': (trace['forward']['busy_us'] / 1e3) if trace and 'forward' in trace else None,
+                'frac_in_kernel_window': (k_flops / (trace['forward']['busy_us'] * 1e-6) / 1e12 / peaks['tf_burst']) if trace and 'forward' in trace else None,
+                'timing': 'kernel_ms / achieved / frac: CUDA events recorded by the command list around the kernel inside every timed step '
+                          '(mean) -- the bracket includes the launch latency the event exposes (it removes the dependent-launch overlap '
+                          'with the prologue kernel); in_kernel_window_ms: the same launch seen from inside (%globaltimer, first CTA past '
+                          'its dependency wait -> last CTA exit, isolated steps), see step_trace',
                 'note': 'achieved/frac use ALGORITHMIC FLOPs (SURVEY 8d); *_executed count what the kernel issues (folded GPI layer, padded K/N)'}
     step_flops = 5 * F * B * n_local                               # N GPI + N online + N target + 2N backward = 5N passes
     step_tflops = step_flops * args.steps / (total_ms * 1e-3) / 1e12
@@ -691,6 +806,15 @@ def main():
             shard = {'ok': False, 'error': f'{type(e).__name__}: {e}'}
         barrier()
 
+    # ---------------- BASELINE config 4 (ii), strong scaling over this run's GPUs ----------------
+    c4s = None
+    if world > 1 and not args.no_secondary and not strong:
+        try:
+            c4s = config4_strong(world, rank, dev, args.precision, barrier)
+        except Exception as e:
+            c4s = {'error': f'{type(e).__name__}: {e}'}
+        barrier()
+
     out = None
     if rank == 0:
         out = {
@@ -706,14 +830,21 @@ def main():
             'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_t) / e2e_steps * 1e3},
             'ms_per_step_median': median_ms,
+            'ms_per_step_bracketed': bracket_ms,         # mean of the per-step CUDA-event brackets (each exposes one launch latency)
+            'timing': ('value / ms_per_step: the K steps as one stream between two CUDA events (inputs larger than L2); '
+                       'ms_per_step_median / _bracketed: an event pair around every step' if args.l2 == 'inputs' else
+                       'value / ms_per_step: sum of the per-step CUDA-event brackets, L2 flushed between steps outside the brackets'),
             'warmup_steps_run': n_warm,                     # >= --warmup: a fixed count on every rank, clocks settled under load
             'gpu_launches': launches,
             'roofline': roofline,
             'step_tflops_per_gpu': step_tflops,
+            'step_trace': trace,
             'gpi_eval': gpi_eval,
         }
         if shard is not None:
             out['shard_check'] = shard
+        if c4s is not None:
+            out['config4_strong_scaling'] = c4s
     if world == 1 and rank == 0:
         cores = os.cpu_count() or 1
         timer = Timer(dev)

@@ -210,6 +210,8 @@ SYMBOLS = {
     'sfgpi_peer_unpack': (C.c_int, [C.POINTER(PeerUnpackArgs), C.c_void_p]),
     'sfgpi_set_option': (C.c_int, [C.c_char_p, C.c_int32]),
     'sfgpi_trace_dump': (None, []),
+    'sfgpi_trace_enable': (None, [C.c_int32]),
+    'sfgpi_trace_read': (C.c_int, [C.c_void_p, C.c_int32]),
     'sfgpi_last_error': (C.c_char_p, []),
     'sfgpi_version': (C.c_int, []),
 }

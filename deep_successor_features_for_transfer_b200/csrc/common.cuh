@@ -26,14 +26,16 @@ int check_launch(const char *what);
 // past its dependency wait, last CTA exit -- so that the gaps BETWEEN the kernels of a step can be read, not only their own
 // durations.  The buffer pointer is a per-translation-unit device global bound lazily by trace_bind() in the launching host code.
 enum { SFGPI_TR_PREP = 0, SFGPI_TR_FWD = 1, SFGPI_TR_TD = 2, SFGPI_TR_DGRAD = 3, SFGPI_TR_WGRAD = 4, SFGPI_TR_ADAM = 5, SFGPI_TR_SLOTS = 8 };
-unsigned long long *trace_buffer();          // gpi.cu: device buffer [SFGPI_TR_SLOTS][3], or NULL when tracing is off
+unsigned long long *trace_buffer();          // gpi.cu: device buffer [SFGPI_TR_SLOTS][3], or NULL while tracing is off
+int trace_generation();                       // gpi.cu: bumped by sfgpi_trace_enable(); a translation unit re-binds when it changed
 static __device__ unsigned long long *g_trace = nullptr;
 static inline void trace_bind() {
-    static bool bound = false;
-    if (bound) return;
+    static int bound_gen = -1;
+    const int gen = trace_generation();
+    if (bound_gen == gen) return;
     unsigned long long *p = trace_buffer();
-    if (p != nullptr) cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
-    bound = true;
+    cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+    bound_gen = gen;
 }
 __device__ __forceinline__ void trace_mark(int slot, int what) {
     if (slot >= 0 && threadIdx.x == 0 && g_trace != nullptr) {

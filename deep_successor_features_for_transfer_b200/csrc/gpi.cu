@@ -20,19 +20,24 @@ bool pdl_enabled() {
     return on;
 }
 
-unsigned long long *trace_buffer() {
-    static unsigned long long *buf = nullptr;
-    static bool init = false;
-    if (!init) {
-        init = true;
-        if (getenv("SFGPI_TRACE") != nullptr && cudaMalloc(&buf, SFGPI_TR_SLOTS * 3 * sizeof(unsigned long long)) == cudaSuccess) {
-            unsigned long long h[SFGPI_TR_SLOTS * 3];
-            for (int i = 0; i < SFGPI_TR_SLOTS; ++i) { h[3 * i] = h[3 * i + 1] = ~0ull; h[3 * i + 2] = 0; }
-            cudaMemcpy(buf, h, sizeof(h), cudaMemcpyHostToDevice);
-        } else buf = nullptr;
-    }
-    return buf;
+static unsigned long long *g_trace_buf = nullptr;
+static int g_trace_on = -1, g_trace_gen = 0;      // -1: not decided yet (env SFGPI_TRACE)
+
+static void trace_reset_buffer() {
+    unsigned long long h[SFGPI_TR_SLOTS * 3];
+    for (int i = 0; i < SFGPI_TR_SLOTS; ++i) { h[3 * i] = h[3 * i + 1] = ~0ull; h[3 * i + 2] = 0; }
+    cudaMemcpy(g_trace_buf, h, sizeof(h), cudaMemcpyHostToDevice);
 }
+unsigned long long *trace_buffer() {
+    if (g_trace_on < 0) g_trace_on = getenv("SFGPI_TRACE") != nullptr ? 1 : 0;
+    if (!g_trace_on) return nullptr;
+    if (g_trace_buf == nullptr) {
+        if (cudaMalloc(&g_trace_buf, SFGPI_TR_SLOTS * 3 * sizeof(unsigned long long)) != cudaSuccess) { g_trace_buf = nullptr; return nullptr; }
+        trace_reset_buffer();
+    }
+    return g_trace_buf;
+}
+int trace_generation() { return g_trace_gen; }
 
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -45,21 +50,37 @@ int check_launch(const char *what) {
 
 }  // namespace sfgpi
 
-// Prints (stderr) and resets the kernel windows collected since the last call; synchronises the device.  No-op unless SFGPI_TRACE=1.
-extern "C" void sfgpi_trace_dump(void) {
-    unsigned long long *buf = sfgpi::trace_buffer();
-    if (buf == nullptr) return;
+// Developer aid, see include/sfgpi.h.  sfgpi_trace_enable: switches the kernel-window trace on / off (takes effect at each
+// kernel family's next launch); sfgpi_trace_read: synchronises the device, copies out [slots][3] = {first CTA entry, first CTA
+// past its dependency wait, last CTA exit} in %globaltimer ns (entry = ~0 for kernels that did not run) and resets the windows;
+// sfgpi_trace_dump: the same, printed to stderr.
+extern "C" void sfgpi_trace_enable(int32_t on) {
+    sfgpi::g_trace_on = on ? 1 : 0;
+    ++sfgpi::g_trace_gen;
+    if (on && sfgpi::trace_buffer() != nullptr) { cudaDeviceSynchronize(); sfgpi::trace_reset_buffer(); }
+}
+
+extern "C" int sfgpi_trace_read(uint64_t *out, int32_t n_slots) {
+    unsigned long long *buf = sfgpi::g_trace_on > 0 ? sfgpi::trace_buffer() : nullptr;
+    if (buf == nullptr || out == nullptr) return 0;
     cudaDeviceSynchronize();
-    unsigned long long h[sfgpi::SFGPI_TR_SLOTS * 3], t0 = ~0ull;
+    unsigned long long h[sfgpi::SFGPI_TR_SLOTS * 3];
     cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const int n = n_slots < sfgpi::SFGPI_TR_SLOTS ? n_slots : sfgpi::SFGPI_TR_SLOTS;
+    for (int i = 0; i < 3 * n; ++i) out[i] = h[i];
+    sfgpi::trace_reset_buffer();
+    return n;
+}
+
+extern "C" void sfgpi_trace_dump(void) {
+    uint64_t h[sfgpi::SFGPI_TR_SLOTS * 3], t0 = ~0ull;
+    if (sfgpi_trace_read(h, sfgpi::SFGPI_TR_SLOTS) == 0) return;
     static const char *name[sfgpi::SFGPI_TR_SLOTS] = {"prep", "forward", "td", "dgrad", "wgrad", "adam", "-", "-"};
     for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i) if (h[3 * i] < t0) t0 = h[3 * i];
     fprintf(stderr, "[sfgpi trace] ns since the first kernel entry: entry / past dependency wait / last exit\n");
     for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i)
         if (h[3 * i + 2] != 0)
             fprintf(stderr, "  %-8s %8lld %8lld %8lld\n", name[i], (long long)(h[3 * i] - t0), (long long)(h[3 * i + 1] - t0), (long long)(h[3 * i + 2] - t0));
-    for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i) { h[3 * i] = h[3 * i + 1] = ~0ull; h[3 * i + 2] = 0; }
-    cudaMemcpy(buf, h, sizeof(h), cudaMemcpyHostToDevice);
 }
 
 namespace sfgpi {

@@ -571,9 +571,14 @@ int sfgpi_peer_unpack(const sfgpi_peer_unpack_args *args, void *stream);
  *                     the layer-pipelined single-tile kernel (csrc/mlp_chain_tc.cu) for launches of <= 148 tiles, 2 = always. */
 int sfgpi_set_option(const char *name, int32_t value);
 
-/* Developer aid: with SFGPI_TRACE=1 in the environment every step kernel records the %globaltimer of its first CTA entry, of
- * the first CTA past its dependency wait and of its last CTA exit; this call synchronises the device, prints the windows
- * collected since the previous call to stderr and resets them.  No-op otherwise. */
+/* Developer aid: the kernel-window trace.  While it is on (SFGPI_TRACE=1 in the environment, or sfgpi_trace_enable(1)) every
+ * kernel of a train step records the %globaltimer of its first CTA entry, of the first CTA past its dependency wait and of its
+ * last CTA exit -- the gaps BETWEEN the kernels of a step, which per-kernel timers do not show.  Slots: 0 prologue, 1 forward,
+ * 2 TD, 3 dgrad, 4 wgrad, 5 Adam.  sfgpi_trace_read synchronises the device, copies [n_slots][3] uint64 ns (entry = all ones
+ * for a kernel that did not run) into `out`, resets the windows and returns the slots written (0: tracing is off);
+ * sfgpi_trace_dump prints the same to stderr. */
+void sfgpi_trace_enable(int32_t on);
+int sfgpi_trace_read(uint64_t *out, int32_t n_slots);
 void sfgpi_trace_dump(void);
 
 const char *sfgpi_last_error(void);
