@@ -25,7 +25,7 @@ int check_launch(const char *what);
 // Developer aid (env SFGPI_TRACE=1, sfgpi_trace_dump): %globaltimer window of every step kernel -- first CTA entry, first CTA
 // past its dependency wait, last CTA exit -- so that the gaps BETWEEN the kernels of a step can be read, not only their own
 // durations.  The buffer pointer is a per-translation-unit device global bound lazily by trace_bind() in the launching host code.
-enum { SFGPI_TR_PREP = 0, SFGPI_TR_FWD = 1, SFGPI_TR_TD = 2, SFGPI_TR_DGRAD = 3, SFGPI_TR_WGRAD = 4, SFGPI_TR_ADAM = 5, SFGPI_TR_SLOTS = 8 };
+enum { SFGPI_TR_PREP = 0, SFGPI_TR_FWD = 1, SFGPI_TR_TD = 2, SFGPI_TR_DGRAD = 3, SFGPI_TR_WGRAD = 4, SFGPI_TR_ADAM = 5, SFGPI_TR_PEER_X = 6, SFGPI_TR_SLOTS = 8 };
 unsigned long long *trace_buffer();          // gpi.cu: device buffer [SFGPI_TR_SLOTS][3], or NULL while tracing is off
 int trace_generation();                       // gpi.cu: bumped by sfgpi_trace_enable(); a translation unit re-binds when it changed
 static __device__ unsigned long long *g_trace = nullptr;

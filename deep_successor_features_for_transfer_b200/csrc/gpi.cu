@@ -75,7 +75,7 @@ extern "C" int sfgpi_trace_read(uint64_t *out, int32_t n_slots) {
 extern "C" void sfgpi_trace_dump(void) {
     uint64_t h[sfgpi::SFGPI_TR_SLOTS * 3], t0 = ~0ull;
     if (sfgpi_trace_read(h, sfgpi::SFGPI_TR_SLOTS) == 0) return;
-    static const char *name[sfgpi::SFGPI_TR_SLOTS] = {"prep", "forward", "td", "dgrad", "wgrad", "adam", "-", "-"};
+    static const char *name[sfgpi::SFGPI_TR_SLOTS] = {"prep", "forward", "td", "dgrad", "wgrad", "adam", "peer_x", "-"};
     for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i) if (h[3 * i] < t0) t0 = h[3 * i];
     fprintf(stderr, "[sfgpi trace] ns since the first kernel entry: entry / past dependency wait / last exit\n");
     for (int i = 0; i < sfgpi::SFGPI_TR_SLOTS; ++i)

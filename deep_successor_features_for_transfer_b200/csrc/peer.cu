@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) peer_reduce_keys_kernel(const __grid_cons
 // the all-gather of x_local = [w (nw) | delta h (nh)] followed by shard_unpack_kernel's arithmetic, pulled from the peers:
 // w_all [world * nw] (global policy order), h = h_prev + sum_r delta_r (rank order: identical on every rank), h_prev = h.
 __global__ void __launch_bounds__(256) peer_unpack_kernel(const __grid_constant__ sfgpi_peer_unpack_args a) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_launch_dependents(SFGPI_TR_PEER_X);
+    pdl_wait(SFGPI_TR_PEER_X);
     if (blockIdx.x == 0 && a.pack_w != nullptr) {
         // fused sfgpi_shard_pack: this rank's x_local = [w | h - h_prev] is written by the signalling CTA before it signals (the
         // local flag slot keeps this kernel's other CTAs, which overwrite h and h_prev, behind it)
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) peer_unpack_kernel(const __grid_constant_
         a.h[k] = acc;
         a.h_prev[k] = acc;
     }
+    trace_exit(SFGPI_TR_PEER_X);
 }
 
 }  // namespace sfgpi
@@ -111,6 +112,7 @@ extern "C" int sfgpi_peer_reduce_keys(const sfgpi_peer_keys_args *a, void *strea
 
 extern "C" int sfgpi_peer_unpack(const sfgpi_peer_unpack_args *a, void *stream) {
     if (!a) { set_error("sfgpi_peer_unpack: null args"); return SFGPI_E_INVALID; }
+    trace_bind();
     if (int rc = check_ctx(a->ctx, "sfgpi_peer_unpack")) return rc;
     if (a->nw < 0 || a->nh < 0 || a->epoch <= 0 || !a->w_all || (a->nh > 0 && (!a->h || !a->h_prev))) {
         set_error("sfgpi_peer_unpack: invalid arguments");
