@@ -44,6 +44,45 @@ struct DgParams {
     int n_main;                      // CTAs running the dgrad tile loop; CTAs [n_main, gridDim.x) are riders (see ex)
 };
 
+// Rolled form of dgrad_epilogue for the hot shapes (no activation, or ReLU gated by the forward's mask words), activation at RUN
+// time: one copy of the code for every layer.  The fully unrolled template cost 17 k cycles on a CTA's first call (instruction
+// fetch: ~150 cycles per 128-byte line of straight-line code) against 5.5 k warm -- and with one tile per CTA there are only three
+// calls.  Body = two 32-column chunks (two TMEM loads in flight), looped over n_pairs.  Same arithmetic (bit-identical).
+__device__ __forceinline__ void dgrad_epilogue_rolled(uint32_t t_lane, uint32_t Arow, int r, bool row_ok, const uint32_t *mask_row, bool relu,
+                                                      int cbase, int n_pairs) {
+    uint32_t v[2][32];
+    uint4 mq = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (relu && row_ok) mq = __ldg(reinterpret_cast<const uint4 *>(mask_row + (cbase >> 5)));
+    if (!row_ok) mq = make_uint4(0u, 0u, 0u, 0u);              // rows past the batch contribute zeros
+    tmem_ld32(t_lane + cbase, v[0]);
+#pragma unroll 1
+    for (int jp = 0; jp < n_pairs; ++jp) {
+        const uint32_t mlo = jp ? mq.z : mq.x, mhi = jp ? mq.w : mq.y;
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+            const int c0 = cbase + (2 * jp + u2) * 32;
+            tmem_wait_ld();
+            if (u2 == 0) tmem_ld32(t_lane + c0 + 32, v[1]);
+            else if (jp + 1 < n_pairs) tmem_ld32(t_lane + c0 + 32, v[0]);
+            const uint32_t(&u)[32] = v[u2];
+            const uint32_t mword = u2 ? mhi : mlo;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float hv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hv[i] = ((mword >> (8 * g + i)) & 1u) ? __uint_as_float(u[8 * g + i]) : 0.0f;      // threshold_backward
+                sts128(Arow + a_chunk_off(r, c0 + 8 * g), pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
+                       pack_bf16x2(hv[6], hv[7]));
+            }
+        }
+    }
+}
+
+// developer aid (env SFGPI_TIMELINE): clock64 stamps of CTA 0 -- [0, 32) epilogue thread 0, [32, 64) MMA issuer, [64] entry, [65] exit
+static __device__ long long g_dg_tl[66];
+static __device__ int g_dg_tl_on = 0;
+#define DG_STAMP(base, cnt) do { if (g_dg_tl_on && blockIdx.x == 0 && (cnt) < 32) g_dg_tl[(base) + (cnt)++] = clock64(); } while (0)
+
 struct DgItem { int row_base, K; };                 // shadow row of the first reduction index, reduction length (mult. of 16)
 
 __device__ __forceinline__ DgItem dg_item(const DgParams &p, int it) {
@@ -137,6 +176,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     const __grid_constant__ sfgpi_td_args ex, int ex_nclu) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents(SFGPI_TR_DGRAD);
+    if (g_dg_tl_on && blockIdx.x == 0 && threadIdx.x == 0) g_dg_tl[64] = clock64();
     if ((int)blockIdx.x >= p.n_main) {
         // Rider CTAs: the TSF expand of the TD step (one policy each).  It depends only on the TD kernel -- this launch's
         // predecessor -- and only the Adam kernel consumes it, so instead of a launch of its own on the step's dependent chain
@@ -209,6 +249,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         {
             const uint32_t leader = elect_one();
             uint32_t n = 0, ready_cnt[2] = {0, 0};
+            int tlm = 0;
             const uint64_t adesc_x = umma_desc_k_sw128(sbase), adesc_y = umma_desc_k_sw128(sbase + kABytes);
             const uint64_t bdesc0 = umma_desc_mn_sw128(W_addr, kBoxBytes);
             const uint32_t idesc = umma_idesc_bf16_major(kTM, kNB, 0u, 1u);
@@ -223,6 +264,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                         mbar_wait_warp(SLOT_READY(slot), ready_cnt[slot] & 1);
                         ++ready_cnt[slot];
                         tc_fence_after();
+                        if (leader) DG_STAMP(32, tlm);
                         const uint32_t d_base = tmem_base + (uint32_t)slot * 256u;
                         // N = 256 MMAs over a pair of adjacent ring stages (four 64-column blocks, LBO apart): half the instructions
                         const bool wide = !(n & 1);
@@ -270,6 +312,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                             }
                         }
                         umma_commit_e(ACC_FULL(slot), leader);
+                        if (leader) DG_STAMP(32, tlm);
                     }
                 }
             }
@@ -284,6 +327,9 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         const int et = threadIdx.x - kEpiWarp0 * 32;
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t full_cnt[2] = {0, 0};
+        int tle = 0;
+#define DG_EPI() do { if (et == 0) DG_STAMP(0, tle); } while (0)
+        DG_EPI();
         // Every tile this kernel produces (the dense dZ_{L-1} chunk, each dZ_lo) is left in the A slot in TMA's swizzled box
         // layout and written to HBM by ONE thread with bulk tensor stores; see the forward kernel for the reasoning and the
         // guard protocol (a slot is rewritten only after its pending store has finished reading it).
@@ -324,6 +370,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                 fence_proxy_async();
                 mbar_arrive(SLOT_READY(slot));
                 store_tile(&tmap_dzo, slot, (min(256, p.ADp) + kKB - 1) / kKB, 0, pl);
+                DG_EPI();
             }
 
             for (int it = 0; it < p.n_items; ++it) {
@@ -336,6 +383,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
                     ++full_cnt[slot];
                     tc_fence_after();
+                    DG_EPI();
                     guard_slot(slot);
                     if (it + 1 < p.n_chunks) {                   // more output-layer chunks: refill the A slot
                         const size_t prow = (size_t)pl * B + (row_ok ? b : 0);
@@ -351,13 +399,16 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
                     const size_t rowi = ((size_t)lo * p.n_pol + pl) * B + (row_ok ? b : 0);
                     const uint4 *act_row = reinterpret_cast<const uint4 *>(p.acts + rowi * kH);
                     const uint32_t *mask_row = p.masks ? p.masks + rowi * 8 : nullptr;
-                    if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
+                    if (act == SFGPI_ACT_NONE || (act == SFGPI_ACT_RELU && mask_row != nullptr))
+                        dgrad_epilogue_rolled(t_lane, Arow, r, row_ok, mask_row, act == SFGPI_ACT_RELU, group * 128, 2);
+                    else if (act == SFGPI_ACT_RELU) dgrad_epilogue<SFGPI_ACT_RELU, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
                     else if (act == SFGPI_ACT_NONE) dgrad_epilogue<SFGPI_ACT_NONE, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
                     else dgrad_epilogue<SFGPI_ACT_TANH, 4>(t_lane, Arow, r, row_ok, act_row, mask_row, group * 128);
                     tc_fence_before();
                     fence_proxy_async();
                     if (lo > 0) mbar_arrive(SLOT_READY(slot));   // dZ_lo is the next MMA's A operand
                     store_tile(&tmap_dz, slot, kH / kKB, 0, lo * p.n_pol + pl);
+                    DG_EPI();
                 }
             }
         }
@@ -371,6 +422,7 @@ mlp_dgrad_tc_kernel(const __grid_constant__ DgParams p, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (g_dg_tl_on && blockIdx.x == 0 && threadIdx.x == 0) g_dg_tl[65] = clock64();
     trace_exit(SFGPI_TR_DGRAD);
 }
 
@@ -656,9 +708,26 @@ extern "C" int sfgpi_mlp_backward_tc(const sfgpi_backward_tc_args *args, void *s
         ex_nclu = sfgpi_td_partials(ex.B);
         riders = ex.n_pol;
     }
+    static const bool dg_tl = getenv("SFGPI_TIMELINE") != nullptr;
+    if (dg_tl) {
+        const int on = 1;
+        long long z[66] = {0};
+        cudaMemcpyToSymbol(g_dg_tl_on, &on, sizeof(on));
+        cudaMemcpyToSymbol(g_dg_tl, z, sizeof(z));
+    }
     launch_pdl(mlp_dgrad_tc_kernel, dim3(dp.n_main + riders), dim3(kThreadsDg), dg_smem, st, dp, tmap_w, tm_dz_st, tm_dzo_st, ex, ex_nclu);
     rc = check_launch("sfgpi_mlp_backward_tc(dgrad)");
     if (rc) return rc;
+    if (dg_tl) {                                                 // developer aid: CTA 0's timeline (cycles since its entry)
+        long long h[66];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_dg_tl, sizeof(h));
+        fprintf(stderr, "[sfgpi dgrad timeline] tiles=%d grid=%d %s; exit %lld\n  epi :", dp.total_pairs, dp.n_main, dp.paired ? "paired" : "one-tile", h[65] - h[64]);
+        for (int i = 0; i < 32 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[64]);
+        fprintf(stderr, "\n  mma :");
+        for (int i = 32; i < 64 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[64]);
+        fprintf(stderr, "\n");
+    }
 
     // ---------------- wgrad ----------------
     WgParams wp;
