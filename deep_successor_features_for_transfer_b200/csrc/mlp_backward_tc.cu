@@ -596,6 +596,9 @@ __global__ void build_xo_kernel(const float *__restrict__ x, int B, int S, __nv_
 }
 
 static int make_tmap_bf16(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims, const uint32_t *box) {
+    TmapKey key = {base, {0, 0, 0}, {0, 0, 0}, rank, 0, 0};
+    for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+    if (tmap_cache_get(key, tm, false)) return SFGPI_OK;
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return SFGPI_E_CUDA; }
     cuuint64_t gdim[3], gstride[2];
@@ -611,6 +614,7 @@ static int make_tmap_bf16(CUtensorMap *tm, const void *base, int rank, const uin
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return SFGPI_E_CUDA; }
+    tmap_cache_get(key, tm, true);
     return SFGPI_OK;
 }
 

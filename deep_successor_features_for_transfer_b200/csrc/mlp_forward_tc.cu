@@ -781,6 +781,8 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
 }
 
 static int make_tmap(CUtensorMap *tm, const void *base, uint64_t rows) {
+    const TmapKey key = {base, {(uint64_t)kH, rows, 0}, {(uint32_t)kKB, (uint32_t)kNB, 0}, 2, 0, 0};
+    if (tmap_cache_get(key, tm, false)) return SFGPI_OK;
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return SFGPI_E_CUDA; }
     const cuuint64_t gdim[2] = {(cuuint64_t)kH, (cuuint64_t)rows};
@@ -791,11 +793,14 @@ static int make_tmap(CUtensorMap *tm, const void *base, uint64_t rows) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return SFGPI_E_CUDA; }
+    tmap_cache_get(key, tm, true);
     return SFGPI_OK;
 }
 
 // 3-D map of a [slabs][rows][256] bf16 tensor, box = {64 columns, 128 rows, 1 slab}: rows past the end of a slab are clipped
 static int make_tmap_acts(CUtensorMap *tm, const void *base, uint64_t slabs, uint64_t rows) {
+    const TmapKey key = {base, {(uint64_t)kH, rows, slabs}, {(uint32_t)kKB, (uint32_t)kTM, 1}, 3, 0, 0};
+    if (tmap_cache_get(key, tm, false)) return SFGPI_OK;
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return SFGPI_E_CUDA; }
     const cuuint64_t gdim[3] = {(cuuint64_t)kH, (cuuint64_t)rows, (cuuint64_t)slabs};
@@ -806,6 +811,7 @@ static int make_tmap_acts(CUtensorMap *tm, const void *base, uint64_t slabs, uin
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(acts) failed (%d)", (int)cr); return SFGPI_E_CUDA; }
+    tmap_cache_get(key, tm, true);
     return SFGPI_OK;
 }
 

@@ -334,5 +334,34 @@ static inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Host-side cache of encoded tensor maps (per translation unit).  A train step needs ~15 maps whose arguments never change from
+// one step to the next; cuTensorMapEncodeTiled costs ~0.5-1 us each and the forward's nine sit on the host's critical path
+// between the prologue launch and the forward launch (4.7 us hand-over in an isolated step, profiles/r02_forward_chain.md).
+// Key = every argument of the encode call; 64 entries, round-robin replacement.
+struct TmapKey {
+    const void *base;
+    uint64_t dims[3];
+    uint32_t box[3];
+    int rank, dtype, swizzle;
+    bool operator==(const TmapKey &o) const {
+        return base == o.base && rank == o.rank && dtype == o.dtype && swizzle == o.swizzle && dims[0] == o.dims[0] && dims[1] == o.dims[1] &&
+               dims[2] == o.dims[2] && box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2];
+    }
+};
+static inline bool tmap_cache_get(const TmapKey &k, CUtensorMap *out, bool store) {
+    static TmapKey keys[64];
+    static CUtensorMap maps[64];
+    static int used = 0, next = 0;
+    if (!store) {
+        for (int i = 0; i < used; ++i)
+            if (keys[i] == k) { *out = maps[i]; return true; }
+        return false;
+    }
+    const int slot = used < 64 ? used++ : (next++ & 63);
+    keys[slot] = k;
+    maps[slot] = *out;
+    return true;
+}
+
 }  // namespace tc
 }  // namespace sfgpi
