@@ -1085,15 +1085,27 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
                     if (dear(order[k]) < dear(order[i])) { int t = order[i]; order[i] = order[k]; order[k] = t; }
             int n_units = 0;
             bool ok = true;
-            // pairs: policy-job q gets an even share of p_target (clipped to the pairs it has)
+            // Which tiles run as singles: a lone tile costs ~1.6x a paired one (nothing hides its MMA phase) and the jobs that save
+            // activations have the longer epilogues, so the singles are taken from the CHEAPEST jobs first (env SFGPI_SCHED_EVEN=1:
+            // an even share of every job, the round-1 rule) and every other tile is paired.
             static int np_buf[0x2000];
+            static const bool even = getenv("SFGPI_SCHED_EVEN") != nullptr;
             int qi = 0, given = 0;
+            int singles_left = total_tiles - 2 * p_target;
             for (int oi = 0; oi < nj && ok; ++oi) {
                 const TcParams &p = m.job[order[oi]];
                 if (p.tiles_per_policy > 0xFFFF) { ok = false; break; }
                 for (int pl = 0; pl < p.a.n_pol; ++pl, ++qi) {
-                    int share = (int)((long long)p_target * (qi + 1) / q_total - (long long)p_target * qi / q_total);
-                    if (share > p.tiles_per_policy / 2) share = p.tiles_per_policy / 2;
+                    int share;
+                    if (even) {
+                        share = (int)((long long)p_target * (qi + 1) / q_total - (long long)p_target * qi / q_total);
+                        if (share > p.tiles_per_policy / 2) share = p.tiles_per_policy / 2;
+                    } else {
+                        int s1 = singles_left < p.tiles_per_policy ? singles_left : p.tiles_per_policy;
+                        if ((p.tiles_per_policy - s1) & 1) s1 += (s1 < p.tiles_per_policy) ? 1 : -1;      // the rest pairs up
+                        singles_left -= s1;
+                        share = (p.tiles_per_policy - s1) / 2;
+                    }
                     np_buf[qi] = share;
                     given += share;
                 }
