@@ -167,6 +167,90 @@ __device__ __noinline__ void gpi_scan_rolled(uint32_t t_acc, uint32_t bias0, int
     }
 }
 
+// ---- the same scan for launches with MANY reward vectors (n_w * A of several hundred columns: BASELINE config 4 scores every
+// policy under 256 vectors = 2304 columns per tile).  There the scan -- not the MMAs -- paces the kernel (in-kernel timeline:
+// 6.4-7 k cycles per 128 columns per epilogue group against ~3.9 k for the chunk's MMAs; ncu: the epilogue warps issue one
+// instruction per ~5 cycles in the loop above -- fixed-latency dependencies, the bias loads behind the TMEM wait, instruction
+// fetch over four inlined copies of the emission), and the loop runs tens of times per tile, so compact-and-rolled no longer
+// matters.  This variant: 16 columns per TMEM load with the next load in flight, the window's biases fetched BEFORE the wait
+// on the TMEM load, max by fmaxf beside the compare (no select on the value chain), and the emission out of line
+// (gpi_emit8: one call per finished block of 8 reward vectors).
+// Requires WB = 8, (c_end - c_begin) % 32 == 0, c_begin % 8 == 0 and no q output; same keys as gpi_scan_rolled<8> bit for bit.
+static __device__ __noinline__ void gpi_emit8(char *pa, char *pt, uint32_t pitch, int n_valid, uint32_t task_id,
+                                              float b0, float b1, float b2, float b3, float b4, float b5, float b6, float b7,
+                                              int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7) {
+    const float bb[8] = {b0, b1, b2, b3, b4, b5, b6, b7};
+    const int ba[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+    if (pa != nullptr) {
+#pragma unroll
+        for (int ws = 0; ws < 8; ++ws)
+            if (ws < n_valid) atomicMax(reinterpret_cast<long long *>(pa + (unsigned long long)ws * pitch), pack_key(bb[ws], (uint32_t)ba[ws]));
+    }
+    if (pt != nullptr) {
+#pragma unroll
+        for (int ws = 0; ws < 8; ++ws)
+            if (ws < n_valid) atomicMax(reinterpret_cast<long long *>(pt + (unsigned long long)ws * pitch), pack_key(bb[ws], task_id));
+    }
+}
+
+static __device__ __noinline__ void gpi_scan_wide8(uint32_t t_acc, uint32_t bias0, int col0_it, int c_begin, int c_end, int A_, int nw,
+                                                  long long *ka, long long *kt, uint32_t kstep, bool row_ok, uint32_t task_id) {
+    const int per_blk = A_ * 8;
+    int blk = c_begin / per_blk;
+    int act_i = (c_begin - blk * per_blk) >> 3;
+    float bb[8];
+    int ba[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
+    const uint32_t pitch = kstep * 8u;                            // bytes between the key rows of consecutive reward vectors
+    // key of reward vector blk * 8 for this thread's state (NULL stays NULL: gpi_emit8 tests it)
+    char *pa = ka ? reinterpret_cast<char *>(ka) + (size_t)blk * 8u * pitch : nullptr;
+    char *pt = kt ? reinterpret_cast<char *>(kt) + (size_t)blk * 8u * pitch : nullptr;
+    auto emit = [&]() {
+        if (row_ok)
+            gpi_emit8(pa, pt, pitch, nw - blk * 8, task_id, bb[0], bb[1], bb[2], bb[3], bb[4], bb[5], bb[6], bb[7], ba[0], ba[1],
+                      ba[2], ba[3], ba[4], ba[5], ba[6], ba[7]);
+#pragma unroll
+        for (int ws = 0; ws < 8; ++ws) { bb[ws] = -INFINITY; ba[ws] = 0; }
+    };
+    auto window = [&](const uint32_t (&u)[16], const float4 (&bz)[4]) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float bv[8] = {bz[2 * j].x, bz[2 * j].y, bz[2 * j].z, bz[2 * j].w, bz[2 * j + 1].x, bz[2 * j + 1].y, bz[2 * j + 1].z, bz[2 * j + 1].w};
+#pragma unroll
+            for (int ws = 0; ws < 8; ++ws) {
+                const float q = __uint_as_float(u[8 * j + ws]) + bv[ws];
+                if (q > bb[ws]) ba[ws] = act_i;                  // (first index wins ties; a NaN never wins, as in the rolled scan)
+                bb[ws] = fmaxf(bb[ws], q);
+            }
+            if (++act_i == A_) {                                 // block complete: 8 keys out, on to the next block
+                emit();
+                act_i = 0;
+                ++blk;
+                if (pa) pa += 8u * (size_t)pitch;
+                if (pt) pt += 8u * (size_t)pitch;
+            }
+        }
+    };
+    uint32_t v[2][16];
+    float4 bz[4];
+    tmem_ld16(t_acc + (uint32_t)(c_begin - col0_it), v[0]);
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bz[i] = lds128(bias0 + 4u * (uint32_t)(c0 + 4 * i));
+        tmem_wait_ld();
+        tmem_ld16(t_acc + (uint32_t)(c0 + 16 - col0_it), v[1]);
+        window(v[0], bz);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bz[i] = lds128(bias0 + 4u * (uint32_t)(c0 + 16 + 4 * i));
+        tmem_wait_ld();
+        if (c0 + 32 < c_end) tmem_ld16(t_acc + (uint32_t)(c0 + 32 - col0_it), v[0]);
+        window(v[1], bz);
+    }
+    if (act_i != 0) emit();                                      // the range ends inside a block: the rest of it merges by atomicMax
+}
+
 // Up to kMaxJobs independent forwards (e.g. online psi(s), GPI on s', target psi(s') of one train step) share ONE launch: the
 // persistent tile loop runs over the concatenated pair lists, so the small per-step forwards fill the machine together
 // instead of queueing as three single-wave kernels.
@@ -176,6 +260,7 @@ struct TcMulti {
     int n_jobs, total_pairs;
     int sched;                       // 1: work units come from the UnitTable (see below)
     int paired;                      // 1: two tiles ping-pong per CTA; 0: one tile per CTA (small launches), see kernel header
+    int wide_min;                    // GPI scans of at least this many folded columns take gpi_scan_wide8
     int pair_start[kMaxJobs + 1];
     TcParams job[kMaxJobs];
 };

@@ -371,7 +371,45 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             int ba[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
-            for (int it = 0; it < p.n_items; ++it) {
+            // GPI over MANY reward vectors (BASELINE config 4: 2304 folded columns = 9 output chunks per tile): the generic item loop
+            // below spends as long on its per-(chunk, slot) set-up -- job fields re-read through register-indexed constant loads,
+            // slot-indexed state in local memory, a page of once-per-chunk straight-line code -- as on the scan itself (ncu source
+            // page: the once-per-chunk instructions collect as many stall samples as the scan's inner loop).  Such jobs take
+            // their output chunks through the lean loop further down: everything chunk-invariant in registers, slots unrolled.
+            const int Lh_u = p.Lh, n_items_u = p.n_items;
+            const int ncol_u = p.gpi ? gpi_ncols(p.nw, A_) : 0;
+            const bool lean_gpi = p.gpi != 0 && !a.w_diag && a.key_stage == nullptr && a.q_out == nullptr && p.nw >= 8 && ncol_u >= m.wide_min;
+            for (int it = 0; it < n_items_u; ++it) {
+                if (lean_gpi && it == 1 + Lh_u) {
+                    const int nw_u = p.nw, n_final_u = p.n_final;
+                    const uint32_t bias_u = bias_addr + 4u * ((1 + Lh_u) * kH);        // folded biases, indexed by absolute column
+                    const uint32_t tid_u = (uint32_t)(a.task_base + pl), kstep_u = (uint32_t)B;
+                    long long *const ka_u = reinterpret_cast<long long *>(a.key_action), *const kt_u = reinterpret_cast<long long *>(a.key_task);
+                    const int b0_u = bs[0], b1_u = n_slots > 1 ? bs[1] : 0;
+#pragma unroll 1
+                    for (int col0 = 0; col0 < n_final_u; col0 += 256) {
+                        const int c_hi = min(min(col0 + 256, n_final_u), ncol_u);
+                        const int cb = col0 + group * 128, ce = min(cb + 128, c_hi);       // each epilogue group: one 128-column half
+                        const int cm = cb < ce ? cb + ((ce - cb) & ~31) : cb;              // whole 32-column windows, then the rest
+                        const bool more = col0 + 256 < n_final_u;
+#pragma unroll
+                        for (int slot = 0; slot < 2; ++slot) {
+                            if (slot >= n_slots) break;
+                            const int b = slot ? b1_u : b0_u;
+                            const uint32_t t_lane = t_lane0 + (uint32_t)slot * 256u;
+                            mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
+                            ++full_cnt[slot];
+                            tc_fence_after();
+                            TL_EPI();
+                            if (cb < cm) gpi_scan_wide8(t_lane, bias_u, col0, cb, cm, A_, nw_u, ka_u ? ka_u + b : nullptr, kt_u ? kt_u + b : nullptr, kstep_u, b < B, tid_u);
+                            if (cm < ce) gpi_scan_rolled<8>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_u ? ka_u + b : nullptr, kt_u ? kt_u + b : nullptr, kstep_u, b < B, tid_u, nullptr);
+                            tc_fence_before();
+                            if (more) slot_ready(slot);                                     // next chunk may overwrite the accumulator
+                            TL_EPI();
+                        }
+                    }
+                    break;
+                }
                 const ItemInfo ii = item_info(p, it);
 #pragma unroll 1
                 for (int slot = 0; slot < n_slots; ++slot) {
@@ -607,17 +645,25 @@ __global__ void pack_bf16_kernel(sfgpi_net_desc net, const float *__restrict__ p
     }
 }
 
-// GPI fold: Wq[pl][wi*A + act][k] = sum_d w[wi][d] * W_out[pl][act*D + d][k]   (fp32 accumulate, bf16 out)
-//           bq[pl][wi*A + act]    = sum_d w[wi][d] * b_out[pl][act*D + d]
-// One block per (pl, folded row); 256 threads = k.
-__global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const float *__restrict__ params, int policy_lo,
-                                                       const float *__restrict__ w, int nw, int w_diag, int nqpad,
-                                                       __nv_bfloat16 *__restrict__ wq, float *__restrict__ bq) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int pl = blockIdx.y, row = blockIdx.x, k = threadIdx.x;
+// GPI fold: Wq[pl][row(wi, act)][k] = sum_d w[wi][d] * W_out[pl][act*D + d][k]   (fp32 accumulate, bf16 out; row order: gpi_scan.cuh)
+//           bq[pl][row(wi, act)]    = sum_d w[wi][d] * b_out[pl][act*D + d]
+// One block per UNIT = (policy, action, up to kFoldBlocksPerUnit consecutive blocks of reward vectors), 256 threads = k: the
+// D rows of W_out that belong to the action are read once (registers for D <= 16) and every folded row of the unit is D fused
+// multiply-adds and one store.  (Round 1 had one block per folded ROW: at BASELINE config 4 -- 256 policies x 2304 rows --
+// that is 590 k blocks of 12 multiply-adds per thread, and the step's prologue took 1.84 ms of a 7.1 ms step at the block
+// scheduler's rate.)  One more unit per policy zeroes the padding rows [n_w-blocks * A, nqpad).
+// Small folds (the headline step: 4 policies x 48 rows) keep one block per row (fold_row): there
+// the serial loop over a unit's rows would only lengthen the step's dependent chain.  Both give the same bits: every output is
+// the same fmaf chain over d = 0 .. D-1.
+constexpr int kFoldBlocksPerUnit = 8;
+constexpr int kFoldUnitMinRows = 4096;                        // folds with fewer rows in total: one block per row
+__host__ __device__ inline int fold_units_per_policy(int nw, int A) {
+    const int wb = gpi_wblock(nw), nblk = (nw + wb - 1) / wb;
+    return A * ((nblk + kFoldBlocksPerUnit - 1) / kFoldBlocksPerUnit) + 1;
+}
+__device__ __forceinline__ void fold_row(const sfgpi_net_desc &net, const float *__restrict__ P, const float *__restrict__ w, int nw,
+                                         int w_diag, int pl, int row, int k, __nv_bfloat16 *__restrict__ wq_pl, float *__restrict__ bq_pl) {
     const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
-    const float *P = params + (size_t)(policy_lo + pl) * net.row_stride;
     float acc = 0.0f, bacc = 0.0f;
     int wi, act;
     gpi_row_to_wa(row, nw, A_, wi, act);
@@ -631,8 +677,70 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
             bacc = fmaf(wd, bo[d], bacc);
         }
     }
-    wq[((size_t)pl * nqpad + row) * kH + k] = __float2bfloat16_rn(acc);
-    if (k == 0) bq[(size_t)pl * nqpad + row] = bacc;
+    wq_pl[(size_t)row * kH + k] = __float2bfloat16_rn(acc);
+    if (k == 0) bq_pl[row] = bacc;
+}
+__device__ __forceinline__ void fold_unit(const sfgpi_net_desc &net, const float *__restrict__ P, const float *__restrict__ w, int nw,
+                                          int w_diag, int pl, int nqpad, int unit, int tid, __nv_bfloat16 *__restrict__ wq_pl,
+                                          float *__restrict__ bq_pl) {
+    const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
+    const int wb = gpi_wblock(nw), nblk = (nw + wb - 1) / wb, nchunk = (nblk + kFoldBlocksPerUnit - 1) / kFoldBlocksPerUnit;
+    const int k2 = (tid & 127) * 2, rl = tid >> 7;            // 2 consecutive k of every 2nd row (more k per thread would cost the
+    if (unit == A_ * nchunk) {                                // prologue kernel's other block ranges their occupancy)
+        for (int row = nblk * wb * A_ + rl; row < nqpad; row += 2) {
+            *reinterpret_cast<uint32_t *>(wq_pl + (size_t)row * kH + k2) = 0u;
+            if (k2 == 0) bq_pl[row] = 0.0f;
+        }
+        return;
+    }
+    const int act = unit / nchunk, b0 = (unit - act * nchunk) * kFoldBlocksPerUnit, b1 = min(b0 + kFoldBlocksPerUnit, nblk);
+    const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH + k2;
+    const float *bo = P + net.b_off[L - 1] + act * D;
+    float2 wr[16];
+    if (D <= 16) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) wr[d] = d < D ? *reinterpret_cast<const float2 *>(Wo + d * kH) : make_float2(0.f, 0.f);
+    }
+    for (int i = b0 * wb + rl; i < b1 * wb; i += 2) {         // i = reward vector (padded count)
+        const int blk = i / wb, ws = i - blk * wb, row = (blk * A_ + act) * wb + ws;
+        float2 acc = make_float2(0.f, 0.f);
+        float bacc = 0.0f;
+        if (i < nw) {                                         // (vectors beyond n_w pad the last block: zero rows)
+            const float *wv = w + (size_t)(w_diag ? pl : i) * D;
+            if (D <= 16) {
+#pragma unroll
+                for (int d = 0; d < 16; ++d) {
+                    if (d < D) {
+                        const float wd = __ldg(wv + d);
+                        acc.x = fmaf(wd, wr[d].x, acc.x);
+                        acc.y = fmaf(wd, wr[d].y, acc.y);
+                    }
+                }
+            } else {
+                for (int d = 0; d < D; ++d) {
+                    const float wd = __ldg(wv + d);
+                    const float2 wo = *reinterpret_cast<const float2 *>(Wo + d * kH);
+                    acc.x = fmaf(wd, wo.x, acc.x);
+                    acc.y = fmaf(wd, wo.y, acc.y);
+                }
+            }
+            if (k2 == 0)
+                for (int d = 0; d < D; ++d) bacc = fmaf(__ldg(wv + d), bo[d], bacc);
+        }
+        *reinterpret_cast<uint32_t *>(wq_pl + (size_t)row * kH + k2) = pack_bf16x2(acc.x, acc.y);
+        if (k2 == 0) bq_pl[row] = bacc;
+    }
+}
+
+__global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const float *__restrict__ params, int policy_lo,
+                                                       const float *__restrict__ w, int nw, int w_diag, int nqpad, int by_unit,
+                                                       __nv_bfloat16 *__restrict__ wq, float *__restrict__ bq) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pl = blockIdx.y;
+    const float *P = params + (size_t)(policy_lo + pl) * net.row_stride;
+    if (by_unit) fold_unit(net, P, w, nw, w_diag, pl, nqpad, blockIdx.x, threadIdx.x, wq + (size_t)pl * nqpad * kH, bq + (size_t)pl * nqpad);
+    else fold_row(net, P, w, nw, w_diag, pl, blockIdx.x, threadIdx.x, wq + (size_t)pl * nqpad * kH, bq + (size_t)pl * nqpad);
 }
 
 // ---- step prologue in ONE launch ---------------------------------------------------------------------------------------------
@@ -643,7 +751,7 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
 // with 128-bit loads and stores in the packs.
 struct PrepParams {
     sfgpi_step_prep_args a;
-    int rows_per_policy, Lh, nqpad;
+    int rows_per_policy, Lh, nqpad, fold_units, fold_by_unit;
     int blk_end[6];                  // exclusive prefix ends of the block ranges: pack 0, pack 1, keys, fold, xo, TSF M / c
     int copy_end[SFGPI_PREP_COPIES]; // ... preceded by the staging copies' ranges (blocks [0, copy_end[5]))
     const void *copy_src_dev[SFGPI_PREP_COPIES];      // device-visible addresses of the (pinned host) sources
@@ -744,28 +852,14 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
             if (i < a.n_keys) k[i] = LLONG_MIN;
             if (i + 1 < a.n_keys) k[i + 1] = LLONG_MIN;
         }
-    } else if (bid < pp.blk_end[3]) {                         // ---- GPI fold: one block per (policy, folded row), thread = k ----
-        const sfgpi_net_desc &net = a.net;
+    } else if (bid < pp.blk_end[3]) {                         // ---- GPI fold: one block per fold unit (large folds) or per folded row ----
         const int u = bid - pp.blk_end[2];
-        const int pl = u / pp.nqpad, row = u - pl * pp.nqpad, k = tid;
-        const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
-        const int nw = a.w_diag ? 1 : a.n_w;
-        const float *P = a.fold_params + (size_t)(a.fold_lo + pl) * net.row_stride;
-        float acc = 0.0f, bacc = 0.0f;
-        int wi, act;
-        gpi_row_to_wa(row, nw, A_, wi, act);
-        if (row < gpi_ncols(nw, A_) && wi < nw) {
-            const float *wv = a.w + (size_t)(a.w_diag ? pl : wi) * D;
-            const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH;
-            const float *bo = P + net.b_off[L - 1] + act * D;
-            for (int d = 0; d < D; ++d) {
-                const float wd = wv[d];
-                acc = fmaf(wd, Wo[d * kH + k], acc);
-                bacc = fmaf(wd, bo[d], bacc);
-            }
-        }
-        reinterpret_cast<__nv_bfloat16 *>(a.wq)[((size_t)pl * pp.nqpad + row) * kH + k] = __float2bfloat16_rn(acc);
-        if (k == 0) a.bq[(size_t)pl * pp.nqpad + row] = bacc;
+        const int per = pp.fold_by_unit ? pp.fold_units : pp.nqpad;
+        const int pl = u / per, unit = u - pl * per;
+        const float *P = a.fold_params + (size_t)(a.fold_lo + pl) * a.net.row_stride;
+        __nv_bfloat16 *wq_pl = reinterpret_cast<__nv_bfloat16 *>(a.wq) + (size_t)pl * pp.nqpad * kH;
+        if (pp.fold_by_unit) fold_unit(a.net, P, a.w, a.w_diag ? 1 : a.n_w, a.w_diag, pl, pp.nqpad, unit, tid, wq_pl, a.bq + (size_t)pl * pp.nqpad);
+        else fold_row(a.net, P, a.w, a.w_diag ? 1 : a.n_w, a.w_diag, pl, unit, tid, wq_pl, a.bq + (size_t)pl * pp.nqpad);
     } else {                                                  // ---- xo[b] = [x[b] | 1 | 0 ...] bf16 [B][64], 8 columns per thread ----
         const int i = (bid - pp.blk_end[3]) * 256 + tid;
         const int b = i >> 3, c0 = (i & 7) * 8, S = a.net.dims[0];
@@ -817,6 +911,7 @@ static int make_tmap_acts(CUtensorMap *tm, const void *base, uint64_t slabs, uin
 
 static int g_two_cta_min = getenv("SFGPI_2CTA_MIN") ? atoi(getenv("SFGPI_2CTA_MIN")) : 0x7fffffff;
 static int g_forward_chain = getenv("SFGPI_CHAIN") ? atoi(getenv("SFGPI_CHAIN")) : 1;
+static int g_wide_min = getenv("SFGPI_WIDE_MIN") ? atoi(getenv("SFGPI_WIDE_MIN")) : 256;
 
 // developer aid (SFGPI_TIMELINE=1): dump CTA 0's role timelines (cycles since the first stamp)
 static void dump_timeline(long long *tl_buf, cudaStream_t st, int n_jobs, int units, int grid, const char *mode) {
@@ -869,6 +964,11 @@ extern "C" int sfgpi_set_option(const char *name, int32_t value) {
         g_forward_chain = value;
         return old;
     }
+    if (name != nullptr && strcmp(name, "gpi_wide_min") == 0) {       // folded GPI columns from which the output chunks take the lean loop (gpi_scan_wide8)
+        const int old = g_wide_min;
+        g_wide_min = value;
+        return old;
+    }
     set_error("sfgpi_set_option: unknown option");
     return -1;
 }
@@ -905,8 +1005,9 @@ extern "C" int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, in
     const int nw = w_diag ? 1 : n_w;
     if (nw < 1) { set_error("sfgpi_fold_gpi: n_w must be >= 1"); return SFGPI_E_INVALID; }
     const int nqpad = sfgpi_gpi_fold_rows(net, nw);
-    dim3 grid(nqpad, n_pol);
-    launch_pdl(fold_gpi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *net, params, policy_lo, w, nw, w_diag, nqpad,
+    const int by_unit = (long long)nqpad * n_pol >= kFoldUnitMinRows ? 1 : 0;
+    dim3 grid(by_unit ? fold_units_per_policy(nw, net->n_actions) : nqpad, n_pol);
+    launch_pdl(fold_gpi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *net, params, policy_lo, w, nw, w_diag, nqpad, by_unit,
                reinterpret_cast<__nv_bfloat16 *>(wq_out), bq_out);
     return check_launch("sfgpi_fold_gpi");
 }
@@ -923,6 +1024,8 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     pp.rows_per_policy = sfgpi_bf16_rows_per_policy(&a.net);
     const int nw = a.w_diag ? 1 : a.n_w;
     pp.nqpad = a.fold_n > 0 ? sfgpi_gpi_fold_rows(&a.net, nw) : 0;
+    pp.fold_units = a.fold_n > 0 ? fold_units_per_policy(nw, a.net.n_actions) : 0;
+    pp.fold_by_unit = (long long)pp.nqpad * a.fold_n >= kFoldUnitMinRows ? 1 : 0;
     if (a.fold_n > 0 && (nw < 1 || !a.fold_params || !a.w || !a.wq || !a.bq)) { set_error("sfgpi_step_prep: incomplete fold arguments"); return SFGPI_E_INVALID; }
     if (a.x != nullptr && (a.B < 0 || !a.xo_bf16 || a.net.dims[0] > 63)) { set_error("sfgpi_step_prep: invalid xo arguments"); return SFGPI_E_INVALID; }
     long long nc = 0;
@@ -953,7 +1056,7 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     }
     if (a.keys != nullptr && a.n_keys > 0) n += ((a.n_keys + 1) / 2 + 255) / 256;
     pp.blk_end[2] = (int)n;
-    if (a.fold_n > 0) n += (long long)pp.nqpad * a.fold_n;
+    if (a.fold_n > 0) n += (long long)(pp.fold_by_unit ? pp.fold_units : pp.nqpad) * a.fold_n;
     pp.blk_end[3] = (int)n;
     if (a.x != nullptr && a.B > 0) n += ((long long)a.B * 8 + 255) / 256;
     pp.blk_end[4] = (int)n;
@@ -996,6 +1099,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
         TcParams &p = m.job[m.n_jobs];
         p.a = a;
         p.gpi = a.w != nullptr ? 1 : 0;
+        { static const bool dry = getenv("SFGPI_GPI_DRY") != nullptr; if (dry && p.gpi) { p.a.key_action = nullptr; p.a.key_task = nullptr; } }   // developer aid: scan without emissions
         if (p.gpi && (a.psi_out || a.sel_out)) {
             set_error("sfgpi_mlp_forward_tc: the GPI form cannot also emit psi / gathered rows (use a separate job)");
             return SFGPI_E_INVALID;
@@ -1035,6 +1139,7 @@ extern "C" int sfgpi_mlp_forward_tc_jobs(const sfgpi_forward_tc_job *jobs, int32
     if (tl_on && !tl_buf) cudaMalloc(&tl_buf, 1280 * sizeof(long long));
     if (tl_on) cudaMemsetAsync(tl_buf, 0, 1280 * sizeof(long long), (cudaStream_t)stream);
     m.timeline = tl_on ? tl_buf : nullptr;
+    m.wide_min = g_wide_min;
     static const int pair_min = getenv("SFGPI_PAIR_MIN") ? atoi(getenv("SFGPI_PAIR_MIN")) : 148;
     // 2-CTA pairs are opt-in (sfgpi_set_option("2cta_min_tiles", n) or env SFGPI_2CTA_MIN): measured on B200 they remove the
     // shared-memory bound of the MMA phase (3100-3300 -> 2300-2600 cycles per tile-layer) but the cluster-scope hand-off makes

@@ -568,7 +568,9 @@ int sfgpi_peer_unpack(const sfgpi_peer_unpack_args *args, void *stream);
  *   "2cta_min_tiles"  tensor-core forward launches with more 128-row tiles than this run as 2-CTA pairs (tcgen05
  *                     cta_group::2, each CTA holds half of every weight block); default: never.
  *   "forward_chain"   which bf16 forward kernel runs: 0 = ping-pong tile pairs always (csrc/mlp_forward_tc.cu), 1 (default) =
- *                     the layer-pipelined single-tile kernel (csrc/mlp_chain_tc.cu) for launches of <= 148 tiles, 2 = always. */
+ *                     the layer-pipelined single-tile kernel (csrc/mlp_chain_tc.cu) for launches of <= 148 tiles, 2 = always.
+ *   "gpi_wide_min"    folded GPI output layers (n_w * A columns, n_w >= 8) of at least this many columns are scanned by the
+ *                     32-column-window variant (gpi_scan_wide8, csrc/forward_tc.cuh) in the pair kernel; default 256. */
 int sfgpi_set_option(const char *name, int32_t value);
 
 /* Developer aid: the kernel-window trace.  While it is on (SFGPI_TRACE=1 in the environment, or sfgpi_trace_enable(1)) every

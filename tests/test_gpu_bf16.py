@@ -573,3 +573,47 @@ def test_bf16_hopper_64_policies_65536_states_spot_check_vs_oracle():
     assert ok, f'{nb} action mismatches outside tolerance'
     ok, nb = gu.argmax_mismatch_ok(q_ref, task_ref, task[spot.cuda()].cpu(), 'task', BF16_TOL)
     assert ok, f'{nb} task mismatches outside tolerance'
+
+
+@pytest.mark.parametrize('NW,B', [(256, 700), (77, 300), (64, 1000), (16, 257)])
+def test_bf16_gpi_wide_scan_equals_rolled_scan(NW, B):
+    """
+    The scan for many reward vectors (gpi_scan_wide8, csrc/forward_tc.cuh: 32-column windows, prefetched TMEM loads, lean
+    emission) must leave exactly the keys of the rolled 8-column scan: action and task keys, vector counts that are not a
+    multiple of 8, ragged row tiles, ranges that end inside a 32-column window (the rest goes through the rolled scan).
+    """
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    from deep_successor_features_for_transfer_b200.library import _stream
+    S, A, D, N = 4, 9, 12, 3
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=73)
+    sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+    lib = sf._library
+    xd = synthetic_transitions(B, S, A, D, gen)[0].cuda()
+    wd = (torch.rand(NW, D, generator=gen) * 0.02 - 0.01).cuda().contiguous()
+    lib._pack('online', 0, N)
+
+    def run(wide_min):
+        ka = torch.empty(NW, B, dtype=torch.int64, device='cuda')
+        kt = torch.empty(NW, B, dtype=torch.int64, device='cuda')
+        _lib.call('sfgpi_keys_fill', ka.data_ptr(), ka.numel(), _stream())
+        _lib.call('sfgpi_keys_fill', kt.data_ptr(), kt.numel(), _stream())
+        a = lib._fwd_args(lib.online, 0, N, xd)
+        a.w, a.n_w, a.w_diag, a.task_base = wd.data_ptr(), NW, 0, 5
+        a.key_action, a.key_task = ka.data_ptr(), kt.data_ptr()
+        wq, bq = lib._fold(a, 'online')
+        old_c = _lib.lib().sfgpi_set_option(b'forward_chain', 0)            # the ping-pong pair kernel (the one large launches take)
+        old_w = _lib.lib().sfgpi_set_option(b'gpi_wide_min', wide_min)
+        try:
+            _lib.call('sfgpi_mlp_forward_tc', C.byref(a), lib._shadow_for('online').data_ptr(), lib.cap, wq.data_ptr(), bq.data_ptr(), _stream())
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().sfgpi_set_option(b'forward_chain', old_c)
+            _lib.lib().sfgpi_set_option(b'gpi_wide_min', old_w)
+        return ka, kt
+
+    ka_w, kt_w = run(0)
+    ka_r, kt_r = run(1 << 30)
+    assert torch.equal(ka_w, ka_r) and torch.equal(kt_w, kt_r)
+    assert int((ka_w == torch.iinfo(torch.int64).min).sum()) == 0
