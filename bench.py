@@ -382,7 +382,7 @@ def time_gpi_eval(world, rank, dev, precision, barrier, reps=10):
 
 
 def measure_steps(cfg, n_local, precision, dev, steps, warmup, timer, single_policy=None, B=None, use_gpi=True, variant='g3',
-                  env=None, count_launches=True):
+                  env=None, count_launches=True, with_trace=False):
     """
     Median / mean ms of one train step on a FRESH agent of `precision` (HBM-resident batches, CUDA events, L2 flushed):
     all-task step (single_policy None) or the sequential step of one policy.  variant g2 = DeepSF.update_successor.
@@ -414,6 +414,12 @@ def measure_steps(cfg, n_local, precision, dev, steps, warmup, timer, single_pol
            'value': B * n_upd / (med * 1e-3), 'unit': 'updates/s' if single_policy is None else 'transitions/s'}
     if count_launches:
         out['launches_per_step'] = launches
+    if with_trace:                                    # per-kernel windows + the HBM-bound kernels' bandwidth at THIS size
+        try:
+            out['step_trace'] = trace_steps(fn, n=5)
+            out['hbm_kernels'] = hbm_kernels(out['step_trace'], dsf._library, B, n_upd, n_local, load_peaks())
+        except Exception as e:
+            out['step_trace'] = {'error': f'{type(e).__name__}: {e}'}
     del dsf, ag
     return out
 
@@ -450,7 +456,7 @@ def secondary_configs(args, dev, timer, cores, with_cpu):
     if not args.no_config4:
         c4 = dict(reacher, beta=30)
         seq = measure_steps(c4, 256, args.precision, dev, 30, 5, timer, single_policy=7)
-        ens = measure_steps(c4, 256, args.precision, dev, 20, 3, timer)
+        ens = measure_steps(c4, 256, args.precision, dev, 20, 3, timer, with_trace=True)
         c4cpu = cpu(c4, 256, 'g3', 4096, [7], 2)
         if c4cpu is not None:
             c4cpu['ensemble_extrapolated'] = {'ms_per_step': c4cpu['ms_per_step'] * 256, 'value': 4096 * 256 / (c4cpu['ms_per_step'] * 256e-3),
@@ -511,6 +517,33 @@ def trace_steps(step_fn, n=9):
     out['what'] = ('isolated steps (device synchronised between them: clocks ramp down a little, so these are upper bounds of the '
                    'in-stream times); busy = first CTA past its dependency wait -> last CTA exit; handover = predecessor\'s last '
                    'exit -> this kernel past its wait')
+    return out
+
+
+def hbm_kernels(trace, lib, B, n_pol, n_w, peaks):
+    """
+    The step's HBM-bound kernels against the measured copy bandwidth: ALGORITHMIC bytes per launch over the
+    in-kernel busy window of the trace.  prologue: fp32 library rows read + bf16 shadow written (online and target: 6 B per
+    parameter each), 8 B per GPI key filled, the GPI fold (read the output layer once, write n_w * A folded rows of 256 bf16 per
+    policy); TD: 4 B (3 D + 3 + 2 S) per (transition, policy) + the 8-byte key; Adam: 28 B per parameter + 4 B per split-K partial.
+    """
+    if not trace:
+        return None
+    sp = lib.spec
+    S, A, D = sp.dims[0], sp.n_actions, sp.n_features
+    n_split = max([ws.get('n_split', 1) for ws in lib._ws.values() if isinstance(ws, dict)] + [1])
+    wb = 8 if n_w >= 8 else (4 if n_w >= 4 else 1)
+    fold_rows = (n_w + wb - 1) // wb * wb * A
+    by = {'prep': n_pol * (2 * 6 * sp.n_params + 4 * A * D * 256 + 2 * 256 * fold_rows) + 8 * n_w * B,
+          'td': n_pol * B * (4 * (3 * D + 3 + 2 * S) + 8),
+          'adam': n_pol * sp.n_params * (28 + 4 * n_split)}
+    out = {'peak_GBps': peaks['hbm'], 'n_split': n_split,
+           'what': 'algorithmic bytes per launch / in-kernel busy window (step_trace), as a fraction of the measured HBM copy bandwidth; '
+                   'at the headline size these launches are latency-bound (a few MB in one wave), at config 4 sizes bandwidth matters'}
+    for k, b in by.items():
+        if k in trace and trace[k].get('busy_us'):
+            gbps = b / (trace[k]['busy_us'] * 1e-6) / 1e9
+            out[k] = {'bytes': b, 'busy_us': trace[k]['busy_us'], 'GBps': gbps, 'frac': gbps / peaks['hbm']}
     return out
 
 
@@ -839,6 +872,7 @@ def main():
             'roofline': roofline,
             'step_tflops_per_gpu': step_tflops,
             'step_trace': trace,
+            'hbm_kernels': hbm_kernels(trace, lib, B, n_local, n_total, peaks) if isinstance(trace, dict) and 'error' not in trace else None,
             'gpi_eval': gpi_eval,
         }
         if shard is not None:

@@ -200,6 +200,7 @@ SYMBOLS = {
     'sfgpi_shard_pack': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'sfgpi_shard_unpack': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_step_prep': (C.c_int, [C.POINTER(StepPrepArgs), C.c_void_p]),
+    'sfgpi_step_prep_launches': (C.c_int, [C.c_void_p]),
     'sfgpi_phi_head_partials': (C.c_int, [C.c_int32]),
     'sfgpi_phi_head': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'sfgpi_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),

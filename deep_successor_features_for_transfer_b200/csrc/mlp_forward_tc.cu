@@ -655,7 +655,7 @@ __global__ void pack_bf16_kernel(sfgpi_net_desc net, const float *__restrict__ p
 // Small folds (the headline step: 4 policies x 48 rows) keep one block per row (fold_row): there
 // the serial loop over a unit's rows would only lengthen the step's dependent chain.  Both give the same bits: every output is
 // the same fmaf chain over d = 0 .. D-1.
-constexpr int kFoldBlocksPerUnit = 8;
+constexpr int kFoldBlocksPerUnit = 32;
 constexpr int kFoldUnitMinRows = 4096;                        // folds with fewer rows in total: one block per row
 __host__ __device__ inline int fold_units_per_policy(int nw, int A) {
     const int wb = gpi_wblock(nw), nblk = (nw + wb - 1) / wb;
@@ -683,64 +683,86 @@ __device__ __forceinline__ void fold_row(const sfgpi_net_desc &net, const float 
 __device__ __forceinline__ void fold_unit(const sfgpi_net_desc &net, const float *__restrict__ P, const float *__restrict__ w, int nw,
                                           int w_diag, int pl, int nqpad, int unit, int tid, __nv_bfloat16 *__restrict__ wq_pl,
                                           float *__restrict__ bq_pl) {
+    __shared__ __align__(16) float w_s[kFoldBlocksPerUnit * 8][16];       // the unit's reward vectors, zero-padded to 16 features
     const int A_ = net.n_actions, D = net.n_features, L = net.n_layers;
-    const int wb = gpi_wblock(nw), nblk = (nw + wb - 1) / wb, nchunk = (nblk + kFoldBlocksPerUnit - 1) / kFoldBlocksPerUnit;
-    const int k2 = (tid & 127) * 2, rl = tid >> 7;            // 2 consecutive k of every 2nd row (more k per thread would cost the
-    if (unit == A_ * nchunk) {                                // prologue kernel's other block ranges their occupancy)
-        for (int row = nblk * wb * A_ + rl; row < nqpad; row += 2) {
-            *reinterpret_cast<uint32_t *>(wq_pl + (size_t)row * kH + k2) = 0u;
-            if (k2 == 0) bq_pl[row] = 0.0f;
+    const int wb = gpi_wblock(nw), wlog = wb == 8 ? 3 : (wb == 4 ? 2 : 0);
+    const int nblk = (nw + wb - 1) / wb, nchunk = (nblk + kFoldBlocksPerUnit - 1) / kFoldBlocksPerUnit;
+    const int k4 = (tid & 63) * 4, rl = tid >> 6;            // 4 consecutive k of every 4th row
+    if (unit == A_ * nchunk) {                                // padding rows
+        for (int row = nblk * wb * A_ + rl; row < nqpad; row += 4) {
+            *reinterpret_cast<uint2 *>(wq_pl + (size_t)row * kH + k4) = make_uint2(0u, 0u);
+            if (k4 == 0) bq_pl[row] = 0.0f;
         }
         return;
     }
     const int act = unit / nchunk, b0 = (unit - act * nchunk) * kFoldBlocksPerUnit, b1 = min(b0 + kFoldBlocksPerUnit, nblk);
-    const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH + k2;
+    const int i0 = b0 * wb, i1 = b1 * wb;                    // reward vectors [i0, i1) (padded count)
+    const float *Wo = P + net.w_off[L - 1] + (size_t)act * D * kH + k4;
     const float *bo = P + net.b_off[L - 1] + act * D;
-    float2 wr[16];
-    if (D <= 16) {
+    const bool small_d = D <= 16;
+    float4 wr[16];
+    if (small_d) {
+#pragma unroll 4
+        for (int e = tid; e < (i1 - i0) * 16; e += 256) {
+            const int i = i0 + (e >> 4), d = e & 15;
+            w_s[e >> 4][d] = (i < nw && d < D) ? w[(size_t)(w_diag ? pl : i) * D + d] : 0.0f;
+        }
 #pragma unroll
-        for (int d = 0; d < 16; ++d) wr[d] = d < D ? *reinterpret_cast<const float2 *>(Wo + d * kH) : make_float2(0.f, 0.f);
+        for (int d = 0; d < 16; ++d) wr[d] = d < D ? *reinterpret_cast<const float4 *>(Wo + d * kH) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
     }
-    for (int i = b0 * wb + rl; i < b1 * wb; i += 2) {         // i = reward vector (padded count)
-        const int blk = i / wb, ws = i - blk * wb, row = (blk * A_ + act) * wb + ws;
-        float2 acc = make_float2(0.f, 0.f);
+    float bor[16];                                           // the action's output biases (every thread: a uniform load each)
+#pragma unroll
+    for (int d = 0; d < 16; ++d) bor[d] = (small_d && d < D) ? bo[d] : 0.0f;
+    for (int i = i0 + rl; i < i1; i += 4) {
+        const int blk = i >> wlog, ws = i & (wb - 1), row = (blk * A_ + act) * wb + ws;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float bacc = 0.0f;
         if (i < nw) {                                         // (vectors beyond n_w pad the last block: zero rows)
             const float *wv = w + (size_t)(w_diag ? pl : i) * D;
-            if (D <= 16) {
+            if (small_d) {
+                const float4 *ws4 = reinterpret_cast<const float4 *>(&w_s[i - i0][0]);
 #pragma unroll
-                for (int d = 0; d < 16; ++d) {
-                    if (d < D) {
-                        const float wd = __ldg(wv + d);
-                        acc.x = fmaf(wd, wr[d].x, acc.x);
-                        acc.y = fmaf(wd, wr[d].y, acc.y);
+                for (int q = 0; q < 4; ++q) {
+                    if (4 * q < D) {
+                        const float4 wq4 = ws4[q];
+                        const float wd[4] = {wq4.x, wq4.y, wq4.z, wq4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (4 * q + u < D) {                  // same fmaf chain over d = 0 .. D-1 as fold_row
+                                acc.x = fmaf(wd[u], wr[4 * q + u].x, acc.x); acc.y = fmaf(wd[u], wr[4 * q + u].y, acc.y);
+                                acc.z = fmaf(wd[u], wr[4 * q + u].z, acc.z); acc.w = fmaf(wd[u], wr[4 * q + u].w, acc.w);
+                                bacc = fmaf(wd[u], bor[4 * q + u], bacc);
+                            }
+                        }
                     }
                 }
             } else {
                 for (int d = 0; d < D; ++d) {
                     const float wd = __ldg(wv + d);
-                    const float2 wo = *reinterpret_cast<const float2 *>(Wo + d * kH);
-                    acc.x = fmaf(wd, wo.x, acc.x);
-                    acc.y = fmaf(wd, wo.y, acc.y);
+                    const float4 wo = *reinterpret_cast<const float4 *>(Wo + d * kH);
+                    acc.x = fmaf(wd, wo.x, acc.x); acc.y = fmaf(wd, wo.y, acc.y);
+                    acc.z = fmaf(wd, wo.z, acc.z); acc.w = fmaf(wd, wo.w, acc.w);
+                    bacc = fmaf(wd, bo[d], bacc);
                 }
             }
-            if (k2 == 0)
-                for (int d = 0; d < D; ++d) bacc = fmaf(__ldg(wv + d), bo[d], bacc);
         }
-        *reinterpret_cast<uint32_t *>(wq_pl + (size_t)row * kH + k2) = pack_bf16x2(acc.x, acc.y);
-        if (k2 == 0) bq_pl[row] = bacc;
+        *reinterpret_cast<uint2 *>(wq_pl + (size_t)row * kH + k4) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+        if (k4 == 0) bq_pl[row] = bacc;
     }
 }
 
+// trace_slot: SFGPI_TR_PREP when the launch is the second half of a step's prologue (sfgpi_step_prep), else -1
 __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const float *__restrict__ params, int policy_lo,
-                                                       const float *__restrict__ w, int nw, int w_diag, int nqpad, int by_unit,
+                                                       const float *__restrict__ w, int nw, int w_diag, int nqpad, int by_unit, int trace_slot,
                                                        __nv_bfloat16 *__restrict__ wq, float *__restrict__ bq) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_launch_dependents(trace_slot);
+    pdl_wait(trace_slot);
     const int pl = blockIdx.y;
     const float *P = params + (size_t)(policy_lo + pl) * net.row_stride;
     if (by_unit) fold_unit(net, P, w, nw, w_diag, pl, nqpad, blockIdx.x, threadIdx.x, wq + (size_t)pl * nqpad * kH, bq + (size_t)pl * nqpad);
     else fold_row(net, P, w, nw, w_diag, pl, blockIdx.x, threadIdx.x, wq + (size_t)pl * nqpad * kH, bq + (size_t)pl * nqpad);
+    if (trace_slot >= 0) trace_exit(trace_slot);
 }
 
 // ---- step prologue in ONE launch ---------------------------------------------------------------------------------------------
@@ -751,7 +773,7 @@ __global__ void __launch_bounds__(256) fold_gpi_kernel(sfgpi_net_desc net, const
 // with 128-bit loads and stores in the packs.
 struct PrepParams {
     sfgpi_step_prep_args a;
-    int rows_per_policy, Lh, nqpad, fold_units, fold_by_unit;
+    int rows_per_policy, Lh, nqpad;
     int blk_end[6];                  // exclusive prefix ends of the block ranges: pack 0, pack 1, keys, fold, xo, TSF M / c
     int copy_end[SFGPI_PREP_COPIES]; // ... preceded by the staging copies' ranges (blocks [0, copy_end[5]))
     const void *copy_src_dev[SFGPI_PREP_COPIES];      // device-visible addresses of the (pinned host) sources
@@ -852,14 +874,11 @@ __global__ void __launch_bounds__(256) step_prep_kernel(const __grid_constant__ 
             if (i < a.n_keys) k[i] = LLONG_MIN;
             if (i + 1 < a.n_keys) k[i + 1] = LLONG_MIN;
         }
-    } else if (bid < pp.blk_end[3]) {                         // ---- GPI fold: one block per fold unit (large folds) or per folded row ----
+    } else if (bid < pp.blk_end[3]) {                         // ---- GPI fold, small folds: one block per folded row (large ones: their own launch) ----
         const int u = bid - pp.blk_end[2];
-        const int per = pp.fold_by_unit ? pp.fold_units : pp.nqpad;
-        const int pl = u / per, unit = u - pl * per;
-        const float *P = a.fold_params + (size_t)(a.fold_lo + pl) * a.net.row_stride;
-        __nv_bfloat16 *wq_pl = reinterpret_cast<__nv_bfloat16 *>(a.wq) + (size_t)pl * pp.nqpad * kH;
-        if (pp.fold_by_unit) fold_unit(a.net, P, a.w, a.w_diag ? 1 : a.n_w, a.w_diag, pl, pp.nqpad, unit, tid, wq_pl, a.bq + (size_t)pl * pp.nqpad);
-        else fold_row(a.net, P, a.w, a.w_diag ? 1 : a.n_w, a.w_diag, pl, unit, tid, wq_pl, a.bq + (size_t)pl * pp.nqpad);
+        const int pl = u / pp.nqpad, row = u - pl * pp.nqpad;
+        fold_row(a.net, a.fold_params + (size_t)(a.fold_lo + pl) * a.net.row_stride, a.w, a.w_diag ? 1 : a.n_w, a.w_diag, pl, row, tid,
+                 reinterpret_cast<__nv_bfloat16 *>(a.wq) + (size_t)pl * pp.nqpad * kH, a.bq + (size_t)pl * pp.nqpad);
     } else {                                                  // ---- xo[b] = [x[b] | 1 | 0 ...] bf16 [B][64], 8 columns per thread ----
         const int i = (bid - pp.blk_end[3]) * 256 + tid;
         const int b = i >> 3, c0 = (i & 7) * 8, S = a.net.dims[0];
@@ -1007,9 +1026,16 @@ extern "C" int sfgpi_fold_gpi(const sfgpi_net_desc *net, const float *params, in
     const int nqpad = sfgpi_gpi_fold_rows(net, nw);
     const int by_unit = (long long)nqpad * n_pol >= kFoldUnitMinRows ? 1 : 0;
     dim3 grid(by_unit ? fold_units_per_policy(nw, net->n_actions) : nqpad, n_pol);
-    launch_pdl(fold_gpi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *net, params, policy_lo, w, nw, w_diag, nqpad, by_unit,
+    launch_pdl(fold_gpi_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *net, params, policy_lo, w, nw, w_diag, nqpad, by_unit, -1,
                reinterpret_cast<__nv_bfloat16 *>(wq_out), bq_out);
     return check_launch("sfgpi_fold_gpi");
+}
+
+// Kernels one sfgpi_step_prep call launches: 2 when the GPI fold is large enough to run as its own launch, else 1.
+extern "C" int sfgpi_step_prep_launches(const sfgpi_step_prep_args *args) {
+    if (!args || args->fold_n <= 0) return 1;
+    const int nw = args->w_diag ? 1 : args->n_w;
+    return (long long)sfgpi_gpi_fold_rows(&args->net, nw) * args->fold_n >= kFoldUnitMinRows ? 2 : 1;
 }
 
 extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
@@ -1024,8 +1050,7 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     pp.rows_per_policy = sfgpi_bf16_rows_per_policy(&a.net);
     const int nw = a.w_diag ? 1 : a.n_w;
     pp.nqpad = a.fold_n > 0 ? sfgpi_gpi_fold_rows(&a.net, nw) : 0;
-    pp.fold_units = a.fold_n > 0 ? fold_units_per_policy(nw, a.net.n_actions) : 0;
-    pp.fold_by_unit = (long long)pp.nqpad * a.fold_n >= kFoldUnitMinRows ? 1 : 0;
+    const bool fold_apart = a.fold_n > 0 && (long long)pp.nqpad * a.fold_n >= kFoldUnitMinRows;       // large fold: its own launch, below
     if (a.fold_n > 0 && (nw < 1 || !a.fold_params || !a.w || !a.wq || !a.bq)) { set_error("sfgpi_step_prep: incomplete fold arguments"); return SFGPI_E_INVALID; }
     if (a.x != nullptr && (a.B < 0 || !a.xo_bf16 || a.net.dims[0] > 63)) { set_error("sfgpi_step_prep: invalid xo arguments"); return SFGPI_E_INVALID; }
     long long nc = 0;
@@ -1056,7 +1081,7 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     }
     if (a.keys != nullptr && a.n_keys > 0) n += ((a.n_keys + 1) / 2 + 255) / 256;
     pp.blk_end[2] = (int)n;
-    if (a.fold_n > 0) n += (long long)(pp.fold_by_unit ? pp.fold_units : pp.nqpad) * a.fold_n;
+    if (a.fold_n > 0 && !fold_apart) n += (long long)pp.nqpad * a.fold_n;
     pp.blk_end[3] = (int)n;
     if (a.x != nullptr && a.B > 0) n += ((long long)a.B * 8 + 255) / 256;
     pp.blk_end[4] = (int)n;
@@ -1070,9 +1095,14 @@ extern "C" int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream) {
     }
     pp.blk_end[5] = (int)n;
     n += nc;
-    if (n == 0) return SFGPI_OK;
     if (n > 0x7fffffffLL) { set_error("sfgpi_step_prep: too many blocks"); return SFGPI_E_INVALID; }
-    launch_pdl(step_prep_kernel, dim3((unsigned)n), dim3(256), tsf_bytes, (cudaStream_t)stream, pp);
+    if (n > 0) launch_pdl(step_prep_kernel, dim3((unsigned)n), dim3(256), tsf_bytes, (cudaStream_t)stream, pp);
+    if (fold_apart) {
+        // Large folds (BASELINE config 4: 256 policies x 2304 folded rows) run as a second launch of the prologue: fold units keep
+        // 16 rows of the output layer in registers (fold_unit), which inside step_prep_kernel would cost the packs their occupancy.
+        launch_pdl(fold_gpi_kernel, dim3(fold_units_per_policy(nw, a.net.n_actions), a.fold_n), dim3(256), 0, (cudaStream_t)stream, a.net,
+                   a.fold_params, a.fold_lo, a.w, nw, a.w_diag, pp.nqpad, 1, (int)SFGPI_TR_PREP, reinterpret_cast<__nv_bfloat16 *>(a.wq), a.bq);
+    }
     return check_launch("sfgpi_step_prep");
 }
 

@@ -1029,7 +1029,8 @@ class PackedSFLibrary:
                 for q, v in enumerate(i):
                     arr[k].i[q] = int(v)
                 launches += _lib.OP_LAUNCHES[arr[k].op] - (1 if op == 'BACKWARD_TC' and b.xo_ready else 0) - (1 if op == 'ADAM' else 0) \
-                    + (1 if op == 'TD' and t.variant == 2 and not t.defer_expand else 0)
+                    + (1 if op == 'TD' and t.variant == 2 and not t.defer_expand else 0) \
+                    + (_lib.lib().sfgpi_step_prep_launches(C.addressof(plan['prep'])) - 1 if op == 'STEP_PREP' else 0)
             if plan['h2d'] is None:
                 plan['h2d'] = [arr[k] for k in range(6)]
             plan['probe'] += [arr[k] for k, (op, p, i) in enumerate(seg) if op == 'NOP' and not p]

@@ -453,6 +453,8 @@ typedef struct {
     int32_t tsf_g_stride, tsf_G, tsf_lo, tsf_n;
 } sfgpi_step_prep_args;
 int sfgpi_step_prep(const sfgpi_step_prep_args *args, void *stream);
+/* Kernels one sfgpi_step_prep call launches: 2 when the GPI fold is large (>= 4096 folded rows: it runs as its own launch), else 1. */
+int sfgpi_step_prep_launches(const sfgpi_step_prep_args *args);
 
 /*
  * Device-resident replay ring (ReplayBuffer.replay, sfdqn.py:54-80): gathers B picked transitions out of the packed ring
