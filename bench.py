@@ -757,6 +757,7 @@ def main():
         ag.update_successor_all(pinned[k % 8], use_gpi=True, host_losses=losses_host)
         stream.synchronize()
     barrier()
+    # (a) synchronous: the host waits for every step's losses before it issues the next step (host time fully exposed)
     check = 0.0
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -765,11 +766,36 @@ def main():
         check += float(losses_host[0, 0])                           # (read it: D2H of the losses every step)
     barrier()
     assert check == check and check > 0.0, 'e2e losses did not reach the host'
+    e2e_sync_s = time.perf_counter() - t0
+    # (b) the same loop reading the losses ONE STEP LATE (what a training loop that logs its losses does): step k is issued, then
+    # the host waits on the event recorded after step k-1 and reads that step's losses from the other of two pinned buffers.
+    # Every step still pulls its batch from pinned host memory and every step's losses are copied back and read inside the
+    # timed region; only the host's per-step work overlaps the device's.
+    lh = [torch.zeros(n_local, 3).pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    for k in range(2):
+        ag.update_successor_all(pinned[k % 8], use_gpi=True, host_losses=lh[k])
+    stream.synchronize()
+    barrier()
+    check = 0.0
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ag.update_successor_all(pinned[k % 8], use_gpi=True, host_losses=lh[k & 1])
+        evs[k & 1].record(stream)
+        if k > 0:
+            evs[(k - 1) & 1].synchronize()
+            check += float(lh[(k - 1) & 1][0, 0])
+    evs[(e2e_steps - 1) & 1].synchronize()
+    check += float(lh[(e2e_steps - 1) & 1][0, 0])
+    barrier()
+    assert check == check and check > 0.0, 'e2e (pipelined) losses did not reach the host'
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_sync_s = float(e2e_t[1])
+    e2e_t = e2e_t[0]
     e2e_val = updates_per_step * e2e_steps / float(e2e_t)
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
     d2h = losses_host.numel() * 4
@@ -861,7 +887,12 @@ def main():
                                                  if lib._peer is not None else 'NCCL: all-reduce(MAX) of packed keys + one all-gather'),
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': float(e2e_t) / e2e_steps * 1e3},
+                    'ms_per_step': float(e2e_t) / e2e_steps * 1e3,
+                    'protocol': 'TSFDQN.update_successor_all(pinned host batch, host_losses=pinned buffer) per step: the prologue kernel pulls the '
+                                'batch over PCIe, the last command copies the losses back; the host reads every step\'s losses one step late '
+                                '(event wait on step k-1 after issuing step k), wall clock around the loop',
+                    'sync_value': updates_per_step * e2e_steps / e2e_sync_s, 'sync_ms_per_step': e2e_sync_s / e2e_steps * 1e3,
+                    'sync_what': 'the same loop with a stream synchronise + read after EVERY step before the next one is issued'},
             'ms_per_step_median': median_ms,
             'ms_per_step_bracketed': bracket_ms,         # mean of the per-step CUDA-event brackets (each exposes one launch latency)
             'timing': ('value / ms_per_step: the K steps as one stream between two CUDA events (inputs larger than L2); '

@@ -143,7 +143,7 @@ class AdamArgs(C.Structure):
                 ('beta1', C.c_double), ('beta2', C.c_double), ('eps', C.c_double), ('loss_part', C.c_void_p),
                 ('n_loss_part', C.c_int32), ('l1_scale', C.c_float), ('l2_scale', C.c_float), ('beta_loss', C.c_float),
                 ('losses', C.c_void_p), ('sequential_shared', C.c_int32), ('consts', C.c_void_p), ('consts_next', C.c_void_p),
-                ('fresh', C.c_int32)]
+                ('fresh', C.c_int32), ('losses_host', C.c_void_p)]
 
 
 class TargetArgs(C.Structure):

@@ -97,6 +97,11 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const __grid_constan
             a.losses[p * 3 + 0] = l1 + a.beta_loss * l2;
             a.losses[p * 3 + 1] = l1;
             a.losses[p * 3 + 2] = l2;
+            if (a.losses_host != nullptr) {                  // the step's result, straight into pinned host memory
+                a.losses_host[p * 3 + 0] = l1 + a.beta_loss * l2;
+                a.losses_host[p * 3 + 1] = l1;
+                a.losses_host[p * 3 + 2] = l2;
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -306,6 +311,11 @@ __global__ void __launch_bounds__(kAdamThreads) adam_flat_kernel(const __grid_co
                 a.losses[p * 3 + 0] = l1 + a.beta_loss * l2;
                 a.losses[p * 3 + 1] = l1;
                 a.losses[p * 3 + 2] = l2;
+                if (a.losses_host != nullptr) {              // the step's result, straight into pinned host memory
+                    a.losses_host[p * 3 + 0] = l1 + a.beta_loss * l2;
+                    a.losses_host[p * 3 + 1] = l1;
+                    a.losses_host[p * 3 + 2] = l2;
+                }
             }
         }
         if (threadIdx.x == 32) {
@@ -325,7 +335,18 @@ using namespace sfgpi;
 
 extern "C" int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream) {
     trace_bind();
-    const sfgpi_adam_args &a = *args;
+    sfgpi_adam_args a_host = *args;
+    if (a_host.losses_host != nullptr) {                     // the kernel needs the device-visible address of the pinned buffer
+        cudaPointerAttributes at;
+        if (a_host.loss_part == nullptr || cudaPointerGetAttributes(&at, a_host.losses_host) != cudaSuccess || at.type != cudaMemoryTypeHost ||
+            !at.devicePointer) {
+            cudaGetLastError();
+            set_error("sfgpi_adam_step: losses_host must be pinned host memory (and needs loss_part)");
+            return SFGPI_E_INVALID;
+        }
+        a_host.losses_host = reinterpret_cast<float *>(at.devicePointer);
+    }
+    const sfgpi_adam_args &a = a_host;
     if (a.n_seg < 1 || a.n_seg > SFGPI_MAX_SEGMENTS || a.n_pol < 1 || (a.step == nullptr && !a.fresh)) {
         set_error("sfgpi_adam_step: invalid arguments");
         return SFGPI_E_INVALID;

@@ -779,13 +779,20 @@ class PackedSFLibrary:
         losses = plan['losses'][plan['ring']]
         ad.losses = losses.data_ptr()
         d2h = plan['d2h_cmd']
+        ad.losses_host = None
         if host_losses is None:
             d2h.op = 0
         else:
             if host_losses.is_cuda or host_losses.dtype != torch.float32 or not host_losses.is_contiguous() \
                     or host_losses.numel() < plan['n_pol'] * 3:
                 raise ValueError('host_losses must be a contiguous CPU float32 tensor with at least n_pol * 3 elements')
-            d2h.op, d2h.p[0], d2h.p[1], d2h.i[0] = _lib.OP['D2H'], host_losses.data_ptr(), losses.data_ptr(), plan['n_pol'] * 12
+            if host_losses.is_pinned():
+                # pinned: the Adam launch's loss block stores the result into the host buffer itself (zero-copy over PCIe) --
+                # no copy command between this step's last kernel and the next step's first, their dependent-launch overlap stays
+                d2h.op = 0
+                ad.losses_host = host_losses.data_ptr()
+            else:
+                d2h.op, d2h.p[0], d2h.p[1], d2h.i[0] = _lib.OP['D2H'], host_losses.data_ptr(), losses.data_ptr(), plan['n_pol'] * 12
         # Adam bias corrections are double-buffered: this launch reads the current buffer of its optimizers and writes the next
         # step's corrections into the other one (no finishing launch).  Optimizers stepped together must be in phase.
         lo_, n_ = plan['lo'], plan['n_pol']

@@ -223,6 +223,10 @@ typedef struct {
     int32_t fresh;                  /* nonzero: every call is the FIRST step of a brand-new optimizer (features/deep_phi.py:170 builds a
                                        new torch.optim.Adam per update): moments start at 0 and are not stored, t = 1, `step` / consts
                                        are neither read nor written; m / v pointers of the segments may be NULL */
+    float *losses_host;             /* optional: PINNED host buffer [n_pol][3]; the block that reduces the losses also stores them
+                                       there (a zero-copy store over PCIe: the step's result reaches the host without a copy
+                                       command between two kernels of the launch chain).  Valid once the launch has completed.
+                                       Pageable memory is refused (SFGPI_E_INVALID): use a stream-ordered copy of `losses` */
 } sfgpi_adam_args;
 
 int sfgpi_adam_step(const sfgpi_adam_args *args, void *stream);
