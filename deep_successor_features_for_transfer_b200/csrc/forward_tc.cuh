@@ -121,6 +121,15 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_lane, uint32_t bias, 
 // of a rolled loop.  Column = (block * A + act) * WB + w_in_block (gpi_scan.cuh), WB | 8.  The range need not start or end at a
 // block boundary: a partially seen block is emitted as it is -- every emission is an atomicMax on the (reward vector, state)
 // key, so the rest of the block (the other epilogue group's half, or the next chunk) merges.
+// one key out (action key and / or task key of one reward vector): out of line, so that the scan below stays a few cache lines
+// of code.  The scan runs once per GPI tile, tens of thousands of cycles apart, and by then its code has left the instruction
+// cache: its first trip pays an instruction fetch per cache line (measured: a first call of the inlined-emission version, 10 KB
+// of code, cost 9-11 k cycles against 2.2 k for a second call right after it -- with or without keys to emit).
+static __device__ __noinline__ void gpi_emit1(long long *ka, long long *kt, float best, int best_a, uint32_t task_id) {
+    if (ka != nullptr) atomicMax(ka, pack_key(best, (uint32_t)best_a));
+    if (kt != nullptr) atomicMax(kt, pack_key(best, task_id));
+}
+
 template <int WB>
 __device__ __noinline__ void gpi_scan_rolled(uint32_t t_acc, uint32_t bias0, int col0_it, int c_begin, int c_end, int A_, int nw,
                                             long long *ka, long long *kt, uint32_t kstep, bool row_ok, uint32_t task_id, float *q_row) {
@@ -131,14 +140,17 @@ __device__ __noinline__ void gpi_scan_rolled(uint32_t t_acc, uint32_t bias0, int
     int ba[WB];
 #pragma unroll
     for (int i = 0; i < WB; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
+    // key of reward vector blk * WB for this thread's state; the pointers advance by one vector per emitted key (NULL stays NULL)
+    const size_t sa = ka ? kstep : 0, st = kt ? kstep : 0;
+    long long *pa = ka ? ka + (size_t)blk * WB * kstep : nullptr, *pt = kt ? kt + (size_t)blk * WB * kstep : nullptr;
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_end; c0 += 8) {
         uint32_t v[8];
-        tmem_ld8(t_acc + (uint32_t)(c0 - col0_it), v);
+            tmem_ld8(t_acc + (uint32_t)(c0 - col0_it), v);
         const float4 b0 = lds128(bias0 + 4u * (uint32_t)c0), b1 = lds128(bias0 + 4u * (uint32_t)(c0 + 4));
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         tmem_wait_ld();
-#pragma unroll
+    #pragma unroll
         for (int j = 0; j < 8 / WB; ++j) {
             const int col = c0 + j * WB;
             if (col < c_end) {                                   // (a range may end inside a trip: c_end is a multiple of WB, not of 8)
@@ -150,17 +162,21 @@ __device__ __noinline__ void gpi_scan_rolled(uint32_t t_acc, uint32_t bias0, int
                 if (q_row != nullptr && blk == 0) q_row[act_i] = __uint_as_float(v[j * WB]) + bv[j * WB];      // reward vector 0
                 ++act_i;
                 if (act_i == A_ || col + WB >= c_end) {          // block complete, or the range ends inside it
-#pragma unroll
+                    // A ROLLED loop over the block's vectors (the running state rotates through slot 0) and one out-of-line
+                    // call per key: ~40 instructions of code per emission site instead of ~30 per key.
+                    const int n_valid = row_ok ? min(WB, nw - blk * WB) : 0;
+#pragma unroll 1
                     for (int ws = 0; ws < WB; ++ws) {
-                        const int wi = blk * WB + ws;
-                        if (row_ok && wi < nw) {
-                            if (ka != nullptr) atomicMax(ka + (size_t)wi * kstep, pack_key(bb[ws], (uint32_t)ba[ws]));
-                            if (kt != nullptr) atomicMax(kt + (size_t)wi * kstep, pack_key(bb[ws], task_id));
-                        }
-                        bb[ws] = -INFINITY;
-                        ba[ws] = 0;
+                        if (ws < n_valid) gpi_emit1(pa, pt, bb[0], ba[0], task_id);
+                        pa += sa;
+                        pt += st;
+#pragma unroll
+                        for (int i = 0; i + 1 < WB; ++i) { bb[i] = bb[i + 1]; ba[i] = ba[i + 1]; }
                     }
+#pragma unroll
+                    for (int i = 0; i < WB; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
                     if (act_i == A_) { act_i = 0; ++blk; }
+                    else { pa -= WB * sa; pt -= WB * st; }       // (range ended inside the block: the vector pointers stay on it)
                 }
             }
         }

@@ -371,17 +371,19 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             int ba[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { bb[i] = -INFINITY; ba[i] = 0; }
-            // GPI over MANY reward vectors (BASELINE config 4: 2304 folded columns = 9 output chunks per tile): the generic item loop
-            // below spends as long on its per-(chunk, slot) set-up -- job fields re-read through register-indexed constant loads,
-            // slot-indexed state in local memory, a page of once-per-chunk straight-line code -- as on the scan itself (ncu source
-            // page: the once-per-chunk instructions collect as many stall samples as the scan's inner loop).  Such jobs take
-            // their output chunks through the lean loop further down: everything chunk-invariant in registers, slots unrolled.
+            // GPI output chunks: the generic item loop below spends as long on its per-(chunk, slot) set-up -- job fields re-read
+            // through register-indexed constant loads, slot-indexed state in local memory, a page of straight-line code that runs
+            // once per chunk and is therefore never in the 32 KB instruction cache -- as on the scan itself (ncu source page at 256
+            // reward vectors: the once-per-chunk instructions collect as many stall samples as the scan's inner loop; in-kernel
+            // stamps at 4 vectors: 3.3 k cycles of set-up ahead of a 5-trip scan).  GPI jobs that write action / task keys only
+            // take their output chunks through the lean loop further down: everything chunk-invariant in registers, slots unrolled.
             const int Lh_u = p.Lh, n_items_u = p.n_items;
             const int ncol_u = p.gpi ? gpi_ncols(p.nw, A_) : 0;
-            const bool lean_gpi = p.gpi != 0 && !a.w_diag && a.key_stage == nullptr && a.q_out == nullptr && p.nw >= 8 && ncol_u >= m.wide_min;
+            const bool lean_gpi = p.gpi != 0 && !a.w_diag && a.key_stage == nullptr && a.q_out == nullptr;
             for (int it = 0; it < n_items_u; ++it) {
                 if (lean_gpi && it == 1 + Lh_u) {
-                    const int nw_u = p.nw, n_final_u = p.n_final;
+                    const int nw_u = p.nw, n_final_u = p.n_final, wblk_u = gpi_wblock(nw_u);
+                    const bool wide_u = wblk_u == 8 && ncol_u >= m.wide_min;
                     const uint32_t bias_u = bias_addr + 4u * ((1 + Lh_u) * kH);        // folded biases, indexed by absolute column
                     const uint32_t tid_u = (uint32_t)(a.task_base + pl), kstep_u = (uint32_t)B;
                     long long *const ka_u = reinterpret_cast<long long *>(a.key_action), *const kt_u = reinterpret_cast<long long *>(a.key_task);
@@ -389,20 +391,28 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
 #pragma unroll 1
                     for (int col0 = 0; col0 < n_final_u; col0 += 256) {
                         const int c_hi = min(min(col0 + 256, n_final_u), ncol_u);
-                        const int cb = col0 + group * 128, ce = min(cb + 128, c_hi);       // each epilogue group: one 128-column half
-                        const int cm = cb < ce ? cb + ((ce - cb) & ~31) : cb;              // whole 32-column windows, then the rest
                         const bool more = col0 + 256 < n_final_u;
 #pragma unroll
                         for (int slot = 0; slot < 2; ++slot) {
                             if (slot >= n_slots) break;
+                            // blocked column orders: each epilogue group takes one 128-column half of the chunk (every emission is an
+                            // atomicMax, so a block cut by the boundary merges); plain order (< 4 vectors): group g scans slot g
+                            const int cb = wblk_u > 1 ? col0 + group * 128 : (group == slot ? col0 : c_hi);
+                            const int ce = wblk_u > 1 ? min(cb + 128, c_hi) : c_hi;
+                            const int cm = (wide_u && cb < ce) ? cb + ((ce - cb) & ~31) : cb;      // whole 32-column windows: gpi_scan_wide8
                             const int b = slot ? b1_u : b0_u;
                             const uint32_t t_lane = t_lane0 + (uint32_t)slot * 256u;
+                            long long *const ka_b = ka_u ? ka_u + b : nullptr, *const kt_b = kt_u ? kt_u + b : nullptr;
                             mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
                             ++full_cnt[slot];
                             tc_fence_after();
                             TL_EPI();
-                            if (cb < cm) gpi_scan_wide8(t_lane, bias_u, col0, cb, cm, A_, nw_u, ka_u ? ka_u + b : nullptr, kt_u ? kt_u + b : nullptr, kstep_u, b < B, tid_u);
-                            if (cm < ce) gpi_scan_rolled<8>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_u ? ka_u + b : nullptr, kt_u ? kt_u + b : nullptr, kstep_u, b < B, tid_u, nullptr);
+                            if (cb < cm) gpi_scan_wide8(t_lane, bias_u, col0, cb, cm, A_, nw_u, ka_b, kt_b, kstep_u, b < B, tid_u);
+                            if (cm < ce) {
+                                if (wblk_u == 8) gpi_scan_rolled<8>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_b, kt_b, kstep_u, b < B, tid_u, nullptr);
+                                else if (wblk_u == 4) gpi_scan_rolled<4>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_b, kt_b, kstep_u, b < B, tid_u, nullptr);
+                                else gpi_scan_rolled<1>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_b, kt_b, kstep_u, b < B, tid_u, nullptr);
+                            }
                             tc_fence_before();
                             if (more) slot_ready(slot);                                     // next chunk may overwrite the accumulator
                             TL_EPI();
