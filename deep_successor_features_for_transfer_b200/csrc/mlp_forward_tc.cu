@@ -315,31 +315,44 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             }
             int bs[2], sel_base[2];
             // ---------------- stage the state tiles as the input layer's A operands (bf16, K padded to 16*ks0) ----------------
+            // Every global load of the unit's head is ISSUED before the first one is consumed: the gather indices of both slots
+            // and (states of <= 8 features) both slots' state rows.  Consumed one after the other -- row, index, next slot's row,
+            // its index -- they were four dependent memory round trips, ~4.4 k cycles at the head of every work unit (stamps).
+            int sidx_v[2] = {0, 0};
+            float xf[2][8];
+            const bool x_pre = S <= 8;
 #pragma unroll
             for (int slot = 0; slot < 2; ++slot) {
                 if (slot >= n_slots) break;
                 const int b = (un.tile0 + slot * un.tstep) * kTM + r;                   // global state index of this thread's row
-                const bool row_ok = b < B;
                 bs[slot] = b;
+                if (a.sel_out != nullptr && b < B)
+                    sidx_v[slot] = a.sel_actions ? (int)a.sel_actions[b] : (int)key_index(a.sel_keys[(size_t)pl * a.sel_key_stride + b]);
+                if (group == 0 && x_pre) {
+                    const float *xr = a.x + (size_t)b * S;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) xf[slot][i] = (b < B && i < S) ? xr[i] : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot) {
+                if (slot >= n_slots) break;
+                const int b = bs[slot];
+                const bool row_ok = b < B;
                 if (group == 0) {
                     const float *xr = a.x + (size_t)b * S;
                     const uint32_t Arow = sbase + (uint32_t)slot * kABytes;
                     for (int c = 0; c < p.ks0 * 16; c += 8) {
                         float xv[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) xv[i] = (row_ok && c + i < S) ? xr[c + i] : 0.0f;
+                        for (int i = 0; i < 8; ++i) xv[i] = x_pre ? (c == 0 ? xf[slot][i] : 0.0f) : ((row_ok && c + i < S) ? xr[c + i] : 0.0f);
                         sts128(Arow + a_chunk_off(r, c), pack_bf16x2(xv[0], xv[1]), pack_bf16x2(xv[2], xv[3]),
                                pack_bf16x2(xv[4], xv[5]), pack_bf16x2(xv[6], xv[7]));
                     }
                     fence_proxy_async();                      // generic-proxy smem writes -> visible to the UMMA (async proxy)
                 }
                 slot_ready(slot);
-                sel_base[slot] = -(1 << 30);
-                if (a.sel_out != nullptr && row_ok) {
-                    const int sidx = a.sel_actions ? (int)a.sel_actions[b]
-                                                   : (int)key_index(a.sel_keys[(size_t)pl * a.sel_key_stride + b]);
-                    sel_base[slot] = sidx * D;
-                }
+                sel_base[slot] = (a.sel_out != nullptr && row_ok) ? sidx_v[slot] * D : -(1 << 30);
             }
             TL_EPI();                                         // state tiles staged
 
