@@ -889,7 +889,7 @@ def main():
             'e2e': {'value': e2e_val, 'unit': 'updates/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_t) / e2e_steps * 1e3,
                     'protocol': 'TSFDQN.update_successor_all(pinned host batch, host_losses=pinned buffer) per step: the prologue kernel pulls the '
-                                'batch over PCIe, the last command copies the losses back; the host reads every step\'s losses one step late '
+                                'batch over PCIe, the Adam launch\'s loss block stores the losses into the pinned host buffer; the host reads every step\'s losses one step late '
                                 '(event wait on step k-1 after issuing step k), wall clock around the loop',
                     'sync_value': updates_per_step * e2e_steps / e2e_sync_s, 'sync_ms_per_step': e2e_sync_s / e2e_steps * 1e3,
                     'sync_what': 'the same loop with a stream synchronise + read after EVERY step before the next one is issued'},
