@@ -270,3 +270,21 @@ def test_planar_flow_module_matches_the_oracle_on_cpu():
     assert torch.allclose(g(x), g_apply(x, spec), atol=1e-6)
     assert issubclass(tsfdqn_nf.TSFDQN, __import__('deep_successor_features_for_transfer_b200.tsfdqn', fromlist=['TSFDQN']).TSFDQN)
     assert tsfdqn_nf.DeepTSF is not None and tsfdqn_nf.ReplayBuffer is not None
+
+
+def test_step_prep_launch_count_follows_the_fold_size():
+    """sfgpi_step_prep_launches: folds of >= 4096 folded rows go out as the prologue's second launch (host logic, no GPU)."""
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200.library import NetSpec
+    spec = NetSpec([4, 256, 256, 256, 108], ['none', 'relu', 'relu', 'none'], 9, 12)
+    pr = _lib.StepPrepArgs()
+    pr.net = spec.desc()
+    L = _lib.lib()
+    assert L.sfgpi_step_prep_launches(C.addressof(pr)) == 1                       # no fold at all
+    for n_pol, n_w, expect in ((4, 4, 1), (256, 256, 2), (1, 256, 1), (2, 256, 2), (52, 8, 2), (51, 8, 1)):
+        pr.fold_n, pr.n_w, pr.w_diag = n_pol, n_w, 0
+        rows = L.sfgpi_gpi_fold_rows(C.byref(pr.net), n_w)
+        assert (rows * n_pol >= 4096) == (expect == 2)
+        assert L.sfgpi_step_prep_launches(C.addressof(pr)) == expect, (n_pol, n_w)
+    pr.fold_n, pr.n_w, pr.w_diag = 256, 256, 1                                    # diagonal: one vector per policy, 16 rows each
+    assert L.sfgpi_step_prep_launches(C.addressof(pr)) == 2

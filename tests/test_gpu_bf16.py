@@ -617,3 +617,68 @@ def test_bf16_gpi_wide_scan_equals_rolled_scan(NW, B):
     ka_r, kt_r = run(1 << 30)
     assert torch.equal(ka_w, ka_r) and torch.equal(kt_w, kt_r)
     assert int((ka_w == torch.iinfo(torch.int64).min).sum()) == 0
+
+
+@pytest.mark.parametrize('S,A,D,N,NW', [(4, 9, 12, 3, 256), (4, 9, 12, 9, 77), (11, 27, 50, 4, 40)])
+def test_large_gpi_fold_by_units_equals_row_by_row(S, A, D, N, NW):
+    """
+    Folds of >= 4096 rows run one block per (policy, action, block-of-vectors) unit (csrc/mlp_forward_tc.cu: fold_unit; inside a
+    train step as the prologue's second launch), smaller ones one block per folded row.  Same fmaf chain per output: the
+    all-policies fold (by units) must equal the policy-by-policy folds (row by row) bit for bit -- D <= 16 (rows in
+    registers) and D = 50 (rows from L1), vector counts that pad the last block, and sfgpi_step_prep's two-launch form.
+    """
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    from deep_successor_features_for_transfer_b200.library import _stream
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N)
+    o, gen = make(S, A, D, N, seed=77)
+    sf = gu.build_g2(meta, oracle=o, hyper=HYPER_BF16)
+    lib = sf._library
+    desc = lib.spec.desc()
+    st = _stream()
+    w = (torch.rand(NW, D, generator=gen) * 0.02 - 0.01).cuda().contiguous()
+    nq = _lib.lib().sfgpi_gpi_fold_rows(C.byref(desc), NW)
+    assert nq * N >= 4096 > nq
+    wq = torch.full((N, nq, 256), 7.0, dtype=torch.bfloat16, device='cuda')
+    bq = torch.full((N, nq), 7.0, device='cuda')
+    _lib.call('sfgpi_fold_gpi', C.byref(desc), lib.online.data_ptr(), 0, N, w.data_ptr(), NW, 0, wq.data_ptr(), bq.data_ptr(), st)
+    wq1 = torch.full((N, nq, 256), 3.0, dtype=torch.bfloat16, device='cuda')
+    bq1 = torch.full((N, nq), 3.0, device='cuda')
+    for i in range(N):
+        _lib.call('sfgpi_fold_gpi', C.byref(desc), lib.online.data_ptr(), i, 1, w.data_ptr(), NW, 0, wq1[i].data_ptr(), bq1[i].data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(wq.view(torch.int16), wq1.view(torch.int16)) and torch.equal(bq, bq1)
+    assert float(wq.float().abs().sum()) > 0
+    # the same fold as the second launch of the step prologue
+    pr = _lib.StepPrepArgs()
+    pr.net = desc
+    pr.fold_params, pr.fold_lo, pr.fold_n = lib.online.data_ptr(), 0, N
+    wq2, bq2 = torch.zeros_like(wq), torch.zeros_like(bq)
+    pr.w, pr.n_w, pr.w_diag, pr.wq, pr.bq = w.data_ptr(), NW, 0, wq2.data_ptr(), bq2.data_ptr()
+    assert _lib.lib().sfgpi_step_prep_launches(C.addressof(pr)) == 2
+    _lib.call('sfgpi_step_prep', C.byref(pr), st)
+    torch.cuda.synchronize()
+    assert torch.equal(wq2.view(torch.int16), wq.view(torch.int16)) and torch.equal(bq2, bq)
+
+
+def test_adam_losses_host_needs_pinned_memory():
+    """sfgpi_adam_args.losses_host: pinned host memory is written by the kernel; pageable memory is refused, loudly."""
+    import ctypes as C
+    from deep_successor_features_for_transfer_b200 import _lib
+    S, A, D, N, B = 4, 9, 12, 2, 256
+    meta = dict(S=S, A=A, D=D, hidden=[256, 256], acts=['relu', 'relu'], N=N, gdim=100, beta=1, use_gpi=True)
+    o, gen = make(S, A, D, N, seed=79, tsf_dim=100)
+    sf, ag = gu.build_g3(meta, oracle=o)
+    sf._library.set_precision('bf16')
+    tr = gu.cuda_tr(synthetic_transitions(B, S, A, D, gen))
+    hl = torch.zeros(N, 3).pin_memory()
+    got = ag.update_successor_all(tr, use_gpi=True, host_losses=hl)
+    torch.cuda.synchronize()
+    assert torch.equal(hl, got.cpu()) and float(hl.abs().sum()) > 0
+    lib = sf._library
+    ad = lib._ws[lib.last_plan_key]['ad']
+    pageable = torch.zeros(N, 3)
+    ad.losses_host = pageable.data_ptr()
+    rc = _lib.lib().sfgpi_adam_step(C.byref(ad), None)
+    assert rc != 0 and b'pinned' in _lib.lib().sfgpi_last_error()
+    ad.losses_host = None
