@@ -197,6 +197,19 @@ static __device__ __noinline__ void gpi_emit8(char *pa, char *pt, uint32_t pitch
                                               int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7) {
     const float bb[8] = {b0, b1, b2, b3, b4, b5, b6, b7};
     const int ba[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+    if (n_valid >= 8) {                                          // all but the last block of a padded vector count: no per-key guards
+        if (pa != nullptr) {
+#pragma unroll
+            for (int ws = 0; ws < 8; ++ws)
+                atomicMax(reinterpret_cast<long long *>(pa + (unsigned long long)ws * pitch), pack_key(bb[ws], (uint32_t)ba[ws]));
+        }
+        if (pt != nullptr) {
+#pragma unroll
+            for (int ws = 0; ws < 8; ++ws)
+                atomicMax(reinterpret_cast<long long *>(pt + (unsigned long long)ws * pitch), pack_key(bb[ws], task_id));
+        }
+        return;
+    }
     if (pa != nullptr) {
 #pragma unroll
         for (int ws = 0; ws < 8; ++ws)
