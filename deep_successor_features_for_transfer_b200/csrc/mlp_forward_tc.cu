@@ -410,8 +410,10 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                             if (slot >= n_slots) break;
                             // blocked column orders: each epilogue group takes one 128-column half of the chunk (every emission is an
                             // atomicMax, so a block cut by the boundary merges); plain order (< 4 vectors): group g scans slot g
-                            const int cb = wblk_u > 1 ? col0 + group * 128 : (group == slot ? col0 : c_hi);
-                            const int ce = wblk_u > 1 ? min(cb + 128, c_hi) : c_hi;
+                            // (a chunk of <= 128 columns -- the headline's 36 -- is shared as well: half of its 8-column trips each)
+                            const int half = c_hi - col0 > 128 ? 128 : ((c_hi - col0 + 15) >> 4) << 3;
+                            const int cb = wblk_u > 1 ? col0 + group * half : (group == slot ? col0 : c_hi);
+                            const int ce = wblk_u > 1 ? min(cb + half, c_hi) : c_hi;
                             const int cm = (wide_u && cb < ce) ? cb + ((ce - cb) & ~31) : cb;      // whole 32-column windows: gpi_scan_wide8
                             const int b = slot ? b1_u : b0_u;
                             const uint32_t t_lane = t_lane0 + (uint32_t)slot * 256u;
