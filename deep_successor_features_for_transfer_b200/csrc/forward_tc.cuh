@@ -183,6 +183,46 @@ __device__ __noinline__ void gpi_scan_rolled(uint32_t t_acc, uint32_t bias0, int
     }
 }
 
+// ---- psi-form output chunk of one accumulator for one thread (= one state): columns [col0, col0 + n_cols), the 8-column trips
+// c_first, c_first + 16, ... (the two epilogue groups alternate).  psi_row: this state's row of the psi output ([A*D] floats, 16-byte
+// aligned when A*D % 4 == 0) or NULL; sel_row: its gathered row [D] or NULL with sel_base = a * D (a negative sel_base: no gather).
+// Out of line and rolled for the same reason as the GPI scan: it runs once per tile.
+static __device__ __noinline__ void psi_out_rolled(uint32_t t_acc, uint32_t bias_chunk, int col0, int n_cols, int c_first, float *psi_row,
+                                                  int AD, float *sel_row, int sel_base, int D, bool row_ok) {
+#pragma unroll 1
+    for (int c0 = c_first; c0 < n_cols; c0 += 16) {
+        uint32_t v[8];
+        tmem_ld8(t_acc + (uint32_t)c0, v);
+        const float4 b0 = lds128(bias_chunk + 4u * (uint32_t)c0), b1 = lds128(bias_chunk + 4u * (uint32_t)(c0 + 4));
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        tmem_wait_ld();
+        const int colb = col0 + c0;
+        float val[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) val[i] = __uint_as_float(v[i]) + bv[i];
+        if (row_ok) {
+            if (psi_row != nullptr) {
+                float *po = psi_row + colb;
+                if ((AD & 3) == 0) {                          // rows are 16-byte aligned: 128-bit stores
+                    if (colb < AD) *reinterpret_cast<float4 *>(po) = make_float4(val[0], val[1], val[2], val[3]);
+                    if (colb + 4 < AD) *reinterpret_cast<float4 *>(po + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (colb + i < AD) po[i] = val[i];
+                }
+            }
+            if (sel_row != nullptr && (unsigned)(colb + 7 - sel_base) < (unsigned)(D + 7)) {         // trip overlaps [sel, sel + D)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned off = (unsigned)(colb + i - sel_base);
+                    if (off < (unsigned)D) sel_row[off] = val[i];
+                }
+            }
+        }
+    }
+}
+
 // ---- the same scan for launches with MANY reward vectors (n_w * A of several hundred columns: BASELINE config 4 scores every
 // policy under 256 vectors = 2304 columns per tile).  There the scan -- not the MMAs -- paces the kernel (in-kernel timeline:
 // 6.4-7 k cycles per 128 columns per epilogue group against ~3.9 k for the chunk's MMAs; ncu: the epilogue warps issue one

@@ -393,6 +393,7 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
             const int Lh_u = p.Lh, n_items_u = p.n_items;
             const int ncol_u = p.gpi ? gpi_ncols(p.nw, A_) : 0;
             const bool lean_gpi = p.gpi != 0 && !a.w_diag && a.key_stage == nullptr && a.q_out == nullptr;
+            const bool lean_psi = p.gpi == 0;
             for (int it = 0; it < n_items_u; ++it) {
                 if (lean_gpi && it == 1 + Lh_u) {
                     const int nw_u = p.nw, n_final_u = p.n_final, wblk_u = gpi_wblock(nw_u);
@@ -428,6 +429,36 @@ mlp_forward_tc_kernel(const __grid_constant__ TcMulti m, const __grid_constant__
                                 else if (wblk_u == 4) gpi_scan_rolled<4>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_b, kt_b, kstep_u, b < B, tid_u, nullptr);
                                 else gpi_scan_rolled<1>(t_lane, bias_u, col0, cm, ce, A_, nw_u, ka_b, kt_b, kstep_u, b < B, tid_u, nullptr);
                             }
+                            tc_fence_before();
+                            if (more) slot_ready(slot);                                     // next chunk may overwrite the accumulator
+                            TL_EPI();
+                        }
+                    }
+                    break;
+                }
+                if (lean_psi && it == 1 + Lh_u) {
+                    // psi-form output chunks (online job: the gathered rows; target job: the full psi rows), same lean shape
+                    const int n_final_u = p.n_final, n_pol_u = a.n_pol;
+                    const uint32_t bias_u = bias_addr + 4u * ((1 + Lh_u) * kH);
+                    float *const psi_u = a.psi_out, *const sel_u = a.sel_out;
+                    const int b0_u = bs[0], b1_u = n_slots > 1 ? bs[1] : 0;
+                    const int sb0_u = sel_base[0], sb1_u = n_slots > 1 ? sel_base[1] : -(1 << 30);
+#pragma unroll 1
+                    for (int col0 = 0; col0 < n_final_u; col0 += 256) {
+                        const int n_cols = min(256, n_final_u - col0);
+                        const bool more = col0 + 256 < n_final_u;
+#pragma unroll
+                        for (int slot = 0; slot < 2; ++slot) {
+                            if (slot >= n_slots) break;
+                            const int b = slot ? b1_u : b0_u;
+                            const uint32_t t_lane = t_lane0 + (uint32_t)slot * 256u;
+                            mbar_wait(ACC_FULL(slot), full_cnt[slot] & 1);
+                            ++full_cnt[slot];
+                            tc_fence_after();
+                            TL_EPI();
+                            psi_out_rolled(t_lane, bias_u + 4u * (uint32_t)col0, col0, n_cols, group * 8,
+                                           psi_u ? psi_u + ((size_t)b * n_pol_u + pl) * AD : nullptr, AD,
+                                           sel_u ? sel_u + ((size_t)pl * B + b) * D : nullptr, slot ? sb1_u : sb0_u, D, b < B);
                             tc_fence_before();
                             if (more) slot_ready(slot);                                     // next chunk may overwrite the accumulator
                             TL_EPI();
